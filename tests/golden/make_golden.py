@@ -1,0 +1,269 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (/root/reference) in the build container.
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  The GPU box has no /root/reference, so the fixtures are
+committed; this script is committed with them so they can be regenerated and audited.
+Each fixture stores its inputs next to the reference outputs.
+SciPy/NumPy versions used are recorded in tests/golden/VERSIONS.json.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+kgeo = ref_shim.install()
+import scipy  # noqa: E402
+from kgeo.bfields import Bfield  # noqa: E402
+from kgeo.emissivities import Emissivity  # noqa: E402
+from kgeo.equatorial_images import make_image  # noqa: E402
+from kgeo.equatorial_lensing import nmax_equatorial, nmax_poloidal, r_equatorial  # noqa: E402
+from kgeo.kerr_raytracing_ana import coords_at_tau, raytrace_ana  # noqa: E402
+from kgeo.kerr_raytracing_utils import (is_outside_crit, mino_total, n_equatorial_crossings,  # noqa: E402
+                                         n_poloidal_orbits, radial_roots, uplus_uminus)
+from kgeo.scipy_ellip_binding import ellip_pi_arr  # noqa: E402
+from kgeo.velocities import Velocity  # noqa: E402
+import scipy.special as sp  # noqa: E402
+
+DEG = np.pi / 180.0
+
+
+def quiet(fn, *args, **kwargs):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*args, **kwargs)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('%-28s %8.1f kB' % (name, os.path.getsize(path) / 1e3))
+
+
+def grid(n, half, n_beta=None, half_beta=None):
+    al = np.linspace(-half, half, n)
+    be = np.linspace(-(half_beta or half), (half_beta or half), n_beta or n)
+    A, B = np.meshgrid(al, be)
+    return A.flatten(), B.flatten()
+
+
+# ---------------------------------------------------------------- special functions
+def special():
+    rng = np.random.default_rng(20261017)
+    # the reference's own (print-only) check list: Pi(0.8; phi | -0.33), scipy_ellip_binding.py:241-256
+    phis = np.array([.026, .1, np.pi / 2., 2.37, 4.1, 6., 7.7, 14.3, 215.])
+    phis = np.concatenate([phis, -phis])
+    ref_list = ellip_pi_arr(np.full(phis.shape, 0.8), phis, np.full(phis.shape, -0.33))
+    # random sweep over the ranges the hot path visits incl. n>1 (rho<0 branch)
+    N = 4000
+    n = np.concatenate([rng.uniform(1e-6, 0.999, N // 2), rng.uniform(1.001, 80., N // 2)])
+    m = np.concatenate([rng.uniform(-70., 0.999, N // 2), rng.uniform(0.001, 0.9999, N // 2)])
+    phi = np.concatenate([rng.uniform(-19., 19., N // 2), rng.uniform(-np.pi, np.pi, N // 2)])
+    pis = ellip_pi_arr(n, phi, m)
+    # special-value masks
+    n_sp = np.array([0.5, 0.5, 1.0, 2.0, np.inf, 0.3, 0.3, 4.0])
+    phi_sp = np.array([5e-11, 1.0, 2.0, np.pi / 4, 1.0, np.pi / 2, -np.pi / 2, np.pi / 6])
+    m_sp = np.array([0.3, -2e14, 0.5, 0.3, 0.2, 0.5, 0.5, 0.9])
+    with np.errstate(all='ignore'):
+        pis_sp = ellip_pi_arr(n_sp, phi_sp, m_sp)
+    # Legendre F, E (cephes) incl. negative parameter; Jacobi; Carlson
+    phi_fe = rng.uniform(-19., 19., N)
+    m_fe = np.concatenate([rng.uniform(-70., 0.0, N // 2), rng.uniform(0.0, 0.99999, N // 2)])
+    F = sp.ellipkinc(phi_fe, m_fe)
+    E = sp.ellipeinc(phi_fe, m_fe)
+    K = sp.ellipk(m_fe)
+    u_j = rng.uniform(-20., 20., N)
+    m_j = np.concatenate([rng.uniform(0.004, 0.9, N // 2), 1.0 - 10.0 ** rng.uniform(-9, -1, N // 2)])
+    sn, cn, dn, am = sp.ellipj(u_j, m_j)
+    x = 10.0 ** rng.uniform(-8, 1, N)
+    y = 10.0 ** rng.uniform(-4, 2.5, N)
+    z = 10.0 ** rng.uniform(-3, 1, N)
+    p = 10.0 ** rng.uniform(-5, 1, N)
+    x[:50] = 0.0
+    save('special',
+         pi_list_phi=phis, pi_list=ref_list,
+         pi_n=n, pi_phi=phi, pi_m=m, pi=pis,
+         pisp_n=n_sp, pisp_phi=phi_sp, pisp_m=m_sp, pisp=pis_sp,
+         fe_phi=phi_fe, fe_m=m_fe, F=F, E=E, K=K,
+         j_u=u_j, j_m=m_j, sn=sn, cn=cn, dn=dn, am=am,
+         c_x=x, c_y=y, c_z=z, c_p=p,
+         rf=sp.elliprf(x, y, z), rd=sp.elliprd(x, y, z), rj=sp.elliprj(x, y, z, p), rc=sp.elliprc(x, y))
+
+
+# ---------------------------------------------------------------- per-ray constants
+SETUP_CASES = [  # (a, th_o, r_o, half-width, n)
+    (0.94, 17 * DEG, 1000., 8., 40),
+    (0.94, 17 * DEG, np.inf, 10., 40),
+    (0.5, 60 * DEG, 1.e5, 9., 32),
+    (0.94, 80 * DEG, 1000., 3., 48),       # contains class-II pixels
+    (0.99, 80 * DEG, np.inf, 3., 48),
+    (0.998, 10 * DEG, 1000., 3., 32),      # class IV + vortical heavy
+    (0.0, 45 * DEG, 1000., 8., 24),        # |a| < MINSPIN branches
+    (0.7, 135 * DEG, 1000., 8., 24),       # th_o > pi/2
+]
+
+
+def setup():
+    out = {}
+    for i, (a, th_o, r_o, half, n) in enumerate(SETUP_CASES):
+        A, B = grid(n, half)
+        lam = -A * np.sin(th_o)
+        eta = (A ** 2 - a ** 2) * np.cos(th_o) ** 2 + B ** 2
+        up, um, ratio, a2um = uplus_uminus(a, th_o, lam.copy(), eta.copy())
+        r1, r2, r3, r4, rclass = radial_roots(a, lam, eta)
+        tmax = mino_total(a, r_o, eta, r1, r2, r3, r4)
+        out.update({
+            'c%d_par' % i: np.array([a, th_o, r_o]), 'c%d_alpha' % i: A, 'c%d_beta' % i: B,
+            'c%d_up' % i: up, 'c%d_um' % i: um, 'c%d_ratio' % i: ratio, 'c%d_a2um' % i: a2um,
+            'c%d_roots' % i: np.array([r1, r2, r3, r4]), 'c%d_rclass' % i: rclass, 'c%d_tmax' % i: tmax,
+            'c%d_outside' % i: is_outside_crit(a, th_o, A, B),
+            'c%d_nmax_eq' % i: quiet(nmax_equatorial, a, r_o, th_o, A, B),
+            'c%d_nmax_pol' % i: quiet(nmax_poloidal, a, r_o, th_o, A, B),
+        })
+    out['ncases'] = np.array(len(SETUP_CASES))
+    save('setup', **out)
+
+
+# ---------------------------------------------------------------- tracks
+TRACK_CASES = [  # (a, th_o, r_o, alpha, beta, ngeo)
+    ('default', 0.94, 20 * DEG, 1.e5, np.linspace(-6, 6, 120), np.zeros(120), 25),   # BASELINE cfg 1, thinned
+    ('grid17', 0.94, 17 * DEG, 1000., *grid(28, 8.), 24),
+    ('classII', 0.94, 80 * DEG, 1000., *grid(30, 3.), 16),
+    ('extremal', 0.998, 10 * DEG, 1000., *grid(20, 3.), 16),
+    ('spin0', 0.0, 45 * DEG, 1000., *grid(16, 8.), 16),
+    ('south', 0.7, 135 * DEG, 1000., *grid(16, 8.), 16),
+    ('midspin', 0.42, 60 * DEG, 1000., *grid(16, 12.), 16),
+]
+
+
+def tracks():
+    for (name, a, th_o, r_o, A, B, ngeo) in TRACK_CASES:
+        with np.errstate(all='ignore'):
+            g = quiet(raytrace_ana, a=a, observer_coords=[0, r_o, th_o, 0], image_coords=[A, B], ngeo=ngeo,
+                      plotdata=False)
+        save('tracks_' + name, par=np.array([a, th_o, r_o, ngeo]), alpha=A, beta=B,
+             tau=g.mino_times, sig=g.affine_times,
+             t=g.geo_coords[0], r=g.geo_coords[1], th=g.geo_coords[2], ph=g.geo_coords[3])
+
+
+# ---------------------------------------------------------------- equatorial lensing / images
+def lensing():
+    out = {}
+    cases = [(0.94, 17 * DEG, np.inf, 10., 48), (0.5, 60 * DEG, 1000., 9., 32), (0.0, 45 * DEG, np.inf, 8., 24),
+             (0.7, 135 * DEG, 1000., 8., 24), (0.99, 85 * DEG, np.inf, 8., 32)]
+    for i, (a, th_o, r_o, half, n) in enumerate(cases):
+        A, B = grid(n, half)
+        out['c%d_par' % i] = np.array([a, th_o, r_o])
+        out['c%d_alpha' % i] = A
+        out['c%d_beta' % i] = B
+        for mbar in range(3):
+            with np.errstate(all='ignore'):
+                rs, Ir, Imax, Nmax = quiet(r_equatorial, a, r_o, th_o, mbar, A, B)
+            out['c%d_m%d' % (i, mbar)] = np.array([rs, Ir, Imax, Nmax])
+        # t, phi at the crossings: scripts/calc_t_equatorial.py:50-62 (needs finite r_o)
+        if np.isfinite(r_o):
+            _, Ir, _, _ = quiet(r_equatorial, a, r_o, th_o, 0, A, B)
+            with np.errstate(all='ignore'):
+                sig, co = quiet(coords_at_tau, a, [0, r_o, th_o, 0], [A, B], Ir, do_phi_and_t=True)
+            out['c%d_cross0' % i] = np.array([sig[0], co[0][0], co[1][0], co[2][0], co[3][0]])
+    out['ncases'] = np.array(len(cases))
+    save('lensing', **out)
+
+
+IMAGE_CASES = [
+    # name, (a, r_o, th_o, mbar_max, half, npix), emissivity, velocity, bfield, kwargs
+    ('default', (0.94, np.inf, 17 * DEG, 2, 10., 64), ('bpl', {}), ('zamo', {}), ('rad', {}), {}),
+    ('testpol', (0.42, np.inf, 60 * DEG, 2, 10., 64), ('ring', {}),
+     ('general', dict(fac_subkep=0.7, beta_phi=0.7, beta_r=0.7)), ('bz_guess', dict(C=1.)),
+     dict(polarization=True, specind=1.)),
+    ('subkep_pol', (0.7, np.inf, 45 * DEG, 2, 10., 48), ('ring', {}),
+     ('general', dict(fac_subkep=0.6, beta_phi=0.8, beta_r=0.7)), ('bz_guess', dict(C=1.)),
+     dict(polarization=True, specind=1.)),
+    ('kep_vert_path', (0.9, 1000., 163 * DEG, 2, 10., 48), ('glm', {}), ('kep', {}), ('vert', {}),
+     dict(polarization=True, pathlength=True, specind=0.5)),
+    ('thermal_genpower', (0.9, np.inf, 30 * DEG, 1, 12., 40),
+     ('thermal', dict(ne0=1.e5, Te0=1.e11, B0=5., bfield_model=True)), ('subkep', dict(fac_subkep=0.8)),
+     ('gen_power', dict(n_I=0.5, p_val=1.0)), dict(polarization=True, pathlength=True)),
+    ('infall_tor', (0.3, np.inf, 50 * DEG, 1, 10., 40), ('constant', {}), ('infall', {}), ('tor', {}), {}),
+    ('gelles_simple', (0.6, np.inf, 40 * DEG, 1, 10., 40), ('bpl', dict(p1=-1.5, p2=-0.3, emiscut_in=3., emiscut_out=9.)),
+     ('gelles', {}), ('simple', dict(Cr=0.5, Cvert=1.0, Cph=-0.7)), dict(polarization=True)),
+    ('simfit_rm1', (0.8, np.inf, 25 * DEG, 1, 10., 40), ('ring', dict(r_ring=5., sigma=0.8)), ('simfit', {}),
+     ('simple_rm1', dict(Cr=1.0, Cvert=0.2, Cph=0.3)), dict(polarization=True)),
+    ('spin0_default', (0.0, np.inf, 45 * DEG, 2, 10., 40), ('bpl', {}), ('zamo', {}), ('rad', {}), {}),
+]
+
+
+def images():
+    for (name, (a, r_o, th_o, mbar_max, half, npx), em, vel, bf, kw) in IMAGE_CASES:
+        psize = 2 * half / npx
+        with np.errstate(all='ignore'):
+            out = quiet(make_image, a, r_o, th_o, mbar_max, -half, half, -half, half, psize,
+                        emissivity=Emissivity(em[0], **em[1]), velocity=Velocity(vel[0], **vel[1]),
+                        bfield=Bfield(bf[0], **bf[1]), **kw)
+        names = ['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np', 'lp', 'Ie'][:len(out)]
+        save('image_' + name, par=np.array([a, r_o, th_o, mbar_max, half, npx]),
+             spec=np.array(json.dumps(dict(em=em, vel=vel, bf=bf, kw=kw))),
+             **{k: v for k, v in zip(names, out)})
+
+
+def models():
+    """Element-wise physics closed forms on a radius grid."""
+    r = np.linspace(1.05, 30., 160)
+    out = {'r': r}
+    spins = [0.0, 0.3, 0.94, -0.5]
+    vels = [('zamo', {}), ('infall', {}), ('kep', {}), ('kep', dict(retrograde=True)), ('subkep', dict(fac_subkep=0.7)),
+            ('general', dict(fac_subkep=0.6, beta_phi=0.8, beta_r=0.7)), ('general', dict(retrograde=True, fac_subkep=0.24, beta_phi=0.42, beta_r=0.24)),
+            ('gelles', {}), ('simfit', {})]
+    bfs = [('rad', {}), ('vert', {}), ('tor', {}), ('simple', dict(Cr=0.5, Cvert=1.0, Cph=-0.7)),
+           ('simple_rm1', dict(Cr=1.0, Cvert=0.2, Cph=0.3)), ('bz_guess', dict(C=1.)), ('bz_guess', dict(C=-1.)),
+           ('gen_power', dict(n_I=0.5, p_val=1.0)), ('gen_power', dict(n_I=0., p_val=0.75, isAbove=False)),
+           ('monopoleA', dict(C=1.))]
+    ems = [('constant', {}), ('bpl', {}), ('bpl', dict(p1=-1.5, p2=-0.3)), ('glm', {}), ('glm', dict(gamma_off=-2, sigma=1.)),
+           ('ring', {}), ('ring', dict(r_ring=4, gamma_off=0.1, sigma=0.6))]
+    out['spins'] = np.array(spins)
+    out['spec'] = np.array(json.dumps(dict(vels=vels, bfs=bfs, ems=ems)))
+    for ia, a in enumerate(spins):
+        rr = r[r > 1 + np.sqrt(1 - a * a) + 0.02]
+        out['a%d_r' % ia] = rr
+        with np.errstate(all='ignore'):
+            for iv, (vt, kw) in enumerate(vels):
+                v = Velocity(vt, **kw)
+                out['a%d_v%d' % (ia, iv)] = np.array([np.broadcast_to(c, rr.shape) for c in v.u_lab(float(a), rr)], dtype=float)
+            for ib, (bt, kw) in enumerate(bfs):
+                b = Bfield(bt, **kw)
+                out['a%d_b%d' % (ia, ib)] = np.array([np.broadcast_to(c, rr.shape) for c in b.bfield_lab(float(a), rr)], dtype=float)
+                out['a%d_bsq%d' % (ia, ib)] = b.bsq(float(a), rr, Velocity('general', fac_subkep=0.6, beta_phi=0.8, beta_r=0.7))
+            for ie, (et, kw) in enumerate(ems):
+                e = Emissivity(et, **kw)
+                out['a%d_e%d' % (ia, ie)] = e.jrest(float(a), rr, g=0.7 + 0 * rr, sinthetab=0.6 + 0 * rr, specind=1.0)
+            e = Emissivity('thermal', ne0=1.e5, Te0=1.e11, B0=5.)
+            out['a%d_ethermal' % ia] = e.jrest(float(a), rr, g=0.7 + 0 * rr, sinthetab=0.6 + 0 * rr, Bmag=3.0 + 0 * rr)
+    save('models', **out)
+
+
+def counts():
+    """n_equatorial_crossings / n_poloidal_orbits on full (ntau, npix) tau arrays."""
+    a, th_o = 0.94, 17 * DEG
+    A, B = grid(20, 8.)
+    tau = np.linspace(0.0, 4.0, 9)[:, None] * np.ones(len(A))[None, :]
+    save('counts', par=np.array([a, th_o]), alpha=A, beta=B, tau=tau,
+         neq=n_equatorial_crossings(a, th_o, A, B, tau), npol=n_poloidal_orbits(a, th_o, A, B, tau))
+
+
+if __name__ == '__main__':
+    np.seterr(all='ignore')
+    special()
+    setup()
+    tracks()
+    lensing()
+    images()
+    models()
+    counts()
+    with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
+        json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

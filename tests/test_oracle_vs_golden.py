@@ -1,0 +1,176 @@
+"""Pins the CPU oracle (oracle/kgeo_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py) and against the reference's own
+known-answer tests.  CPU only."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import kgeo_oracle as ko
+from helpers import assert_close, image_models
+
+np.seterr(all='ignore')
+TIGHT = 1e-13   # the oracle follows the reference's operation order with the same SciPy
+
+
+def test_pi_against_reference(golden):
+    g = golden('special')
+    assert_close(ko.legendre_pi(np.full(18, 0.8), g['pi_list_phi'], np.full(18, -0.33)), g['pi_list'], TIGHT, what='Pi list')
+    assert_close(ko.legendre_pi(g['pi_n'], g['pi_phi'], g['pi_m']), g['pi'], 0.0, what='Pi sweep')
+    assert_close(ko.legendre_pi(g['pisp_n'], g['pisp_phi'], g['pisp_m']), g['pisp'], TIGHT, what='Pi special')
+
+
+def test_pi_against_mpmath():
+    """The reference's print-only self check (scipy_ellip_binding.py:241-256) turned into an assertion."""
+    import mpmath
+    phis = [.026, .1, np.pi / 2., 2.37, 4.1, 6., 7.7, 14.3, 215.]
+    for phi in phis + [-p for p in phis]:
+        want = float(mpmath.re(mpmath.ellippi(0.8, phi, -0.33)))
+        got = float(ko.legendre_pi(np.array([0.8]), np.array([phi]), np.array([-0.33]))[0])
+        assert abs(got / want - 1) < 2e-13
+
+
+def test_setup_against_reference(golden):
+    g = golden('setup')
+    for i in range(int(g['ncases'])):
+        a, th_o, r_o = g['c%d_par' % i]
+        A, B = g['c%d_alpha' % i], g['c%d_beta' % i]
+        lam, eta = ko.conserved(a, th_o, A, B)
+        up, um, ratio, a2um = ko.angular_consts(a, th_o, lam, eta)
+        for got, key in ((up, 'up'), (um, 'um'), (ratio, 'ratio'), (a2um, 'a2um')):
+            assert_close(got, g['c%d_%s' % (i, key)], 0.0, what='case %d %s' % (i, key))
+        r1, r2, r3, r4, region = ko.quartic_roots(a, lam, eta)
+        roots = g['c%d_roots' % i]
+        for got, ref in zip((r1, r2, r3, r4), roots):
+            assert np.array_equal(got, ref)
+        assert np.array_equal(region, g['c%d_rclass' % i])
+        assert_close(ko.mino_total(a, r_o, eta, r1, r2, r3, r4), g['c%d_tmax' % i], 0.0, what='tau_tot %d' % i)
+        assert np.array_equal(ko.outside_crit(a, th_o, A, B), g['c%d_outside' % i])
+        assert_close(ko.nmax_equatorial(a, r_o, th_o, A, B), g['c%d_nmax_eq' % i], 0.0, what='nmax_eq %d' % i)
+        assert_close(ko.nmax_poloidal(a, r_o, th_o, A, B), g['c%d_nmax_pol' % i], TIGHT, what='nmax_pol %d' % i)
+
+
+@pytest.mark.parametrize('name', ['default', 'grid17', 'classII', 'extremal', 'spin0', 'south', 'midspin'])
+def test_tracks_against_reference(golden, name):
+    g = golden('tracks_' + name)
+    a, th_o, r_o, ngeo = g['par']
+    tau, sig, (t, r, th, ph) = ko.raytrace(float(a), [0, float(r_o), float(th_o), 0], [g['alpha'], g['beta']], int(ngeo))
+    assert_close(tau, g['tau'], 0.0, what='tau')
+    for got, key in ((sig, 'sig'), (t, 't'), (r, 'r'), (th, 'th'), (ph, 'ph')):
+        assert_close(got, g[key], TIGHT, floor=1e-3, what='%s %s' % (name, key))
+
+
+def test_lensing_against_reference(golden):
+    g = golden('lensing')
+    for i in range(int(g['ncases'])):
+        a, th_o, r_o = g['c%d_par' % i]
+        A, B = g['c%d_alpha' % i], g['c%d_beta' % i]
+        for mbar in range(3):
+            got = np.array(ko.r_equatorial(float(a), float(r_o), float(th_o), mbar, A, B))
+            assert_close(got, g['c%d_m%d' % (i, mbar)], TIGHT, floor=1e-6, what='r_equatorial %d/%d' % (i, mbar))
+        key = 'c%d_cross0' % i
+        if key in g.files:
+            Ir = g['c%d_m0' % i][1]
+            sig, co = ko.coords_at_tau(float(a), [0, float(r_o), float(th_o), 0], [A, B], Ir)
+            got = np.array([sig[0], co[0][0], co[1][0], co[2][0], co[3][0]])
+            assert_close(got, g[key], TIGHT, floor=1e-3, what='crossing coords %d' % i)
+
+
+IMAGES = ['default', 'testpol', 'subkep_pol', 'kep_vert_path', 'thermal_genpower', 'infall_tor', 'gelles_simple',
+          'simfit_rm1', 'spin0_default']
+
+
+@pytest.mark.parametrize('name', IMAGES)
+def test_images_against_reference(golden, name):
+    g = golden('image_' + name)
+    a, r_o, th_o, mbar_max, half, npx = g['par']
+    em, vel, bf, kw = image_models(g['spec'])
+    out = ko.make_image(float(a), float(r_o), float(th_o), int(mbar_max), -half, half, -half, half, 2 * half / npx,
+                        em, vel, bf, **kw)
+    names = ['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np', 'lp', 'Ie'][:len(out)]
+    for got, key in zip(out, names):
+        assert_close(got, g[key], 1e-12, floor=1e-300, what='%s %s' % (name, key))
+
+
+def test_models_against_reference(golden):
+    g = golden('models')
+    spec = json.loads(str(g['spec']))
+    genvel = dict(type='general', fac_subkep=0.6, beta_phi=0.8, beta_r=0.7)
+    for ia, a in enumerate(g['spins']):
+        a = float(a)
+        r = g['a%d_r' % ia]
+        for iv, (vt, kw) in enumerate(spec['vels']):
+            got = np.array([np.broadcast_to(c, r.shape) for c in ko.velocity_u_lab(dict(type=vt, **kw), a, r)])
+            assert_close(got, g['a%d_v%d' % (ia, iv)], TIGHT, what='vel %s a=%g' % (vt, a))
+        for ib, (bt, kw) in enumerate(spec['bfs']):
+            got = np.array([np.broadcast_to(c, r.shape) for c in ko.bfield_lab(dict(type=bt, **kw), a, r)])
+            assert_close(got, g['a%d_b%d' % (ia, ib)], TIGHT, what='bfield %s a=%g' % (bt, a))
+            assert_close(ko.bfield_bsq(dict(type=bt, **kw), genvel, a, r), g['a%d_bsq%d' % (ia, ib)], TIGHT,
+                         what='bsq %s a=%g' % (bt, a))
+        for ie, (et, kw) in enumerate(spec['ems']):
+            got = ko.emissivity_jrest(dict(type=et, **kw), a, r, g=0.7 + 0 * r, sinthb=0.6 + 0 * r, specind=1.0)
+            assert_close(got, g['a%d_e%d' % (ia, ie)], TIGHT, what='emis %s a=%g' % (et, a))
+        got = ko.emissivity_jrest(dict(type='thermal', ne0=1.e5, Te0=1.e11, B0=5.), a, r, g=0.7 + 0 * r,
+                                  sinthb=0.6 + 0 * r, Bmag=3.0 + 0 * r)
+        assert_close(got, g['a%d_ethermal' % ia], TIGHT, what='thermal a=%g' % a)
+
+
+def test_counts_against_reference(golden):
+    g = golden('counts')
+    a, th_o = g['par']
+    assert_close(ko.n_equatorial(float(a), float(th_o), g['alpha'], g['beta'], g['tau']), g['neq'], 0.0, what='neq')
+    assert_close(ko.n_poloidal(float(a), float(th_o), g['alpha'], g['beta'], g['tau']), g['npol'], TIGHT, what='npol')
+
+
+# ----- the reference's own known-answer tests, run against the oracle -----------------------------
+def test_ipole_velocity_general():
+    """tests/test_velocities.py:77-104 of the reference."""
+    tests = {
+        (0, 1, 0.7, 0.7, 0.3, 4.0): [1.65511, -0.243725, 0, 0.141355],
+        (0, 0.3, 0.1, 0.4, 0.9375, 1.6): [14.0203, -0.934042, 0, 3.63511],
+        (0, 0.1, 0.36, 0.72, 0.1707, 3.4): [2.04774, -0.549666, 0, 0.0269644],
+        (1, 0.24, 0.42, 0.24, 0.42, 10.): [1.19678, -0.340182, 0, -0.00297456],
+        (1, 0.24, 0.42, 0.24, 0.42, 3.5): [2.23166, -0.71236, 0, 0.0121293],
+    }
+    for (retro, fs, bp, br, a, r), want in tests.items():
+        vel = dict(type='general', retrograde=bool(retro), fac_subkep=fs, beta_phi=bp, beta_r=br)
+        got = np.array([np.squeeze(c) for c in ko.velocity_u_lab(vel, a, np.array([r]))], dtype=float)
+        assert np.allclose(got, want, rtol=1e-5)
+
+
+def test_ipole_bfield_bz_guess():
+    """tests/test_bfields.py:8-26 of the reference."""
+    tests = {(1, 0.5, 2.9): -0.201073, (1, 0.5, 3.7): -0.141622, (1, 0.5, 10.): -0.0832697,
+             (1, 0.9375, 1.35): -382.704, (1, 0.9375, 2.8): -0.546836, (-1, 0.9375, 2.8): -0.546836}
+    for (C, a, r), want in tests.items():
+        B = ko.bfield_lab(dict(type='bz_guess', C=C), a, np.array([r]))
+        assert np.allclose(want, B[2] / B[0], rtol=1e-5)
+
+
+def test_ipole_emissivity():
+    """tests/test_emissivities.py:5-43 of the reference."""
+    glm = dict(gamma_off=-2, sigma=1.)
+    ring = dict(r_ring=4, gamma_off=0.1, sigma=0.6)
+    tests = [('constant', 0, 1, {}, 1), ('bpl', 0.3, 8, {}, 0.022089), ('bpl', 0.3, 25, {}, 0.00023715),
+             ('bpl', 0.4, 3, {}, 0.36913), ('bpl', 0.5, 10, {}, 0.0085085), ('bpl', 0.9, 3.141593, {}, 0.15376),
+             ('bpl', 0.3679, 3.141593, {}, 0.33512), ('glm', 0.3679, 3.141593, {}, 0.19198), ('glm', 0.5, 5, {}, 0.069270),
+             ('glm', 0.3, 5, {}, 0.066282), ('glm', 0.83, 9, {}, 0.014741), ('glm', 0.3679, 3.1415927, glm, 0.30569),
+             ('glm', 0.4, 5, glm, 0.19078), ('ring', 0.3679, 3.141593, {}, 0.061782), ('ring', 0.4, 5, {}, 0.75227),
+             ('ring', 0.83, 9, {}, 0.00067951), ('ring', 0.5, 2.4, ring, 0.16079), ('ring', 0.318, 7, ring, 0.017807),
+             ('ring', 0.1, 5., ring, 0.32917)]
+    for (model, a, r, kw, want) in tests:
+        assert np.isclose(ko.emissivity_jrest(dict(type=model, **kw), a, np.array([float(r)])), want, rtol=1e-4)
+
+
+def test_ipole_midplane_rays():
+    """tests/test_geodesics_kerr_ana.py:47-75 of the reference (5 of the 15 rays; the GPU test runs all)."""
+    tests = {(0.42, 60., -9., 0.): (-0.103693, -8.09784), (0.42, 60., 6., 0.): (877.845, -13.6213),
+             (0.9, 10., 1., 0.): (-0.518830, -0.632352), (0.73, 35., 0.0001, -1.): (1.02201, 1.13478),
+             (0.73, 35., 0.0001, 4.): (-2.11221, 1.02322)}
+    for (a, inc, al, be), want in tests.items():
+        _, _, (t, r, th, ph) = ko.raytrace(a, [0, 1000., inc / 180. * np.pi, 0], [np.array([al]), np.array([be])], 10000)
+        r, th, ph = r[:, 0], th[:, 0], ph[:, 0]
+        x, y, z = r * np.sin(th) * np.cos(ph), r * np.sin(th) * np.sin(ph), r * np.cos(th)
+        if z[0] > z[1]:
+            x, y, z = x[::-1], y[::-1], z[::-1]
+        assert np.allclose([np.interp(0, z, x), np.interp(0, z, y)], want, rtol=1e-3)
