@@ -1,0 +1,199 @@
+/* kgeo_b200 -- C ABI of the B200-native analytic Kerr ray tracer (libkgeo_b200.so, sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of achael/kgeo: the per-pixel analytic null-geodesic solve and the
+ * equatorial image pipeline built on it.  The reference has no native code; its only FFI is ctypes -> libgsl for the
+ * elliptic integral Pi (kgeo/gsl_ellip_binding.py:142-152, 3 doubles in -> 1 double out) and its "plugin seam" is the
+ * module-level backend switch in kgeo/kerr_raytracing_ana.py:31-43.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  Every function returns 0 on success, a positive cudaError_t value on a
+ *    CUDA failure, or a negative KGEO_E_* code on bad arguments; kgeo_last_error() returns a static description.
+ *  - `*_dev` pointers are DEVICE pointers owned by the caller (8-byte aligned); the library allocates nothing behind
+ *    them.  The `*_host` entry points take HOST buffers, stage through device memory internally and return when the
+ *    results are in the host buffers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points are stream-ordered and
+ *    asynchronous, thread-safe, and keep no global state.
+ *  - Numerical trouble surfaces as NaN/inf in the outputs, never as an error code (as in the reference,
+ *    kgeo/scipy_ellip_binding.py:138-162).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails with cudaErrorNoDevice.
+ */
+#ifndef KGEO_B200_H
+#define KGEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGEO_B200_ABI_VERSION 1
+
+#define KGEO_E_BADARG (-1)   /* NULL pointer, negative size, inconsistent shapes */
+#define KGEO_E_RANGE (-2)    /* |a| >= 1, r_o < 100, th_o outside (0,pi) or == pi/2 (the reference's own checks) */
+#define KGEO_E_MODEL (-3)    /* unknown physics model id */
+
+/* Observer / black hole: (a, r_o, th_o) of observer_coords = [t, r_o, th_o, ph] (kgeo/kerr_raytracing_ana.py:46-71). */
+typedef struct kgeo_observer {
+    double a;     /* spin, |a| < 1 */
+    double r_o;   /* observer radius >= 100, may be +inf for the lensing/image entry points */
+    double th_o;  /* inclination in (0,pi), != pi/2 */
+} kgeo_observer;
+
+/* setup modes: the reference's whole-array guards np.any(eta>0), np.any(eta<=0) (kerr_raytracing_ana.py:217,300) and
+ * the low-spin eta clamp that only the track entry points apply (:80-82) */
+#define KGEO_MODE_ANY_ETA_POS 1
+#define KGEO_MODE_ANY_ETA_NONPOS 2
+#define KGEO_MODE_CLAMP_LOWSPIN_ETA 4
+#define KGEO_MODE_INPUT_LAM_ETA 8 /* kgeo_ray_summary only: the two input arrays hold (lam, eta), not (alpha, beta) */
+
+/* ---- physics models of the equatorial image (kgeo/velocities.py, kgeo/bfields.py, kgeo/emissivities.py) ---- */
+enum kgeo_velocity_type { KGEO_VEL_ZAMO = 0, KGEO_VEL_INFALL, KGEO_VEL_KEP, KGEO_VEL_SUBKEP, KGEO_VEL_GENERAL,
+                          KGEO_VEL_GELLES, KGEO_VEL_SIMFIT };
+enum kgeo_bfield_type { KGEO_B_SIMPLE = 0, KGEO_B_SIMPLE_RM1, KGEO_B_BZ_GUESS, KGEO_B_GEN_POWER, KGEO_B_MONOPOLE_A };
+enum kgeo_emissivity_type { KGEO_EM_CONSTANT = 0, KGEO_EM_BPL, KGEO_EM_GLM, KGEO_EM_RING, KGEO_EM_THERMAL };
+
+/* Parameter meaning per type (defaults as in the reference constructors):
+ *  velocity: ZAMO/INFALL: none.  KEP: p[0]=retrograde.  SUBKEP: p[0]=retrograde, p[1]=fac_subkep.
+ *            GENERAL: p[0]=retrograde, p[1]=fac_subkep, p[2]=beta_phi, p[3]=beta_r.  GELLES: p[0]=beta, p[1]=chi.
+ *            SIMFIT: p[0]=ell_isco, p[1]=vr_isco, p[2]=p1, p[3]=p2, p[4]=dd.                 (velocities.py:26-68)
+ *  bfield:   SIMPLE/SIMPLE_RM1: p[0]=Cr, p[1]=Cvert, p[2]=Cph ('rad','vert','tor' are SIMPLE with unit coefficients).
+ *            BZ_GUESS: p[0]=C.  GEN_POWER: p[0]=n_I, p[1]=p_val, p[2]=isAbove.  MONOPOLE_A: p[0]=C, p[1]=omegafac.
+ *                                                                                            (bfields.py:36-91)
+ *  emissivity: BPL: p[0]=p1, p[1]=p2.  GLM: p[0]=gamma_off, p[1]=sigma.  RING: p[0]=r_ring, p[1]=gamma_off, p[2]=sigma.
+ *            THERMAL: p[0]=Rb, p[1]=ne0, p[2]=Te0, p[3]=B0, p[4]=alpha_n, p[5]=alpha_T, p[6]=alpha_B, p[7]=bfield_model.
+ *            emiscut_in / emiscut_out as in Emissivity.__init__.                              (emissivities.py:39-72)
+ */
+typedef struct kgeo_models {
+    int32_t velocity_type;
+    int32_t bfield_type;
+    int32_t emissivity_type;
+    int32_t reserved;
+    double velocity_p[8];
+    double bfield_p[8];
+    double emissivity_p[8];
+    double emiscut_in;
+    double emiscut_out;
+} kgeo_models;
+
+/* Image options = keyword arguments of Iobs / make_image (kgeo/equatorial_images.py:23-32,124-127). */
+typedef struct kgeo_image_opts {
+    int32_t mbar_min;      /* orders mbar_min..mbar_max are produced (make_image: 0..mbar_max; Iobs: mbar..mbar) */
+    int32_t mbar_max;
+    int32_t polarization;  /* 0/1 */
+    int32_t pathlength;    /* 0/1 */
+    double specind;
+    double diskangle;
+    double nu_obs;
+} kgeo_image_opts;
+
+int kgeo_abi_version(void);
+const char* kgeo_last_error(void);
+/* number of CUDA devices visible to the library, or a negative/positive error code */
+int kgeo_device_count(int* count);
+/* doubles per ray in the ray-constant workspace (slot-major SoA: slot s of ray i at w[s*npix + i]) */
+int kgeo_ray_workspace_slots(void);
+/* cumulative number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long kgeo_launch_count(void);
+
+/* ---- element-wise special functions (device pointers) --------------------------------------------------------
+ * Replace scipy.special.elliprf/elliprd/elliprj/elliprc, ellipkinc/ellipeinc/ellipk, ellipj as used at the call sites
+ * listed in SURVEY.md 8(c), the libgsl bindings gsl_sf_ellint_RF_e/RJ_e/RC_e (kgeo/gsl_ellip_binding.py:142-152), and
+ * ellip_pi_arr(n,phi,m) (kgeo/scipy_ellip_binding.py:87-237; same special-value conventions). */
+int kgeo_special_rf(size_t n, const double* x_dev, const double* y_dev, const double* z_dev, double* out_dev, void* stream);
+int kgeo_special_rd(size_t n, const double* x_dev, const double* y_dev, const double* z_dev, double* out_dev, void* stream);
+int kgeo_special_rj(size_t n, const double* x_dev, const double* y_dev, const double* z_dev, const double* p_dev,
+                    double* out_dev, void* stream);
+int kgeo_special_rc(size_t n, const double* x_dev, const double* y_dev, double* out_dev, void* stream);
+int kgeo_special_ellipk(size_t n, const double* m_dev, double* out_dev, void* stream);
+int kgeo_special_ellipkinc(size_t n, const double* phi_dev, const double* m_dev, double* out_dev, void* stream);
+int kgeo_special_ellipeinc(size_t n, const double* phi_dev, const double* m_dev, double* out_dev, void* stream);
+int kgeo_special_ellippi(size_t n, const double* n_dev, const double* phi_dev, const double* m_dev, double* out_dev,
+                         void* stream);
+int kgeo_special_ellipj(size_t n, const double* u_dev, const double* m_dev, double* sn_dev, double* cn_dev,
+                        double* dn_dev, double* am_dev, void* stream);
+
+/* ---- per-ray setup --------------------------------------------------------------------------------------------
+ * Replaces radial_roots, mino_total, uplus_uminus, angular_turning (kgeo/kerr_raytracing_utils.py:242-548) and the
+ * observer-side antiderivatives of th_integrate / r_integrate (kgeo/kerr_raytracing_ana.py:231-251,312-327,431-434,
+ * 508-510,583-584).  w_dev: kgeo_ray_workspace_slots()*npix doubles; flags_dev: npix int32. */
+int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
+                   double* w_dev, int32_t* flags_dev, void* stream);
+/* Unpacked per-ray summary for the host API: roots_dev[8*npix] = Re r1..r4, Im r1..r4 (plane-major), rclass_dev = the
+ * reference's region label 1..4 (0 on a boundary), tau_tot_dev, u_plus/u_minus/uratio/a2u_minus, outside_dev =
+ * is_outside_crit, thplus/thminus = angular_turning's turning points.  Any output may be NULL.
+ * (kerr_raytracing_utils.py:242-328,330-380,382-548,794-826) */
+int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
+                     double* roots_dev, int32_t* rclass_dev, double* tau_tot_dev, double* uplus_dev, double* uminus_dev,
+                     double* uratio_dev, double* a2uminus_dev, double* outside_dev, double* thplus_dev,
+                     double* thminus_dev, void* stream);
+/* mino_total(a, r_o, eta, r1..r4) from caller-supplied roots (kerr_raytracing_utils.py:382-548):
+ * roots_dev[8*n] = Re r1..r4, Im r1..r4 plane-major; out_dev[n]. */
+int kgeo_mino_total(const kgeo_observer* obs, size_t n, const double* roots_dev, double* out_dev, void* stream);
+
+/* ---- geodesic tracks --------------------------------------------------------------------------------------------
+ * Replaces coords_at_tau / raytrace_ana / th_integrate / r_integrate (kgeo/kerr_raytracing_ana.py:46-193,195-633).
+ * One thread per (ray, Mino-time sample).  Outputs are [ntau, ld] row-major (sample-major, ray fastest), exactly the
+ * reference's (ngeo, npix) arrays when ld == npix; any output pointer may be NULL (not materialised).
+ *  tau_dev == NULL : samples are numpy.linspace(0, maxtaufrac*tau_tot, ntau) per ray (raytrace_ana :93-94);
+ *  tau_dev != NULL : [ntau, tau_ld] user Mino times (coords_at_tau).
+ *  full == 0       : only r and theta are computed (do_phi_and_t=False), t/phi/sigma outputs are zero-filled. */
+int kgeo_tracks(const kgeo_observer* obs, size_t npix, const double* w_dev, const int32_t* flags_dev, size_t ntau,
+                double maxtaufrac, const double* tau_dev, size_t tau_ld, int full, double* t_dev, double* r_dev,
+                double* th_dev, double* ph_dev, double* sig_dev, double* tau_out_dev, size_t ld, void* stream);
+/* Fused convenience: setup + tracks in one call, device pointers; w/flags scratch supplied by the caller. */
+int kgeo_raytrace(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
+                  size_t ngeo, double maxtaufrac, double* w_dev, int32_t* flags_dev, double* t_dev, double* r_dev,
+                  double* th_dev, double* ph_dev, double* sig_dev, double* tau_out_dev, size_t ld, void* stream);
+/* Host-buffer entry point (the end-to-end path): alpha/beta and all outputs are HOST pointers, [ngeo, npix]. */
+int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode,
+                       size_t ngeo, double maxtaufrac, double* t, double* r, double* th, double* ph, double* sig,
+                       double* tau_out, int device);
+
+/* ---- crossing counts (kgeo/kerr_raytracing_utils.py:551-684) ---------------------------------------------------
+ * n_equatorial_crossings / n_poloidal_orbits at Mino times tau_dev[ntau, npix]; outputs [ntau, npix], may be NULL. */
+int kgeo_crossing_counts(const kgeo_observer* obs, size_t npix, const double* beta_dev, const double* w_dev,
+                         const int32_t* flags_dev, size_t ntau, const double* tau_dev, double* neq_dev,
+                         double* npol_dev, void* stream);
+
+/* ---- equatorial lensing (kgeo/equatorial_lensing.py:22-196) ----------------------------------------------------
+ * r_equatorial for mbar = mbar_lo .. mbar_hi in one pass: outputs are [(mbar_hi-mbar_lo+1), npix] planes
+ * (r_s, Ir, Nmax per order) and [npix] (Imax, n_poloidal = nmax_poloidal); any may be NULL. */
+int kgeo_r_equatorial(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev,
+                      int mbar_lo, int mbar_hi, double* rs_dev, double* Ir_dev, double* Nmax_dev, double* Imax_dev,
+                      double* npol_dev, void* stream);
+
+/* ---- equatorial image (kgeo/equatorial_images.py:23-544) -------------------------------------------------------
+ * Fused n = mbar_min..mbar_max image: per pixel one setup, then per order the crossing radius, redshift, (polarization,)
+ * emissivity and Stokes I,Q,U.  Planes are [mbar_max-mbar_min+1, npix] (order-major); the Python wrapper exposes them with the
+ * reference's (npix, mbar_max+1) indexing.  nmax_dev = Nmax of the last order, npol_dev = nmax_poloidal, imax_dev = the
+ * total Mino time (Iobs's Imax; -1 for vortical rays); lp/Ie only when opts->pathlength.  Any output may be NULL. */
+int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                          const double* alpha_dev, const double* beta_dev, double* I_dev, double* Q_dev, double* U_dev,
+                          double* r_dev, double* Ir_dev, double* g_dev, double* sinthb_dev, double* nmax_dev,
+                          double* npol_dev, double* imax_dev, double* lp_dev, double* Ie_dev, void* stream);
+/* Host-buffer variant (end-to-end path).  Same layouts, HOST pointers. */
+int kgeo_equatorial_image_host(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts,
+                               size_t npix, const double* alpha, const double* beta, double* I, double* Q, double* U,
+                               double* r, double* Ir, double* g, double* sinthb, double* nmax, double* npol,
+                               double* imax, double* lp, double* Ie, int device);
+
+/* ---- element-wise physics closed forms (device pointers) -------------------------------------------------------
+ * Velocity.u_lab (kgeo/velocities.py:70-96), Bfield.bfield_lab / Bfield.bsq (kgeo/bfields.py:93-131,365-396),
+ * Emissivity.jrest (kgeo/emissivities.py:83-118) in the equatorial plane.  g/sinthb/Bmag may be NULL in jrest. */
+int kgeo_velocity_u_lab(const kgeo_models* models, double a, size_t n, const double* r_dev, double* u0_dev,
+                        double* u1_dev, double* u2_dev, double* u3_dev, void* stream);
+int kgeo_bfield_lab(const kgeo_models* models, double a, size_t n, const double* r_dev, double* B1_dev, double* B2_dev,
+                    double* B3_dev, double* bsq_dev, void* stream);
+int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const double* r_dev, const double* g_dev,
+                          const double* sinthb_dev, const double* Bmag_dev, double nu_obs, double specind,
+                          double* j_dev, void* stream);
+
+/* ---- measurement helper: sustained DFMA rate of the device (the measured FP64 roofline denominator) ------------ */
+int kgeo_fp64_peak_probe(int iters, double* flops_per_launch, float* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGEO_B200_H */

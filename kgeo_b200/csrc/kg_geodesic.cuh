@@ -1,0 +1,765 @@
+// Per-ray setup and per-(ray, Mino time) evaluation of the analytic Kerr null geodesic (Gralla & Lupsasca 2019a,b).
+//
+// Replaces, for the hot path, kgeo/kerr_raytracing_utils.py (uplus_uminus :276-328, radial_roots :330-380,
+// mino_total :382-548, n_equatorial_crossings :605-684, n_poloidal_orbits :551-603, is_outside_crit :794-826) and
+// kgeo/kerr_raytracing_ana.py (th_integrate :195-365, r_integrate :368-633, S1_S2 :638-663, R1_R2 :666-683).
+//
+// Layout: `ray_setup` reduces a pixel (alpha, beta) to NW doubles + one flag word ("ray constants"): everything that
+// does not depend on the Mino time, including the observer-side antiderivatives and the complete integrals needed
+// for period bookkeeping.  `theta_eval` / `radial_eval` then cost one Jacobi ladder and one shared Carlson bundle
+// each per Mino-time sample.  The constants are addressed through an accessor so the same code runs from a
+// register array (fused setup), shared memory, or a strided SoA workspace in HBM.
+//
+// What is deliberately different from the reference's arithmetic (same mathematics):
+//  * the quartic is solved in real arithmetic (resolvent cubic + two quadratics), branch choices as in the
+//    reference's complex solve;
+//  * amplitudes are never formed: F(am(u)|m) = u, sin/cos of the amplitude are sn/cn, period reduction is done
+//    on u with the K(m) that falls out of the AGM ladder;
+//  * E - F is evaluated as -(m/3) s^3 RD directly (no cancellation, no 1/k, so the a -> 0 limit needs no
+//    special case), and all Pi's of one amplitude share one duplication track.
+#pragma once
+#include "kg_special.cuh"
+
+namespace kg {
+
+constexpr double kMinSpin = 1.0e-4;  // kgeo/kerr_raytracing_utils.py:9
+constexpr double kEP = 1.0e-12;      // kgeo/kerr_raytracing_utils.py:12
+
+// ------------------------------------------------------------------------------------------------------------
+struct Observer {
+    double a, r_o, th_o;
+    double a2, rplus, rminus, sth, cth, cth2;
+    int ro_inf, lowspin, north;
+};
+
+KG_HD Observer make_observer(double a, double r_o, double th_o) {
+    Observer o;
+    o.a = a;
+    o.r_o = r_o;
+    o.th_o = th_o;
+    o.a2 = a * a;
+    double q = sqrt(1.0 - a * a);
+    o.rplus = 1.0 + q;
+    o.rminus = 1.0 - q;
+    o.sth = sin(th_o);
+    o.cth = cos(th_o);
+    o.cth2 = o.cth * o.cth;
+    o.ro_inf = isinf(r_o) ? 1 : 0;
+    o.lowspin = (fabs(a) < kMinSpin) ? 1 : 0;
+    o.north = (th_o < kHalfPi) ? 1 : 0;
+    return o;
+}
+
+// eta = (alpha^2 - a^2) cos^2(th_o) + beta^2 with every operation rounded separately (no FMA contraction), so that the
+// sign of eta -- which selects the polar class -- is decided exactly as in NumPy (kgeo/kerr_raytracing_ana.py:77)
+KG_HD double conserved_eta(const Observer& o, double alpha, double beta) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(alpha, alpha), -o.a2), o.cth2), __dmul_rn(beta, beta));
+#else
+    volatile double aa = alpha * alpha, bb = beta * beta;
+    volatile double d = aa - o.a2;
+    volatile double e = d * o.cth2;
+    return e + bb;
+#endif
+}
+
+// ---- ray-constant slots --------------------------------------------------------------------------------------
+enum Slot {
+    S_LAM = 0, S_ETA, S_TAUTOT,
+    // polar motion
+    T_W,      // sqrt(|a^2 u_-|): snarg = T_X0 - T_W * tau
+    T_X0,     // T_W * s_o * Gth_o
+    T_M,      // reciprocal-modulus parameter m = k/(k-1) in [0,1)
+    T_SQ,     // sqrt(1-m)
+    T_K,      // K(m)
+    T_KPAR,   // Legendre parameter k < 0 of the reference's formulas
+    T_A, T_B, // theta = acos(T_A*sinPhi) (ordinary) | acos(h*sqrt(T_A + T_B sin^2 nu)) (vortical, h in flags)
+    T_N,      // characteristic of the Pi in G_phi
+    T_D2, T_D3, T_GPH0,         // G_phi = D3*(snarg + pi_tail) + D2*j - GPH0
+    T_C1, T_C2, T_C3, T_GT0,    // G_t   = C3*snarg + C2*j + C1 * s^3 RD     - GT0
+    T_F0, T_KC,                 // F0 = F(asin(cos th_o/sqrt u+)|k), K(k): crossing bookkeeping (ordinary only)
+    // radial motion, common
+    R_K,      // parameter k2 | k3 | k4
+    R_SC,     // X = R_X0 - R_SC * tau
+    R_X0,
+    R_KC,     // K(k)  (complete), R_EC = E(k)
+    R_EC,
+    R_N0, R_N1, R_N2,           // three Pi characteristics
+    R_PC0, R_PC1, R_PC2,        // Pi(n_i|k) - K(k)
+    R_PO0, R_PO1, R_PO2,        // observer-side values: case 2: Pi(n_i;aux|k); case 3: R1(al_i,aux); case 4: S1(al_i,aux)
+    R_EO,                       // case 2: E(aux|k);  case 3: R2(al0,aux);  case 4: S2(g0,aux)
+    R_Q0, R_Q1, R_Q2, R_Q3, R_Q4, R_Q5, R_Q6, R_Q7, R_Q8, R_Q9, R_Q10, R_Q11, R_Q12, R_Q13, R_Q14, R_Q15,
+    NW
+};
+// case-specific meaning of the R_Q* slots
+//  case 2: Q0..Q3 = r1..r4, Q4 = sqrt(r31 r42), Q5 = H_o
+//  case 3: Q0 = r1, Q1 = r2, Q2 = A, Q3 = B, Q4..Q6 = al0, alp, alm, Q7..Q9 = p1(al_i), Q10 = sqrt(AB)
+//  case 4: Q0 = a2, Q1 = b1, Q2 = g0, Q3 = gp, Q4 = gm, Q5..Q7 = p2(al_i), Q8 = pref, Q9 = x4rp, Q10 = x4rm
+
+enum Flag {
+    F_TH_ORD = 1, F_TH_VORT = 2,          // polar class (neither: theta outputs stay 0, as in the reference)
+    F_CASE2 = 4, F_CASE3 = 8, F_CASE4 = 16,
+    F_SPOS = 32,                          // s_o = my_sign(beta) = +1
+    F_HPOS = 64,                          // h = +1 (th_o <= pi/2)
+    F_REGION_SHIFT = 8,                   // bits 8..10: region label 0..4 of radial_roots
+    F_OUTSIDE = 1 << 12,                  // is_outside_crit
+    F_LOWSPIN = 1 << 13
+};
+
+struct Roots {
+    double re[4], im[4];   // r1..r4 (im of r1 = -im of r2, im of r3 = -im of r4)
+    int c12, c34;          // complex pair flags
+    int region;
+};
+
+KG_HD void angular_consts(const Observer& o, double lam, double eta, double* up_, double* um_, double* ratio_,
+                          double* a2um_) {
+    // kgeo/kerr_raytracing_utils.py:276-328
+    double up, um;
+    if (o.lowspin) {
+        up = eta / (eta + lam * lam);
+        um = up;
+    } else {
+        double dth = 0.5 * (1.0 - (eta + lam * lam) / o.a2);
+        double rt = sqrt(dth * dth + eta / o.a2);
+        up = dth + rt;
+        um = dth - rt;
+    }
+    if (o.cth2 - up > 0.0) up = o.cth2;
+    if (up * up > 1.0) up = 1.0;
+    if (um == 0.0) um = (eta < 0.0) ? kEP : -kEP;
+    if (eta < 0.0 && (o.cth2 - um) < 0.0) um = o.cth2;
+    *up_ = up;
+    *um_ = um;
+    if (o.lowspin) {
+        *ratio_ = 0.0;
+        *a2um_ = -(eta + lam * lam);
+    } else {
+        *ratio_ = up / um;
+        *a2um_ = o.a2 * um;
+    }
+}
+
+KG_HD Roots quartic_roots(const Observer& o, double lam, double eta) {
+    // kgeo/kerr_raytracing_utils.py:330-380 in real arithmetic
+    Roots R;
+    double a = o.a;
+    double A = o.a2 - eta - lam * lam;
+    double B = 2.0 * (eta + (lam - a) * (lam - a));
+    double C = -o.a2 * eta;
+    double P = -(A * A) / 12.0 - C;
+    double Q = (-A / 3.0) * ((A * A) / 36.0 - C) - (B * B) / 8.0;
+    double disc = 4.0 * (P * P * P) + 27.0 * (Q * Q);
+    double xi0;
+    if (disc >= 0.0) {
+        double h = sqrt(disc / 108.0);
+        xi0 = cbrt(-0.5 * Q + h) + cbrt(-0.5 * Q - h) - A / 3.0;
+    } else {
+        // omega_+/-^3 = -Q/2 +/- i h : principal cube roots are conjugate, the sum is 2 |w|^(1/3) cos(arg/3)
+        double h = sqrt(-disc / 108.0);
+        double mag = sqrt(0.25 * Q * Q + h * h);
+        double ang = atan2(h, -0.5 * Q);
+        xi0 = 2.0 * cbrt(mag) * cos(ang / 3.0) - A / 3.0;
+    }
+    double z = sqrt(0.5 * xi0);
+    double d12 = (-0.5 * A - z * z) + 0.25 * B / z;
+    double d34 = (-0.5 * A - z * z) - 0.25 * B / z;
+    R.c12 = d12 < 0.0;
+    R.c34 = d34 < 0.0;
+    if (R.c12) {
+        double s = sqrt(-d12);
+        R.re[0] = -z; R.re[1] = -z; R.im[0] = -s; R.im[1] = s;
+    } else {
+        double s = sqrt(d12);
+        R.re[0] = -z - s; R.re[1] = -z + s; R.im[0] = 0.0; R.im[1] = 0.0;
+    }
+    if (R.c34) {
+        double s = sqrt(-d34);
+        R.re[2] = z; R.re[3] = z; R.im[2] = -s; R.im[3] = s;
+    } else {
+        double s = sqrt(d34);
+        R.re[2] = z - s; R.re[3] = z + s; R.im[2] = 0.0; R.im[3] = 0.0;
+    }
+    int region = 0;
+    if (R.c12) region = 4;
+    else if (R.c34) region = 3;
+    else if (R.re[3] < o.rplus) region = 2;
+    else if (R.re[3] > o.rplus) region = 1;
+    R.region = region;
+    return R;
+}
+
+// ---- Legendre integrals of an amplitude given by (sin, cos), |phi| <= pi ----------------------------------------
+// F, E and NP Pi's; amplitudes beyond pi/2 are reflected (phi = +/-pi + phi_r).  With Kc/RDc/PicTail supplied by
+// the caller when known (pass NaN to have them computed on demand).
+template <int NP>
+KG_HD void legendre_sc(double s, double c, double m, const double* n, double* F, double* E, double* Pi) {
+    double j = 0.0;
+    if (c < 0.0) {
+        j = (s >= 0.0) ? 1.0 : -1.0;
+        s = -s;
+        c = -c;
+    }
+    double c2 = c * c, y = fma(-m * s, s, 1.0);
+    PiPrep pp[NP > 0 ? NP : 1];
+    double pa[NP > 0 ? NP : 1], rj[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        pp[i] = pi_prepare(n[i], s, c2, y);
+        pa[i] = pp[i].p;
+    }
+    double rf, rd;
+    carlson_bundle<NP, true, true>(c2, y, pa, &rf, &rd, rj);
+    double Fr = s * rf;
+    double Er = Fr - (m * (1.0 / 3.0)) * cube(s) * rd;
+    double Kc = 0.0, RDc = 0.0;
+    if (j != 0.0) {
+        Kc = ellip_K(m);
+        RDc = ellip_RDc(m);
+    }
+    *F = (j != 0.0) ? fma(2.0 * j, Kc, Fr) : Fr;
+    *E = (j != 0.0) ? fma(2.0 * j, Kc - (m * (1.0 / 3.0)) * RDc, Er) : Er;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        double v = Fr + pi_finish(n[i], s, c2, y, Fr, pp[i], rj[i]);
+        if (j != 0.0) v += 2.0 * j * (Kc + ellip_PicTail(n[i], m));
+        Pi[i] = v;
+    }
+}
+
+KG_HD double legendre_F_sc(double s, double c, double m) {
+    double F, E;
+    legendre_sc<0>(s, c, m, nullptr, &F, &E, nullptr);
+    return F;
+}
+
+// ---- total Mino time from given roots (kgeo/kerr_raytracing_utils.py:382-548) ------------------------------------------
+// Stand-alone version for the helper API mino_total(a, r_o, eta, r1..r4); ray_setup computes the same quantity in
+// passing from its own case constants.
+KG_HD double tau_total_of(const Observer& o, const Roots& R) {
+    const double rp = o.rplus, r_o = o.r_o;
+    if (R.c12) {
+        double a1 = R.im[3], b1 = R.re[3], a2 = R.im[1], b2 = R.re[1];
+        double CC = sqrt(sq(a1 - a2) + sq(b1 - b2)), DD = sqrt(sq(a1 + a2) + sq(b1 - b2));
+        double k4 = (4.0 * CC * DD) / sq(CC + DD);
+        double g0 = sqrt((4.0 * a2 * a2 - sq(CC - DD)) / (sq(CC + DD) - 4.0 * a2 * a2));
+        double x4rp = (rp + b1) / a2;
+        double ig = 1.0 / sqrt(1.0 + g0 * g0);
+        double so, co;
+        if (o.ro_inf) {
+            so = ig;
+            co = -g0 * ig;
+        } else {
+            double x4ro = (r_o + b1) / a2, ix = 1.0 / sqrt(1.0 + x4ro * x4ro);
+            so = (x4ro + g0) * ix * ig;
+            co = (1.0 - x4ro * g0) * ix * ig;
+        }
+        double ixp = 1.0 / sqrt(1.0 + x4rp * x4rp);
+        double sh = (x4rp + g0) * ixp * ig, ch = (1.0 - x4rp * g0) * ixp * ig;
+        double pref = 2.0 / (CC + DD);
+        return pref * legendre_F_sc(so, co, k4) - pref * legendre_F_sc(sh, ch, k4);
+    }
+    if (R.c34) {
+        double a1 = R.im[3], b1 = R.re[3], rr1 = R.re[0], rr2 = R.re[1];
+        double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2;
+        double AA = sqrt(a1 * a1 + sq(b1 - rr2)), BB = sqrt(a1 * a1 + sq(b1 - rr1));
+        double k3 = (sq(AA + BB) - rr21 * rr21) / (4.0 * AA * BB);
+        double x3rp = (AA * rrp1 - BB * rrp2) / (AA * rrp1 + BB * rrp2);
+        double x3ro = o.ro_inf ? (AA - BB) / (AA + BB)
+                               : (AA * (r_o - rr1) - BB * (r_o - rr2)) / (AA * (r_o - rr1) + BB * (r_o - rr2));
+        double pref = 1.0 / sqrt(AA * BB);
+        double so = sqrt(fmax(0.0, (1.0 - x3ro) * (1.0 + x3ro))), sh = sqrt(fmax(0.0, (1.0 - x3rp) * (1.0 + x3rp)));
+        return pref * legendre_F_sc(so, x3ro, k3) - pref * legendre_F_sc(sh, x3rp, k3);
+    }
+    double q1 = R.re[0], q2 = R.re[1], q3 = R.re[2], q4 = R.re[3];
+    double rr31 = q3 - q1, rr32 = q3 - q2, rr41 = q4 - q1, rr42 = q4 - q2;
+    double k2 = (rr32 * rr41) / (rr31 * rr42);
+    double x2ro = o.ro_inf ? sqrt(rr31 / rr41) : sqrt((rr31 * (r_o - q4)) / (rr41 * (r_o - q3)));
+    double pref = 2.0 / sqrt(rr31 * rr42);
+    double I2ro = pref * legendre_F_sc(x2ro, sqrt(fmax(0.0, (1.0 - x2ro) * (1.0 + x2ro))), k2);
+    if (q3 < rp) {
+        double x2rp = sqrt((rr31 * (rp - q4)) / (rr41 * (rp - q3)));
+        return I2ro - pref * legendre_F_sc(x2rp, sqrt(fmax(0.0, (1.0 - x2rp) * (1.0 + x2rp))), k2);
+    }
+    if (q3 > rp) return 2.0 * I2ro;
+    return 0.0;
+}
+
+// ---- GL19a auxiliary integrals ------------------------------------------------------------------------------------
+// R1, R2 (B62, B65; kgeo/kerr_raytracing_ana.py:666-683).  sn, cn, dn = sin, cos, sqrt(1-j sin^2) of the amplitude.
+KG_HD double R1_of(double al, double p1, double nn, double sn, double dn, double Pi) {
+    double f1 = 0.5 * p1 * log(fabs((p1 * dn + sn) / (p1 * dn - sn)));
+    return (Pi - al * f1) / (1.0 - al * al);
+}
+KG_HD double R2_of(double al, double j, double nn, double sn, double cn, double dn, double F, double E, double R1) {
+    double al2 = al * al, den = j + (1.0 - j) * al2;
+    double R2 = (F - (al2 / den) * (E - al * sn * dn / (1.0 + al * cn))) / (al2 - 1.0);
+    return R2 + (2.0 * j - nn) * R1 / den;
+}
+// S1, S2 (B92, B93; kgeo/kerr_raytracing_ana.py:638-663)
+KG_HD double S1_of(double al, double p2, double dn, double F, double Pi) {
+    double al2 = al * al;
+    double f2 = 0.5 * p2 * log(fabs(((1.0 - p2) * (1.0 + p2 * dn)) / ((1.0 + p2) * (1.0 - p2 * dn))));
+    return (F + al2 * Pi - al * f2) / (1.0 + al2);
+}
+KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double F, double E, double S1) {
+    double al2 = al * al, al2p1 = 1.0 + al2, al2j = 1.0 - j + al2;
+    // (al - tan)/(1 + al tan) written with sn, cn so that cn -> 0 is harmless
+    double S2a = (1.0 - j) * F + al2 * E + al2 * dn * (al * cn - sn) / (cn + al * sn) - al2 * al;
+    S2a = -S2a / (al2p1 * al2j);
+    return S2a + S1 * (1.0 / al2p1 + (1.0 - j) / al2j);
+}
+
+// ---- ray setup -------------------------------------------------------------------------------------------------------
+// any_eta_pos / any_eta_nonpos reproduce the reference's whole-array guards `np.any(eta>0)` / `np.any(eta<=0)`
+// (kgeo/kerr_raytracing_ana.py:217,300): they are properties of the CALL, computed once by the host wrapper.
+enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4 };
+// PHI_T = false skips every constant that only the phi / t / sigma integrals need (image and lensing paths).
+template <bool PHI_T>
+KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, double* w, int* flags_out) {
+    const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
+    for (int i = 0; i < NW; ++i) w[i] = 0.0;
+    int flags = 0;
+    double lam = -alpha * o.sth;
+    double eta = conserved_eta(o, alpha, beta);
+    if (o.lowspin && (mode & M_CLAMP_LOWSPIN_ETA) && eta < 0.0) eta = kEP;   // kgeo/kerr_raytracing_ana.py:80-82 (tracks only)
+    if (o.lowspin) flags |= F_LOWSPIN;
+    w[S_LAM] = lam;
+    w[S_ETA] = eta;
+    double s_o = (beta >= 0.0) ? 1.0 : -1.0;
+    if (beta >= 0.0) flags |= F_SPOS;
+    if (o.th_o <= kHalfPi) flags |= F_HPOS;
+
+    double up, um, ratio, a2um;
+    angular_consts(o, lam, eta, &up, &um, &ratio, &a2um);
+
+    // ---------------- polar motion (kgeo/kerr_raytracing_ana.py:216-363) ----------------
+    if (any_eta_pos && eta >= 0.0) {
+        flags |= F_TH_ORD;
+        double k = ratio;                        // <= 0
+        double pref = 1.0 / sqrt(-a2um);
+        double so = o.cth / sqrt(up);            // sin of the observer amplitude, in [-1,1]
+        double co = sqrt(fmax(0.0, (1.0 - so) * (1.0 + so)));
+        double F0, E0 = 0.0, Pi0 = 0.0;
+        if (PHI_T) legendre_sc<1>(so, co, k, &up, &F0, &E0, &Pi0);
+        else F0 = legendre_F_sc(so, co, k);
+        double m = k / (k - 1.0);
+        double sq1m = sqrt(1.0 - m);
+        double Km = ellip_K(m);
+        double Kk = sq1m * Km;                   // K(k) for the negative parameter
+        double RDc = PHI_T ? ellip_RDc(k) : 0.0;
+        double PicT = PHI_T ? ellip_PicTail(up, k) : 0.0;      // Pi(u+|k) - K(k); +inf when u+ == 1
+        w[T_W] = sqrt(-a2um);
+        w[T_X0] = w[T_W] * s_o * (-pref * F0);
+        w[T_M] = m;
+        w[T_SQ] = sq1m;
+        w[T_K] = Km;
+        w[T_KPAR] = k;
+        w[T_A] = -s_o * sqrt(up);
+        w[T_N] = up;
+        w[T_D2] = 2.0 * pref * PicT;
+        w[T_D3] = pref;
+        w[T_GPH0] = s_o * (-pref * Pi0);
+        double ct = up * pref * (1.0 / 3.0);
+        w[T_C1] = ct;
+        w[T_C2] = 2.0 * ct * RDc;
+        w[T_C3] = 0.0;
+        // Gt_o = 2 u+ pref (E - F)/(2k) = -(u+ pref/3) s^3 RD, with E - F = -(k/3) s^3 RD
+        if (PHI_T) {
+            double EmF_over_k = (k != 0.0) ? (E0 - F0) / k : -(1.0 / 3.0) * cube(so) * carlson_rd(co * co, 1.0, 1.0);
+            w[T_GT0] = s_o * (up * pref * EmF_over_k);
+        }
+        w[T_F0] = F0;
+        w[T_KC] = Kk;
+    } else if (any_eta_nonpos && eta < 0.0) {
+        flags |= F_TH_VORT;
+        double h = (o.th_o <= kHalfPi) ? 1.0 : -1.0;
+        double prefA = 1.0 / sqrt(a2um);
+        double prefB = prefA / (1.0 - um);
+        double prefC = sqrt(um / o.a2);
+        double so = sqrt((o.cth2 - um) / (up - um));
+        double co = sqrt(fmax(0.0, (1.0 - so) * (1.0 + so)));
+        double k = 1.0 - ratio;
+        double nch = (up - um) / (1.0 - um);
+        double F0, E0 = 0.0, Pi0 = 0.0;
+        if (PHI_T) legendre_sc<1>(so, co, k, &nch, &F0, &E0, &Pi0);
+        else F0 = legendre_F_sc(so, co, k);
+        double m = k / (k - 1.0);
+        double sq1m = sqrt(1.0 - m);
+        double Km = ellip_K(m);
+        double Kk = sq1m * Km;
+        double Ek = PHI_T ? ellip_Ec(k) : 0.0;
+        double PicT = PHI_T ? ellip_PicTail(nch, k) : 0.0;
+        w[T_W] = sqrt(a2um);
+        w[T_X0] = w[T_W] * s_o * (-h * prefA * F0);
+        w[T_M] = m;
+        w[T_SQ] = sq1m;
+        w[T_K] = Km;
+        w[T_KPAR] = k;
+        w[T_A] = um;
+        w[T_B] = up - um;
+        w[T_N] = nch;
+        w[T_D2] = 2.0 * prefB * PicT;
+        w[T_D3] = prefB;
+        w[T_GPH0] = s_o * (-h * prefB * Pi0);
+        w[T_C1] = -prefC * k * (1.0 / 3.0);
+        w[T_C2] = 2.0 * prefC * (Ek - Kk);
+        w[T_C3] = prefC;
+        w[T_GT0] = s_o * (-h * prefC * E0);
+    }
+
+    // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
+    Roots R = quartic_roots(o, lam, eta);
+    flags |= (R.region << F_REGION_SHIFT);
+    if (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) flags |= F_OUTSIDE;   // utils :817-824
+    const double rp = o.rplus, rm = o.rminus, r_o = o.r_o;
+    double tau_tot = 0.0;
+
+    if (R.c12) {  // ---- case 4 ----
+        flags |= F_CASE4;
+        double a1 = R.im[3], b1 = R.re[3], a2 = R.im[1], b2 = R.re[1];
+        double CC = sqrt(sq(a1 - a2) + sq(b1 - b2));
+        double DD = sqrt(sq(a1 + a2) + sq(b1 - b2));
+        double k4 = (4.0 * CC * DD) / sq(CC + DD);
+        double x4rp = (rp + b1) / a2, x4rm = (rm + b1) / a2;
+        double g0 = sqrt((4.0 * a2 * a2 - sq(CC - DD)) / (sq(CC + DD) - 4.0 * a2 * a2));
+        double gp = (g0 * x4rp - 1.0) / (g0 + x4rp);
+        double gm = (g0 * x4rm - 1.0) / (g0 + x4rm);
+        double pref = 2.0 / (CC + DD);
+        // aux = atan(x4ro) + atan(g0) as (sin, cos)
+        double ig = 1.0 / sqrt(1.0 + g0 * g0);
+        double sa, ca;
+        if (o.ro_inf) {
+            sa = ig;
+            ca = -g0 * ig;
+        } else {
+            double x4ro = (r_o + b1) / a2;
+            double ix = 1.0 / sqrt(1.0 + x4ro * x4ro);
+            sa = (x4ro + g0) * ix * ig;
+            ca = (1.0 - x4ro * g0) * ix * ig;
+        }
+        double nn[3] = {1.0 + g0 * g0, 1.0 + gp * gp, 1.0 + gm * gm};
+        double al[3] = {g0, gp, gm};
+        double Fo, Eo = 0.0, Pio[3] = {0.0, 0.0, 0.0};
+        if (PHI_T) legendre_sc<3>(sa, ca, k4, nn, &Fo, &Eo, Pio);
+        else Fo = legendre_F_sc(sa, ca, k4);
+        w[R_K] = k4;
+        w[R_SC] = 1.0 / pref;
+        w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
+        if (PHI_T) {
+            double dno = sqrt(fma(-k4 * sa, sa, 1.0));
+            w[R_KC] = ellip_K(k4);
+            w[R_EC] = ellip_Ec(k4);
+            for (int i = 0; i < 3; ++i) {
+                double p2 = sqrt((1.0 + al[i] * al[i]) / (1.0 - k4 + al[i] * al[i]));
+                w[R_N0 + i] = nn[i];
+                w[R_PC0 + i] = ellip_PicTail(nn[i], k4);
+                w[R_Q5 + i] = p2;
+                w[R_PO0 + i] = S1_of(al[i], p2, dno, Fo, Pio[i]);
+            }
+            w[R_EO] = S2_of(g0, k4, sa, ca, dno, Fo, Eo, w[R_PO0]);
+        }
+        w[R_Q0] = a2; w[R_Q1] = b1; w[R_Q2] = g0; w[R_Q3] = gp; w[R_Q4] = gm;
+        w[R_Q8] = pref; w[R_Q9] = x4rp; w[R_Q10] = x4rm;
+        // tau_tot (utils :412-442): horizon amplitude atan(x4rp) + atan(g0)
+        double ixp = 1.0 / sqrt(1.0 + x4rp * x4rp);
+        double sh = (x4rp + g0) * ixp * ig, ch = (1.0 - x4rp * g0) * ixp * ig;
+        tau_tot = pref * Fo - pref * legendre_F_sc(sh, ch, k4);
+    }
+    if (R.c34 && !R.c12) {  // ---- case 3 ----
+        flags |= F_CASE3;
+        double a1 = R.im[3], b1 = R.re[3], rr1 = R.re[0], rr2 = R.re[1];
+        double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2, rrm1 = rm - rr1, rrm2 = rm - rr2;
+        double AA = sqrt(a1 * a1 + sq(b1 - rr2));
+        double BB = sqrt(a1 * a1 + sq(b1 - rr1));
+        double k3 = (sq(AA + BB) - rr21 * rr21) / (4.0 * AA * BB);
+        double x3rp = (AA * rrp1 - BB * rrp2) / (AA * rrp1 + BB * rrp2);
+        double x3rm = (AA * rrm1 - BB * rrm2) / (AA * rrm1 + BB * rrm2);
+        double x3ro = o.ro_inf ? (AA - BB) / (AA + BB)
+                               : (AA * (r_o - rr1) - BB * (r_o - rr2)) / (AA * (r_o - rr1) + BB * (r_o - rr2));
+        double al[3] = {(BB + AA) / (BB - AA), -1.0 / x3rp, -1.0 / x3rm};
+        double nn[3], p1[3];
+        for (int i = 0; i < 3; ++i) {
+            double al2 = al[i] * al[i];
+            nn[i] = al2 / (al2 - 1.0);
+            p1[i] = sqrt((al2 - 1.0) / (k3 + (1.0 - k3) * al2));
+        }
+        double sqAB = sqrt(AA * BB);
+        double ca = x3ro, sa = sqrt(fmax(0.0, (1.0 - ca) * (1.0 + ca)));
+        double Fo, Eo = 0.0, Pio[3] = {0.0, 0.0, 0.0};
+        if (PHI_T) legendre_sc<3>(sa, ca, k3, nn, &Fo, &Eo, Pio);
+        else Fo = legendre_F_sc(sa, ca, k3);
+        w[R_K] = k3;
+        w[R_SC] = sqAB;
+        w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
+        if (PHI_T) {
+            double dno = sqrt(fma(-k3 * sa, sa, 1.0));
+            w[R_KC] = ellip_K(k3);
+            w[R_EC] = ellip_Ec(k3);
+            for (int i = 0; i < 3; ++i) {
+                w[R_N0 + i] = nn[i];
+                w[R_PC0 + i] = ellip_PicTail(nn[i], k3);
+                w[R_Q4 + i] = al[i];
+                w[R_Q7 + i] = p1[i];
+                w[R_PO0 + i] = R1_of(al[i], p1[i], nn[i], sa, dno, Pio[i]);
+            }
+            w[R_EO] = R2_of(al[0], k3, nn[0], sa, ca, dno, Fo, Eo, w[R_PO0]);
+        }
+        w[R_Q0] = rr1; w[R_Q1] = rr2; w[R_Q2] = AA; w[R_Q3] = BB; w[R_Q10] = sqAB;
+        // tau_tot (utils :445-482): horizon amplitude acos(x3rp)
+        double sh = sqrt(fmax(0.0, (1.0 - x3rp) * (1.0 + x3rp)));
+        tau_tot = Fo / sqAB - legendre_F_sc(sh, x3rp, k3) / sqAB;
+    }
+    if (!R.c34 && !R.c12) {  // ---- case 2 (regions I and II) ----
+        flags |= F_CASE2;
+        double q1 = R.re[0], q2 = R.re[1], q3 = R.re[2], q4 = R.re[3];
+        double rr31 = q3 - q1, rr32 = q3 - q2, rr41 = q4 - q1, rr42 = q4 - q2, rr43 = q4 - q3;
+        double rrp3 = rp - q3, rrm3 = rm - q3, rrp4 = rp - q4, rrm4 = rm - q4;
+        double k2 = (rr32 * rr41) / (rr31 * rr42);
+        double x2ro = o.ro_inf ? sqrt(rr31 / rr41) : sqrt((rr31 * (r_o - q4)) / (rr41 * (r_o - q3)));
+        double root = sqrt(rr31 * rr42);
+        double nn[3] = {rr41 / rr31, (rrp3 * rr41) / (rrp4 * rr31), (rrm3 * rr41) / (rrm4 * rr31)};
+        double sa = x2ro, ca = sqrt(fmax(0.0, (1.0 - sa) * (1.0 + sa)));
+        double Fo, Eo = 0.0, Pio[3] = {0.0, 0.0, 0.0};
+        if (PHI_T) legendre_sc<3>(sa, ca, k2, nn, &Fo, &Eo, Pio);
+        else Fo = legendre_F_sc(sa, ca, k2);
+        w[R_K] = k2;
+        w[R_SC] = 0.5 * root;
+        w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
+        if (PHI_T) {
+            w[R_KC] = ellip_K(k2);
+            w[R_EC] = ellip_Ec(k2);
+            for (int i = 0; i < 3; ++i) {
+                w[R_N0 + i] = nn[i];
+                w[R_PC0 + i] = ellip_PicTail(nn[i], k2);
+                w[R_PO0 + i] = Pio[i];
+            }
+            w[R_EO] = Eo;
+        }
+        w[R_Q0] = q1; w[R_Q1] = q2; w[R_Q2] = q3; w[R_Q3] = q4; w[R_Q4] = root;
+        double Rpot_o = (r_o - q1) * (r_o - q2) * (r_o - q3) * (r_o - q4);
+        w[R_Q5] = sqrt(Rpot_o) / (r_o - q3);   // H_o (NaN for r_o = inf, as in the reference)
+        // tau_tot (utils :485-546): note the reference tests r3 (not r4) against r_+
+        double Iro = 2.0 * Fo / root;
+        if (q3 < rp) {
+            double x2rp = sqrt((rr31 * (rp - q4)) / (rr41 * (rp - q3)));
+            double ch = sqrt(fmax(0.0, (1.0 - x2rp) * (1.0 + x2rp)));
+            tau_tot = Iro - 2.0 * legendre_F_sc(x2rp, ch, k2) / root;
+        } else if (q3 > rp) {
+            tau_tot = 2.0 * Iro;
+        }
+    }
+    w[S_TAUTOT] = tau_tot;
+    *flags_out = flags;
+}
+
+// ---- per-sample evaluation ---------------------------------------------------------------------------------------
+struct Point {
+    double t, r, th, ph, sig;
+};
+
+// reduce a Jacobi argument by half periods: u = 2K j + u_r, |u_r| <= K; returns j and the sign (-1)^j
+KG_HD double reduce_half_periods(double u, double K, double* ur, double* sgn) {
+    double j = rint(u / (2.0 * K));
+    if (!(K < kInf)) j = 0.0;
+    *ur = fma(-2.0 * K, j, u);
+    *sgn = (fabs(fmod(j, 2.0)) == 1.0) ? -1.0 : 1.0;
+    return j;
+}
+
+template <class W>
+KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, double* Gph, double* Gt) {
+    *th = 0.0; *Gph = 0.0; *Gt = 0.0;
+    if (!(flags & (F_TH_ORD | F_TH_VORT))) return;
+    double snarg = fma(-w(T_W), tau, w(T_X0));
+    double sq1m = w(T_SQ), m = w(T_M);
+    double sn, cn, dn, Km;
+    jacobi_sncndn(snarg / sq1m, m, &sn, &cn, &dn, &Km);
+    double idn = 1.0 / dn;
+    double sinA = sq1m * sn * idn;            // sin(am(snarg|k)), kgeo/kerr_raytracing_ana.py:275
+    if (flags & F_TH_ORD) {
+        *th = acos(w(T_A) * sinA);            // :280
+    } else {
+        double h = (flags & F_HPOS) ? 1.0 : -1.0;
+        *th = acos(h * sqrt(fma(w(T_B), sinA * sinA, w(T_A))));   // :355
+    }
+    if (!full) return;
+    double ur, sg;
+    double j = reduce_half_periods(snarg / sq1m, Km, &ur, &sg);
+    double s = sg * sinA, c = sg * cn * idn;
+    double c2 = c * c, y = idn * idn;         // 1 - k sin^2 = 1/dn(u|m)^2
+    double n = w(T_N);
+    PiPrep pp = pi_prepare(n, s, c2, y);
+    double rf, rd, rj;
+    carlson_bundle<1, false, true>(c2, y, &pp.p, &rf, &rd, &rj);
+    double Fr = ur * sq1m;                    // F(phi_r|k)
+    double tail = pi_finish(n, s, c2, y, Fr, pp, rj);          // Pi - F on the reduced amplitude
+    double gph = w(T_D3) * (snarg + tail);
+    double gt = fma(w(T_C3), snarg, w(T_C1) * cube(s) * rd);
+    if (j != 0.0) {
+        gph = fma(w(T_D2), j, gph);           // +inf when n == 1 (kgeo/scipy_ellip_binding.py:149)
+        gt = fma(w(T_C2), j, gt);
+    }
+    *Gph = gph - w(T_GPH0);
+    *Gt = gt - w(T_GT0);
+}
+
+// Legendre E and three Pi's at the amplitude am(X|k) from the Jacobi functions at X
+template <class W>
+KG_HD void radial_legendre(const W& w, double X, double Kc, double sn, double cn, double dn, double* E, double* Pi) {
+    double k = w(R_K);
+    double Xr, sg;
+    double j = reduce_half_periods(X, Kc, &Xr, &sg);
+    double s = sg * sn, c2 = cn * cn, y = dn * dn;
+    PiPrep pp[3];
+    double pa[3], rj[3], rf, rd;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        pp[i] = pi_prepare(w(R_N0 + i), s, c2, y);
+        pa[i] = pp[i].p;
+    }
+    carlson_bundle<3, false, true>(c2, y, pa, &rf, &rd, rj);
+    double e = Xr - (k * (1.0 / 3.0)) * cube(s) * rd;
+    if (j != 0.0) e = fma(2.0 * j, w(R_EC), e);
+    *E = e;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double v = Xr + pi_finish(w(R_N0 + i), s, c2, y, Xr, pp[i], rj[i]);
+        if (j != 0.0) v += 2.0 * j * (w(R_KC) + w(R_PC0 + i));
+        Pi[i] = v;
+    }
+}
+
+template <class W>
+KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, bool full, double* r_s, double* Iph,
+                       double* It, double* Isig) {
+    double X = fma(-w(R_SC), tau, w(R_X0));
+    double k = w(R_K);
+    double sn, cn, dn, Kc;
+    jacobi_sncndn(X, k, &sn, &cn, &dn, &Kc);
+    double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
+    const double rp = o.rplus, rm = o.rminus;
+    if (flags & F_CASE2) {
+        double q1 = w(R_Q0), q2 = w(R_Q1), q3 = w(R_Q2), q4 = w(R_Q3), root = w(R_Q4);
+        double rr31 = q3 - q1, rr41 = q4 - q1, rr43 = q4 - q3;
+        double sn2 = sn * sn;
+        double den = rr31 - rr41 * sn2;
+        double rs = (q4 * rr31 - q3 * rr41 * sn2) / den;                      // :592-594
+        *r_s = rs;
+        if (full) {
+            double E, Pi[3];
+            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
+            double rrp3 = rp - q3, rrm3 = rm - q3, rrp4 = rp - q4, rrm4 = rm - q4;
+            double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) / (den * den);   // :600-603
+            double H = drs / (rs - q3) - w(R_Q5);
+            double c = 2.0 / root;
+            double Pi_1 = c * (Pi[0] - w(R_PO0));
+            double Pi_p = c * (rr43 / (rrp3 * rrp4)) * (Pi[1] - w(R_PO1));
+            double Pi_m = c * (rr43 / (rrm3 * rrm4)) * (Pi[2] - w(R_PO2));
+            I1 = q3 * (-tau) + rr43 * Pi_1;
+            I2 = H - 0.5 * (q1 * q4 + q2 * q3) * (-tau) - root * (E - w(R_EO));
+            Ip = tau / rrp3 - Pi_p;
+            Im = tau / rrm3 - Pi_m;
+        }
+    } else if (flags & F_CASE3) {
+        double rr1 = w(R_Q0), rr2 = w(R_Q1), AA = w(R_Q2), BB = w(R_Q3), sqAB = w(R_Q10);
+        *r_s = ((BB * rr2 - AA * rr1) + (BB * rr2 + AA * rr1) * cn) / ((BB - AA) + (BB + AA) * cn);   // :516-519
+        if (full) {
+            double E, Pi[3];
+            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
+            double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2, rrm1 = rm - rr1, rrm2 = rm - rr2;
+            double R1a[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) R1a[i] = R1_of(w(R_Q4 + i), w(R_Q7 + i), w(R_N0 + i), sn, dn, Pi[i]);
+            double R2a = R2_of(w(R_Q4), k, w(R_N0), sn, cn, dn, X, E, R1a[0]);
+            double dm = (flags & F_LOWSPIN) ? 0.0 : (R1a[2] - w(R_PO2));      // :529-534
+            double fac = 2.0 * rr21 * sqAB;
+            double Pi_1 = (fac / (BB * BB - AA * AA)) * (R1a[0] - w(R_PO0));
+            double Pi_2 = sq(fac / (BB * BB - AA * AA)) * (R2a - w(R_EO));
+            double Pi_p = (fac / (BB * rrp2 - AA * rrp1)) * (R1a[1] - w(R_PO1));
+            double Pi_m = (fac / (BB * rrm2 - AA * rrm1)) * dm;
+            double pr = (BB * rr2 + AA * rr1) / (BB + AA);
+            I1 = pr * (-tau) + Pi_1;
+            I2 = pr * pr * (-tau) + 2.0 * pr * Pi_1 + sqAB * Pi_2;
+            Ip = -((BB + AA) * (-tau) + Pi_p) / (BB * rrp2 + AA * rrp1);
+            Im = -((BB + AA) * (-tau) + Pi_m) / (BB * rrm2 + AA * rrm1);
+        }
+    } else {  // case 4
+        double a2 = w(R_Q0), b1 = w(R_Q1), g0 = w(R_Q2);
+        *r_s = -a2 * (g0 * cn - sn) / (cn + g0 * sn) - b1;                   // :441 with sc = sn/cn
+        if (full) {
+            double E, Pi[3];
+            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
+            double pref = w(R_Q8), x4rp = w(R_Q9), x4rm = w(R_Q10);
+            double S1a[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) S1a[i] = S1_of(w(R_Q2 + i), w(R_Q5 + i), dn, X, Pi[i]);
+            double S2a = S2_of(g0, k, sn, cn, dn, X, E, S1a[0]);
+            double aa0 = (a2 / g0) * (1.0 + g0 * g0);
+            double Pi_1 = pref * aa0 * (S1a[0] - w(R_PO0));
+            double Pi_2 = pref * (aa0 * aa0) * (S2a - w(R_EO));
+            double Pi_p = pref * (1.0 + g0 * g0) / (g0 * g0 + g0 * x4rp) * (S1a[1] - w(R_PO1));
+            double Pi_m = pref * (1.0 + g0 * g0) / (g0 * g0 + g0 * x4rm) * (S1a[2] - w(R_PO2));
+            double aa1 = a2 / g0 - b1;
+            I1 = aa1 * (-tau) - Pi_1;
+            I2 = (aa1 * aa1) * (-tau) - 2.0 * aa1 * Pi_1 + Pi_2;
+            Ip = g0 / (a2 - a2 * g0 * x4rp) * (-tau - Pi_p);
+            Im = g0 / (a2 - a2 * g0 * x4rm) * (-tau - Pi_m);
+        }
+    }
+    if (!full) {
+        *Iph = 0.0; *It = 0.0; *Isig = 0.0;
+        return;
+    }
+    // kgeo/kerr_raytracing_ana.py:626-631
+    double a = o.a, lam = w(S_LAM);
+    double d = rp - rm;
+    *Iph = (2.0 * a / d) * ((rp - 0.5 * a * lam) * Ip - (rm - 0.5 * a * lam) * Im);
+    double ItA = (4.0 / d) * ((rp * rp - 0.5 * a * lam * rp) * Ip - (rm * rm - 0.5 * a * lam * rm) * Im);
+    *It = ItA + 4.0 * (-tau) + 2.0 * I1 + I2;
+    *Isig = I2;
+}
+
+// one full point (kgeo/kerr_raytracing_ana.py:172-188)
+template <class W>
+KG_HD Point point_eval(const W& w, const Observer& o, int flags, double tau, bool full) {
+    Point p;
+    double Gph, Gt, Iph, It, Isig;
+    theta_eval(w, flags, tau, full, &p.th, &Gph, &Gt);
+    radial_eval(w, o, flags, tau, full, &p.r, &Iph, &It, &Isig);
+    p.sig = Isig + o.a2 * Gt;
+    p.t = It + o.a2 * Gt;
+    p.ph = Iph + w(S_LAM) * Gph;
+    return p;
+}
+
+// ---- crossing counts -------------------------------------------------------------------------------------------
+// n_equatorial_crossings (utils :605-684) and n_poloidal_orbits (:551-603) at Mino time tau
+template <class W>
+KG_HD double n_equatorial_at(const W& w, const Observer& o, int flags, double beta, double tau) {
+    if (!(w(S_ETA) > 0.0)) return -2.0;
+    double F0 = w(T_F0), K = w(T_KC), ww = w(T_W);
+    bool first = o.north ? (beta <= 0.0) : (beta >= 0.0);
+    double sgn = (o.north == (first ? 1 : 0)) ? -1.0 : 1.0;   // north&first: -F0 ; north&!first: +F0 ; south: mirrored
+    double v = floor((tau * ww + sgn * F0) / (2.0 * K));
+    return first ? v : v - 1.0;
+}
+template <class W>
+KG_HD double n_poloidal_at(const W& w, double tau) {
+    if (!(w(S_ETA) > 0.0)) return -2.0;
+    return (w(T_W) * tau) / (4.0 * w(T_KC));
+}
+
+// accessor over a plain array (registers / local)
+struct ArrayW {
+    const double* p;
+    KG_HD double operator()(int i) const { return p[i]; }
+};
+// accessor over a strided SoA workspace: slot i of pixel `pix` lives at base[i*stride + pix]
+struct StridedW {
+    const double* base;
+    long long stride;
+    KG_HD double operator()(int i) const { return base[(long long)i * stride]; }
+};
+
+}  // namespace kg

@@ -1,0 +1,761 @@
+// libkgeo_b200.so -- CUDA kernels (sm_100a) and the C ABI declared in include/kgeo_b200.h.
+//
+// Kernels
+//   ray_setup_kernel   one thread per ray: conserved quantities, quartic roots, root class, tau_tot, observer-side
+//                      antiderivatives and complete integrals -> slot-major SoA workspace (coalesced in the ray index).
+//   track_kernel       the hot kernel.  A CTA owns a tile of 32 consecutive rays; their constants are staged once in
+//                      shared memory ([slot][lane], conflict free), then each warp walks Mino-time samples: one thread
+//                      per (ray, sample), lanes = consecutive rays of one sample, so every store instruction writes one
+//                      contiguous 256-byte row segment of the reference's (ngeo, npix) arrays and every branch on the
+//                      root class is taken by 32 neighbouring pixels together.
+//   image_kernel       fused equatorial image: per pixel one setup in registers/local memory, then all orders
+//                      mbar_min..mbar_max (crossing time, crossing radius, redshift, polarization, emissivity); no
+//                      geodesic array ever goes through HBM.
+//   plus element-wise kernels for the special functions and the physics closed forms.
+//
+// FP64 vector pipe bound; no tensor cores (there is no contraction in this path).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/kgeo_b200.h"
+#include "kg_image.cuh"
+
+using namespace kg;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail_arg(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "kgeo_b200: %s", what);
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "kgeo_b200: CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), where);
+    return (int)e;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);   \
+    } while (0)
+#define LAUNCHED(name)                                        \
+    do {                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        cudaError_t e_ = cudaGetLastError();                  \
+        if (e_ != cudaSuccess) return fail_cuda(e_, name);    \
+    } while (0)
+
+static int check_observer(const kgeo_observer* obs, bool allow_inf) {
+    if (!obs) return fail_arg(KGEO_E_BADARG, "observer is NULL");
+    if (!(fabs(obs->a) < 1.0)) return fail_arg(KGEO_E_RANGE, "a should be a float in range (-1,1)");
+    if (!(obs->r_o >= 100.0)) return fail_arg(KGEO_E_RANGE, "r_o should be a float > 100");
+    if (!allow_inf && isinf(obs->r_o)) return fail_arg(KGEO_E_RANGE, "r_o must be finite for this entry point");
+    if (!(obs->th_o > 0.0 && obs->th_o < kPi) || obs->th_o == 0.5 * kPi)
+        return fail_arg(KGEO_E_RANGE, "th_o should be a float in range (0,pi/2) or (pi/2,pi)");
+    return 0;
+}
+static int check_models(const kgeo_models* m) {
+    if (!m) return fail_arg(KGEO_E_BADARG, "models is NULL");
+    if (m->velocity_type < 0 || m->velocity_type > KGEO_VEL_SIMFIT) return fail_arg(KGEO_E_MODEL, "unknown velocity model");
+    if (m->bfield_type < 0 || m->bfield_type > KGEO_B_MONOPOLE_A) return fail_arg(KGEO_E_MODEL, "unknown bfield model");
+    if (m->emissivity_type < 0 || m->emissivity_type > KGEO_EM_THERMAL) return fail_arg(KGEO_E_MODEL, "unknown emissivity model");
+    return 0;
+}
+
+static inline unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// element-wise special-function kernels
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 128;
+
+#define EW_INDEX                                                        \
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           \
+    if (i >= n) return;
+
+__global__ void __launch_bounds__(EW_THREADS) ew_rf_kernel(size_t n, const double* x, const double* y, const double* z, double* o) {
+    EW_INDEX
+    o[i] = carlson_rf(x[i], y[i], z[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_rd_kernel(size_t n, const double* x, const double* y, const double* z, double* o) {
+    EW_INDEX
+    o[i] = carlson_rd(x[i], y[i], z[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_rj_kernel(size_t n, const double* x, const double* y, const double* z, const double* p, double* o) {
+    EW_INDEX
+    o[i] = carlson_rj(x[i], y[i], z[i], p[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_rc_kernel(size_t n, const double* x, const double* y, double* o) {
+    EW_INDEX
+    o[i] = carlson_rc(x[i], y[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_K_kernel(size_t n, const double* m, double* o) {
+    EW_INDEX
+    o[i] = ellip_K(m[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_F_kernel(size_t n, const double* phi, const double* m, double* o) {
+    EW_INDEX
+    o[i] = ellip_F(phi[i], m[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_E_kernel(size_t n, const double* phi, const double* m, double* o) {
+    EW_INDEX
+    o[i] = ellip_E(phi[i], m[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_Pi_kernel(size_t n, const double* nn, const double* phi, const double* m, double* o) {
+    EW_INDEX
+    o[i] = ellip_Pi_ref(nn[i], phi[i], m[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const double* u, const double* m, double* sn, double* cn,
+                                                               double* dn, double* am) {
+    EW_INDEX
+    double s, c, d, K;
+    jacobi_sncndn(u[i], m[i], &s, &c, &d, &K);
+    if (sn) sn[i] = s;
+    if (cn) cn[i] = c;
+    if (dn) dn[i] = d;
+    if (am) am[i] = jacobi_am(u[i], s, c, K);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-ray setup
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SETUP_THREADS = 64;
+
+template <bool PHI_T>
+__global__ void __launch_bounds__(SETUP_THREADS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
+                                                                  const double* __restrict__ beta, int mode,
+                                                                  double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    double w[NW];
+    int fl;
+    ray_setup<PHI_T>(o, alpha[i], beta[i], mode, w, &fl);
+#pragma unroll
+    for (int s = 0; s < NW; ++s) w_out[(size_t)s * npix + i] = w[s];
+    flags_out[i] = fl;
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS) ray_summary_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
+                                                                    const double* __restrict__ beta, int mode, double* roots,
+                                                                    int32_t* rclass, double* tau_tot, double* uplus,
+                                                                    double* uminus, double* uratio, double* a2uminus,
+                                                                    double* outside, double* thplus, double* thminus) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    double al = alpha[i], be = beta[i];
+    double lam, eta;
+    if (mode & KGEO_MODE_INPUT_LAM_ETA) {   // the two input arrays are (lam, eta) instead of (alpha, beta)
+        lam = al;
+        eta = be;
+    } else {
+        lam = -al * o.sth;
+        eta = conserved_eta(o, al, be);
+    }
+    if (o.lowspin && (mode & M_CLAMP_LOWSPIN_ETA) && eta < 0.0) eta = kEP;
+    if (roots || rclass || outside) {
+        Roots R = quartic_roots(o, lam, eta);
+        if (roots) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                roots[(size_t)k * npix + i] = R.re[k];
+                roots[(size_t)(4 + k) * npix + i] = R.im[k];
+            }
+        }
+        if (rclass) rclass[i] = R.region;
+        if (outside) outside[i] = (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) ? 1.0 : 0.0;
+    }
+    if (uplus || uminus || uratio || a2uminus || thplus || thminus) {
+        double up, um, ratio, a2um;
+        angular_consts(o, lam, eta, &up, &um, &ratio, &a2um);
+        if (thplus) thplus[i] = (eta < 0.0) ? acos(sqrt(um)) : acos(-sqrt(up));   // kerr_raytracing_utils.py:257-262
+        if (thminus) thminus[i] = acos(sqrt(up));
+        if (uplus) uplus[i] = up;
+        if (uminus) uminus[i] = um;
+        if (uratio) uratio[i] = ratio;
+        if (a2uminus) a2uminus[i] = a2um;
+    }
+    if (tau_tot) tau_tot[i] = tau_total_of(o, quartic_roots(o, lam, eta));
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, size_t n, const double* __restrict__ roots,
+                                                                   double* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Roots R;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        R.re[k] = roots[(size_t)k * n + i];
+        R.im[k] = roots[(size_t)(4 + k) * n + i];
+    }
+    R.c12 = R.im[0] != 0.0;                 // mask_IV  (kerr_raytracing_utils.py:412)
+    R.c34 = R.im[2] != 0.0;                 // mask_III (:445)
+    R.region = 0;
+    out[i] = tau_total_of(o, R);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the track kernel
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TRK_WARPS = 4;
+constexpr int TRK_THREADS = 32 * TRK_WARPS;
+
+struct SmemW {
+    const double* p;   // &sw[0][lane]
+    __device__ __forceinline__ double operator()(int i) const { return p[i * 32]; }
+};
+
+struct TrackOut {
+    double* t;
+    double* r;
+    double* th;
+    double* ph;
+    double* sig;
+    double* tau;
+};
+
+template <bool FULL>
+__global__ void __launch_bounds__(TRK_THREADS) track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
+                                                            const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
+                                                            const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
+                                                            size_t ld, int k_begin, int k_end, int chunk) {
+    __shared__ double sw[NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t pix = (size_t)blockIdx.x * 32 + lane;
+    const bool live = pix < npix;
+    for (int s = warp; s < NW; s += TRK_WARPS) sw[s][lane] = live ? w_in[(size_t)s * npix + pix] : 0.0;
+    __syncthreads();
+    if (!live) return;
+    const int fl = flags_in[pix];
+    SmemW W{&sw[0][lane]};
+    // this launch covers samples [k_begin, k_end) of the ntau-sample track; output row = k - k_begin
+    const int k0 = k_begin + blockIdx.y * chunk;
+    const int k1 = min(k_end, k0 + chunk);
+    // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
+    const double stop = maxtaufrac * W(S_TAUTOT);
+    const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+    for (int k = k0 + warp; k < k1; k += TRK_WARPS) {
+        double tau;
+        if (tau_in) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
+        else tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
+        Point p = point_eval(W, o, fl, tau, FULL);
+        const size_t q = (size_t)(k - k_begin) * ld + pix;
+        if (out.r) __stcs(out.r + q, p.r);
+        if (out.th) __stcs(out.th + q, p.th);
+        if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
+        if (out.ph) __stcs(out.ph + q, FULL ? p.ph : 0.0);
+        if (out.sig) __stcs(out.sig + q, FULL ? p.sig : 0.0);
+        if (out.tau) __stcs(out.tau + q, tau);
+    }
+}
+
+__global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o, size_t npix, const double* __restrict__ beta,
+                                                                      const double* __restrict__ w_in,
+                                                                      const int32_t* __restrict__ flags_in, int ntau,
+                                                                      const double* __restrict__ tau_in, double* neq,
+                                                                      double* npol) {
+    size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    StridedW W{w_in + pix, (long long)npix};
+    int fl = flags_in[pix];
+    double b = beta[pix];
+    for (int k = blockIdx.y; k < ntau; k += gridDim.y) {
+        size_t q = (size_t)k * npix + pix;
+        double tau = tau_in[q];
+        if (neq) neq[q] = n_equatorial_at(W, o, fl, b, tau);
+        if (npol) npol[q] = n_poloidal_at(W, tau);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// equatorial lensing / image
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int IMG_THREADS = 64;
+
+__global__ void __launch_bounds__(IMG_THREADS) r_equatorial_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
+                                                                   const double* __restrict__ beta, int mbar_lo, int mbar_hi,
+                                                                   double* rs_out, double* Ir_out, double* Nmax_out,
+                                                                   double* Imax_out, double* npol_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    double w[NW];
+    int fl;
+    double be = beta[i];
+    ray_setup<false>(o, alpha[i], be, M_ANY_ETA_POS, w, &fl);
+    ArrayW W{w};
+    const bool reg = w[S_ETA] > 0.0;
+    if (Imax_out) Imax_out[i] = reg ? w[S_TAUTOT] : -1.0;
+    if (npol_out) npol_out[i] = n_poloidal_at(W, w[S_TAUTOT]);
+    for (int mbar = mbar_lo; mbar <= mbar_hi; ++mbar) {
+        double rs = -1.0, Ir = -1.0, Nmax = -2.0;
+        if (reg) {
+            crossing_time(W, o, be, mbar, &Ir, &Nmax);
+            double d0, d1, d2;
+            radial_eval(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
+            if (Nmax < (double)mbar) rs = 0.0;
+        }
+        size_t q = (size_t)(mbar - mbar_lo) * npix + i;
+        if (rs_out) rs_out[q] = rs;
+        if (Ir_out) Ir_out[q] = Ir;
+        if (Nmax_out) Nmax_out[q] = Nmax;
+    }
+}
+
+struct ImageOut {
+    double *I, *Q, *U, *r, *Ir, *g, *sinthb, *nmax, *npol, *imax, *lp, *Ie;
+};
+
+__global__ void __launch_bounds__(IMG_THREADS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
+                                                            const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                            ImageOut out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    double w[NW];
+    int fl;
+    double al = alpha[i], be = beta[i];
+    ray_setup<false>(o, al, be, M_ANY_ETA_POS, w, &fl);
+    ArrayW W{w};
+    if (out.npol) out.npol[i] = n_poloidal_at(W, w[S_TAUTOT]);
+    if (out.imax) out.imax[i] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
+    double lastN = -2.0;
+    for (int mbar = opt.mbar_min; mbar <= opt.mbar_max; ++mbar) {
+        OrderOut v = image_order(W, o, fl, M, opt, al, be, mbar);
+        size_t q = (size_t)(mbar - opt.mbar_min) * npix + i;
+        if (out.I) out.I[q] = v.I;
+        if (out.Q) out.Q[q] = v.Q;
+        if (out.U) out.U[q] = v.U;
+        if (out.r) out.r[q] = v.r;
+        if (out.Ir) out.Ir[q] = v.Ir;
+        if (out.g) out.g[q] = v.g;
+        if (out.sinthb) out.sinthb[q] = v.sinthb;
+        if (out.lp) out.lp[q] = v.lp;
+        if (out.Ie) out.Ie[q] = v.Ie;
+        lastN = v.Nmax;
+    }
+    if (out.nmax) out.nmax[i] = lastN;
+}
+
+// element-wise physics
+__global__ void __launch_bounds__(EW_THREADS) ew_velocity_kernel(kgeo_models M, double a, size_t n, const double* r, double* u0,
+                                                                 double* u1, double* u2, double* u3) {
+    EW_INDEX
+    U4 u = velocity_u_lab(M, a, r[i]);
+    if (u0) u0[i] = u.u0;
+    if (u1) u1[i] = u.u1;
+    if (u2) u2[i] = u.u2;
+    if (u3) u3[i] = u.u3;
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_bfield_kernel(kgeo_models M, double a, size_t n, const double* r, double* B1,
+                                                               double* B2, double* B3, double* bsq) {
+    EW_INDEX
+    double b1, b2, b3;
+    bfield_lab(M, a, r[i], &b1, &b2, &b3);
+    if (B1) B1[i] = b1;
+    if (B2) B2[i] = b2;
+    if (B3) B3[i] = b3;
+    if (bsq) bsq[i] = bfield_bsq(M, a, r[i], velocity_u_lab(M, a, r[i]));
+}
+__global__ void __launch_bounds__(EW_THREADS) ew_emissivity_kernel(kgeo_models M, double a, size_t n, const double* r,
+                                                                   const double* g, const double* sinthb, const double* Bmag,
+                                                                   double nu_obs, double specind, double* j) {
+    EW_INDEX
+    j[i] = emissivity_jrest(M, a, r[i], g != nullptr, g ? g[i] : 1.0, sinthb != nullptr, sinthb ? sinthb[i] : 1.0,
+                            Bmag ? Bmag[i] : 0.0, nu_obs, specind);
+}
+
+// FP64 roofline probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double seed, double* sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1.0e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;   // never true; keeps the chains alive
+}
+
+// RAII helpers of the host-buffer entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+struct StreamPair {
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    ~StreamPair() {
+        for (int i = 0; i < 2; ++i) {
+            if (done[i]) cudaEventDestroy(done[i]);
+            if (drained[i]) cudaEventDestroy(drained[i]);
+        }
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int kgeo_abi_version(void) { return KGEO_B200_ABI_VERSION; }
+const char* kgeo_last_error(void) { return g_err; }
+int kgeo_device_count(int* count) {
+    if (!count) return fail_arg(KGEO_E_BADARG, "count is NULL");
+    *count = 0;
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+int kgeo_ray_workspace_slots(void) { return NW; }
+long long kgeo_launch_count(void) { return g_launches.load(); }
+
+#define EW_ENTRY(kernel, ...)                                                             \
+    if (n == 0) return 0;                                                                 \
+    kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
+    LAUNCHED(#kernel);                                                                    \
+    return 0;
+
+int kgeo_special_rf(size_t n, const double* x, const double* y, const double* z, double* out, void* stream) {
+    if (n && (!x || !y || !z || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_rf: NULL pointer");
+    EW_ENTRY(ew_rf_kernel, n, x, y, z, out)
+}
+int kgeo_special_rd(size_t n, const double* x, const double* y, const double* z, double* out, void* stream) {
+    if (n && (!x || !y || !z || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_rd: NULL pointer");
+    EW_ENTRY(ew_rd_kernel, n, x, y, z, out)
+}
+int kgeo_special_rj(size_t n, const double* x, const double* y, const double* z, const double* p, double* out, void* stream) {
+    if (n && (!x || !y || !z || !p || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_rj: NULL pointer");
+    EW_ENTRY(ew_rj_kernel, n, x, y, z, p, out)
+}
+int kgeo_special_rc(size_t n, const double* x, const double* y, double* out, void* stream) {
+    if (n && (!x || !y || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_rc: NULL pointer");
+    EW_ENTRY(ew_rc_kernel, n, x, y, out)
+}
+int kgeo_special_ellipk(size_t n, const double* m, double* out, void* stream) {
+    if (n && (!m || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_ellipk: NULL pointer");
+    EW_ENTRY(ew_K_kernel, n, m, out)
+}
+int kgeo_special_ellipkinc(size_t n, const double* phi, const double* m, double* out, void* stream) {
+    if (n && (!phi || !m || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_ellipkinc: NULL pointer");
+    EW_ENTRY(ew_F_kernel, n, phi, m, out)
+}
+int kgeo_special_ellipeinc(size_t n, const double* phi, const double* m, double* out, void* stream) {
+    if (n && (!phi || !m || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_ellipeinc: NULL pointer");
+    EW_ENTRY(ew_E_kernel, n, phi, m, out)
+}
+int kgeo_special_ellippi(size_t n, const double* nn, const double* phi, const double* m, double* out, void* stream) {
+    if (n && (!nn || !phi || !m || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_special_ellippi: NULL pointer");
+    EW_ENTRY(ew_Pi_kernel, n, nn, phi, m, out)
+}
+int kgeo_special_ellipj(size_t n, const double* u, const double* m, double* sn, double* cn, double* dn, double* am,
+                        void* stream) {
+    if (n && (!u || !m)) return fail_arg(KGEO_E_BADARG, "kgeo_special_ellipj: NULL pointer");
+    EW_ENTRY(ew_jacobi_kernel, n, u, m, sn, cn, dn, am)
+}
+
+int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* w,
+                   int32_t* flags, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!alpha || !beta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_setup: NULL pointer");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, (cudaStream_t)stream>>>(o, npix, alpha, beta,
+                                                                                                    mode, w, flags);
+    LAUNCHED("ray_setup_kernel");
+    return 0;
+}
+
+int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* roots,
+                     int32_t* rclass, double* tau_tot, double* uplus, double* uminus, double* uratio, double* a2uminus,
+                     double* outside, double* thplus, double* thminus, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_summary: NULL pointer");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    ray_summary_kernel<<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, (cudaStream_t)stream>>>(
+        o, npix, alpha, beta, mode, roots, rclass, tau_tot, uplus, uminus, uratio, a2uminus, outside, thplus, thminus);
+    LAUNCHED("ray_summary_kernel");
+    return 0;
+}
+
+int kgeo_mino_total(const kgeo_observer* obs, size_t n, const double* roots, double* out, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (n && (!roots || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_mino_total: NULL pointer");
+    if (n == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    mino_total_kernel<<<grid_for(n, SETUP_THREADS), SETUP_THREADS, 0, (cudaStream_t)stream>>>(o, n, roots, out);
+    LAUNCHED("mino_total_kernel");
+    return 0;
+}
+
+static int launch_tracks(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
+                         int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
+                         cudaStream_t stream) {
+    // samples [k_begin, k_end) of an ntau-sample track; output (and tau) rows are indexed by (k - k_begin)
+    const unsigned tiles = (unsigned)((npix + 31) / 32);
+    const int ns = k_end - k_begin;
+    // enough CTAs to fill 148 SMs several times over even for a single image row
+    const int want = 148 * 8;
+    int ychunks = (int)((want + tiles - 1) / tiles);
+    int per = (ns + ychunks - 1) / ychunks;
+    per = ((per + TRK_WARPS - 1) / TRK_WARPS) * TRK_WARPS;
+    if (per < TRK_WARPS) per = TRK_WARPS;
+    ychunks = (ns + per - 1) / per;
+    if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
+    dim3 grid(tiles, (unsigned)ychunks);
+    if (full)
+        track_kernel<true><<<grid, TRK_THREADS, 0, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
+                                                             k_begin, k_end, per);
+    else
+        track_kernel<false><<<grid, TRK_THREADS, 0, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
+                                                              k_begin, k_end, per);
+    LAUNCHED("track_kernel");
+    return 0;
+}
+
+int kgeo_tracks(const kgeo_observer* obs, size_t npix, const double* w, const int32_t* flags, size_t ntau, double maxtaufrac,
+                const double* tau, size_t tau_ld, int full, double* t, double* r, double* th, double* ph, double* sig,
+                double* tau_out, size_t ld, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: NULL workspace");
+    if (ld < npix || (tau && tau_ld < npix)) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: leading dimension smaller than npix");
+    if (ntau > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: ntau too large");
+    if (npix == 0 || ntau == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    TrackOut out{t, r, th, ph, sig, tau_out};
+    return launch_tracks(o, npix, w, flags, ntau, 0, (int)ntau, maxtaufrac, tau, tau_ld, full, out, ld, (cudaStream_t)stream);
+}
+
+int kgeo_raytrace(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, size_t ngeo,
+                  double maxtaufrac, double* w, int32_t* flags, double* t, double* r, double* th, double* ph, double* sig,
+                  double* tau_out, size_t ld, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    rc = kgeo_ray_setup(obs, npix, alpha, beta, mode, w, flags, stream);
+    if (rc) return rc;
+    return kgeo_tracks(obs, npix, w, flags, ngeo, maxtaufrac, nullptr, 0, 1, t, r, th, ph, sig, tau_out, ld, stream);
+}
+
+int kgeo_crossing_counts(const kgeo_observer* obs, size_t npix, const double* beta, const double* w, const int32_t* flags,
+                         size_t ntau, const double* tau, double* neq, double* npol, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && ntau && (!beta || !w || !flags || !tau)) return fail_arg(KGEO_E_BADARG, "kgeo_crossing_counts: NULL pointer");
+    if (npix == 0 || ntau == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    dim3 grid(grid_for(npix, TRK_THREADS), (unsigned)(ntau < 1024 ? ntau : 1024));
+    crossing_counts_kernel<<<grid, TRK_THREADS, 0, (cudaStream_t)stream>>>(o, npix, beta, w, flags, (int)ntau, tau, neq, npol);
+    LAUNCHED("crossing_counts_kernel");
+    return 0;
+}
+
+int kgeo_r_equatorial(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mbar_lo, int mbar_hi,
+                      double* rs, double* Ir, double* Nmax, double* Imax, double* npol, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_r_equatorial: NULL pointer");
+    if (mbar_lo < 0 || mbar_hi < mbar_lo) return fail_arg(KGEO_E_BADARG, "kgeo_r_equatorial: bad mbar range");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    r_equatorial_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, npix, alpha, beta, mbar_lo,
+                                                                                              mbar_hi, rs, Ir, Nmax, Imax, npol);
+    LAUNCHED("r_equatorial_kernel");
+    return 0;
+}
+
+int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                          const double* alpha, const double* beta, double* I, double* Q, double* U, double* r, double* Ir,
+                          double* g, double* sinthb, double* nmax, double* npol, double* imax, double* lp, double* Ie,
+                          void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    rc = check_models(models);
+    if (rc) return rc;
+    if (!opts) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image: opts is NULL");
+    if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image: bad mbar range");
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image: NULL pointer");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    ImageOut out{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr};
+    image_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
+    LAUNCHED("image_kernel");
+    return 0;
+}
+
+int kgeo_velocity_u_lab(const kgeo_models* models, double a, size_t n, const double* r, double* u0, double* u1, double* u2,
+                        double* u3, void* stream) {
+    int rc = check_models(models);
+    if (rc) return rc;
+    if (n && !r) return fail_arg(KGEO_E_BADARG, "kgeo_velocity_u_lab: NULL pointer");
+    EW_ENTRY(ew_velocity_kernel, *models, a, n, r, u0, u1, u2, u3)
+}
+int kgeo_bfield_lab(const kgeo_models* models, double a, size_t n, const double* r, double* B1, double* B2, double* B3,
+                    double* bsq, void* stream) {
+    int rc = check_models(models);
+    if (rc) return rc;
+    if (n && !r) return fail_arg(KGEO_E_BADARG, "kgeo_bfield_lab: NULL pointer");
+    EW_ENTRY(ew_bfield_kernel, *models, a, n, r, B1, B2, B3, bsq)
+}
+int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const double* r, const double* g, const double* sinthb,
+                          const double* Bmag, double nu_obs, double specind, double* j, void* stream) {
+    int rc = check_models(models);
+    if (rc) return rc;
+    if (n && (!r || !j)) return fail_arg(KGEO_E_BADARG, "kgeo_emissivity_jrest: NULL pointer");
+    EW_ENTRY(ew_emissivity_kernel, *models, a, n, r, g, sinthb, Bmag, nu_obs, specind, j)
+}
+
+int kgeo_fp64_peak_probe(int iters, double* flops_per_launch, float* ms, void* stream) {
+    if (iters <= 0 || !flops_per_launch || !ms) return fail_arg(KGEO_E_BADARG, "kgeo_fp64_peak_probe: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    CU(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters, 1.0, sink);   // warm-up
+    LAUNCHED("dfma_probe_kernel");
+    CU(cudaEventRecord(e0, st));
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    LAUNCHED("dfma_probe_kernel");
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(ms, e0, e1));
+    *flops_per_launch = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host-buffer entry points (the end-to-end path)
+// ---------------------------------------------------------------------------------------------------------------------
+// Sample slabs are computed on one stream while the previous slab drains to the host on another (two device slab
+// buffers per output).  The host arrays may be pageable or pinned; pinned arrays get true asynchronous DMA.
+int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, size_t ngeo,
+                       double maxtaufrac, double* t, double* r, double* th, double* ph, double* sig, double* tau_out,
+                       int device) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_raytrace_host: NULL pointer");
+    if (ngeo > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_raytrace_host: ngeo too large");
+    if (npix == 0 || ngeo == 0) return 0;
+    CU(cudaSetDevice(device));
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    double* host[6] = {t, r, th, ph, sig, tau_out};
+    int nout = 0;
+    for (int i = 0; i < 6; ++i) nout += host[i] != nullptr;
+    StreamPair sp;
+    CU(cudaStreamCreateWithFlags(&sp.compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&sp.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&sp.done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sp.drained[i], cudaEventDisableTiming));
+    }
+    DevBuf d_alpha, d_beta, d_w, d_flags;
+    CU(d_alpha.alloc(npix * sizeof(double)));
+    CU(d_beta.alloc(npix * sizeof(double)));
+    CU(d_w.alloc((size_t)NW * npix * sizeof(double)));
+    CU(d_flags.alloc(npix * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
+    CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
+    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, sp.compute>>>(
+        o, npix, d_alpha.as<double>(), d_beta.as<double>(), mode, d_w.as<double>(), d_flags.as<int32_t>());
+    LAUNCHED("ray_setup_kernel");
+    if (nout == 0) {
+        CU(cudaStreamSynchronize(sp.compute));
+        return 0;
+    }
+    // slab = as many samples as fit ~256 MiB per output array (at least TRK_WARPS samples)
+    size_t slab = (size_t)(256u << 20) / (npix * sizeof(double));
+    if (slab < (size_t)TRK_WARPS) slab = TRK_WARPS;
+    if (slab > ngeo) slab = ngeo;
+    DevBuf d_out[2][6];
+    for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < 6; ++i)
+            if (host[i]) CU(d_out[b][i].alloc(slab * npix * sizeof(double)));
+    int nslab = (int)((ngeo + slab - 1) / slab);
+    for (int s = 0; s < nslab; ++s) {
+        int b = s & 1;
+        size_t k0 = (size_t)s * slab, k1 = k0 + slab < ngeo ? k0 + slab : ngeo;
+        if (s >= 2) CU(cudaStreamWaitEvent(sp.compute, sp.drained[b], 0));
+        TrackOut out{host[0] ? d_out[b][0].as<double>() : nullptr, host[1] ? d_out[b][1].as<double>() : nullptr,
+                     host[2] ? d_out[b][2].as<double>() : nullptr, host[3] ? d_out[b][3].as<double>() : nullptr,
+                     host[4] ? d_out[b][4].as<double>() : nullptr, host[5] ? d_out[b][5].as<double>() : nullptr};
+        rc = launch_tracks(o, npix, d_w.as<double>(), d_flags.as<int32_t>(), ngeo, (int)k0, (int)k1, maxtaufrac, nullptr, 0, 1,
+                           out, npix, sp.compute);
+        if (rc) return rc;
+        CU(cudaEventRecord(sp.done[b], sp.compute));
+        CU(cudaStreamWaitEvent(sp.copy, sp.done[b], 0));
+        for (int i = 0; i < 6; ++i)
+            if (host[i])
+                CU(cudaMemcpyAsync(host[i] + k0 * npix, d_out[b][i].p, (k1 - k0) * npix * sizeof(double), cudaMemcpyDeviceToHost,
+                                   sp.copy));
+        CU(cudaEventRecord(sp.drained[b], sp.copy));
+    }
+    CU(cudaStreamSynchronize(sp.copy));
+    CU(cudaStreamSynchronize(sp.compute));
+    return 0;
+}
+
+int kgeo_equatorial_image_host(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                               const double* alpha, const double* beta, double* I, double* Q, double* U, double* r, double* Ir,
+                               double* g, double* sinthb, double* nmax, double* npol, double* imax, double* lp, double* Ie,
+                               int device) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    rc = check_models(models);
+    if (rc) return rc;
+    if (!opts) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_host: opts is NULL");
+    if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_host: bad mbar range");
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_host: NULL pointer");
+    if (npix == 0) return 0;
+    CU(cudaSetDevice(device));
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct Guard {
+        cudaStream_t s;
+        ~Guard() { cudaStreamDestroy(s); }
+    } guard{st};
+    const size_t norder = (size_t)(opts->mbar_max - opts->mbar_min + 1);
+    constexpr int NOUT = 12;
+    double* host[NOUT] = {I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr,
+                          opts->pathlength ? Ie : nullptr};
+    const size_t planes[NOUT] = {norder, norder, norder, norder, norder, norder, norder, 1, 1, 1, norder, norder};
+    DevBuf d_alpha, d_beta, d_out[NOUT];
+    CU(d_alpha.alloc(npix * sizeof(double)));
+    CU(d_beta.alloc(npix * sizeof(double)));
+    for (int i = 0; i < NOUT; ++i)
+        if (host[i]) CU(d_out[i].alloc(planes[i] * npix * sizeof(double)));
+    CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = kgeo_equatorial_image(obs, models, opts, npix, d_alpha.as<double>(), d_beta.as<double>(), d_out[0].as<double>(),
+                               d_out[1].as<double>(), d_out[2].as<double>(), d_out[3].as<double>(), d_out[4].as<double>(),
+                               d_out[5].as<double>(), d_out[6].as<double>(), d_out[7].as<double>(), d_out[8].as<double>(),
+                               d_out[9].as<double>(), d_out[10].as<double>(), d_out[11].as<double>(), st);
+    if (rc) return rc;
+    for (int i = 0; i < NOUT; ++i)
+        if (host[i]) CU(cudaMemcpyAsync(host[i], d_out[i].p, planes[i] * npix * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""Drop-in for kgeo/kerr_raytracing_utils.py on the hot path: the Geodesics result type and the per-ray helper
+functions, computed by libkgeo_b200.so kernels (no NumPy arithmetic on geodesic quantities here).
+
+Out of scope: plotgeos / savegeos / loadgeos (matplotlib / h5py host-side code) and n_angular_turnings.
+"""
+import numpy as np
+
+from . import _checks, _engine
+
+MINSPIN = 1.e-4  # kgeo/kerr_raytracing_utils.py:9
+EP = 1.e-12      # kgeo/kerr_raytracing_utils.py:12
+
+
+def _np(x):
+    return x.cpu().numpy() if hasattr(x, "cpu") else x
+
+
+class Geodesics(object):
+    """Result of raytrace_ana (kgeo/kerr_raytracing_utils.py:15-93): same fields and properties.
+
+    The track arrays live on the GPU (`*_device` attributes, [ngeo, npix] float64 torch tensors); the reference's
+    NumPy-valued fields (`mino_times`, `affine_times`, `geo_coords`) are materialised on first access and cached.
+    Arrays that were not produced by the launch (e.g. sigma / tau when memory is tight) are recomputed on demand by
+    the same kernel through `_recompute`.
+    """
+
+    def __init__(self, a, observer_coords, image_coords, mino_times, affine_times, geo_coords, _bundle=None,
+                 _recompute=None):
+        self.a = a
+        self.observer_coords = observer_coords
+        self.image_coords = image_coords
+        self._dev = dict(tau=mino_times, sig=affine_times)
+        for name, arr in zip(("t", "r", "th", "ph"), geo_coords):
+            self._dev[name] = arr
+        self._host = {}
+        self._bundle = _bundle
+        self._recompute = _recompute
+
+    # ---- lazy host views ----
+    def device_array(self, name):
+        """[ngeo, npix] CUDA tensor of 't','r','th','ph','sig','tau' (NumPy inputs are returned unchanged)."""
+        if self._dev.get(name) is None:
+            if self._recompute is None:
+                raise RuntimeError("Geodesics: array %r was not computed" % name)
+            self._dev[name] = self._recompute(name)
+        return self._dev[name]
+
+    def _get(self, name):
+        if name not in self._host:
+            self._host[name] = _np(self.device_array(name))
+        return self._host[name]
+
+    @property
+    def mino_times(self):
+        return self._get("tau")
+
+    @property
+    def affine_times(self):
+        return self._get("sig")
+
+    @property
+    def geo_coords(self):
+        return [self._get("t"), self._get("r"), self._get("th"), self._get("ph")]
+
+    # observer
+    @property
+    def t_o(self):
+        return self.observer_coords[0]
+
+    @property
+    def r_o(self):
+        return self.observer_coords[1]
+
+    @property
+    def th_o(self):
+        return self.observer_coords[2]
+
+    @property
+    def ph_o(self):
+        return self.observer_coords[3]
+
+    # image
+    @property
+    def alpha(self):
+        return self.image_coords[0]
+
+    @property
+    def beta(self):
+        return self.image_coords[1]
+
+    @property
+    def npix(self):
+        return len(self.alpha)
+
+    @property
+    def lam(self):
+        return -self.alpha * np.sin(self.th_o)
+
+    @property
+    def eta(self):
+        return (self.alpha ** 2 - self.a ** 2) * np.cos(self.th_o) ** 2 + self.beta ** 2
+
+    @property
+    def n_poloidal(self):  # fractional number of poloidal orbits
+        return n_poloidal_orbits(self.a, self.th_o, self.alpha, self.beta, self.device_array("tau"))
+
+    @property
+    def nmax_eq(self):  # number of equatorial crossings
+        return n_equatorial_crossings(self.a, self.th_o, self.alpha, self.beta, self.device_array("tau")[-1])
+
+    # geodesics
+    @property
+    def tausteps(self):
+        return self.mino_times
+
+    @property
+    def tautot(self):
+        return self.mino_times[-1]
+
+    @property
+    def affinesteps(self):
+        return self.affine_times
+
+    @property
+    def t_s(self):
+        return self._get("t")
+
+    @property
+    def r_s(self):
+        return self._get("r")
+
+    @property
+    def th_s(self):
+        return self._get("th")
+
+    @property
+    def ph_s(self):
+        return self._get("ph")
+
+    @property
+    def sig_s(self):
+        return self.affine_times
+
+    def plotgeos(self, *args, **kwargs):
+        raise NotImplementedError("plotgeos is host-side matplotlib code outside the accelerated path (SURVEY 8f)")
+
+    def savegeos(self, *args, **kwargs):
+        raise NotImplementedError("savegeos is host-side h5py code outside the accelerated path (SURVEY 8f)")
+
+
+def _lam_eta_arrays(lam, eta):
+    if not isinstance(lam, np.ndarray):
+        lam = np.array([lam]).flatten()
+    if not isinstance(eta, np.ndarray):
+        eta = np.array([eta]).flatten()
+    if len(lam) != len(eta):
+        raise Exception("lam, eta are different shapes!")
+    return np.asarray(lam, dtype=np.float64), np.asarray(eta, dtype=np.float64)
+
+
+def my_sign(x):
+    """sign with sign(0) = +1 (kgeo/kerr_raytracing_utils.py:857-864)"""
+    x = np.asarray(x)
+    return np.where(x < 0, -1.0, 1.0)
+
+
+def uplus_uminus(a, th_o, lam, eta):
+    """(u_plus, u_minus, uratio, a2u_minus) -- kgeo/kerr_raytracing_utils.py:276-328"""
+    _checks.check_spin(a)
+    lam, eta = _lam_eta_arrays(lam, eta)
+    out = _engine.ray_summary_lam_eta(a, 1000., th_o, lam, eta, want=("uplus", "uminus", "uratio", "a2uminus"))
+    return tuple(_np(out[k]) for k in ("uplus", "uminus", "uratio", "a2uminus"))
+
+
+def angular_turning(a, th_o, lam, eta):
+    """(u_plus, u_minus, th_plus, th_minus, thclass) -- kgeo/kerr_raytracing_utils.py:242-274"""
+    _checks.check_spin(a)
+    lam, eta = _lam_eta_arrays(lam, eta)
+    out = _engine.ray_summary_lam_eta(a, 1000., th_o, lam, eta, want=("uplus", "uminus", "thplus", "thminus"))
+    thclass = np.zeros(lam.shape).astype(int)
+    thclass[eta > 0] = 1
+    thclass[eta < 0] = 2
+    thclass[eta == 0] = 3
+    return (_np(out["uplus"]), _np(out["uminus"]), _np(out["thplus"]), _np(out["thminus"]), thclass)
+
+
+def radial_roots(a, lam, eta):
+    """(r1, r2, r3, r4, rclass) with complex128 roots -- kgeo/kerr_raytracing_utils.py:330-380"""
+    _checks.check_spin(a)
+    lam, eta = _lam_eta_arrays(lam, eta)
+    out = _engine.ray_summary_lam_eta(a, 1000., 0.25 * np.pi, lam, eta, want=("roots", "rclass"))
+    roots = _np(out["roots"])
+    r = [roots[k] + 1j * roots[4 + k] for k in range(4)]
+    return (r[0], r[1], r[2], r[3], _np(out["rclass"]).astype(int))
+
+
+def mino_total(a, r_o, eta, r1, r2, r3, r4):
+    """Total Mino time to the horizon / back to infinity -- kgeo/kerr_raytracing_utils.py:382-548"""
+    _checks.check_spin(a)
+    if not (isinstance(r_o, float) and (r_o >= 100)):
+        raise Exception("r_o should be a float > 100")
+    eta = np.atleast_1d(np.asarray(eta, dtype=np.float64))
+    roots = np.stack([np.real(np.atleast_1d(r)) for r in (r1, r2, r3, r4)] +
+                     [np.imag(np.atleast_1d(r)) for r in (r1, r2, r3, r4)]).astype(np.float64)
+    return _np(_engine.mino_total_from_roots(a, r_o, eta, roots))
+
+
+def is_outside_crit(a, th_o, alpha, beta):
+    """1 outside the critical curve, else 0 -- kgeo/kerr_raytracing_utils.py:794-826"""
+    _checks.check_spin(a)
+    alpha, beta = _checks.pixel_arrays(alpha, beta)
+    out = _engine.ray_summary(a, 1000., th_o, alpha, beta, want=("outside",))
+    return _np(out["outside"])
+
+
+def _counts(a, th_o, alpha, beta, tau, which):
+    _checks.check_spin(a)
+    alpha, beta = _checks.pixel_arrays(alpha, beta)
+    shape = tuple(tau.shape)
+    if shape[-1] != len(alpha):
+        raise Exception("tau has incompatible shape in n_poloidal_orbits!" if which == "pol"
+                        else "tau has incompatible shape in n_equatorial_crossings!")
+    bundle = _engine.RayBundle(a, 1000., th_o, alpha, beta, clamp_lowspin=False, mode=1)
+    neq, npol = bundle.crossing_counts(tau, want_eq=(which == "eq"), want_pol=(which == "pol"))
+    res = neq if which == "eq" else npol
+    return _np(res).reshape(shape)
+
+
+def n_poloidal_orbits(a, th_o, alpha, beta, tau):
+    """Fractional number of poloidal orbits at Mino time tau (GL19b Eq 35) -- kgeo/kerr_raytracing_utils.py:551-603"""
+    return _counts(a, th_o, alpha, beta, tau, "pol")
+
+
+def n_equatorial_crossings(a, th_o, alpha, beta, tau):
+    """Number of equatorial crossings up to Mino time tau (GL19b Eq 82) -- kgeo/kerr_raytracing_utils.py:605-684"""
+    return _counts(a, th_o, alpha, beta, tau, "eq")

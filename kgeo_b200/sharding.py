@@ -1,0 +1,113 @@
+"""Row sharding of the image plane over the GPUs of one box (one process per GPU, torch.distributed).
+
+The per-pixel computation has no cross-pixel dependence, so there is NO data-path collective: every rank traces its own
+contiguous block of image rows.  The only communication is the final gather of the (small) image planes to one rank
+(NCCL over NVLink on GPUs, gloo in the CPU tests); geodesic tracks stay sharded on the devices that produced them
+(1024^2 x 500 samples x 4 coordinates is 16.8 GB, 4096^2 is 268 GB -- they are consumed where they are).
+"""
+import numpy as np
+
+
+def row_range(nrows, rank, world):
+    """Contiguous block [r0, r1) of `nrows` image rows owned by `rank` of `world` (sizes differ by at most one)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of size %d" % (rank, world))
+    base, extra = divmod(int(nrows), int(world))
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def all_row_ranges(nrows, world):
+    return [row_range(nrows, r, world) for r in range(world)]
+
+
+def shard_pixels(alpha, beta, ncols, rank, world):
+    """Slice flattened row-major pixel arrays (row = constant beta, as produced by np.meshgrid(alphas, betas)) to the
+    rows owned by `rank`.  Returns (alpha_local, beta_local, (r0, r1))."""
+    alpha = np.asarray(alpha)
+    beta = np.asarray(beta)
+    if alpha.shape != beta.shape or alpha.ndim != 1 or alpha.size % ncols:
+        raise ValueError("alpha/beta must be flattened [nrows*ncols] arrays")
+    nrows = alpha.size // ncols
+    r0, r1 = row_range(nrows, rank, world)
+    return alpha[r0 * ncols:r1 * ncols], beta[r0 * ncols:r1 * ncols], (r0, r1)
+
+
+def gather_rows(local, nrows, ncols, dst=0, group=None):
+    """Gather row-sharded planes to rank `dst`.
+
+    local: tensor [..., rows_local*ncols] (any leading plane dimensions) on every rank, laid out row-major in the pixel
+    index.  Returns the assembled [..., nrows*ncols] tensor on `dst` and None elsewhere.  Uses all_gather on equal-size
+    padded buffers when the split is uneven (NCCL has no ragged gather) -- the planes are small (184 B/pixel).
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ranges = all_row_ranges(nrows, world)
+    lead = tuple(local.shape[:-1])
+    maxrows = max(r1 - r0 for r0, r1 in ranges)
+    buf = torch.zeros(lead + (maxrows * ncols,), dtype=local.dtype, device=local.device)
+    buf[..., :local.shape[-1]] = local
+    if rank == dst:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+    else:
+        parts = None
+    if dist.get_backend(group) == "nccl":
+        # NCCL gather: all ranks send to dst over NVLink
+        dist.gather(buf, gather_list=parts, dst=dst, group=group)
+    else:
+        dist.gather(buf, gather_list=parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty(lead + (nrows * ncols,), dtype=local.dtype, device=local.device)
+    for (r0, r1), p in zip(ranges, parts):
+        out[..., r0 * ncols:r1 * ncols] = p[..., :(r1 - r0) * ncols]
+    return out
+
+
+def make_image_sharded(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, beta_max, psize, dst=0, group=None,
+                       **kwargs):
+    """make_image with the pixel rows sharded over the ranks of `group`; rank `dst` returns the reference-shaped tuple
+    (as equatorial_images.make_image), other ranks return None.  Needs an initialised NCCL process group."""
+    import torch
+    import torch.distributed as dist
+    from . import equatorial_images as ei
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    alpha_arr, beta_arr = ei.pixel_grid(alpha_min, alpha_max, beta_min, beta_max, psize)
+    n_alpha = int(np.floor(alpha_max - alpha_min) / psize)
+    nrows = alpha_arr.size // n_alpha
+    al, be, _ = shard_pixels(alpha_arr, beta_arr, n_alpha, rank, world)
+    pathlength = bool(kwargs.get("pathlength", False))
+    out = ei.image_device(a, r_o, th_o, 0, mbar_max, al, be,
+                          kwargs.get("emissivity", ei.emis_default), kwargs.get("velocity", ei.vel_default),
+                          kwargs.get("bfield", ei.bfield_default), kwargs.get("polarization", False), pathlength,
+                          kwargs.get("specind", ei.SPECIND), kwargs.get("diskangle", ei.DISKANGLE),
+                          kwargs.get("nu_obs", ei.OBSFREQ))
+    names = ["I", "Q", "U", "r", "Ir", "g", "sinthb"] + (["lp", "Ie"] if pathlength else [])
+    planes = torch.stack([out[k] for k in names])                       # [nplane, norder, npix_local]
+    scal = torch.stack([out["nmax"], out["npol"]])                      # [2, npix_local]
+    planes = gather_rows(planes, nrows, n_alpha, dst, group)
+    scal = gather_rows(scal, nrows, n_alpha, dst, group)
+    if rank != dst:
+        return None
+    P = planes.cpu().numpy()
+    S = scal.cpu().numpy()
+    res = tuple(P[i].T for i in range(7)) + (S[0], S[1])
+    if pathlength:
+        res = res + (P[7].T, P[8].T)
+    return res
+
+
+def raytrace_sharded(a, observer_coords, image_coords, ncols, ngeo, maxtaufrac=1. - 1.e-10, group=None):
+    """raytrace_ana on this rank's block of image rows; the returned Geodesics holds the LOCAL shard on this rank's GPU
+    (tracks are never gathered).  Returns (geodesics, (row0, row1))."""
+    import torch.distributed as dist
+    from .kerr_raytracing_ana import raytrace_ana
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    al, be, rows = shard_pixels(image_coords[0], image_coords[1], ncols, rank, world)
+    geos = raytrace_ana(a, observer_coords, [np.ascontiguousarray(al), np.ascontiguousarray(be)], ngeo=ngeo,
+                        maxtaufrac=maxtaufrac, plotdata=False)
+    return geos, rows

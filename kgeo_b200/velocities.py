@@ -1,0 +1,84 @@
+"""Velocity model descriptor with the constructor and u_lab interface of kgeo/velocities.py:23-96.
+The closed forms run on the device (kg_image.cuh); 'fromfile' and 'driftframe' are outside the accelerated path."""
+import ctypes
+
+import numpy as np
+
+from . import _engine, _lib
+
+# defaults of the reference (kgeo/velocities.py:14-21)
+BETA = 0.3
+CHI = -150 * (np.pi / 180.)
+ELLISCO = 1.
+VRISCO = 2.
+P1 = 6.
+P2 = 2.
+DD = 0.2
+
+
+class Velocity(object):
+    """lab frame velocity as a function of r in the equatorial plane"""
+
+    def __init__(self, veltype="kep", **kwargs):
+        self.veltype = veltype
+        self.kwargs = kwargs
+        if self.veltype == 'zamo' or self.veltype == 'infall':
+            pass
+        elif self.veltype == 'kep' or self.veltype == 'cunningham':
+            self.retrograde = self.kwargs.get('retrograde', False)
+        elif self.veltype == 'subkep' or self.veltype == 'cunningham_subkep':
+            self.retrograde = self.kwargs.get('retrograde', False)
+            self.fac_subkep = self.kwargs.get('fac_subkep', 1)
+        elif self.veltype == 'general':
+            self.retrograde = self.kwargs.get('retrograde', False)
+            self.fac_subkep = self.kwargs.get('fac_subkep', 1)
+            self.beta_phi = self.kwargs.get('beta_phi', 1)
+            self.beta_r = self.kwargs.get('beta_r', 1)
+        elif self.veltype == 'gelles':
+            self.gelles_beta = self.kwargs.get('gelles_beta', BETA)
+            self.gelles_chi = self.kwargs.get('gelles_chi', CHI)
+        elif self.veltype == 'simfit':
+            self.ell_isco = self.kwargs.get('ell_isco', ELLISCO)
+            self.vr_isco = self.kwargs.get('vr_isco', VRISCO)
+            self.p1 = self.kwargs.get('p1', P1)
+            self.p2 = self.kwargs.get('p2', P2)
+            self.dd = self.kwargs.get('dd', DD)
+        elif self.veltype in ('fromfile', 'driftframe'):
+            raise NotImplementedError("Velocity(%r) needs host tables / root finds and is outside the accelerated path "
+                                      "(SURVEY 8f)" % self.veltype)
+        else:
+            raise Exception("veltype %s not recognized in Velocity!" % self.veltype)
+
+    def descriptor(self):
+        """(type id, parameter list) for kgeo_models.velocity_*"""
+        v = self.veltype
+        if v == 'zamo':
+            return _lib.VEL['zamo'], []
+        if v == 'infall':
+            return _lib.VEL['infall'], []
+        if v in ('kep', 'cunningham'):
+            return _lib.VEL['kep'], [float(bool(self.retrograde))]
+        if v in ('subkep', 'cunningham_subkep'):
+            return _lib.VEL['subkep'], [float(bool(self.retrograde)), float(self.fac_subkep)]
+        if v == 'general':
+            return _lib.VEL['general'], [float(bool(self.retrograde)), float(self.fac_subkep), float(self.beta_phi),
+                                         float(self.beta_r)]
+        if v == 'gelles':
+            return _lib.VEL['gelles'], [float(self.gelles_beta), float(self.gelles_chi)]
+        return _lib.VEL['simfit'], [float(self.ell_isco), float(self.vr_isco), float(self.p1), float(self.p2),
+                                    float(self.dd)]
+
+    def u_lab(self, a, r, th=np.pi / 2., retqty=False):
+        """Return lab frame contravariant velocity vector (u0, u1, u2, u3) at radii r (equatorial plane)"""
+        from .models import pack_models
+        if not isinstance(r, np.ndarray):
+            r = np.array([r]).flatten()
+        L = _lib.lib()
+        M = pack_models(velocity=self)
+        dev = _engine.device()
+        dr = _engine.to_device(r.ravel(), dev)
+        n = int(dr.numel())
+        outs = [_engine.empty((n,), dev) for _ in range(4)]
+        _lib.check(L.kgeo_velocity_u_lab(ctypes.byref(M), float(a), n, _engine.dptr(dr), *[_engine.dptr(o) for o in outs],
+                                         _engine.stream_ptr()))
+        return tuple(o.cpu().numpy().reshape(r.shape) for o in outs)

