@@ -50,19 +50,6 @@ KG_HD Observer make_observer(double a, double r_o, double th_o) {
     return o;
 }
 
-// eta = (alpha^2 - a^2) cos^2(th_o) + beta^2 with every operation rounded separately (no FMA contraction), so that the
-// sign of eta -- which selects the polar class -- is decided exactly as in NumPy (kgeo/kerr_raytracing_ana.py:77)
-KG_HD double conserved_eta(const Observer& o, double alpha, double beta) {
-#if defined(__CUDA_ARCH__)
-    return __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(alpha, alpha), -o.a2), o.cth2), __dmul_rn(beta, beta));
-#else
-    volatile double aa = alpha * alpha, bb = beta * beta;
-    volatile double d = aa - o.a2;
-    volatile double e = d * o.cth2;
-    return e + bb;
-#endif
-}
-
 // ---- ray-constant slots --------------------------------------------------------------------------------------
 enum Slot {
     S_LAM = 0, S_ETA, S_TAUTOT,
@@ -112,58 +99,125 @@ struct Roots {
     int region;
 };
 
+// Individually rounded IEEE operations (no FMA contraction).  The few quantities that decide a CLAMP or a CLASS in the
+// reference (eta, u_+, u_-) are formed with exactly NumPy's operation order: a one-ulp difference in u_+ next to the
+// clamp u_+ >= cos^2(th_o) moves the observer's polar amplitude by sqrt(ulp) ~ 1e-8 (rays with beta = 0 start exactly at a
+// polar turning point), which would show up as a 1e-8 shift of theta(tau) and phi(tau) against the reference.
+#if defined(__CUDA_ARCH__)
+KG_HD double mul_rn(double x, double y) { return __dmul_rn(x, y); }
+KG_HD double add_rn(double x, double y) { return __dadd_rn(x, y); }
+KG_HD double div_rn(double x, double y) { return __ddiv_rn(x, y); }
+KG_HD double sqrt_rn(double x) { return __dsqrt_rn(x); }
+#else
+KG_HD double mul_rn(double x, double y) { volatile double r = x * y; return r; }
+KG_HD double add_rn(double x, double y) { volatile double r = x + y; return r; }
+KG_HD double div_rn(double x, double y) { volatile double r = x / y; return r; }
+KG_HD double sqrt_rn(double x) { volatile double r = sqrt(x); return r; }
+#endif
+
+// eta = (alpha^2 - a^2) cos^2(th_o) + beta^2 (kgeo/kerr_raytracing_ana.py:77)
+KG_HD double conserved_eta(const Observer& o, double alpha, double beta) {
+    return add_rn(mul_rn(add_rn(mul_rn(alpha, alpha), -o.a2), o.cth2), mul_rn(beta, beta));
+}
+
 KG_HD void angular_consts(const Observer& o, double lam, double eta, double* up_, double* um_, double* ratio_,
                           double* a2um_) {
-    // kgeo/kerr_raytracing_utils.py:276-328
+    // kgeo/kerr_raytracing_utils.py:276-328, operation for operation
     double up, um;
+    const double lam2 = mul_rn(lam, lam);
     if (o.lowspin) {
-        up = eta / (eta + lam * lam);
+        up = div_rn(eta, add_rn(eta, lam2));
         um = up;
     } else {
-        double dth = 0.5 * (1.0 - (eta + lam * lam) / o.a2);
-        double rt = sqrt(dth * dth + eta / o.a2);
-        up = dth + rt;
-        um = dth - rt;
+        double dth = mul_rn(0.5, add_rn(1.0, -div_rn(add_rn(eta, lam2), o.a2)));
+        double rt = sqrt_rn(add_rn(mul_rn(dth, dth), div_rn(eta, o.a2)));
+        up = add_rn(dth, rt);
+        um = add_rn(dth, -rt);
     }
     if (o.cth2 - up > 0.0) up = o.cth2;
-    if (up * up > 1.0) up = 1.0;
+    if (mul_rn(up, up) > 1.0) up = 1.0;
     if (um == 0.0) um = (eta < 0.0) ? kEP : -kEP;
     if (eta < 0.0 && (o.cth2 - um) < 0.0) um = o.cth2;
     *up_ = up;
     *um_ = um;
     if (o.lowspin) {
         *ratio_ = 0.0;
-        *a2um_ = -(eta + lam * lam);
+        *a2um_ = -add_rn(eta, lam2);
     } else {
-        *ratio_ = up / um;
-        *a2um_ = o.a2 * um;
+        *ratio_ = div_rn(up, um);
+        *a2um_ = mul_rn(o.a2, um);
     }
 }
 
-KG_HD Roots quartic_roots(const Observer& o, double lam, double eta) {
-    // kgeo/kerr_raytracing_utils.py:330-380 in real arithmetic
-    Roots R;
-    double a = o.a;
-    double A = o.a2 - eta - lam * lam;
-    double B = 2.0 * (eta + (lam - a) * (lam - a));
-    double C = -o.a2 * eta;
-    double P = -(A * A) / 12.0 - C;
-    double Q = (-A / 3.0) * ((A * A) / 36.0 - C) - (B * B) / 8.0;
-    double disc = 4.0 * (P * P * P) + 27.0 * (Q * Q);
-    double xi0;
-    if (disc >= 0.0) {
-        double h = sqrt(disc / 108.0);
-        xi0 = cbrt(-0.5 * Q + h) + cbrt(-0.5 * Q - h) - A / 3.0;
-    } else {
-        // omega_+/-^3 = -Q/2 +/- i h : principal cube roots are conjugate, the sum is 2 |w|^(1/3) cos(arg/3)
-        double h = sqrt(-disc / 108.0);
-        double mag = sqrt(0.25 * Q * Q + h * h);
-        double ang = atan2(h, -0.5 * Q);
-        xi0 = 2.0 * cbrt(mag) * cos(ang / 3.0) - A / 3.0;
+// Newton polish of a root of r^4 + A r^2 + B r + C (real root, or the upper member x + i y of a complex pair)
+KG_HD void polish_real(double A, double B, double C, double* r_) {
+    double r = *r_;
+    for (int it = 0; it < 2; ++it) {
+        double f = fma(fma(fma(r, r, A), r, B), r, C);
+        double fp = fma(fma(4.0 * r, r, 2.0 * A), r, B);
+        double step = f / fp;
+        if (!(fabs(step) <= 1.0e-6 * fmax(1.0, fabs(r)))) break;
+        r -= step;
     }
-    double z = sqrt(0.5 * xi0);
-    double d12 = (-0.5 * A - z * z) + 0.25 * B / z;
-    double d34 = (-0.5 * A - z * z) - 0.25 * B / z;
+    *r_ = r;
+}
+KG_HD void polish_complex(double A, double B, double C, double* x_, double* y_) {
+    double x = *x_, y = *y_;
+    for (int it = 0; it < 2; ++it) {
+        // w^2, then Horner in complex arithmetic: f = ((w^2 + A) w + B) w + C, f' = (4 w^2 + 2A) w + B
+        double w2r = fma(x, x, -y * y), w2i = 2.0 * x * y;
+        double t1r = w2r + A, t1i = w2i;
+        double t2r = fma(t1r, x, -t1i * y) + B, t2i = fma(t1r, y, t1i * x);
+        double fr = fma(t2r, x, -t2i * y) + C, fi = fma(t2r, y, t2i * x);
+        double g1r = fma(4.0, w2r, 2.0 * A), g1i = 4.0 * w2i;
+        double gr = fma(g1r, x, -g1i * y) + B, gi = fma(g1r, y, g1i * x);
+        double den = fma(gr, gr, gi * gi);
+        double sr = fma(fr, gr, fi * gi) / den, si = fma(fi, gr, -fr * gi) / den;
+        if (!(fabs(sr) + fabs(si) <= 1.0e-6 * fmax(1.0, fabs(x) + fabs(y)))) break;
+        x -= sr;
+        y -= si;
+    }
+    *x_ = x;
+    *y_ = y;
+}
+
+KG_HD Roots quartic_roots(const Observer& o, double lam, double eta, bool polish = false) {
+    // kgeo/kerr_raytracing_utils.py:330-380 in real arithmetic.  The Ferrari resolvent loses digits by cancellation
+    // (xi0 = omega_+ + omega_- - A/3), so the reference's own roots carry ~1e-11 relative noise at high spin; to land on
+    // the SAME roots the coefficient chain is evaluated with individually rounded operations in NumPy's order.
+    Roots R;
+    const double a = o.a, a2 = o.a2;
+    const double lam2 = mul_rn(lam, lam);
+    const double A = add_rn(add_rn(a2, -eta), -lam2);
+    const double lma = add_rn(lam, -a);
+    const double B = mul_rn(2.0, add_rn(eta, mul_rn(lma, lma)));
+    const double C = mul_rn(-a2, eta);
+    const double AA = mul_rn(A, A);
+    const double P = add_rn(div_rn(-AA, 12.0), -C);
+    const double Q = add_rn(mul_rn(div_rn(-A, 3.0), add_rn(div_rn(AA, 36.0), -C)), -div_rn(mul_rn(B, B), 8.0));
+    const double disc = add_rn(mul_rn(4.0, mul_rn(mul_rn(P, P), P)), mul_rn(27.0, mul_rn(Q, Q)));
+    const double mhq = mul_rn(-0.5, Q);
+    const double A3 = div_rn(A, 3.0);
+    double xi0;
+    // NumPy divides a complex array by a real as  x * (1/y)  (Smith's algorithm with a zero imaginary part), so the
+    // reference's disc/108, theta/3 and 0.25 B/z are each a reciprocal followed by a product: two roundings, kept here.
+    const double inv108 = div_rn(1.0, 108.0), inv3 = div_rn(1.0, 3.0);
+    if (disc >= 0.0) {
+        double h = sqrt_rn(mul_rn(disc, inv108));
+        xi0 = add_rn(add_rn(cbrt(add_rn(mhq, h)), cbrt(add_rn(mhq, -h))), -A3);
+    } else {
+        // omega_+/-^3 = -Q/2 +/- i h: the cube roots with the largest real part are complex conjugates
+        double h = sqrt_rn(mul_rn(-disc, inv108));
+        double mag = hypot(mhq, h);
+        double ang = atan2(h, mhq);
+        double re = mul_rn(cbrt(mag), cos(mul_rn(ang, inv3)));
+        xi0 = add_rn(add_rn(re, re), -A3);
+    }
+    const double z = sqrt_rn(mul_rn(0.5, xi0));
+    const double base = add_rn(mul_rn(-0.5, A), -mul_rn(z, z));
+    const double bz = mul_rn(mul_rn(0.25, B), div_rn(1.0, z));
+    const double d12 = add_rn(base, bz);
+    const double d34 = add_rn(base, -bz);
     R.c12 = d12 < 0.0;
     R.c34 = d34 < 0.0;
     if (R.c12) {
@@ -186,6 +240,25 @@ KG_HD Roots quartic_roots(const Observer& o, double lam, double eta) {
     else if (R.re[3] < o.rplus) region = 2;
     else if (R.re[3] > o.rplus) region = 1;
     R.region = region;
+    // Optional (KGEO_MODE_POLISH_ROOTS): with the class fixed exactly as the reference fixes it, polish the root VALUES by
+    // two Newton steps on r^4 + A r^2 + B r + C.  Ferrari's formulas lose up to 6 digits (measured against 50-digit
+    // roots: the reference's r2 is off by 4e-10 relative at a=0.94, alpha=3.29, beta=1.20, and tau_tot by 4e-11).
+    // Polished roots are accurate to ~1e-16 but no longer share the reference's rounding noise, so PARITY with the
+    // reference is better without it (default off).  Pairs closer than 1e-4 are left untouched.
+    if (polish) {
+        const double scale = fmax(1.0, fabs(z));
+        const double s12 = sqrt(fabs(d12)), s34 = sqrt(fabs(d34));
+        if (s12 > 1.0e-4 * scale) {
+            if (R.c12) polish_complex(A, B, C, &R.re[1], &R.im[1]);
+            else { polish_real(A, B, C, &R.re[0]); polish_real(A, B, C, &R.re[1]); }
+            if (R.c12) { R.re[0] = R.re[1]; R.im[0] = -R.im[1]; }
+        }
+        if (s34 > 1.0e-4 * scale) {
+            if (R.c34) polish_complex(A, B, C, &R.re[3], &R.im[3]);
+            else { polish_real(A, B, C, &R.re[2]); polish_real(A, B, C, &R.re[3]); }
+            if (R.c34) { R.re[2] = R.re[3]; R.im[2] = -R.im[3]; }
+        }
+    }
     return R;
 }
 
@@ -313,7 +386,7 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 // ---- ray setup -------------------------------------------------------------------------------------------------------
 // any_eta_pos / any_eta_nonpos reproduce the reference's whole-array guards `np.any(eta>0)` / `np.any(eta<=0)`
 // (kgeo/kerr_raytracing_ana.py:217,300): they are properties of the CALL, computed once by the host wrapper.
-enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4 };
+enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4, M_INPUT_LAM_ETA = 8, M_POLISH_ROOTS = 16 };
 // PHI_T = false skips every constant that only the phi / t / sigma integrals need (image and lensing paths).
 template <bool PHI_T>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, double* w, int* flags_out) {
@@ -409,7 +482,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
     }
 
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
-    Roots R = quartic_roots(o, lam, eta);
+    Roots R = quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0);
     flags |= (R.region << F_REGION_SHIFT);
     if (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) flags |= F_OUTSIDE;   // utils :817-824
     const double rp = o.rplus, rm = o.rminus, r_o = o.r_o;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) ray_summary_kernel(Observer o, 
     }
     if (o.lowspin && (mode & M_CLAMP_LOWSPIN_ETA) && eta < 0.0) eta = kEP;
     if (roots || rclass || outside) {
-        Roots R = quartic_roots(o, lam, eta);
+        Roots R = quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0);
         if (roots) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) ray_summary_kernel(Observer o, 
         if (uratio) uratio[i] = ratio;
         if (a2uminus) a2uminus[i] = a2um;
     }
-    if (tau_tot) tau_tot[i] = tau_total_of(o, quartic_roots(o, lam, eta));
+    if (tau_tot) tau_tot[i] = tau_total_of(o, quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0));
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, size_t n, const double* __restrict__ roots,

@@ -7,7 +7,7 @@ PI = ctypes.POINTER(ctypes.c_int)
 
 def build(name):
     so = os.path.join(HERE, '_%s.so' % name)
-    subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=fast', '-shared', '-fPIC', '-o', so,
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=fast', *os.environ.get('HOSTSIM_FLAGS', '').split(), '-shared', '-fPIC', '-o', so,
                            os.path.join(HERE, name + '.cpp')])
     return ctypes.CDLL(so)
 

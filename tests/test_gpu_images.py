@@ -141,7 +141,8 @@ def test_images_against_reference(golden, kg, name):
         assert np.array_equal(got == 0, ref == 0), "%s %s: zero mask differs" % (name, key)
         if key in ('Q', 'U'):      # Q, U change sign: gate relative to the pixel's total intensity
             den = np.where(ref_I != 0, np.abs(ref_I), 1.0)
-            assert np.max(np.abs(got - ref) / den) <= IMAGE_RTOL, key
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), key
+            assert np.nanmax(np.abs(got - ref) / den) <= IMAGE_RTOL, key
         elif key in ('n',):
             assert np.array_equal(got, ref)
         else:
