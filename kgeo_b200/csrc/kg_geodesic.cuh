@@ -75,7 +75,10 @@ enum Slot {
     R_PC0, R_PC1, R_PC2,        // Pi(n_i|k) - K(k)
     R_PO0, R_PO1, R_PO2,        // observer-side values: case 2: Pi(n_i;aux|k); case 3: R1(al_i,aux); case 4: S1(al_i,aux)
     R_EO,                       // case 2: E(aux|k);  case 3: R2(al0,aux);  case 4: S2(g0,aux)
-    R_Q0, R_Q1, R_Q2, R_Q3, R_Q4, R_Q5, R_Q6, R_Q7, R_Q8, R_Q9, R_Q10, R_Q11, R_Q12, R_Q13, R_Q14, R_Q15,
+    R_Q0, R_Q1, R_Q2, R_Q3, R_Q4, R_Q5, R_Q6, R_Q7, R_Q8, R_Q9, R_Q10,
+    T_ISQ,                      // 1 / T_SQ
+    T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
+    R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
     NW
 };
 // case-specific meaning of the R_Q* slots
@@ -361,7 +364,7 @@ KG_HD double tau_total_of(const Observer& o, const Roots& R) {
 // ---- GL19a auxiliary integrals ------------------------------------------------------------------------------------
 // R1, R2 (B62, B65; kgeo/kerr_raytracing_ana.py:666-683).  sn, cn, dn = sin, cos, sqrt(1-j sin^2) of the amplitude.
 KG_HD double R1_of(double al, double p1, double nn, double sn, double dn, double Pi) {
-    double f1 = 0.5 * p1 * log(fabs((p1 * dn + sn) / (p1 * dn - sn)));
+    double f1 = 0.5 * p1 * kg_log(fabs((p1 * dn + sn) / (p1 * dn - sn)));
     return (Pi - al * f1) / (1.0 - al * al);
 }
 KG_HD double R2_of(double al, double j, double nn, double sn, double cn, double dn, double F, double E, double R1) {
@@ -372,7 +375,7 @@ KG_HD double R2_of(double al, double j, double nn, double sn, double cn, double 
 // S1, S2 (B92, B93; kgeo/kerr_raytracing_ana.py:638-663)
 KG_HD double S1_of(double al, double p2, double dn, double F, double Pi) {
     double al2 = al * al;
-    double f2 = 0.5 * p2 * log(fabs(((1.0 - p2) * (1.0 + p2 * dn)) / ((1.0 + p2) * (1.0 - p2 * dn))));
+    double f2 = 0.5 * p2 * kg_log(fabs(((1.0 - p2) * (1.0 + p2 * dn)) / ((1.0 + p2) * (1.0 - p2 * dn))));
     return (F + al2 * Pi - al * f2) / (1.0 + al2);
 }
 KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double F, double E, double S1) {
@@ -426,6 +429,8 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_X0] = w[T_W] * s_o * (-pref * F0);
         w[T_M] = m;
         w[T_SQ] = sq1m;
+        w[T_ISQ] = 1.0 / sq1m;
+        jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = -s_o * sqrt(up);
@@ -467,6 +472,8 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_X0] = w[T_W] * s_o * (-h * prefA * F0);
         w[T_M] = m;
         w[T_SQ] = sq1m;
+        w[T_ISQ] = 1.0 / sq1m;
+        jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = um;
@@ -517,6 +524,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k4, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k4);
         w[R_K] = k4;
+        jacobi_make_ladder(k4, &w[R_LAD]);
         w[R_SC] = 1.0 / pref;
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
         if (PHI_T) {
@@ -563,6 +571,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k3, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k3);
         w[R_K] = k3;
+        jacobi_make_ladder(k3, &w[R_LAD]);
         w[R_SC] = sqAB;
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
         if (PHI_T) {
@@ -597,6 +606,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k2, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k2);
         w[R_K] = k2;
+        jacobi_make_ladder(k2, &w[R_LAD]);
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
         if (PHI_T) {
@@ -626,6 +636,14 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
     *flags_out = flags;
 }
 
+// view of the workspace starting at a base slot (used for the ladders)
+template <class W>
+struct SlotView {
+    W w;
+    int base;
+    KG_HD double operator()(int i) const { return w(base + i); }
+};
+
 // ---- per-sample evaluation ---------------------------------------------------------------------------------------
 struct Point {
     double t, r, th, ph, sig;
@@ -636,7 +654,7 @@ KG_HD double reduce_half_periods(double u, double K, double* ur, double* sgn) {
     double j = rint(u / (2.0 * K));
     if (!(K < kInf)) j = 0.0;
     *ur = fma(-2.0 * K, j, u);
-    *sgn = (fabs(fmod(j, 2.0)) == 1.0) ? -1.0 : 1.0;
+    *sgn = (((long long)j) & 1LL) ? -1.0 : 1.0;
     return j;
 }
 
@@ -645,20 +663,22 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
     *th = 0.0; *Gph = 0.0; *Gt = 0.0;
     if (!(flags & (F_TH_ORD | F_TH_VORT))) return;
     double snarg = fma(-w(T_W), tau, w(T_X0));
-    double sq1m = w(T_SQ), m = w(T_M);
-    double sn, cn, dn, Km;
-    jacobi_sncndn(snarg / sq1m, m, &sn, &cn, &dn, &Km);
+    double sq1m = w(T_SQ);
+    const double uarg = snarg * w(T_ISQ);
+    const SnCnDn jt = jacobi_from_ladder(SlotView<W>{w, T_LAD}, uarg);
+    const double sn = jt.sn, cn = jt.cn, dn = jt.dn;
+    const double Km = w(T_K);
     double idn = 1.0 / dn;
     double sinA = sq1m * sn * idn;            // sin(am(snarg|k)), kgeo/kerr_raytracing_ana.py:275
     if (flags & F_TH_ORD) {
-        *th = acos(w(T_A) * sinA);            // :280
+        *th = kg_acos(w(T_A) * sinA);         // :280
     } else {
         double h = (flags & F_HPOS) ? 1.0 : -1.0;
-        *th = acos(h * sqrt(fma(w(T_B), sinA * sinA, w(T_A))));   // :355
+        *th = kg_acos(h * sqrt(fma(w(T_B), sinA * sinA, w(T_A))));   // :355
     }
     if (!full) return;
     double ur, sg;
-    double j = reduce_half_periods(snarg / sq1m, Km, &ur, &sg);
+    double j = reduce_half_periods(uarg, Km, &ur, &sg);
     double s = sg * sinA, c = sg * cn * idn;
     double c2 = c * c, y = idn * idn;         // 1 - k sin^2 = 1/dn(u|m)^2
     double n = w(T_N);
@@ -708,9 +728,12 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
                        double* It, double* Isig) {
     double X = fma(-w(R_SC), tau, w(R_X0));
     double k = w(R_K);
-    double sn, cn, dn, Kc;
-    jacobi_sncndn(X, k, &sn, &cn, &dn, &Kc);
+    const SnCnDn jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
+    const double sn = jr.sn, cn = jr.cn, dn = jr.dn;
     double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
+    // E and the three Pi's at am(X|k): one shared Carlson bundle for every radial case
+    double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
+    if (full) radial_legendre(w, X, w(R_KC), sn, cn, dn, &E, Pi);
     const double rp = o.rplus, rm = o.rminus;
     if (flags & F_CASE2) {
         double q1 = w(R_Q0), q2 = w(R_Q1), q3 = w(R_Q2), q4 = w(R_Q3), root = w(R_Q4);
@@ -720,8 +743,6 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         double rs = (q4 * rr31 - q3 * rr41 * sn2) / den;                      // :592-594
         *r_s = rs;
         if (full) {
-            double E, Pi[3];
-            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
             double rrp3 = rp - q3, rrm3 = rm - q3, rrp4 = rp - q4, rrm4 = rm - q4;
             double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) / (den * den);   // :600-603
             double H = drs / (rs - q3) - w(R_Q5);
@@ -738,8 +759,6 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         double rr1 = w(R_Q0), rr2 = w(R_Q1), AA = w(R_Q2), BB = w(R_Q3), sqAB = w(R_Q10);
         *r_s = ((BB * rr2 - AA * rr1) + (BB * rr2 + AA * rr1) * cn) / ((BB - AA) + (BB + AA) * cn);   // :516-519
         if (full) {
-            double E, Pi[3];
-            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
             double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2, rrm1 = rm - rr1, rrm2 = rm - rr2;
             double R1a[3];
 #pragma unroll
@@ -761,8 +780,6 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         double a2 = w(R_Q0), b1 = w(R_Q1), g0 = w(R_Q2);
         *r_s = -a2 * (g0 * cn - sn) / (cn + g0 * sn) - b1;                   // :441 with sc = sn/cn
         if (full) {
-            double E, Pi[3];
-            radial_legendre(w, X, Kc, sn, cn, dn, &E, Pi);
             double pref = w(R_Q8), x4rp = w(R_Q9), x4rm = w(R_Q10);
             double S1a[3];
 #pragma unroll

@@ -19,8 +19,10 @@
 
 #if defined(__CUDACC__)
 #define KG_HD __host__ __device__ __forceinline__
+#define KG_NOINLINE __host__ __device__ __noinline__
 #else
 #define KG_HD inline
+#define KG_NOINLINE inline
 #endif
 
 namespace kg {
@@ -37,8 +39,76 @@ KG_HD double cube(double x) { return x * x * x; }
 KG_HD double max3(double a, double b, double c) { return fmax(a, fmax(b, c)); }
 KG_HD double kg_nan() { return kInf - kInf; }
 
+// ---- hot-loop arithmetic ---------------------------------------------------------------------------------------------
+// The IEEE-rounded sqrt / division that nvcc emits cost ~45 / ~32 SASS instructions each (seed + Newton + fix-up paths),
+// and the per-sample evaluation needs ~60 square roots and ~30 divisions.  The fused kernels use these instead: the
+// MUFU seed (20 good bits), ONE third-order Newton step (error -> e^3 ~ 1e-18) and one residual correction, i.e. 6-9
+// DFMA-class instructions, result within 1 ulp, no fix-up branches.  Arguments outside (1e-290, 1e290) -- which the
+// Carlson / Landen recurrences never produce except exact zeros -- take the library path.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double kg_rcp_seed(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double kg_rsqrt_seed(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __noinline__ double kg_sqrt_slow(double x) { return sqrt(x); }
+__device__ __noinline__ double kg_rsqrt_slow(double x) { return 1.0 / sqrt(x); }
+__device__ __noinline__ double kg_div_slow(double a, double b) { return a / b; }
+// 1/sqrt(x), x in (1e-290, 1e290)
+__device__ __forceinline__ double frsqrt(double x) {
+    if (!(x > 1.0e-290 && x < 1.0e290)) return kg_rsqrt_slow(x);
+    double y = kg_rsqrt_seed(x);
+    double t = fma(-(x * y), y, 1.0);                 // 1 - x y^2
+    double u = fma(0.375, t, 0.5) * t;                // t/2 + 3 t^2/8
+    y = fma(y, u, y);
+    t = fma(-(x * y), y, 1.0);                        // residual correction
+    return fma(0.5 * y, t, y);
+}
+__device__ __forceinline__ double fsqrt(double x) {
+    if (!(x > 1.0e-290 && x < 1.0e290)) return kg_sqrt_slow(x);
+    double y = kg_rsqrt_seed(x);
+    double t = fma(-(x * y), y, 1.0);
+    double u = fma(0.375, t, 0.5) * t;
+    y = fma(y, u, y);
+    double g = x * y;
+    double d = fma(-g, g, x);
+    return fma(0.5 * y, d, g);
+}
+__device__ __forceinline__ double fdiv(double a, double b) {
+    double ab = fabs(b);
+    if (!(ab > 1.0e-290 && ab < 1.0e290)) return kg_div_slow(a, b);
+    double r = kg_rcp_seed(b);
+    double t = fma(-b, r, 1.0);
+    double u = fma(t, t, t);                          // t + t^2
+    r = fma(r, u, r);
+    double q = a * r;
+    double rem = fma(-b, q, a);
+    return fma(rem, r, q);
+}
+__device__ __forceinline__ double frcp(double b) { return fdiv(1.0, b); }
+#else
+KG_HD double frsqrt(double x) { return 1.0 / sqrt(x); }
+KG_HD double fsqrt(double x) { return sqrt(x); }
+KG_HD double fdiv(double a, double b) { return a / b; }
+KG_HD double frcp(double b) { return 1.0 / b; }
+#endif
+
 // RC(1, b) with e = b - 1 given separately (both cancellation-free), e > -1:
 //   atan(sqrt e)/sqrt e   (e>0),   atanh(sqrt -e)/sqrt -e = log((1+s)/sqrt(b))/s, s = sqrt(-e)   (e<0)
+// closed forms (out of line: one copy serves every Pi track of the fused kernels)
+KG_NOINLINE double rc1p_closed(double e, double b) {
+    if (e > 0.0) {
+        double s = sqrt(e);
+        return atan(s) / s;
+    }
+    double s = sqrt(-e);
+    return log((1.0 + s) / sqrt(b)) / s;
+}
 KG_HD double rc1p(double e, double b) {
     if (fabs(e) < 0.02) {
         // sum_k (-e)^k / (2k+1), k = 0..8   (0.02^9/19 < 3e-17), Horner in (-e)
@@ -54,12 +124,7 @@ KG_HD double rc1p(double e, double b) {
         h = fma(h, me, 1.0);
         return h;
     }
-    if (e > 0.0) {
-        double s = sqrt(e);
-        return atan(s) / s;
-    }
-    double s = sqrt(-e);
-    return log((1.0 + s) / sqrt(b)) / s;
+    return rc1p_closed(e, b);
 }
 
 // ---- degree-7 tails (DLMF 19.36.1, 19.36.2) --------------------------------------------------------------
@@ -167,22 +232,24 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         Aj[i] = (x + y + z + 2.0 * p[i]) * 0.2;
         sj[i] = 0.0;
     }
+#pragma unroll 1
     for (int n = 0; n < kMaxDup; ++n) {
         // convergence of every requested integral (deviation of each argument from that integral's mean)
-        double dev = 0.0;
-        if (WANT_RF) dev = fmax(dev, max3(fabs(Af - x), fabs(Af - y), fabs(Af - z)) / Af);
-        if (WANT_RD) dev = fmax(dev, max3(fabs(Ad - x), fabs(Ad - y), fabs(Ad - z)) / Ad);
+        bool more = false;
+        if (WANT_RF) more = more || !(max3(fabs(Af - x), fabs(Af - y), fabs(Af - z)) < kSeriesTol * Af);
+        if (WANT_RD) more = more || !(max3(fabs(Ad - x), fabs(Ad - y), fabs(Ad - z)) < kSeriesTol * Ad);
 #pragma unroll
         for (int i = 0; i < NP; ++i)
-            dev = fmax(dev, fmax(max3(fabs(Aj[i] - x), fabs(Aj[i] - y), fabs(Aj[i] - z)), fabs(Aj[i] - p[i])) / Aj[i]);
-        if (!(dev >= kSeriesTol)) break;
-        double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+            more = more || !(fmax(max3(fabs(Aj[i] - x), fabs(Aj[i] - y), fabs(Aj[i] - z)), fabs(Aj[i] - p[i])) < kSeriesTol * Aj[i]);
+        if (!more) break;
+        if (!(x == x && y == y)) break;                             // NaN arguments: nothing to converge to
+        double sx = fsqrt(x), sy = fsqrt(y), sz = fsqrt(z);
         double lam = fma(sx, sy, fma(sy, sz, sz * sx));
-        if (WANT_RD) sd += f / (sz * (z + lam));
+        if (WANT_RD) sd += fdiv(f, sz * (z + lam));
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            double sp = sqrt(p[i]);
-            double id = 1.0 / ((sp + sx) * (sp + sy) * (sp + sz));
+            double sp = fsqrt(p[i]);
+            double id = frcp((sp + sx) * (sp + sy) * (sp + sz));
             double e = (sp - sx) * (sp - sy) * (sp - sz) * id;
             double b = 2.0 * sp * (p[i] + lam) * id;                // = 1 + e without cancellation
             sj[i] += f * id * rc1p(e, b);
@@ -197,27 +264,26 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         f *= 0.25;
     }
     if (WANT_RF) {
-        double iA = 1.0 / Af;
+        double ys = frsqrt(Af), iA = ys * ys;
         double X = (Af - x) * iA, Y = (Af - y) * iA, Z = -(X + Y);
-        *rf = rf_series(X * Y - Z * Z, X * Y * Z) * sqrt(iA);
+        *rf = rf_series(X * Y - Z * Z, X * Y * Z) * ys;
     }
     if (WANT_RD) {
-        double iA = 1.0 / Ad;
+        double ys = frsqrt(Ad), iA = ys * ys;
         double X = (Ad - x) * iA, Y = (Ad - y) * iA, Z = -(X + Y) * (1.0 / 3.0);
         double XY = X * Y, Z2 = Z * Z;
-        *rd = f * rj_series(XY - 6.0 * Z2, (3.0 * XY - 8.0 * Z2) * Z, 3.0 * (XY - Z2) * Z2, XY * Z2 * Z) * iA * sqrt(iA) +
-              3.0 * sd;
+        *rd = f * rj_series(XY - 6.0 * Z2, (3.0 * XY - 8.0 * Z2) * Z, 3.0 * (XY - Z2) * Z2, XY * Z2 * Z) * (iA * ys) + 3.0 * sd;
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        double iA = 1.0 / Aj[i];
+        double ys = frsqrt(Aj[i]), iA = ys * ys;
         double X = (Aj[i] - x) * iA, Y = (Aj[i] - y) * iA, Z = (Aj[i] - z) * iA, P = -(X + Y + Z) * 0.5;
         double XYZ = X * Y * Z, P2 = P * P;
         double E2 = X * Y + X * Z + Y * Z - 3.0 * P2;
         double E3 = XYZ + 2.0 * E2 * P + 4.0 * P2 * P;
         double E4 = (2.0 * XYZ + E2 * P + 3.0 * P2 * P) * P;
         double E5 = XYZ * P2;
-        rj[i] = f * rj_series(E2, E3, E4, E5) * iA * sqrt(iA) + 6.0 * sj[i];
+        rj[i] = f * rj_series(E2, E3, E4, E5) * (iA * ys) + 6.0 * sj[i];
     }
 }
 
@@ -240,15 +306,19 @@ KG_HD PiPrep pi_prepare(double n, double s, double c2, double y) {
     }
     return o;
 }
+// Cauchy principal value for rho < 0 (out of line: one copy for every Pi of the fused kernels)
+KG_NOINLINE double pi_finish_pv(double s3n, double s, double c2, double y, double F, double p, double rho, double rj) {
+    double q = -rho, xy = c2 * y, pq = p * q;
+    double t = sqrt(xy / (xy + pq));
+    double ath = 0.5 * log((1.0 + t) / (1.0 - t));                 // = sqrt(xy) * RC(xy+pq, pq)
+    double cpv = ((p - 1.0) * rj - 3.0 * (F / s) + 3.0 * ath / sqrt(xy + pq)) / (q + 1.0);
+    return s3n * cpv;
+}
 KG_HD double pi_finish(double n, double s, double c2, double y, double F, const PiPrep& pp, double rj) {
     double s3n = (n * (1.0 / 3.0)) * cube(s);
     if (pp.rho > 0.0) return s3n * rj;
     if (pp.rho == 0.0) return kInf;
-    double q = -pp.rho, xy = c2 * y, pq = pp.p * q;
-    double t = sqrt(xy / (xy + pq));
-    double ath = 0.5 * log((1.0 + t) / (1.0 - t));                 // = sqrt(xy) * RC(xy+pq, pq)
-    double cpv = ((pp.p - 1.0) * rj - 3.0 * (F / s) + 3.0 * ath / sqrt(xy + pq)) / (q + 1.0);
-    return s3n * cpv;
+    return pi_finish_pv(s3n, s, c2, y, F, pp.p, pp.rho, rj);
 }
 
 // ---- complete integrals --------------------------------------------------------------------------------------
@@ -388,6 +458,94 @@ KG_HD void jacobi_sncndn(double u, double m, double* sn, double* cn, double* dn,
     *sn = s;
     *cn = co;
     *dn = d;
+}
+
+// ---- Jacobi functions from a precomputed AGM ladder ---------------------------------------------------------------
+// The ladder (a_i, g_i) depends only on the parameter m, i.e. on the RAY, not on the Mino time: the per-ray setup
+// stores it once and every (ray, sample) evaluation skips the ~6 square roots of the descent.
+// Layout: L[0] = index of the last level (or -1 for m == 1), L[1] = c = last arithmetic mean,
+//         L[2+3i] = a_i, L[3+3i] = 1/a_i, L[4+3i] = g_i.
+constexpr int kLadderLevels = 10;
+constexpr int kLadderSize = 2 + 3 * kLadderLevels;
+
+KG_HD void jacobi_make_ladder(double m, double* L) {
+    for (int i = 0; i < kLadderSize; ++i) L[i] = 0.0;
+    double mc = 1.0 - m;
+    if (!(mc > 0.0)) {
+        L[0] = -1.0;
+        L[1] = (mc == 0.0) ? 1.0 : kg_nan();
+        return;
+    }
+    double a = 1.0, g, c = 1.0;
+    int l = 0;
+    for (int i = 0; i < kLadderLevels; ++i) {
+        l = i;
+        g = sqrt(mc);
+        L[2 + 3 * i] = a;
+        L[3 + 3 * i] = 1.0 / a;
+        L[4 + 3 * i] = g;
+        c = 0.5 * (a + g);
+        if (fabs(a - g) <= 1.5e-8 * a) break;
+        mc = g * a;
+        a = c;
+    }
+    L[0] = (double)l;
+    L[1] = c;
+}
+
+// out-of-line libm calls shared by every call site of the fused kernels (code size: the track kernel must stay
+// inside the instruction cache)
+KG_NOINLINE double kg_log(double x) { return log(x); }
+KG_NOINLINE double kg_acos(double x) { return acos(x); }
+
+struct SnCnDn {
+    double sn, cn, dn;
+};
+
+KG_NOINLINE void jacobi_m1(double u, double* sn, double* cn, double* dn) {
+    double ch = cosh(u);
+    *sn = tanh(u);
+    *cn = 1.0 / ch;
+    *dn = 1.0 / ch;
+}
+
+template <class A>
+KG_NOINLINE SnCnDn jacobi_from_ladder(const A L, double u) {
+    SnCnDn o;
+    const int l = (int)L(0);
+    const double c = L(1);
+    if (l < 0) {   // m == 1: hyperbolic limit
+        jacobi_m1(u, &o.sn, &o.cn, &o.dn);
+        return o;
+    }
+    double uu = u * c;
+    double s, co;
+#if defined(__CUDA_ARCH__)
+    sincos(uu, &s, &co);
+#else
+    s = sin(uu);
+    co = cos(uu);
+#endif
+    double d = 1.0;
+    if (s != 0.0) {
+        double aa = fdiv(co, s);
+        double cc = c * aa;
+#pragma unroll 1
+        for (int i = l; i >= 0; --i) {
+            const double b = L(2 + 3 * i), ib = L(3 + 3 * i), g = L(4 + 3 * i);
+            aa *= cc;
+            cc *= d;
+            d = fdiv(g + aa, b + aa);
+            aa = cc * ib;
+        }
+        aa = frsqrt(fma(cc, cc, 1.0));
+        s = (s >= 0.0) ? aa : -aa;
+        co = cc * s;
+    }
+    o.sn = s;
+    o.cn = co;
+    o.dn = d;
+    return o;
 }
 
 // amplitude am(u|m), continuous in u (scipy.special.ellipj's 4th output)
