@@ -83,7 +83,8 @@ class KgeoError(Exception):
 
 
 def library_path():
-    return _build.LIBPATH
+    # KGEO_B200_LIB lets a developer point at an alternative build of the SAME library (kernel tuning experiments)
+    return os.environ.get("KGEO_B200_LIB") or _build.LIBPATH
 
 
 def lib():

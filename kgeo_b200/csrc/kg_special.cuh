@@ -43,8 +43,8 @@ KG_HD double kg_nan() { return kInf - kInf; }
 // The IEEE-rounded sqrt / division that nvcc emits cost ~45 / ~32 SASS instructions each (seed + Newton + fix-up paths),
 // and the per-sample evaluation needs ~60 square roots and ~30 divisions.  The fused kernels use these instead: the
 // MUFU seed (20 good bits), ONE third-order Newton step (error -> e^3 ~ 1e-18) and one residual correction, i.e. 6-9
-// DFMA-class instructions, result within 1 ulp, no fix-up branches.  Arguments outside (1e-290, 1e290) -- which the
-// Carlson / Landen recurrences never produce except exact zeros -- take the library path.
+// DFMA-class instructions, result within 1 ulp, no fix-up branches and no range checks: the Carlson / Landen recurrences
+// only produce arguments in (1e-290, 1e290) or exact zeros (handled in fsqrt).
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ double kg_rcp_seed(double x) {
     double r;
@@ -56,12 +56,8 @@ __device__ __forceinline__ double kg_rsqrt_seed(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     return r;
 }
-__device__ __noinline__ double kg_sqrt_slow(double x) { return sqrt(x); }
-__device__ __noinline__ double kg_rsqrt_slow(double x) { return 1.0 / sqrt(x); }
-__device__ __noinline__ double kg_div_slow(double a, double b) { return a / b; }
 // 1/sqrt(x), x in (1e-290, 1e290)
 __device__ __forceinline__ double frsqrt(double x) {
-    if (!(x > 1.0e-290 && x < 1.0e290)) return kg_rsqrt_slow(x);
     double y = kg_rsqrt_seed(x);
     double t = fma(-(x * y), y, 1.0);                 // 1 - x y^2
     double u = fma(0.375, t, 0.5) * t;                // t/2 + 3 t^2/8
@@ -69,9 +65,9 @@ __device__ __forceinline__ double frsqrt(double x) {
     t = fma(-(x * y), y, 1.0);                        // residual correction
     return fma(0.5 * y, t, y);
 }
+// sqrt(x) for x = 0 or x in (1e-290, 1e290); sqrt(0) = 0 comes out of the arithmetic when the seed is forced to 0
 __device__ __forceinline__ double fsqrt(double x) {
-    if (!(x > 1.0e-290 && x < 1.0e290)) return kg_sqrt_slow(x);
-    double y = kg_rsqrt_seed(x);
+    double y = (x > 0.0) ? kg_rsqrt_seed(x) : ((x == 0.0) ? 0.0 : kg_nan());
     double t = fma(-(x * y), y, 1.0);
     double u = fma(0.375, t, 0.5) * t;
     y = fma(y, u, y);
@@ -79,9 +75,8 @@ __device__ __forceinline__ double fsqrt(double x) {
     double d = fma(-g, g, x);
     return fma(0.5 * y, d, g);
 }
+// a / b for |b| in (1e-290, 1e290) (no zero / infinity handling: the hot loops never divide by them)
 __device__ __forceinline__ double fdiv(double a, double b) {
-    double ab = fabs(b);
-    if (!(ab > 1.0e-290 && ab < 1.0e290)) return kg_div_slow(a, b);
     double r = kg_rcp_seed(b);
     double t = fma(-b, r, 1.0);
     double u = fma(t, t, t);                          // t + t^2
@@ -96,6 +91,24 @@ KG_HD double frsqrt(double x) { return 1.0 / sqrt(x); }
 KG_HD double fsqrt(double x) { return sqrt(x); }
 KG_HD double fdiv(double a, double b) { return a / b; }
 KG_HD double frcp(double b) { return 1.0 / b; }
+#endif
+
+// Series coefficients live in the constant bank on the device: an FP64 literal costs two UMOV instructions per use,
+// a constant-bank operand costs none.
+#define KG_SERIES_COEFFS                                                                                             \
+    {1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0, /* 0-7  rc1p   */ \
+     1.0 / 10.0, 1.0 / 14.0, 1.0 / 24.0, 3.0 / 44.0, 5.0 / 208.0, 3.0 / 104.0, 1.0 / 16.0,       /* 8-14 RF     */ \
+     3.0 / 14.0, 1.0 / 6.0, 9.0 / 88.0, 3.0 / 22.0, 9.0 / 52.0, 3.0 / 26.0, 1.0 / 16.0, 3.0 / 40.0, 3.0 / 20.0,     \
+     45.0 / 272.0, 9.0 / 68.0,                                                                   /* 15-25 RJ/RD */ \
+     0.0075, 0.375, 0.25, 0.2, 1.0 / 3.0, 0.5}                                                   /* 26-31 misc  */
+#if defined(__CUDACC__)
+__constant__ double kc_dev[32] = KG_SERIES_COEFFS;
+#endif
+static const double kc_host[32] = KG_SERIES_COEFFS;
+#if defined(__CUDA_ARCH__)
+#define KC(i) kc_dev[i]
+#else
+#define KC(i) kc_host[i]
 #endif
 
 // RC(1, b) with e = b - 1 given separately (both cancellation-free), e > -1:
@@ -113,14 +126,14 @@ KG_HD double rc1p(double e, double b) {
     if (fabs(e) < 0.02) {
         // sum_k (-e)^k / (2k+1), k = 0..8   (0.02^9/19 < 3e-17), Horner in (-e)
         double me = -e;
-        double h = 1.0 / 17.0;
-        h = fma(h, me, 1.0 / 15.0);
-        h = fma(h, me, 1.0 / 13.0);
-        h = fma(h, me, 1.0 / 11.0);
-        h = fma(h, me, 1.0 / 9.0);
-        h = fma(h, me, 1.0 / 7.0);
-        h = fma(h, me, 1.0 / 5.0);
-        h = fma(h, me, 1.0 / 3.0);
+        double h = KC(0);
+        h = fma(h, me, KC(1));
+        h = fma(h, me, KC(2));
+        h = fma(h, me, KC(3));
+        h = fma(h, me, KC(4));
+        h = fma(h, me, KC(5));
+        h = fma(h, me, KC(6));
+        h = fma(h, me, KC(7));
         h = fma(h, me, 1.0);
         return h;
     }
@@ -129,13 +142,12 @@ KG_HD double rc1p(double e, double b) {
 
 // ---- degree-7 tails (DLMF 19.36.1, 19.36.2) --------------------------------------------------------------
 KG_HD double rf_series(double E2, double E3) {
-    return 1.0 - E2 * (1.0 / 10.0) + E3 * (1.0 / 14.0) + E2 * E2 * (1.0 / 24.0) - E2 * E3 * (3.0 / 44.0) -
-           E2 * E2 * E2 * (5.0 / 208.0) + E3 * E3 * (3.0 / 104.0) + E2 * E2 * E3 * (1.0 / 16.0);
+    return 1.0 - E2 * KC(8) + E3 * KC(9) + E2 * E2 * KC(10) - E2 * E3 * KC(11) - E2 * E2 * E2 * KC(12) + E3 * E3 * KC(13) +
+           E2 * E2 * E3 * KC(14);
 }
 KG_HD double rj_series(double E2, double E3, double E4, double E5) {
-    return 1.0 - E2 * (3.0 / 14.0) + E3 * (1.0 / 6.0) + E2 * E2 * (9.0 / 88.0) - E4 * (3.0 / 22.0) -
-           E2 * E3 * (9.0 / 52.0) + E5 * (3.0 / 26.0) - E2 * E2 * E2 * (1.0 / 16.0) + E3 * E3 * (3.0 / 40.0) +
-           E2 * E4 * (3.0 / 20.0) + E2 * E2 * E3 * (45.0 / 272.0) - (E3 * E4 + E2 * E5) * (9.0 / 68.0);
+    return 1.0 - E2 * KC(15) + E3 * KC(16) + E2 * E2 * KC(17) - E4 * KC(18) - E2 * E3 * KC(19) + E5 * KC(20) -
+           E2 * E2 * E2 * KC(21) + E3 * E3 * KC(22) + E2 * E4 * KC(23) + E2 * E2 * E3 * KC(24) - (E3 * E4 + E2 * E5) * KC(25);
 }
 
 // ---- stand-alone Carlson integrals (general arguments; exported for the element-wise C-ABI) ---------------
@@ -232,17 +244,20 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         Aj[i] = (x + y + z + 2.0 * p[i]) * 0.2;
         sj[i] = 0.0;
     }
+    // Every deviation (mean - argument) shrinks by EXACTLY 4 per duplication step ((A+lam)/4 - (x+lam)/4 = (A-x)/4), so the
+    // largest initial deviation Q0 is measured once and the test per step is Q0 * 4^-n < tol * (smallest mean).
+    double Q0 = 0.0, Amin = kInf;
+    if (WANT_RF) { Q0 = fmax(Q0, max3(fabs(Af - x), fabs(Af - y), fabs(Af - z))); Amin = fmin(Amin, Af); }
+    if (WANT_RD) { Q0 = fmax(Q0, max3(fabs(Ad - x), fabs(Ad - y), fabs(Ad - z))); Amin = fmin(Amin, Ad); }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        Q0 = fmax(Q0, fmax(max3(fabs(Aj[i] - x), fabs(Aj[i] - y), fabs(Aj[i] - z)), fabs(Aj[i] - p[i])));
+        Amin = fmin(Amin, Aj[i]);
+    }
+    if (!(Q0 == Q0) || !(Amin == Amin)) Q0 = 0.0;                     // NaN arguments: nothing to converge to
 #pragma unroll 1
     for (int n = 0; n < kMaxDup; ++n) {
-        // convergence of every requested integral (deviation of each argument from that integral's mean)
-        bool more = false;
-        if (WANT_RF) more = more || !(max3(fabs(Af - x), fabs(Af - y), fabs(Af - z)) < kSeriesTol * Af);
-        if (WANT_RD) more = more || !(max3(fabs(Ad - x), fabs(Ad - y), fabs(Ad - z)) < kSeriesTol * Ad);
-#pragma unroll
-        for (int i = 0; i < NP; ++i)
-            more = more || !(fmax(max3(fabs(Aj[i] - x), fabs(Aj[i] - y), fabs(Aj[i] - z)), fabs(Aj[i] - p[i])) < kSeriesTol * Aj[i]);
-        if (!more) break;
-        if (!(x == x && y == y)) break;                             // NaN arguments: nothing to converge to
+        if (Q0 * f < kSeriesTol * Amin) break;
         double sx = fsqrt(x), sy = fsqrt(y), sz = fsqrt(z);
         double lam = fma(sx, sy, fma(sy, sz, sz * sx));
         if (WANT_RD) sd += fdiv(f, sz * (z + lam));
@@ -258,6 +273,7 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         }
         if (WANT_RF) Af = (Af + lam) * 0.25;
         if (WANT_RD) Ad = (Ad + lam) * 0.25;
+        Amin = (Amin + lam) * 0.25;
         x = (x + lam) * 0.25;
         y = (y + lam) * 0.25;
         z = (z + lam) * 0.25;

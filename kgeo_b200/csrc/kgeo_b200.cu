@@ -201,7 +201,17 @@ __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, s
 // ---------------------------------------------------------------------------------------------------------------------
 // the track kernel
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TRK_WARPS = 4;
+// 20 warps on one 32-ray tile, one CTA per SM: measured fastest on B200 for BASELINE cfg 3 (78.7 ms; 16 warps 82.7 ms;
+// 4 warps x 4 CTAs 93.5 ms; 8 x 2 87.3 ms) -- warps of one tile take the same root-class branches, so they share
+// instruction-cache lines (the "no instruction" stall per issue drops from 3.1 to 0.4), and 96 registers per thread
+// allow 20 resident warps.
+#ifndef KG_TRK_WARPS
+#define KG_TRK_WARPS 20
+#endif
+#ifndef KG_TRK_MINBLOCKS
+#define KG_TRK_MINBLOCKS 1
+#endif
+constexpr int TRK_WARPS = KG_TRK_WARPS;
 constexpr int TRK_THREADS = 32 * TRK_WARPS;
 
 struct SmemW {
@@ -219,7 +229,7 @@ struct TrackOut {
 };
 
 template <bool FULL>
-__global__ void __launch_bounds__(TRK_THREADS) track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
+__global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS) track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
                                                             const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
                                                             const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
                                                             size_t ld, int k_begin, int k_end, int chunk) {
