@@ -251,3 +251,19 @@ def test_image_argument_checks(kg):
         kg.Velocity('nonsense')
     with pytest.raises(Exception, match="all field coefficients are 0"):
         kg.Bfield('simple')
+
+
+def test_multi_gpu_sharded_image_and_tracks():
+    """N-GPU path under torchrun + NCCL (skipped on a single-GPU box): tests/dist_check.py."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)),
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_check.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert "dist_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
