@@ -195,3 +195,31 @@ def test_argument_checks(kg):
         kg.coords_at_tau(0.5, [0, 1000., 0.3, 0], [A, A], np.zeros((3, 5)))
     g = kg.raytrace_ana(0.5, [0, 1000., 0.3, 0], [3.0, 4.0], ngeo=5, plotdata=False)   # scalars are wrapped
     assert g.r_s.shape == (5, 1)
+
+
+def test_edge_shapes_and_special_inputs(kg):
+    """Ragged / degenerate shapes: empty pixel list, npix not a multiple of the 32-ray tile, ngeo = 1 and 2, one Mino
+    time per ray, NaN pixel coordinates (NaN out, neighbours untouched), a sample count that is not a multiple of the warps."""
+    obs = [0, 1000., 17 * np.pi / 180, 0]
+    g0 = kg.raytrace_ana(0.94, obs, [np.zeros(0), np.zeros(0)], ngeo=5, plotdata=False)
+    assert g0.r_s.shape == (5, 0)
+    rng = np.random.default_rng(7)
+    A, B = rng.uniform(-8, 8, 77), rng.uniform(-8, 8, 77)
+    whole = kg.raytrace_ana(0.94, obs, [A, B], ngeo=23, plotdata=False)
+    for n in (1, 31, 33, 77):
+        part = kg.raytrace_ana(0.94, obs, [A[:n].copy(), B[:n].copy()], ngeo=23, plotdata=False)
+        for w, p in zip(whole.geo_coords, part.geo_coords):
+            assert np.array_equal(w[:, :n], p, equal_nan=True)
+    one = kg.raytrace_ana(0.94, obs, [A, B], ngeo=1, plotdata=False)       # linspace(0, stop, 1) = [0]
+    assert one.r_s.shape == (1, 77) and not one.mino_times.any()
+    assert np.max(np.abs(one.r_s[0] / 1000. - 1)) < 1e-9
+    two = kg.raytrace_ana(0.94, obs, [A, B], ngeo=2, plotdata=False)
+    assert np.array_equal(two.mino_times[1], whole.mino_times[-1])         # last sample = maxtaufrac * tau_tot exactly
+    A2, B2 = A.copy(), B.copy()
+    A2[5] = np.nan
+    bad = kg.raytrace_ana(0.94, obs, [A2, B2], ngeo=23, plotdata=False)
+    assert np.isnan(bad.r_s[:, 5]).all()
+    keep = np.arange(77) != 5
+    assert np.array_equal(bad.r_s[:, keep], whole.r_s[:, keep], equal_nan=True)
+    sig, (t, r, th, ph) = kg.coords_at_tau(0.94, obs, [A, B], np.full(77, 0.1))
+    assert r.shape == (1, 77) and np.isfinite(r).all()
