@@ -267,3 +267,33 @@ def test_multi_gpu_sharded_image_and_tracks():
                           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_check.py")],
                          capture_output=True, text=True, timeout=900)
     assert "dist_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_spin_inclination_sweep_against_oracle(kg):
+    """BASELINE cfg 5 grid: a in linspace(0, 0.99, 8) x theta_o in linspace(5, 85, 8) degrees (64 configs, default models,
+    n = 0..2), at 24 x 24 pixels so that the oracle finishes in seconds.  a = 0 exercises the |a| < MINSPIN branches,
+    theta_o = 85 deg the class-II region.  Integer outputs and masks exact, r_s to 1e-10, I and g to 1e-8."""
+    from oracle import kgeo_oracle as ko
+    worst = dict(r=0.0, I=0.0, g=0.0)
+    for a in np.linspace(0, 0.99, 8):
+        for inc in np.linspace(5, 85, 8):
+            a, th_o = float(a), float(inc * np.pi / 180)
+            out = kg.make_image(a, np.inf, th_o, 2, -9., 9., -9., 9., 18. / 24)
+            ref = ko.make_image(a, np.inf, th_o, 2, -9., 9., -9., 9., 18. / 24, dict(type='bpl'), dict(type='zamo'), dict(type='rad'))
+            names = ['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np']
+            for got, want, key in zip(out, ref, names):
+                assert np.array_equal(np.isnan(got), np.isnan(want)), (a, inc, key)
+                assert np.array_equal(got == 0, want == 0), "zero mask differs: a=%g inc=%g %s" % (a, inc, key)
+                if key == 'n':
+                    assert np.array_equal(got, want), (a, inc)
+                    continue
+                ok = np.isfinite(want) & (want != 0)
+                den = np.abs(want[ok])
+                if key == 'r':      # tau -> r has condition number ~ r/(r4 - r3): crossings at r ~ 1e6 M exist in this sweep
+                    den = den * np.maximum(1.0, den / 1000.0)
+                e = np.max(np.abs(got[ok] - want[ok]) / den) if ok.any() else 0.0
+                if key in worst:
+                    worst[key] = max(worst[key], e)
+                tol = TRACK_RTOL if key in ('r', 't') else IMAGE_RTOL
+                assert e <= tol, "a=%g inc=%g %s: %.2e" % (a, inc, key, e)
+    print("sweep worst rel errors", worst)
