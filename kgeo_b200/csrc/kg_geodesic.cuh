@@ -29,6 +29,7 @@ constexpr double kEP = 1.0e-12;      // kgeo/kerr_raytracing_utils.py:12
 struct Observer {
     double a, r_o, th_o;
     double a2, rplus, rminus, sth, cth, cth2;
+    double c_iph, c_it;   // 2a/(r+ - r-), 4/(r+ - r-) of the I_phi / I_t assembly (kerr_raytracing_ana.py:627-630)
     int ro_inf, lowspin, north;
 };
 
@@ -41,6 +42,8 @@ KG_HD Observer make_observer(double a, double r_o, double th_o) {
     double q = sqrt(1.0 - a * a);
     o.rplus = 1.0 + q;
     o.rminus = 1.0 - q;
+    o.c_iph = 2.0 * a / (o.rplus - o.rminus);
+    o.c_it = 4.0 / (o.rplus - o.rminus);
     o.sth = sin(th_o);
     o.cth = cos(th_o);
     o.cth2 = o.cth * o.cth;
@@ -77,6 +80,7 @@ enum Slot {
     R_EO,                       // case 2: E(aux|k);  case 3: R2(al0,aux);  case 4: S2(g0,aux)
     R_Q0, R_Q1, R_Q2, R_Q3, R_Q4, R_Q5, R_Q6, R_Q7, R_Q8, R_Q9, R_Q10,
     T_ISQ,                      // 1 / T_SQ
+    T_I2K, R_I2K,               // 1/(2 K(m)), 1/(2 K(k)) (0 when K is infinite)
     T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
     R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
     NW
@@ -363,27 +367,37 @@ KG_HD double tau_total_of(const Observer& o, const Roots& R) {
 
 // ---- GL19a auxiliary integrals ------------------------------------------------------------------------------------
 // R1, R2 (B62, B65; kgeo/kerr_raytracing_ana.py:666-683).  sn, cn, dn = sin, cos, sqrt(1-j sin^2) of the amplitude.
-KG_HD double R1_of(double al, double p1, double nn, double sn, double dn, double Pi) {
-    double f1 = 0.5 * p1 * kg_log(fabs((p1 * dn + sn) / (p1 * dn - sn)));
-    return (Pi - al * f1) / (1.0 - al * al);
+// FAST = true (per-sample code): divisions by the 1-ulp fdiv of kg_special.cuh; FAST = false (per-ray setup): IEEE.
+template <bool FAST>
+KG_HD double qdiv(double a, double b) {
+    return FAST ? fdiv(a, b) : a / b;
 }
+template <bool FAST = false>
+KG_HD double R1_of(double al, double p1, double nn, double sn, double dn, double Pi) {
+    double f1 = 0.5 * p1 * kg_log(fabs(qdiv<FAST>(p1 * dn + sn, p1 * dn - sn)));
+    return qdiv<FAST>(Pi - al * f1, 1.0 - al * al);
+}
+template <bool FAST = false>
 KG_HD double R2_of(double al, double j, double nn, double sn, double cn, double dn, double F, double E, double R1) {
-    double al2 = al * al, den = j + (1.0 - j) * al2;
-    double R2 = (F - (al2 / den) * (E - al * sn * dn / (1.0 + al * cn))) / (al2 - 1.0);
-    return R2 + (2.0 * j - nn) * R1 / den;
+    double al2 = al * al, iden = qdiv<FAST>(1.0, j + (1.0 - j) * al2);
+    double R2 = qdiv<FAST>(F - (al2 * iden) * (E - qdiv<FAST>(al * sn * dn, 1.0 + al * cn)), al2 - 1.0);
+    return R2 + (2.0 * j - nn) * R1 * iden;
 }
 // S1, S2 (B92, B93; kgeo/kerr_raytracing_ana.py:638-663)
+template <bool FAST = false>
 KG_HD double S1_of(double al, double p2, double dn, double F, double Pi) {
     double al2 = al * al;
-    double f2 = 0.5 * p2 * kg_log(fabs(((1.0 - p2) * (1.0 + p2 * dn)) / ((1.0 + p2) * (1.0 - p2 * dn))));
-    return (F + al2 * Pi - al * f2) / (1.0 + al2);
+    double f2 = 0.5 * p2 * kg_log(fabs(qdiv<FAST>((1.0 - p2) * (1.0 + p2 * dn), (1.0 + p2) * (1.0 - p2 * dn))));
+    return qdiv<FAST>(F + al2 * Pi - al * f2, 1.0 + al2);
 }
+template <bool FAST = false>
 KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double F, double E, double S1) {
     double al2 = al * al, al2p1 = 1.0 + al2, al2j = 1.0 - j + al2;
     // (al - tan)/(1 + al tan) written with sn, cn so that cn -> 0 is harmless
-    double S2a = (1.0 - j) * F + al2 * E + al2 * dn * (al * cn - sn) / (cn + al * sn) - al2 * al;
-    S2a = -S2a / (al2p1 * al2j);
-    return S2a + S1 * (1.0 / al2p1 + (1.0 - j) / al2j);
+    double S2a = (1.0 - j) * F + al2 * E + qdiv<FAST>(al2 * dn * (al * cn - sn), cn + al * sn) - al2 * al;
+    double i1 = qdiv<FAST>(1.0, al2p1), i2 = qdiv<FAST>(1.0, al2j);
+    S2a = -S2a * (i1 * i2);
+    return S2a + S1 * (i1 + (1.0 - j) * i2);
 }
 
 // ---- ray setup -------------------------------------------------------------------------------------------------------
@@ -430,6 +444,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_M] = m;
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
+        w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
         jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
@@ -473,6 +488,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_M] = m;
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
+        w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
         jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
@@ -530,6 +546,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) {
             double dno = sqrt(fma(-k4 * sa, sa, 1.0));
             w[R_KC] = ellip_K(k4);
+            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
             w[R_EC] = ellip_Ec(k4);
             for (int i = 0; i < 3; ++i) {
                 double p2 = sqrt((1.0 + al[i] * al[i]) / (1.0 - k4 + al[i] * al[i]));
@@ -577,6 +594,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) {
             double dno = sqrt(fma(-k3 * sa, sa, 1.0));
             w[R_KC] = ellip_K(k3);
+            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
             w[R_EC] = ellip_Ec(k3);
             for (int i = 0; i < 3; ++i) {
                 w[R_N0 + i] = nn[i];
@@ -611,6 +629,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
         if (PHI_T) {
             w[R_KC] = ellip_K(k2);
+            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
             w[R_EC] = ellip_Ec(k2);
             for (int i = 0; i < 3; ++i) {
                 w[R_N0 + i] = nn[i];
@@ -620,6 +639,14 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
             w[R_EO] = Eo;
         }
         w[R_Q0] = q1; w[R_Q1] = q2; w[R_Q2] = q3; w[R_Q3] = q4; w[R_Q4] = root;
+        if (PHI_T) {   // per-ray factors of the case-2 assembly, so that the per-sample code has no division by a constant
+            double c = 2.0 / root;
+            w[R_Q6] = c;
+            w[R_Q7] = c * (rr43 / (rrp3 * rrp4));
+            w[R_Q8] = c * (rr43 / (rrm3 * rrm4));
+            w[R_Q9] = 1.0 / rrp3;
+            w[R_Q10] = 1.0 / rrm3;
+        }
         double Rpot_o = (r_o - q1) * (r_o - q2) * (r_o - q3) * (r_o - q4);
         w[R_Q5] = sqrt(Rpot_o) / (r_o - q3);   // H_o (NaN for r_o = inf, as in the reference)
         // tau_tot (utils :485-546): note the reference tests r3 (not r4) against r_+
@@ -650,9 +677,8 @@ struct Point {
 };
 
 // reduce a Jacobi argument by half periods: u = 2K j + u_r, |u_r| <= K; returns j and the sign (-1)^j
-KG_HD double reduce_half_periods(double u, double K, double* ur, double* sgn) {
-    double j = rint(u / (2.0 * K));
-    if (!(K < kInf)) j = 0.0;
+KG_HD double reduce_half_periods(double u, double K, double i2K, double* ur, double* sgn) {
+    double j = rint(u * i2K);               // i2K = 1/(2K), 0 when K = inf
     *ur = fma(-2.0 * K, j, u);
     *sgn = (((long long)j) & 1LL) ? -1.0 : 1.0;
     return j;
@@ -668,7 +694,7 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
     const SnCnDn jt = jacobi_from_ladder(SlotView<W>{w, T_LAD}, uarg);
     const double sn = jt.sn, cn = jt.cn, dn = jt.dn;
     const double Km = w(T_K);
-    double idn = 1.0 / dn;
+    double idn = frcp(dn);
     double sinA = sq1m * sn * idn;            // sin(am(snarg|k)), kgeo/kerr_raytracing_ana.py:275
     if (flags & F_TH_ORD) {
         *th = kg_acos(w(T_A) * sinA);         // :280
@@ -678,7 +704,7 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
     }
     if (!full) return;
     double ur, sg;
-    double j = reduce_half_periods(uarg, Km, &ur, &sg);
+    double j = reduce_half_periods(uarg, Km, w(T_I2K), &ur, &sg);
     double s = sg * sinA, c = sg * cn * idn;
     double c2 = c * c, y = idn * idn;         // 1 - k sin^2 = 1/dn(u|m)^2
     double n = w(T_N);
@@ -702,7 +728,7 @@ template <class W>
 KG_HD void radial_legendre(const W& w, double X, double Kc, double sn, double cn, double dn, double* E, double* Pi) {
     double k = w(R_K);
     double Xr, sg;
-    double j = reduce_half_periods(X, Kc, &Xr, &sg);
+    double j = reduce_half_periods(X, Kc, w(R_I2K), &Xr, &sg);
     double s = sg * sn, c2 = cn * cn, y = dn * dn;
     PiPrep pp[3];
     double pa[3], rj[3], rf, rd;
@@ -743,17 +769,16 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         double rs = (q4 * rr31 - q3 * rr41 * sn2) / den;                      // :592-594
         *r_s = rs;
         if (full) {
-            double rrp3 = rp - q3, rrm3 = rm - q3, rrp4 = rp - q4, rrm4 = rm - q4;
-            double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) / (den * den);   // :600-603
-            double H = drs / (rs - q3) - w(R_Q5);
-            double c = 2.0 / root;
-            double Pi_1 = c * (Pi[0] - w(R_PO0));
-            double Pi_p = c * (rr43 / (rrp3 * rrp4)) * (Pi[1] - w(R_PO1));
-            double Pi_m = c * (rr43 / (rrm3 * rrm4)) * (Pi[2] - w(R_PO2));
+            double iden = frcp(den);
+            double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) * (iden * iden);   // :600-603
+            double H = fdiv(drs, rs - q3) - w(R_Q5);
+            double Pi_1 = w(R_Q6) * (Pi[0] - w(R_PO0));
+            double Pi_p = w(R_Q7) * (Pi[1] - w(R_PO1));
+            double Pi_m = w(R_Q8) * (Pi[2] - w(R_PO2));
             I1 = q3 * (-tau) + rr43 * Pi_1;
             I2 = H - 0.5 * (q1 * q4 + q2 * q3) * (-tau) - root * (E - w(R_EO));
-            Ip = tau / rrp3 - Pi_p;
-            Im = tau / rrm3 - Pi_m;
+            Ip = tau * w(R_Q9) - Pi_p;
+            Im = tau * w(R_Q10) - Pi_m;
         }
     } else if (flags & F_CASE3) {
         double rr1 = w(R_Q0), rr2 = w(R_Q1), AA = w(R_Q2), BB = w(R_Q3), sqAB = w(R_Q10);
@@ -762,19 +787,20 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
             double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2, rrm1 = rm - rr1, rrm2 = rm - rr2;
             double R1a[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) R1a[i] = R1_of(w(R_Q4 + i), w(R_Q7 + i), w(R_N0 + i), sn, dn, Pi[i]);
-            double R2a = R2_of(w(R_Q4), k, w(R_N0), sn, cn, dn, X, E, R1a[0]);
+            for (int i = 0; i < 3; ++i) R1a[i] = R1_of<true>(w(R_Q4 + i), w(R_Q7 + i), w(R_N0 + i), sn, dn, Pi[i]);
+            double R2a = R2_of<true>(w(R_Q4), k, w(R_N0), sn, cn, dn, X, E, R1a[0]);
             double dm = (flags & F_LOWSPIN) ? 0.0 : (R1a[2] - w(R_PO2));      // :529-534
             double fac = 2.0 * rr21 * sqAB;
-            double Pi_1 = (fac / (BB * BB - AA * AA)) * (R1a[0] - w(R_PO0));
-            double Pi_2 = sq(fac / (BB * BB - AA * AA)) * (R2a - w(R_EO));
-            double Pi_p = (fac / (BB * rrp2 - AA * rrp1)) * (R1a[1] - w(R_PO1));
-            double Pi_m = (fac / (BB * rrm2 - AA * rrm1)) * dm;
-            double pr = (BB * rr2 + AA * rr1) / (BB + AA);
+            double f0 = fdiv(fac, BB * BB - AA * AA);
+            double Pi_1 = f0 * (R1a[0] - w(R_PO0));
+            double Pi_2 = sq(f0) * (R2a - w(R_EO));
+            double Pi_p = fdiv(fac, BB * rrp2 - AA * rrp1) * (R1a[1] - w(R_PO1));
+            double Pi_m = fdiv(fac, BB * rrm2 - AA * rrm1) * dm;
+            double pr = fdiv(BB * rr2 + AA * rr1, BB + AA);
             I1 = pr * (-tau) + Pi_1;
             I2 = pr * pr * (-tau) + 2.0 * pr * Pi_1 + sqAB * Pi_2;
-            Ip = -((BB + AA) * (-tau) + Pi_p) / (BB * rrp2 + AA * rrp1);
-            Im = -((BB + AA) * (-tau) + Pi_m) / (BB * rrm2 + AA * rrm1);
+            Ip = -fdiv((BB + AA) * (-tau) + Pi_p, BB * rrp2 + AA * rrp1);
+            Im = -fdiv((BB + AA) * (-tau) + Pi_m, BB * rrm2 + AA * rrm1);
         }
     } else {  // case 4
         double a2 = w(R_Q0), b1 = w(R_Q1), g0 = w(R_Q2);
@@ -783,18 +809,19 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
             double pref = w(R_Q8), x4rp = w(R_Q9), x4rm = w(R_Q10);
             double S1a[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) S1a[i] = S1_of(w(R_Q2 + i), w(R_Q5 + i), dn, X, Pi[i]);
-            double S2a = S2_of(g0, k, sn, cn, dn, X, E, S1a[0]);
-            double aa0 = (a2 / g0) * (1.0 + g0 * g0);
+            for (int i = 0; i < 3; ++i) S1a[i] = S1_of<true>(w(R_Q2 + i), w(R_Q5 + i), dn, X, Pi[i]);
+            double S2a = S2_of<true>(g0, k, sn, cn, dn, X, E, S1a[0]);
+            double a2g = fdiv(a2, g0);
+            double aa0 = a2g * (1.0 + g0 * g0);
             double Pi_1 = pref * aa0 * (S1a[0] - w(R_PO0));
             double Pi_2 = pref * (aa0 * aa0) * (S2a - w(R_EO));
-            double Pi_p = pref * (1.0 + g0 * g0) / (g0 * g0 + g0 * x4rp) * (S1a[1] - w(R_PO1));
-            double Pi_m = pref * (1.0 + g0 * g0) / (g0 * g0 + g0 * x4rm) * (S1a[2] - w(R_PO2));
-            double aa1 = a2 / g0 - b1;
+            double Pi_p = fdiv(pref * (1.0 + g0 * g0), g0 * g0 + g0 * x4rp) * (S1a[1] - w(R_PO1));
+            double Pi_m = fdiv(pref * (1.0 + g0 * g0), g0 * g0 + g0 * x4rm) * (S1a[2] - w(R_PO2));
+            double aa1 = a2g - b1;
             I1 = aa1 * (-tau) - Pi_1;
             I2 = (aa1 * aa1) * (-tau) - 2.0 * aa1 * Pi_1 + Pi_2;
-            Ip = g0 / (a2 - a2 * g0 * x4rp) * (-tau - Pi_p);
-            Im = g0 / (a2 - a2 * g0 * x4rm) * (-tau - Pi_m);
+            Ip = fdiv(g0, a2 - a2 * g0 * x4rp) * (-tau - Pi_p);
+            Im = fdiv(g0, a2 - a2 * g0 * x4rm) * (-tau - Pi_m);
         }
     }
     if (!full) {
@@ -803,9 +830,8 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     }
     // kgeo/kerr_raytracing_ana.py:626-631
     double a = o.a, lam = w(S_LAM);
-    double d = rp - rm;
-    *Iph = (2.0 * a / d) * ((rp - 0.5 * a * lam) * Ip - (rm - 0.5 * a * lam) * Im);
-    double ItA = (4.0 / d) * ((rp * rp - 0.5 * a * lam * rp) * Ip - (rm * rm - 0.5 * a * lam * rm) * Im);
+    *Iph = o.c_iph * ((rp - 0.5 * a * lam) * Ip - (rm - 0.5 * a * lam) * Im);
+    double ItA = o.c_it * ((rp * rp - 0.5 * a * lam * rp) * Ip - (rm * rm - 0.5 * a * lam * rm) * Im);
     *It = ItA + 4.0 * (-tau) + 2.0 * I1 + I2;
     *Isig = I2;
 }

@@ -65,9 +65,9 @@ __device__ __forceinline__ double frsqrt(double x) {
     t = fma(-(x * y), y, 1.0);                        // residual correction
     return fma(0.5 * y, t, y);
 }
-// sqrt(x) for x = 0 or x in (1e-290, 1e290); sqrt(0) = 0 comes out of the arithmetic when the seed is forced to 0
+// sqrt(x) for x in (1e-300, 1e290) (callers clamp exact zeros to 1e-300)
 __device__ __forceinline__ double fsqrt(double x) {
-    double y = (x > 0.0) ? kg_rsqrt_seed(x) : ((x == 0.0) ? 0.0 : kg_nan());
+    double y = kg_rsqrt_seed(x);
     double t = fma(-(x * y), y, 1.0);
     double u = fma(0.375, t, 0.5) * t;
     y = fma(y, u, y);
@@ -233,6 +233,10 @@ KG_HD double carlson_rj(double x, double y, double z, double p) {
 // RJ_i: (x+y+z+2p_i)/5) which obeys the same recurrence A <- (A+lambda)/4.
 template <int NP, bool WANT_RF, bool WANT_RD>
 KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, double* rd, double* rj) {
+    // cos^2 of an amplitude at a turning point is an exact 0: RF/RD/RJ(1e-300, y, 1, p) equal the x = 0 values to ~1e-150
+    // relative, and the clamp keeps the seed-based square root free of special cases; 0*x keeps a NaN a NaN.
+    x = fma(0.0, x, fmax(x, 1.0e-300));
+    y = fma(0.0, y, fmax(y, 1.0e-300));
     double z = 1.0;
     double p[NP > 0 ? NP : 1], Aj[NP > 0 ? NP : 1], sj[NP > 0 ? NP : 1];
     double Af = (x + y + z) * (1.0 / 3.0);
@@ -246,12 +250,14 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
     }
     // Every deviation (mean - argument) shrinks by EXACTLY 4 per duplication step ((A+lam)/4 - (x+lam)/4 = (A-x)/4), so the
     // largest initial deviation Q0 is measured once and the test per step is Q0 * 4^-n < tol * (smallest mean).
+    // a mean lies inside the range of its arguments, so its largest deviation is max(A - lowest, highest - A)
     double Q0 = 0.0, Amin = kInf;
-    if (WANT_RF) { Q0 = fmax(Q0, max3(fabs(Af - x), fabs(Af - y), fabs(Af - z))); Amin = fmin(Amin, Af); }
-    if (WANT_RD) { Q0 = fmax(Q0, max3(fabs(Ad - x), fabs(Ad - y), fabs(Ad - z))); Amin = fmin(Amin, Ad); }
+    const double lo3 = fmin(fmin(x, y), z), hi3 = fmax(fmax(x, y), z);
+    if (WANT_RF) { Q0 = fmax(Q0, fmax(Af - lo3, hi3 - Af)); Amin = fmin(Amin, Af); }
+    if (WANT_RD) { Q0 = fmax(Q0, fmax(Ad - lo3, hi3 - Ad)); Amin = fmin(Amin, Ad); }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        Q0 = fmax(Q0, fmax(max3(fabs(Aj[i] - x), fabs(Aj[i] - y), fabs(Aj[i] - z)), fabs(Aj[i] - p[i])));
+        Q0 = fmax(Q0, fmax(Aj[i] - fmin(lo3, p[i]), fmax(hi3, p[i]) - Aj[i]));
         Amin = fmin(Amin, Aj[i]);
     }
     if (!(Q0 == Q0) || !(Amin == Amin)) Q0 = 0.0;                     // NaN arguments: nothing to converge to
@@ -325,9 +331,10 @@ KG_HD PiPrep pi_prepare(double n, double s, double c2, double y) {
 // Cauchy principal value for rho < 0 (out of line: one copy for every Pi of the fused kernels)
 KG_NOINLINE double pi_finish_pv(double s3n, double s, double c2, double y, double F, double p, double rho, double rj) {
     double q = -rho, xy = c2 * y, pq = p * q;
-    double t = sqrt(xy / (xy + pq));
-    double ath = 0.5 * log((1.0 + t) / (1.0 - t));                 // = sqrt(xy) * RC(xy+pq, pq)
-    double cpv = ((p - 1.0) * rj - 3.0 * (F / s) + 3.0 * ath / sqrt(xy + pq)) / (q + 1.0);
+    double isq = frsqrt(xy + pq);                                  // xy + pq > 0 here
+    double t = fsqrt(fmax(xy, 1.0e-300)) * isq;
+    double ath = 0.5 * log(fdiv(1.0 + t, 1.0 - t));                // = sqrt(xy) * RC(xy+pq, pq)
+    double cpv = fdiv((p - 1.0) * rj - 3.0 * fdiv(F, s) + 3.0 * ath * isq, q + 1.0);
     return s3n * cpv;
 }
 KG_HD double pi_finish(double n, double s, double c2, double y, double F, const PiPrep& pp, double rj) {
