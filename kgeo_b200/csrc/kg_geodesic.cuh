@@ -405,7 +405,10 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 // (kgeo/kerr_raytracing_ana.py:217,300): they are properties of the CALL, computed once by the host wrapper.
 enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4, M_INPUT_LAM_ETA = 8, M_POLISH_ROOTS = 16 };
 // PHI_T = false skips every constant that only the phi / t / sigma integrals need (image and lensing paths).
-template <bool PHI_T>
+// LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
+// workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
+// AGM descent inline instead.
+template <bool PHI_T, bool LADDER = true>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, double* w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     for (int i = 0; i < NW; ++i) w[i] = 0.0;
@@ -445,7 +448,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        jacobi_make_ladder(m, &w[T_LAD]);
+        if (LADDER) jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = -s_o * sqrt(up);
@@ -489,7 +492,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        jacobi_make_ladder(m, &w[T_LAD]);
+        if (LADDER) jacobi_make_ladder(m, &w[T_LAD]);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = um;
@@ -540,7 +543,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k4, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k4);
         w[R_K] = k4;
-        jacobi_make_ladder(k4, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k4, &w[R_LAD]);
         w[R_SC] = 1.0 / pref;
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
         if (PHI_T) {
@@ -588,7 +591,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k3, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k3);
         w[R_K] = k3;
-        jacobi_make_ladder(k3, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k3, &w[R_LAD]);
         w[R_SC] = sqAB;
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
         if (PHI_T) {
@@ -624,7 +627,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k2, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k2);
         w[R_K] = k2;
-        jacobi_make_ladder(k2, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k2, &w[R_LAD]);
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
         if (PHI_T) {
@@ -749,12 +752,18 @@ KG_HD void radial_legendre(const W& w, double X, double Kc, double sn, double cn
     }
 }
 
-template <class W>
+template <class W, bool LADDER = true>
 KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, bool full, double* r_s, double* Iph,
                        double* It, double* Isig) {
     double X = fma(-w(R_SC), tau, w(R_X0));
     double k = w(R_K);
-    const SnCnDn jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
+    SnCnDn jr;
+    if (LADDER) {
+        jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
+    } else {
+        double Kunused;
+        jacobi_sncndn(X, k, &jr.sn, &jr.cn, &jr.dn, &Kunused);
+    }
     const double sn = jr.sn, cn = jr.cn, dn = jr.dn;
     double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
     // E and the three Pi's at am(X|k): one shared Carlson bundle for every radial case

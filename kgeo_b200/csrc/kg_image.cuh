@@ -303,7 +303,7 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
     double Ir, Nmax;
     crossing_time(w, o, beta, mbar, &Ir, &Nmax);
     double rs, d0, d1, d2;
-    radial_eval(w, o, flags, Ir, false, &rs, &d0, &d1, &d2);
+    radial_eval<W, false>(w, o, flags, Ir, false, &rs, &d0, &d1, &d2);
     if (Nmax < (double)mbar) rs = 0.0;   // :188
     out.r = rs;
     out.Ir = Ir;

@@ -122,6 +122,25 @@ KG_NOINLINE double rc1p_closed(double e, double b) {
     double s = sqrt(-e);
     return log((1.0 + s) / sqrt(b)) / s;
 }
+// same with b = 1 + e = 2 sp (p + lam) id formed only on the (rare) closed-form path
+KG_HD double rc1p(double e, double b);
+KG_HD double rc1p_series(double e);
+KG_HD double rc1p_lazy(double e, double sp, double ppl, double id) {
+    if (fabs(e) < 0.02) return rc1p_series(e);
+    return rc1p_closed(e, 2.0 * sp * ppl * id);
+}
+KG_HD double rc1p_series(double e) {
+    double me = -e;
+    double h = KC(0);
+    h = fma(h, me, KC(1));
+    h = fma(h, me, KC(2));
+    h = fma(h, me, KC(3));
+    h = fma(h, me, KC(4));
+    h = fma(h, me, KC(5));
+    h = fma(h, me, KC(6));
+    h = fma(h, me, KC(7));
+    return fma(h, me, 1.0);
+}
 KG_HD double rc1p(double e, double b) {
     if (fabs(e) < 0.02) {
         // sum_k (-e)^k / (2k+1), k = 0..8   (0.02^9/19 < 3e-17), Horner in (-e)
@@ -238,7 +257,7 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
     x = fma(0.0, x, fmax(x, 1.0e-300));
     y = fma(0.0, y, fmax(y, 1.0e-300));
     double z = 1.0;
-    double p[NP > 0 ? NP : 1], Aj[NP > 0 ? NP : 1], sj[NP > 0 ? NP : 1];
+    double p[NP > 0 ? NP : 1], Aj[NP > 0 ? NP : 1], sj[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1];
     double Af = (x + y + z) * (1.0 / 3.0);
     double Ad = (x + y + 3.0 * z) * 0.2;
     double sd = 0.0, f = 1.0;
@@ -247,6 +266,7 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         p[i] = p_in[i];
         Aj[i] = (x + y + z + 2.0 * p[i]) * 0.2;
         sj[i] = 0.0;
+        dl[i] = (p[i] - x) * (p[i] - y) * (p[i] - z);   // delta_0; delta_n = delta_0 / 64^n exactly (Carlson 1995, eq. 2.19)
     }
     // Every deviation (mean - argument) shrinks by EXACTLY 4 per duplication step ((A+lam)/4 - (x+lam)/4 = (A-x)/4), so the
     // largest initial deviation Q0 is measured once and the test per step is Q0 * 4^-n < tol * (smallest mean).
@@ -267,13 +287,14 @@ KG_HD void carlson_bundle(double x, double y, const double* p_in, double* rf, do
         double sx = fsqrt(x), sy = fsqrt(y), sz = fsqrt(z);
         double lam = fma(sx, sy, fma(sy, sz, sz * sx));
         if (WANT_RD) sd += fdiv(f, sz * (z + lam));
+        const double f3 = f * f * f;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             double sp = fsqrt(p[i]);
             double id = frcp((sp + sx) * (sp + sy) * (sp + sz));
-            double e = (sp - sx) * (sp - sy) * (sp - sz) * id;
-            double b = 2.0 * sp * (p[i] + lam) * id;                // = 1 + e without cancellation
-            sj[i] += f * id * rc1p(e, b);
+            // e_n = (sp-sx)(sp-sy)(sp-sz)/d_n = delta_n / d_n^2
+            double e = (dl[i] * f3) * (id * id);
+            sj[i] += f * id * rc1p_lazy(e, sp, p[i] + lam, id);
             p[i] = (p[i] + lam) * 0.25;
             Aj[i] = (Aj[i] + lam) * 0.25;
         }

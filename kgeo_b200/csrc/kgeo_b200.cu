@@ -284,9 +284,15 @@ __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o
 // ---------------------------------------------------------------------------------------------------------------------
 // equatorial lensing / image
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int IMG_THREADS = 64;
+#ifndef KG_IMG_THREADS
+#define KG_IMG_THREADS 64
+#endif
+#ifndef KG_IMG_MINBLOCKS
+#define KG_IMG_MINBLOCKS 16
+#endif
+constexpr int IMG_THREADS = KG_IMG_THREADS;
 
-__global__ void __launch_bounds__(IMG_THREADS) r_equatorial_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
+__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                    const double* __restrict__ beta, int mbar_lo, int mbar_hi,
                                                                    double* rs_out, double* Ir_out, double* Nmax_out,
                                                                    double* Imax_out, double* npol_out) {
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(IMG_THREADS) r_equatorial_kernel(Observer o, s
     double w[NW];
     int fl;
     double be = beta[i];
-    ray_setup<false>(o, alpha[i], be, M_ANY_ETA_POS, w, &fl);
+    ray_setup<false, false>(o, alpha[i], be, M_ANY_ETA_POS, w, &fl);
     ArrayW W{w};
     const bool reg = w[S_ETA] > 0.0;
     if (Imax_out) Imax_out[i] = reg ? w[S_TAUTOT] : -1.0;
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(IMG_THREADS) r_equatorial_kernel(Observer o, s
         if (reg) {
             crossing_time(W, o, be, mbar, &Ir, &Nmax);
             double d0, d1, d2;
-            radial_eval(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
+            radial_eval<ArrayW, false>(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
             if (Nmax < (double)mbar) rs = 0.0;
         }
         size_t q = (size_t)(mbar - mbar_lo) * npix + i;
@@ -319,7 +325,7 @@ struct ImageOut {
     double *I, *Q, *U, *r, *Ir, *g, *sinthb, *nmax, *npol, *imax, *lp, *Ie;
 };
 
-__global__ void __launch_bounds__(IMG_THREADS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
+__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
                                                             const double* __restrict__ alpha, const double* __restrict__ beta,
                                                             ImageOut out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(IMG_THREADS) image_kernel(Observer o, kgeo_mod
     double w[NW];
     int fl;
     double al = alpha[i], be = beta[i];
-    ray_setup<false>(o, al, be, M_ANY_ETA_POS, w, &fl);
+    ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
     ArrayW W{w};
     if (out.npol) out.npol[i] = n_poloidal_at(W, w[S_TAUTOT]);
     if (out.imax) out.imax[i] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;

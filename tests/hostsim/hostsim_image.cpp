@@ -10,7 +10,7 @@ void hs_image(double a, double r_o, double th_o, const kgeo_models* M, const kge
     std::vector<double> w(NW);
     for (int i = 0; i < n; ++i) {
         int fl;
-        ray_setup<false>(o, alpha[i], beta[i], M_ANY_ETA_POS, w.data(), &fl);
+        ray_setup<false, false>(o, alpha[i], beta[i], M_ANY_ETA_POS, w.data(), &fl);
         ArrayW W{w.data()};
         npol[i] = n_poloidal_at(W, w[S_TAUTOT]);
         imax[i] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
@@ -30,7 +30,7 @@ void hs_requatorial(double a, double r_o, double th_o, int n, const double* alph
     std::vector<double> w(NW);
     for (int i = 0; i < n; ++i) {
         int fl;
-        ray_setup<false>(o, alpha[i], beta[i], M_ANY_ETA_POS, w.data(), &fl);
+        ray_setup<false, false>(o, alpha[i], beta[i], M_ANY_ETA_POS, w.data(), &fl);
         ArrayW W{w.data()};
         bool reg = w[S_ETA] > 0.0;
         Imax_o[i] = reg ? w[S_TAUTOT] : -1.0;
@@ -40,7 +40,7 @@ void hs_requatorial(double a, double r_o, double th_o, int n, const double* alph
             if (reg) {
                 crossing_time(W, o, beta[i], mbar, &Ir, &Nmax);
                 double d0, d1, d2;
-                radial_eval(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
+                radial_eval<ArrayW, false>(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
                 if (Nmax < (double)mbar) rs = 0.0;
             }
             size_t q = (size_t)(mbar - mlo) * n + i;
