@@ -223,3 +223,31 @@ def test_edge_shapes_and_special_inputs(kg):
     assert np.array_equal(bad.r_s[:, keep], whole.r_s[:, keep], equal_nan=True)
     sig, (t, r, th, ph) = kg.coords_at_tau(0.94, obs, [A, B], np.full(77, 0.1))
     assert r.shape == (1, 77) and np.isfinite(r).all()
+
+
+def test_more_than_2_pow_32_points_in_one_launch(kg):
+    """BASELINE cfg 4 scale: one launch producing > 2^32 points (4096 x 2100 pixels x 500 samples = 4.3e9, a 34 GB array):
+    64-bit indexing end to end.  The far corner of the big array must equal, bit for bit, a small launch on the same rays."""
+    import torch
+    from kgeo_b200 import _engine
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs 60 GB of free HBM")
+    a, r_o, th_o = 0.94, 1000., 17 * np.pi / 180
+    ncol, nrow, ngeo = 4096, 2100, 500
+    x = np.linspace(-10, 10, ncol)
+    y = np.linspace(-10, 10, nrow)
+    A, B = [np.ascontiguousarray(v.flatten()) for v in np.meshgrid(x, y)]
+    assert A.size * ngeo > 2 ** 32
+    big = _engine.RayBundle(a, r_o, th_o, A, B)
+    r = big.tracks(ntau=ngeo, maxtaufrac=1. - 1.e-10, want=("r",))["r"]
+    assert tuple(r.shape) == (ngeo, A.size)
+    head = r[0]
+    assert float(torch.quantile((head[::97] / r_o - 1).abs(), 0.999)) < 1e-9
+    tail_big = r[:, -64:].cpu().numpy()
+    del r, big
+    torch.cuda.empty_cache()
+    small = _engine.RayBundle(a, r_o, th_o, A[-64:].copy(), B[-64:].copy())
+    tail_small = small.tracks(ntau=ngeo, maxtaufrac=1. - 1.e-10, want=("r",))["r"].cpu().numpy()
+    assert np.array_equal(tail_big, tail_small, equal_nan=True)
+    assert np.isfinite(tail_big[:-1]).all()
