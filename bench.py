@@ -4,7 +4,7 @@
 One "step" = one pass of the hot path over the workload: per-ray setup kernel + fused track kernel producing
 r, theta, phi, t for every (pixel, Mino-time sample) of BASELINE config 3 (1024 x 1024 pixels x 500 samples, a=0.94,
 theta_o=17 deg, r_o=1000, +-10 M).  With N>1 ranks (one process per GPU under torchrun) every rank traces its own
-1024-row block of a (1024*N) x 1024 image plane -- weak scaling, no data-path collective.
+1024 interleaved rows (row % N == rank) of a (1024*N) x 1024 image plane -- weak scaling, no data-path collective.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -39,10 +39,12 @@ BYTES_PER_POINT = 32.0      # r, theta, phi, t written once
 
 
 def workload_pixels(rank, world, side=NPIX_SIDE):
-    """Rows [rank*side, (rank+1)*side) of the (side*world) x side plane spanning +-10 M (cfg 3 when world == 1)."""
+    """Rows rank, rank+world, ... of the (side*world) x side plane spanning +-10 M (cfg 3 when world == 1).  Rows are
+    interleaved so that every rank sees the same mix of root classes: rays through the shadow cost more than
+    rays that escape, and contiguous row blocks would make the central ranks the stragglers."""
     x = np.linspace(-HALF_FOV, HALF_FOV, side)
     y_all = np.linspace(-HALF_FOV, HALF_FOV, side * world)
-    y = y_all[rank * side:(rank + 1) * side]
+    y = y_all[rank::world]
     A, B = np.meshgrid(x, y)
     return np.ascontiguousarray(A.flatten()), np.ascontiguousarray(B.flatten())
 
@@ -374,7 +376,7 @@ def run_ours(args):
                                "Mino-time samples -> r,theta,phi,t (per GPU; N GPUs trace a (1024N)x1024 plane by rows)",
                    "points_per_gpu_per_step": npts_rank, "outputs": "r,theta,phi,t fp64 [500, 1048576] = 16.8 GB per step",
                    "l2": "each step writes 16.8 GB (>> 126 MB L2) and re-reads no output; no flush needed",
-                   "parallelism": "rows x%d, no collective" % world},
+                   "parallelism": "rows interleaved over %d rank(s), no collective" % world},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "secondary": secondary,
     }

@@ -21,6 +21,25 @@ def all_row_ranges(nrows, world):
     return [row_range(nrows, r, world) for r in range(world)]
 
 
+def row_indices(nrows, rank, world, interleave=False):
+    """Image rows owned by `rank`: a contiguous block (default) or every world-th row (`interleave=True`, better load
+    balance: rows through the shadow are more expensive than rows of escaping rays)."""
+    if interleave:
+        if not (0 <= rank < world):
+            raise ValueError("rank %d outside world of size %d" % (rank, world))
+        return np.arange(rank, nrows, world)
+    r0, r1 = row_range(nrows, rank, world)
+    return np.arange(r0, r1)
+
+
+def shard_pixels_interleaved(alpha, beta, ncols, rank, world):
+    """As shard_pixels, for the interleaved distribution; returns (alpha_local, beta_local, row_index_array)."""
+    alpha = np.asarray(alpha).reshape(-1, ncols)
+    beta = np.asarray(beta).reshape(-1, ncols)
+    ix = row_indices(alpha.shape[0], rank, world, interleave=True)
+    return np.ascontiguousarray(alpha[ix].ravel()), np.ascontiguousarray(beta[ix].ravel()), ix
+
+
 def shard_pixels(alpha, beta, ncols, rank, world):
     """Slice flattened row-major pixel arrays (row = constant beta, as produced by np.meshgrid(alphas, betas)) to the
     rows owned by `rank`.  Returns (alpha_local, beta_local, (r0, r1))."""
@@ -33,8 +52,8 @@ def shard_pixels(alpha, beta, ncols, rank, world):
     return alpha[r0 * ncols:r1 * ncols], beta[r0 * ncols:r1 * ncols], (r0, r1)
 
 
-def gather_rows(local, nrows, ncols, dst=0, group=None):
-    """Gather row-sharded planes to rank `dst`.
+def gather_rows(local, nrows, ncols, dst=0, group=None, interleave=False):
+    """Gather row-sharded planes to rank `dst` (rows distributed as by row_indices).
 
     local: tensor [..., rows_local*ncols] (any leading plane dimensions) on every rank, laid out row-major in the pixel
     index.  Returns the assembled [..., nrows*ncols] tensor on `dst` and None elsewhere.  Uses all_gather on equal-size
@@ -44,9 +63,9 @@ def gather_rows(local, nrows, ncols, dst=0, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    ranges = all_row_ranges(nrows, world)
+    rows = [row_indices(nrows, r, world, interleave) for r in range(world)]
     lead = tuple(local.shape[:-1])
-    maxrows = max(r1 - r0 for r0, r1 in ranges)
+    maxrows = max(len(ix) for ix in rows)
     buf = torch.zeros(lead + (maxrows * ncols,), dtype=local.dtype, device=local.device)
     buf[..., :local.shape[-1]] = local
     if rank == dst:
@@ -60,14 +79,15 @@ def gather_rows(local, nrows, ncols, dst=0, group=None):
         dist.gather(buf, gather_list=parts, dst=dst, group=group)
     if rank != dst:
         return None
-    out = torch.empty(lead + (nrows * ncols,), dtype=local.dtype, device=local.device)
-    for (r0, r1), p in zip(ranges, parts):
-        out[..., r0 * ncols:r1 * ncols] = p[..., :(r1 - r0) * ncols]
-    return out
+    out = torch.empty(lead + (nrows, ncols), dtype=local.dtype, device=local.device)
+    for ix, p in zip(rows, parts):
+        if len(ix):
+            out[..., torch.as_tensor(ix, device=local.device), :] = p[..., :len(ix) * ncols].reshape(lead + (len(ix), ncols))
+    return out.reshape(lead + (nrows * ncols,))
 
 
 def make_image_sharded(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, beta_max, psize, dst=0, group=None,
-                       **kwargs):
+                       interleave=True, **kwargs):
     """make_image with the pixel rows sharded over the ranks of `group`; rank `dst` returns the reference-shaped tuple
     (as equatorial_images.make_image), other ranks return None.  Needs an initialised NCCL process group."""
     import torch
@@ -78,7 +98,10 @@ def make_image_sharded(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, b
     alpha_arr, beta_arr = ei.pixel_grid(alpha_min, alpha_max, beta_min, beta_max, psize)
     n_alpha = int(np.floor(alpha_max - alpha_min) / psize)
     nrows = alpha_arr.size // n_alpha
-    al, be, _ = shard_pixels(alpha_arr, beta_arr, n_alpha, rank, world)
+    if interleave:
+        al, be, _ = shard_pixels_interleaved(alpha_arr, beta_arr, n_alpha, rank, world)
+    else:
+        al, be, _ = shard_pixels(alpha_arr, beta_arr, n_alpha, rank, world)
     pathlength = bool(kwargs.get("pathlength", False))
     out = ei.image_device(a, r_o, th_o, 0, mbar_max, al, be,
                           kwargs.get("emissivity", ei.emis_default), kwargs.get("velocity", ei.vel_default),
@@ -88,8 +111,8 @@ def make_image_sharded(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, b
     names = ["I", "Q", "U", "r", "Ir", "g", "sinthb"] + (["lp", "Ie"] if pathlength else [])
     planes = torch.stack([out[k] for k in names])                       # [nplane, norder, npix_local]
     scal = torch.stack([out["nmax"], out["npol"]])                      # [2, npix_local]
-    planes = gather_rows(planes, nrows, n_alpha, dst, group)
-    scal = gather_rows(scal, nrows, n_alpha, dst, group)
+    planes = gather_rows(planes, nrows, n_alpha, dst, group, interleave)
+    scal = gather_rows(scal, nrows, n_alpha, dst, group, interleave)
     if rank != dst:
         return None
     P = planes.cpu().numpy()

@@ -33,10 +33,15 @@ def _worker(rank, world, port, nrows, ncols, q):
         planes = torch.from_numpy(np.stack([np.stack([al + 10 * be, al * be]), np.stack([al - be, al + be])]))  # [2,2,n]
         out = sharding.gather_rows(planes, nrows, ncols, dst=0)
         vec = sharding.gather_rows(torch.from_numpy(np.ascontiguousarray(al)), nrows, ncols, dst=0)
+        # interleaved distribution (row % world == rank)
+        al2, be2, ix = sharding.shard_pixels_interleaved(A.flatten(), B.flatten(), ncols, rank, world)
+        assert np.array_equal(ix % world, np.full(len(ix), rank))
+        out2 = sharding.gather_rows(torch.from_numpy(np.stack([al2 + 10 * be2, al2 * be2])), nrows, ncols, dst=0, interleave=True)
         if rank == 0:
+            assert np.array_equal(out2.numpy(), out.numpy()[0])
             q.put((out.numpy(), vec.numpy()))
         else:
-            assert out is None and vec is None
+            assert out is None and vec is None and out2 is None
         dist.barrier()
     finally:
         dist.destroy_process_group()
