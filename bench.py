@@ -121,6 +121,28 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------------------------
+def local_cpu_affinity(gpu_index):
+    """Bind this process to the CPUs nvidia-smi reports as local to the GPU, so that the pinned result buffers of the e2e
+    leg are first-touched on the NUMA node next to the GPU's PCIe root.  Returns the CPU list description or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+        header = [h.strip() for h in out[0].split("\t")]
+        col = next(i for i, h in enumerate(header) if "CPU Affinity" in h)
+        row = next(l for l in out[1:] if l.startswith("GPU%d" % gpu_index))
+        spec = [c.strip() for c in row.split("\t")][col]
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -257,6 +279,7 @@ def run_ours(args):
 
     # ---- e2e through the host-buffer C ABI ----
     e2e = None
+    pin_cpus = local_cpu_affinity(local)     # pinned result buffers on the GPU's own NUMA node (first touch)
     try:
         import psutil
         avail = psutil.virtual_memory().available
@@ -289,7 +312,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": world * e_npix * NGEO / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": 16 * e_npix,
            "d2h_bytes_per_step": 32 * e_npix * NGEO, "steps": e_steps, "ms_per_step": float(te.item()) * 1e3,
-           "pixels_per_rank": e_npix,
+           "pixels_per_rank": e_npix, "host_cpu_affinity": pin_cpus,
            "note": "kgeo_raytrace_host: host alpha/beta -> setup + track kernels in 256 MiB sample slabs overlapped with "
                    "D2H into pinned host r/theta/phi/t arrays; wall clock around the blocking C call"}
     if not np.isfinite(host[1][1, ::997].numpy()).all():
@@ -323,7 +346,10 @@ def run_ours(args):
     nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12
     roofline = {
         "bound": "fp64", "kernel": "track_kernel<true>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": None,
+        "frac": (ach_tf / peak_tf) if peak_tf else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one track_kernel launch on this workload, from the committed
+        # ncu --set full capture (profiles/r01_track_kernel_final_ncu_full_subset.csv): 0.96 GB + 16.74 GB; algorithmic 16.78 GB
+        "traffic": 17.70e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/launch",
         "peak_source": "DFMA-chain probe (kgeo_fp64_peak_probe) measured live on this GPU; MEASURED_PEAKS.json has no "
                        "FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s" % nominal_tf,
         "flop_per_point": FLOP_PER_POINT, "points_per_launch": npts_rank, "kernel_ms": tk * 1e3,
@@ -337,28 +363,39 @@ def run_ours(args):
     secondary = None
     try:
         from kgeo_b200 import equatorial_images as ei
+        from kgeo_b200.models import pack_models
         side = 4096
         x = np.linspace(-HALF_FOV, HALF_FOV, side)
         IA, IB = [np.ascontiguousarray(v.flatten()) for v in np.meshgrid(x, x)]
+        npx = side * side
         dIA, dIB = _engine.to_device(IA, dev), _engine.to_device(IB, dev)
-        run_img = lambda: ei.image_device(SPIN, np.inf, th_o, 0, 2, dIA, dIB, ei.emis_default, ei.vel_default,
-                                          ei.bfield_default, False, False, ei.SPECIND, ei.DISKANGLE, ei.OBSFREQ, dev=dev)
+        planes = [torch.empty((3, npx), dtype=torch.float64, device=dev) for _ in range(7)]
+        scal = [torch.empty((npx,), dtype=torch.float64, device=dev) for _ in range(3)]
+        iobs = _engine.observer_struct(SPIN, float("inf"), th_o)
+        M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
+        opts = _lib.ImageOpts(0, 2, 0, 0, float(ei.SPECIND), ei.DISKANGLE, ei.OBSFREQ)
+
+        def run_img():
+            _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(opts), npx, _engine.dptr(dIA),
+                                               _engine.dptr(dIB), *[_engine.dptr(p) for p in planes],
+                                               *[_engine.dptr(v) for v in scal], null, null, stream))
         run_img()
         torch.cuda.synchronize()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         i0.record()
-        for _ in range(3):
-            res_img = run_img()
+        for _ in range(5):
+            run_img()
         i1.record()
         torch.cuda.synchronize()
-        img_ms = i0.elapsed_time(i1) / 3
-        npx = side * side
+        img_ms = i0.elapsed_time(i1) / 5
+        if not bool(torch.isfinite(planes[0][0, ::9973]).all()):
+            raise RuntimeError("non-finite image")
         secondary = {"metric": "equatorial image pixels/s (n=0..2, all orders fused)", "value": npx / (img_ms * 1e-3),
                      "unit": "pixels/s", "workload": "4096x4096 px, a=0.94, theta_o=17deg, r_o=inf, bpl/zamo/rad (BASELINE cfg 2 "
-                     "models at cfg 4 size)", "ms": img_ms, "includes": "output allocation + image_kernel",
+                     "models at cfg 4 size)", "ms": img_ms, "includes": "image_kernel only (outputs preallocated, resident)",
                      "fp64_frac": 3000.0 * npx / (img_ms * 1e-3) / 1e12 / peak_tf if peak_tf else None,
                      "hbm_gbs": 184.0 * npx / (img_ms * 1e-3) / 1e9}
-        del res_img, dIA, dIB
+        del planes, scal, dIA, dIB
     except Exception as exc:                                       # the headline metric must still be reported
         secondary = {"error": repr(exc)}
 
