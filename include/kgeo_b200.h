@@ -48,6 +48,8 @@ typedef struct kgeo_observer {
 #define KGEO_MODE_CLAMP_LOWSPIN_ETA 4
 #define KGEO_MODE_INPUT_LAM_ETA 8 /* kgeo_ray_summary only: the two input arrays hold (lam, eta), not (alpha, beta) */
 #define KGEO_MODE_POLISH_ROOTS 16 /* extension: Newton-polish the quartic roots (more accurate than the reference; off by default) */
+#define KGEO_MODE_CARLSON_ONLY 32 /* evaluate E and Pi of every sample by Carlson duplication (the reference's algorithm); by default
+                                     rays away from the critical curve use per-ray theta-function series (same values, ~2x faster) */
 
 /* ---- physics models of the equatorial image (kgeo/velocities.py, kgeo/bfields.py, kgeo/emissivities.py) ---- */
 enum kgeo_velocity_type { KGEO_VEL_ZAMO = 0, KGEO_VEL_INFALL, KGEO_VEL_KEP, KGEO_VEL_SUBKEP, KGEO_VEL_GENERAL,

@@ -4,6 +4,7 @@ torch is used for device memory, streams and (in sharding.py) torch.distributed 
 libkgeo_b200.so.  Nothing here computes geodesics on the CPU.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -94,6 +95,8 @@ def setup_mode(a, th_o, alpha, beta, clamp_lowspin):
         mode |= _lib.MODE_ANY_ETA_POS
     if np.any(eta <= 0):
         mode |= _lib.MODE_ANY_ETA_NONPOS
+    if os.environ.get("KGEO_B200_CARLSON_ONLY"):   # A/B switch: the reference's duplication algorithm for every sample
+        mode |= _lib.MODE_CARLSON_ONLY
     return mode, clamped
 
 

@@ -13,6 +13,7 @@ c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
 KGEO_E_BADARG, KGEO_E_RANGE, KGEO_E_MODEL = -1, -2, -3
 MODE_ANY_ETA_POS, MODE_ANY_ETA_NONPOS, MODE_CLAMP_LOWSPIN_ETA, MODE_INPUT_LAM_ETA = 1, 2, 4, 8
+MODE_POLISH_ROOTS, MODE_CARLSON_ONLY = 16, 32
 
 
 class Observer(ctypes.Structure):

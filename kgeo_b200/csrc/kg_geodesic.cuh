@@ -19,6 +19,7 @@
 //    special case), and all Pi's of one amplitude share one duplication track.
 #pragma once
 #include "kg_special.cuh"
+#include "kg_theta_layout.cuh"
 
 namespace kg {
 
@@ -83,6 +84,10 @@ enum Slot {
     T_I2K, R_I2K,               // 1/(2 K(m)), 1/(2 K(k)) (0 when K is infinite)
     T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
     R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
+    // theta-function path (kg_theta.cuh): polar block = base + 1 Pi, radial block = base + 3 Pi
+    T_TH_G, T_TH_IM, T_TH_SLOPE, T_TH_COEF,       // 1 + (E/K - 1)/m, 1/m, G_phi slope and coefficient
+    T_TH, T_TH_END = T_TH + TB_SIZE + TP_SIZE - 1,
+    R_TH, R_TH_END = R_TH + TB_SIZE + 3 * TP_SIZE - 1,
     NW
 };
 // case-specific meaning of the R_Q* slots
@@ -97,7 +102,9 @@ enum Flag {
     F_HPOS = 64,                          // h = +1 (th_o <= pi/2)
     F_REGION_SHIFT = 8,                   // bits 8..10: region label 0..4 of radial_roots
     F_OUTSIDE = 1 << 12,                  // is_outside_crit
-    F_LOWSPIN = 1 << 13
+    F_LOWSPIN = 1 << 13,
+    F_TH_THETA = 1 << 14,                 // polar motion may use the theta-function path
+    F_R_THETA = 1 << 15                   // radial motion may use the theta-function path
 };
 
 struct Roots {
@@ -312,6 +319,9 @@ KG_HD double legendre_F_sc(double s, double c, double m) {
     legendre_sc<0>(s, c, m, nullptr, &F, &E, nullptr);
     return F;
 }
+}  // namespace kg
+#include "kg_theta.cuh"
+namespace kg {
 
 // ---- total Mino time from given roots (kgeo/kerr_raytracing_utils.py:382-548) ------------------------------------------
 // Stand-alone version for the helper API mino_total(a, r_o, eta, r1..r4); ray_setup computes the same quantity in
@@ -400,10 +410,42 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
     return S2a + S1 * (i1 + (1.0 - j) * i2);
 }
 
+// ---- theta blocks of a motion (setup) -------------------------------------------------------------------------------------
+// Builds base + NP Pi blocks at w[slot...]; returns true when the theta path is usable for every integral of the motion.
+KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double* blk) {
+    ThetaRay r = theta_ray(m);
+    int J = theta_make_base(r, blk);
+    bool ok = r.ok != 0;
+    for (int i = 0; i < NP; ++i) {
+        int Ji = theta_make_pi(r, n[i], nmm ? nmm[i] : n[i] - m, omn ? omn[i] : 1.0 - n[i], blk + TB_SIZE + i * TP_SIZE);
+        if (Ji < 0) ok = false;
+        else if (Ji > J) J = Ji;
+    }
+    if (J > kThJM) J = kThJM;
+    blk[TB_J] = (double)J;
+    blk[TB_OK] = ok ? 1.0 : 0.0;
+    return ok;
+}
+
+// polar motion: Legendre parameter k < 0 of the reference, Jacobi parameter m = k/(k-1); with sin(phi) = sqrt(1-m) sd(w|m):
+//   Pi(n; phi | k) = sqrt(1-m) [ (m/n') w + (1 - m/n') Pi(n'; am w | m) ],  n' = m + n (1 - m)   (m < n' < 1: circular case)
+//   (F - E)(phi | k) / k = sqrt(1-m) [ (1 + (E/K - 1)/m) w + Z(w)/m - sn w cn w / dn w ]
+KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double Km, double n, double D3, double* w, int* flags) {
+    const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
+    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, &w[T_TH]);
+    const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
+    const double mn = m / npr;
+    w[T_TH_SLOPE] = D3 * sq1m * fma(1.0 - mn, A, mn);
+    w[T_TH_COEF] = D3 * sq1m * (1.0 - mn) * P;
+    w[T_TH_G] = 1.0 - ellip_RDc(m) / (3.0 * Km);
+    w[T_TH_IM] = 1.0 / m;
+    if (ok && !o.lowspin && m > 1.0e-6) *flags |= F_TH_THETA;
+}
+
 // ---- ray setup -------------------------------------------------------------------------------------------------------
 // any_eta_pos / any_eta_nonpos reproduce the reference's whole-array guards `np.any(eta>0)` / `np.any(eta<=0)`
 // (kgeo/kerr_raytracing_ana.py:217,300): they are properties of the CALL, computed once by the host wrapper.
-enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4, M_INPUT_LAM_ETA = 8, M_POLISH_ROOTS = 16 };
+enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4, M_INPUT_LAM_ETA = 8, M_POLISH_ROOTS = 16, M_CARLSON_ONLY = 32 };
 // PHI_T = false skips every constant that only the phi / t / sigma integrals need (image and lensing paths).
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
@@ -467,6 +509,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         }
         w[T_F0] = F0;
         w[T_KC] = Kk;
+        if (PHI_T && LADDER) polar_theta_setup(o, m, sq1m, Km, up, pref, w, &flags);
     } else if (any_eta_nonpos && eta < 0.0) {
         flags |= F_TH_VORT;
         double h = (o.th_o <= kHalfPi) ? 1.0 : -1.0;
@@ -505,6 +548,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_C2] = 2.0 * prefC * (Ek - Kk);
         w[T_C3] = prefC;
         w[T_GT0] = s_o * (-h * prefC * E0);
+        if (PHI_T && LADDER) polar_theta_setup(o, m, sq1m, Km, nch, prefB, w, &flags);
     }
 
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
@@ -513,6 +557,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
     if (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) flags |= F_OUTSIDE;   // utils :817-824
     const double rp = o.rplus, rm = o.rminus, r_o = o.r_o;
     double tau_tot = 0.0;
+    double th_k = -1.0, th_n[3] = {0.0, 0.0, 0.0};   // Jacobi parameter and Pi characteristics for the theta-function blocks
 
     if (R.c12) {  // ---- case 4 ----
         flags |= F_CASE4;
@@ -544,6 +589,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         else Fo = legendre_F_sc(sa, ca, k4);
         w[R_K] = k4;
         if (LADDER) jacobi_make_ladder(k4, &w[R_LAD]);
+        th_k = k4; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 1.0 / pref;
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
         if (PHI_T) {
@@ -592,6 +638,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         else Fo = legendre_F_sc(sa, ca, k3);
         w[R_K] = k3;
         if (LADDER) jacobi_make_ladder(k3, &w[R_LAD]);
+        th_k = k3; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = sqAB;
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
         if (PHI_T) {
@@ -628,6 +675,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         else Fo = legendre_F_sc(sa, ca, k2);
         w[R_K] = k2;
         if (LADDER) jacobi_make_ladder(k2, &w[R_LAD]);
+        th_k = k2; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
         if (PHI_T) {
@@ -663,6 +711,9 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         }
     }
     w[S_TAUTOT] = tau_tot;
+    if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0 && theta_make_motion(3, th_k, th_n, nullptr, nullptr, &w[R_TH]))
+        flags |= F_R_THETA;
+    if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA);
     *flags_out = flags;
 }
 
@@ -692,6 +743,24 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
     *th = 0.0; *Gph = 0.0; *Gt = 0.0;
     if (!(flags & (F_TH_ORD | F_TH_VORT))) return;
     double snarg = fma(-w(T_W), tau, w(T_X0));
+    if (flags & F_TH_THETA) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
+        const double sq1m_ = w(T_SQ), ua = snarg * w(T_ISQ);
+        double L = 0.0;
+        const ThetaOut t = full ? theta_eval_motion<W, 1>(w, T_TH, ua, &L) : theta_eval_motion<W, 0>(w, T_TH, ua, &L);
+        const double idn_ = frcp(t.dn);
+        const double sinA_ = sq1m_ * t.sn * idn_;
+        if (flags & F_TH_ORD) {
+            *th = kg_acos(w(T_A) * sinA_);
+        } else {
+            double h = (flags & F_HPOS) ? 1.0 : -1.0;
+            *th = kg_acos(h * sqrt(fma(w(T_B), sinA_ * sinA_, w(T_A))));
+        }
+        if (!full) return;
+        *Gph = fma(w(T_TH_SLOPE), ua, w(T_TH_COEF) * L) - w(T_GPH0);
+        const double Dtot = sq1m_ * (fma(w(T_TH_G), ua, t.Z * w(T_TH_IM)) - t.sn * t.cn * idn_);
+        *Gt = fma(w(T_C3), snarg, 3.0 * w(T_C1) * Dtot) - w(T_GT0);
+        return;
+    }
     double sq1m = w(T_SQ);
     const double uarg = snarg * w(T_ISQ);
     const SnCnDn jt = jacobi_from_ladder(SlotView<W>{w, T_LAD}, uarg);
@@ -758,17 +827,30 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     double X = fma(-w(R_SC), tau, w(R_X0));
     double k = w(R_K);
     SnCnDn jr;
-    if (LADDER) {
-        jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
+    double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
+    // E and the three Pi's at am(X|k), shared by every radial case
+    double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
+    if (LADDER && (flags & F_R_THETA)) {   // theta-function path (kg_theta.cuh)
+        double L[3] = {0.0, 0.0, 0.0};
+        const ThetaOut t = full ? theta_eval_motion<W, 3>(w, R_TH, X, L) : theta_eval_motion<W, 0>(w, R_TH, X, L);
+        jr.sn = t.sn; jr.cn = t.cn; jr.dn = t.dn;
+        if (full) {
+            E = fma(w(R_TH + TB_EOKM1), X, X) + t.Z;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                Pi[i] = fma(w(R_TH + TB_SIZE + i * TP_SIZE + TP_A), X, w(R_TH + TB_SIZE + i * TP_SIZE + TP_P) * L[i]);
+        }
     } else {
-        double Kunused;
-        jacobi_sncndn(X, k, &jr.sn, &jr.cn, &jr.dn, &Kunused);
+        if (LADDER) {
+            jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
+        } else {
+            double Kunused;
+            jacobi_sncndn(X, k, &jr.sn, &jr.cn, &jr.dn, &Kunused);
+        }
+        // one shared Carlson bundle
+        if (full) radial_legendre(w, X, w(R_KC), jr.sn, jr.cn, jr.dn, &E, Pi);
     }
     const double sn = jr.sn, cn = jr.cn, dn = jr.dn;
-    double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
-    // E and the three Pi's at am(X|k): one shared Carlson bundle for every radial case
-    double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
-    if (full) radial_legendre(w, X, w(R_KC), sn, cn, dn, &E, Pi);
     const double rp = o.rplus, rm = o.rminus;
     if (flags & F_CASE2) {
         double q1 = w(R_Q0), q2 = w(R_Q1), q3 = w(R_Q2), q4 = w(R_Q3), root = w(R_Q4);

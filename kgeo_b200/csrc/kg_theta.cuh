@@ -1,0 +1,243 @@
+// Theta-function evaluation of sn/cn/dn, E and Pi along a ray (sm_100a).
+//
+// Why: along one ray the Jacobi parameter m and the characteristics n_i of the elliptic integrals are CONSTANTS; only the
+// Mino phase u changes from sample to sample.  Carlson duplication (the SciPy / GSL algorithm the reference uses through
+// kgeo/scipy_ellip_binding.py:87-237) re-derives everything from scratch for every sample: ~4.5 duplication steps, each
+// with 3 + NP square roots, NP reciprocals and NP short series.  With the nome q = exp(-pi K'/K) of the ray the same
+// functions are Fourier-type series in v = pi u / 2K whose coefficients are per-ray constants:
+//
+//   sn u = [th3(0)/th2(0)] th1(v)/th4(v),  cn u = [th4(0)/th2(0)] th2(v)/th4(v),  dn u = [th4(0)/th3(0)] th3(v)/th4(v)
+//   E(am u|m) = (E/K) u + Z(u),   Z(u) = (pi/2K) th4'(v)/th4(v)
+//   Pi(n; am u|m) = u + P(a) [ u Z(a) + (1/2) ln( th4(v - va) / th4(v + va) ) ],   sn^2(a|m) = n/m,  P = sn a/(cn a dn a)
+//
+// (Jacobi's form of the third-kind integral).  The constant a is real for 0 < n < m, b + iK' for n > 1 (the logarithm turns
+// into ln|th1(v - vb)/th1(v + vb)|: exactly the Cauchy principal value the reference takes for 1 - n sin^2 phi < 0,
+// scipy_ellip_binding.py:207-230), K + ib for m < n < 1 and ib for n < 0 (the logarithm turns into the argument of
+// th3 resp. th4 at v - i beta).  All four forms were checked against 40-digit quadrature in research/theta_pi_*.py
+// (<= 5e-15 relative in float64).  The series converge like q^(j^2): over BASELINE cfg 3 the median nome is 8e-4 (polar)
+// and 0.017 (radial), i.e. 2-4 terms; rays with q > 0.3 or an ill-conditioned prefactor (next to the critical curve,
+// n -> m, n -> 1) keep the Carlson path, decided once per ray in the setup.
+#pragma once
+#include "kg_theta_layout.cuh"
+
+namespace kg {
+
+// F(psi|m) and D(psi|m) = (F - E)/m = s^3 RD / 3 for an amplitude given by (sin, cos) in the first quadrant
+KG_HD void legendre_F_D(double s, double c, double m, double* F, double* D) {
+    double c2 = c * c, y = fma(-m * s, s, 1.0);
+    double rf, rd;
+    carlson_bundle<0, true, true>(c2, y, nullptr, &rf, &rd, nullptr);
+    *F = s * rf;
+    *D = cube(s) * rd * (1.0 / 3.0);
+}
+
+struct ThetaRay {
+    double m, K, Kp, q, eokm1, eokm1p;   // eokm1p = E(m')/K' - 1
+    int ok;
+};
+
+KG_HD ThetaRay theta_ray(double m) {
+    ThetaRay r;
+    r.m = m;
+    r.ok = (m > 1.0e-12 && m < 1.0) ? 1 : 0;
+    if (!r.ok) {
+        r.K = r.Kp = r.q = r.eokm1 = r.eokm1p = 0.0;
+        return r;
+    }
+    double mp = 1.0 - m;
+    r.K = ellip_K(m);
+    r.Kp = ellip_K(mp);
+    r.q = exp(-kPi * r.Kp / r.K);
+    r.eokm1 = -m * ellip_RDc(m) / (3.0 * r.K);
+    r.eokm1p = -mp * ellip_RDc(mp) / (3.0 * r.Kp);
+    if (!(r.q <= 0.3)) r.ok = 0;
+    return r;
+}
+
+// base block of a motion; returns the number of harmonics needed by the base series
+KG_HD int theta_make_base(const ThetaRay& r, double* out) {
+    for (int i = 0; i < TB_SIZE; ++i) out[i] = 0.0;
+    if (!r.ok) return 0;
+    out[TB_W] = kHalfPi / r.K;
+    out[TB_EOKM1] = r.eokm1;
+    double t2 = 0.0, t3 = 1.0, t4 = 1.0, sg = 1.0;
+    int J = kThJM;
+    for (int j = 0; j < kThJM; ++j) {
+        double qe = pow(r.q, (double)((j + 1) * (j + 1)));
+        double qo = pow(r.q, (j + 0.5) * (j + 0.5));
+        out[TB_QO + j] = 2.0 * sg * qo;      // (-1)^j
+        out[TB_QE + j] = -2.0 * sg * qe;     // (-1)^(j+1)
+        t2 += 2.0 * qo;
+        t3 += 2.0 * qe;
+        t4 += -2.0 * sg * qe;
+        if (J == kThJM && qe < 1.0e-19 && qo < 1.0e-19) J = j;     // harmonics 1..j (even) / 0..j-1 (odd) suffice
+        sg = -sg;
+    }
+    if (J < 1) J = 1;
+    out[TB_R1] = t3 / t2;
+    out[TB_R2] = t4 / t2;
+    out[TB_R3] = t4 / t3;
+    return J;
+}
+
+// one Pi block; returns the number of harmonics it needs, or -1 when the theta form is unusable for this (n, m)
+// nmm = n - m and omn = 1 - n are passed separately so that callers who know them without cancellation (the polar motion:
+// n' - m = n (1 - m), 1 - n' = (1 - n)(1 - m)) keep full accuracy next to the edges n -> m, n -> 1.
+KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, double* out) {
+    for (int i = 0; i < TP_SIZE; ++i) out[i] = 0.0;
+    out[TP_A] = 1.0;
+    if (!r.ok || !(n == n)) return -1;
+    const double m = r.m, mp = 1.0 - m, q = r.q;
+    const double edge = 1.0e-6;
+    if (n == 0.0) return 1;                                    // Pi = F = u
+    if (fabs(nmm) < edge * m || fabs(omn) < edge) return -1;
+    double sh, P, Zs;
+    int kind;
+    if (n > 0.0 && n < m) {              // a real: sn a = sqrt(n/m)
+        double s = sqrt(n / m), c = sqrt(-nmm / m), d = sqrt(omn);
+        double F, D;
+        legendre_F_D(s, c, m, &F, &D);
+        Zs = -m * D - r.eokm1 * F;                            // Z(a) = E(a) - (E/K) a
+        P = s / (c * d);
+        sh = kHalfPi * F / r.K;
+        kind = 0;
+    } else if (n > 1.0) {                // a = b + iK': sn b = 1/sqrt(n)
+        double s = sqrt(1.0 / n), c = sqrt(-omn / n), d = sqrt(nmm / n);
+        double F, D;
+        legendre_F_D(s, c, m, &F, &D);
+        Zs = (-m * D - r.eokm1 * F) + c * d / s;              // Z(b) + cs b dn b
+        P = -s / (c * d);
+        sh = kHalfPi * F / r.K;
+        kind = 1;
+    } else {                             // imaginary shift, complementary modulus
+        double s, c, d;
+        if (n < 0.0) {                   // a = ib: sc^2(b|m') = -n/m
+            double t = sqrt(-n / m);
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+        } else {                         // a = K + ib: dn^2(b|m') = m/n
+            s = sqrt(nmm / (n * mp));
+            c = sqrt(m * omn / (n * mp));
+        }
+        d = (n < 0.0) ? sqrt(fma(-mp * s, s, 1.0)) : sqrt(m / n);
+        double F, D;
+        legendre_F_D(s, c, mp, &F, &D);
+        double Zbp = -mp * D - r.eokm1p * F;                  // Z(b|m')
+        double Zd = d * s / c - Zbp - kPi * F / (2.0 * r.K * r.Kp);
+        if (n < 0.0) {
+            P = -(s * c / d);
+            Zs = Zd;
+        } else {
+            P = -(d / (mp * s * c));
+            Zs = Zd - m * s / (c * d);
+        }
+        sh = kHalfPi * F / r.K;
+        kind = 2;
+    }
+    if (!(fabs(P) <= 300.0) || !(Zs == Zs)) return -1;
+    out[TP_KIND] = (double)kind;
+    out[TP_P] = P;
+    out[TP_A] = fma(P, Zs, 1.0);
+    int J = -1;
+    double sg = 1.0;
+    for (int j = 0; j < kThJM; ++j) {
+        double cx, sy, mag;
+        if (kind == 0) {                 // 2 (-1)^(j+1) q^((j+1)^2) {cos, sin}(2 (j+1) sh)
+            double qe = -2.0 * sg * pow(q, (double)((j + 1) * (j + 1)));
+            cx = qe * cos(2.0 * (j + 1) * sh);
+            sy = qe * sin(2.0 * (j + 1) * sh);
+            mag = fabs(qe);
+        } else if (kind == 1) {          // 2 (-1)^j q^((j+1/2)^2) {cos, sin}((2j+1) sh); th1(v -+ sh) = X -+ Y
+            double qo = 2.0 * sg * pow(q, (j + 0.5) * (j + 0.5));
+            cx = qo * cos((2.0 * j + 1.0) * sh);
+            sy = -qo * sin((2.0 * j + 1.0) * sh);             // th1(v -+ sh) = X +- Y: L = (1/2) ln|th1(v-sh)/th1(v+sh)| = (1/2) ln|(X+Y)/(X-Y)|
+            mag = fabs(qo);
+        } else {                         // th4 (n<0): 2 (-1)^(j+1) q^(..) {cosh, sinh};  th3 (m<n<1): 2 q^(..) {cosh, sinh}
+            double qe = 2.0 * pow(q, (double)((j + 1) * (j + 1))) * ((n < 0.0) ? -sg : 1.0);
+            cx = qe * cosh(2.0 * (j + 1) * sh);
+            sy = qe * sinh(2.0 * (j + 1) * sh);
+            mag = fabs(cx);
+        }
+        out[TP_C + j] = cx;
+        out[TP_S + j] = sy;
+        if (J < 0 && mag < 1.0e-19) J = j;
+        sg = -sg;
+    }
+    if (J < 0) {
+        // not converged within the stored harmonics
+        double last = fabs(out[TP_C + kThJM - 1]) + fabs(out[TP_S + kThJM - 1]);
+        if (last > 1.0e-17) return -1;
+        J = kThJM;
+    }
+    if (J < 1) J = 1;
+    return J;
+}
+
+// ---- per-sample evaluation ------------------------------------------------------------------------------------------
+// Out: sn, cn, dn, Z(u) and L_i (i < NP) of the motion whose base block starts at slot `base`; Pi blocks follow the base block.
+struct ThetaOut {
+    double sn, cn, dn, Z;
+};
+
+template <class W, int NP>
+KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
+    const int J = (int)w(base + TB_J);
+    const double v = w(base + TB_W) * u;
+    double sv, cv;
+#if defined(__CUDA_ARCH__)
+    sincos(v, &sv, &cv);
+#else
+    sv = sin(v);
+    cv = cos(v);
+#endif
+    const double c1 = fma(cv, cv, -sv * sv), s1 = 2.0 * sv * cv;   // cos 2v, sin 2v
+    // even harmonics (c_j, s_j) = (cos 2jv, sin 2jv) and odd ones (co_j, so_j) = (cos, sin)((2j+1)v) by rotation
+    double ce = c1, se = s1;          // j = 1
+    double co = cv, so = sv;          // j = 0
+    double th1 = 0.0, th2 = 0.0, th3 = 1.0, th4 = 1.0, dth4 = 0.0, sg = 1.0, jj = 1.0;
+    double X[NP > 0 ? NP : 1], Y[NP > 0 ? NP : 1];
+    int kind[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        kind[i] = (int)w(base + TB_SIZE + i * TP_SIZE + TP_KIND);
+        X[i] = (kind[i] == 1) ? 0.0 : 1.0;
+        Y[i] = 0.0;
+    }
+#pragma unroll 1
+    for (int j = 0; j < J; ++j) {
+        const double qe = w(base + TB_QE + j), qo = w(base + TB_QO + j);   // 2(-1)^(j+1) q^((j+1)^2), 2(-1)^j q^((j+1/2)^2)
+        th4 = fma(qe, ce, th4);
+        th3 = fma(-sg * qe, ce, th3);            // 2 q^((j+1)^2) cos
+        dth4 = fma(-2.0 * jj * qe, se, dth4);
+        th1 = fma(qo, so, th1);
+        th2 = fma(sg * qo, co, th2);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int pb = base + TB_SIZE + i * TP_SIZE;
+            const double hc = (kind[i] == 1) ? so : ce;
+            const double hs = (kind[i] == 1) ? co : se;
+            X[i] = fma(w(pb + TP_C + j), hc, X[i]);
+            Y[i] = fma(w(pb + TP_S + j), hs, Y[i]);
+        }
+        // next harmonics: multiply by e^(2iv)
+        double cen = fma(ce, c1, -se * s1), sen = fma(se, c1, ce * s1);
+        double con = fma(co, c1, -so * s1), son = fma(so, c1, co * s1);
+        ce = cen; se = sen; co = con; so = son;
+        sg = -sg;
+        jj += 1.0;
+    }
+    ThetaOut o;
+    const double i4 = frcp(th4);
+    o.sn = w(base + TB_R1) * th1 * i4;
+    o.cn = w(base + TB_R2) * th2 * i4;
+    o.dn = w(base + TB_R3) * th3 * i4;
+    o.Z = w(base + TB_W) * dth4 * i4;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        if (kind[i] == 2) L[i] = atan2(Y[i], X[i]);
+        else L[i] = 0.5 * kg_log(fabs(fdiv(X[i] + Y[i], X[i] - Y[i])));
+    }
+    return o;
+}
+
+}  // namespace kg

@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS) track_kernel(Ob
                                                             const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
                                                             const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
                                                             size_t ld, int k_begin, int k_end, int chunk) {
-    __shared__ double sw[NW][32];
+    extern __shared__ double sw_dyn[];                 // [NW][32] ray constants of this tile (61 KB: dynamic shared memory)
+    double (*sw)[32] = reinterpret_cast<double (*)[32]>(sw_dyn);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t pix = (size_t)blockIdx.x * 32 + lane;
     const bool live = pix < npix;
@@ -532,12 +533,16 @@ static int launch_tracks(const Observer& o, size_t npix, const double* w, const 
     ychunks = (ns + per - 1) / per;
     if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
     dim3 grid(tiles, (unsigned)ychunks);
-    if (full)
-        track_kernel<true><<<grid, TRK_THREADS, 0, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
-                                                             k_begin, k_end, per);
-    else
-        track_kernel<false><<<grid, TRK_THREADS, 0, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
-                                                              k_begin, k_end, per);
+    const size_t smem = (size_t)NW * 32 * sizeof(double);
+    if (full) {
+        CU(cudaFuncSetAttribute(track_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<true><<<grid, TRK_THREADS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
+                                                                k_begin, k_end, per);
+    } else {
+        CU(cudaFuncSetAttribute(track_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        track_kernel<false><<<grid, TRK_THREADS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
+                                                                 k_begin, k_end, per);
+    }
     LAUNCHED("track_kernel");
     return 0;
 }

@@ -1,0 +1,43 @@
+// Developer-only host harness: compiles the __host__ __device__ per-ray / per-sample functions of kgeo_b200/csrc with the
+// HOST compiler so that algorithm changes can be compared with the oracle without a GPU.  It is NOT part of the product:
+// libkgeo_b200.so never contains or calls this, and kgeo_b200/ never loads it (the product has no CPU path).
+//   g++ -O2 -ffp-contract=off -shared -fPIC -I../../kgeo_b200/csrc hostsim.cpp -o _hostsim.so
+#include <cstddef>
+#include <cstdint>
+#include "kg_geodesic.cuh"
+
+using namespace kg;
+
+extern "C" {
+
+int hostsim_slots() { return NW; }
+int hostsim_slot(int which) { const int v[] = {T_TH, R_TH, R_K, T_M, S_TAUTOT, TB_SIZE, TP_SIZE, R_N0}; return v[which]; }
+
+// tracks for npix rays, ntau samples each (numpy.linspace(0, maxtaufrac*tau_tot, ntau)); outputs [ntau][npix] row-major.
+// force: 0 = flags as computed, 1 = clear the theta-function flags (Carlson path everywhere)
+int hostsim_tracks(double a, double r_o, double th_o, size_t npix, const double* alpha, const double* beta, int mode,
+                   int ntau, double maxtaufrac, int force, double* t, double* r, double* th, double* ph, double* sig,
+                   int32_t* flags_out, double* w_out) {
+    Observer o = make_observer(a, r_o, th_o);
+    double w[NW];
+    for (size_t i = 0; i < npix; ++i) {
+        int fl;
+        ray_setup<true, true>(o, alpha[i], beta[i], mode, w, &fl);
+        if (force == 1) fl &= ~(F_TH_THETA | F_R_THETA);
+        if (force == 2) fl &= ~F_TH_THETA;
+        if (force == 3) fl &= ~F_R_THETA;
+        if (flags_out) flags_out[i] = fl;
+        if (w_out) for (int s = 0; s < NW; ++s) w_out[(size_t)s * npix + i] = w[s];
+        ArrayW W{w};
+        const double stop = maxtaufrac * w[S_TAUTOT];
+        const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+        for (int k = 0; k < ntau; ++k) {
+            double tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
+            Point p = point_eval(W, o, fl, tau, true);
+            size_t q = (size_t)k * npix + i;
+            t[q] = p.t; r[q] = p.r; th[q] = p.th; ph[q] = p.ph; sig[q] = p.sig;
+        }
+    }
+    return 0;
+}
+}

@@ -62,7 +62,7 @@ def test_tracks_against_reference(golden, kg, name):
     geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [g['alpha'], g['beta']], ngeo=int(ngeo), plotdata=False)
     ref = {k: g[k] for k in ('tau', 'sig', 't', 'r', 'th', 'ph')}
     ref.update(a=a, r_o=r_o)
-    assert_tracks_close(_as_dict(geos), ref, what=name)
+    assert_tracks_close(_as_dict(geos), ref, what=name, pixels=(th_o, g['alpha'], g['beta']))
     assert geos.npix == len(g['alpha']) and geos.tautot.shape == (len(g['alpha']),)
 
 
@@ -77,7 +77,7 @@ def test_tracks_against_oracle_seeded(kg):
         tau, sig, (t, r, th, ph) = ko.raytrace(a, [0, r_o, th_o, 0], [A, B], 40)
         geos = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=40, plotdata=False)
         ref = dict(tau=tau, sig=sig, t=t, r=r, th=th, ph=ph, a=a, r_o=r_o)
-        assert_tracks_close(_as_dict(geos), ref, what='seeded a=%g inc=%g' % (a, inc))
+        assert_tracks_close(_as_dict(geos), ref, what='seeded a=%g inc=%g' % (a, inc), pixels=(th_o, A, B))
 
 
 def test_coords_at_tau_matches_raytrace_and_partial_mode(golden, kg):
@@ -87,7 +87,8 @@ def test_coords_at_tau_matches_raytrace_and_partial_mode(golden, kg):
     sig, (t, r, th, ph) = kg.coords_at_tau(a, obs, [g['alpha'], g['beta']], g['tau'])
     ref = {k: g[k] for k in ('tau', 'sig', 't', 'r', 'th', 'ph')}
     ref.update(a=a, r_o=r_o)
-    assert_tracks_close(dict(tau=g['tau'], sig=sig, t=t, r=r, th=th, ph=ph), ref, what='coords_at_tau')
+    assert_tracks_close(dict(tau=g['tau'], sig=sig, t=t, r=r, th=th, ph=ph), ref, what='coords_at_tau',
+                        pixels=(th_o, g['alpha'], g['beta']))
     # do_phi_and_t=False: r, theta identical, the rest zero (kerr_raytracing_ana.py:389-400)
     sig0, (t0, r0, th0, ph0) = kg.coords_at_tau(a, obs, [g['alpha'], g['beta']], g['tau'], do_phi_and_t=False)
     assert np.array_equal(r0, r) and np.array_equal(th0, th)
