@@ -104,7 +104,9 @@ enum Flag {
     F_OUTSIDE = 1 << 12,                  // is_outside_crit
     F_LOWSPIN = 1 << 13,
     F_TH_THETA = 1 << 14,                 // polar motion may use the theta-function path
-    F_R_THETA = 1 << 15                   // radial motion may use the theta-function path
+    F_R_THETA = 1 << 15,                  // radial motion may use the theta-function path
+    F_R_K100 = 1 << 16,                   // ... and its three Pi blocks have kinds (1, 0, 0): rays that turn outside the horizon
+    F_R_K111 = 1 << 17                    // ... kinds (1, 1, 1): plunging rays (see theta_eval_motion)
 };
 
 struct Roots {
@@ -280,7 +282,7 @@ KG_HD Roots quartic_roots(const Observer& o, double lam, double eta, bool polish
 // F, E and NP Pi's; amplitudes beyond pi/2 are reflected (phi = +/-pi + phi_r).  With Kc/RDc/PicTail supplied by
 // the caller when known (pass NaN to have them computed on demand).
 template <int NP>
-KG_HD void legendre_sc(double s, double c, double m, const double* n, double* F, double* E, double* Pi) {
+KG_NOINLINE void legendre_sc(double s, double c, double m, const double* n, double* F, double* E, double* Pi) {
     double j = 0.0;
     if (c < 0.0) {
         j = (s >= 0.0) ? 1.0 : -1.0;
@@ -412,7 +414,8 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 
 // ---- theta blocks of a motion (setup) -------------------------------------------------------------------------------------
 // Builds base + NP Pi blocks at w[slot...]; returns true when the theta path is usable for every integral of the motion.
-KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double* blk) {
+template <class P>
+KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, P blk) {
     ThetaRay r = theta_ray(m);
     int J = theta_make_base(r, blk);
     bool ok = r.ok != 0;
@@ -430,16 +433,17 @@ KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const doub
 // polar motion: Legendre parameter k < 0 of the reference, Jacobi parameter m = k/(k-1); with sin(phi) = sqrt(1-m) sd(w|m):
 //   Pi(n; phi | k) = sqrt(1-m) [ (m/n') w + (1 - m/n') Pi(n'; am w | m) ],  n' = m + n (1 - m)   (m < n' < 1: circular case)
 //   (F - E)(phi | k) / k = sqrt(1-m) [ (1 + (E/K - 1)/m) w + Z(w)/m - sn w cn w / dn w ]
-KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double Km, double n, double D3, double* w, int* flags) {
+template <class WP>
+KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double Km, double n, double D3, WP w, int* flags) {
     const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
-    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, &w[T_TH]);
+    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, w + T_TH);
     const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
     const double mn = m / npr;
     w[T_TH_SLOPE] = D3 * sq1m * fma(1.0 - mn, A, mn);
     w[T_TH_COEF] = D3 * sq1m * (1.0 - mn) * P;
     w[T_TH_G] = 1.0 - ellip_RDc(m) / (3.0 * Km);
     w[T_TH_IM] = 1.0 / m;
-    if (ok && !o.lowspin && m > 1.0e-6) *flags |= F_TH_THETA;
+    if (ok && !o.lowspin && m > 1.0e-6 && w[T_TH + TB_SIZE + TP_KIND] == 2.0) *flags |= F_TH_THETA;
 }
 
 // ---- ray setup -------------------------------------------------------------------------------------------------------
@@ -450,8 +454,8 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
 // AGM descent inline instead.
-template <bool PHI_T, bool LADDER = true>
-KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, double* w, int* flags_out) {
+template <bool PHI_T, bool LADDER = true, class P = double*>
+KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     for (int i = 0; i < NW; ++i) w[i] = 0.0;
     int flags = 0;
@@ -490,7 +494,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        if (LADDER) jacobi_make_ladder(m, &w[T_LAD]);
+        if (LADDER) jacobi_make_ladder(m, w + T_LAD);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = -s_o * sqrt(up);
@@ -535,7 +539,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        if (LADDER) jacobi_make_ladder(m, &w[T_LAD]);
+        if (LADDER) jacobi_make_ladder(m, w + T_LAD);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = um;
@@ -588,7 +592,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k4, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k4);
         w[R_K] = k4;
-        if (LADDER) jacobi_make_ladder(k4, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k4, w + R_LAD);
         th_k = k4; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 1.0 / pref;
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
@@ -637,7 +641,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k3, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k3);
         w[R_K] = k3;
-        if (LADDER) jacobi_make_ladder(k3, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k3, w + R_LAD);
         th_k = k3; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = sqAB;
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
@@ -674,7 +678,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         if (PHI_T) legendre_sc<3>(sa, ca, k2, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k2);
         w[R_K] = k2;
-        if (LADDER) jacobi_make_ladder(k2, &w[R_LAD]);
+        if (LADDER) jacobi_make_ladder(k2, w + R_LAD);
         th_k = k2; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
@@ -711,8 +715,13 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, dou
         }
     }
     w[S_TAUTOT] = tau_tot;
-    if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0 && theta_make_motion(3, th_k, th_n, nullptr, nullptr, &w[R_TH]))
+    if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0 && theta_make_motion(3, th_k, th_n, nullptr, nullptr, w + R_TH)) {
         flags |= F_R_THETA;
+        const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
+                     k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
+        if (k0 == 1.0 && k1 == 0.0 && k2 == 0.0) flags |= F_R_K100;
+        if (k0 == 1.0 && k1 == 1.0 && k2 == 1.0) flags |= F_R_K111;
+    }
     if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA);
     *flags_out = flags;
 }
@@ -746,7 +755,7 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
     if (flags & F_TH_THETA) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
         const double sq1m_ = w(T_SQ), ua = snarg * w(T_ISQ);
         double L = 0.0;
-        const ThetaOut t = full ? theta_eval_motion<W, 1>(w, T_TH, ua, &L) : theta_eval_motion<W, 0>(w, T_TH, ua, &L);
+        const ThetaOut t = full ? theta_eval_motion<W, 1, 0x2>(w, T_TH, ua, &L) : theta_eval_motion<W, 0, 0>(w, T_TH, ua, &L);
         const double idn_ = frcp(t.dn);
         const double sinA_ = sq1m_ * t.sn * idn_;
         if (flags & F_TH_ORD) {
@@ -832,7 +841,11 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
     if (LADDER && (flags & F_R_THETA)) {   // theta-function path (kg_theta.cuh)
         double L[3] = {0.0, 0.0, 0.0};
-        const ThetaOut t = full ? theta_eval_motion<W, 3>(w, R_TH, X, L) : theta_eval_motion<W, 0>(w, R_TH, X, L);
+        ThetaOut t;
+        if (!full) t = theta_eval_motion<W, 0, 0>(w, R_TH, X, L);
+        else if (flags & F_R_K100) t = theta_eval_motion<W, 3, 0x001>(w, R_TH, X, L);
+        else if (flags & F_R_K111) t = theta_eval_motion<W, 3, 0x111>(w, R_TH, X, L);
+        else t = theta_eval_motion<W, 3, kKindsGeneric>(w, R_TH, X, L);
         jr.sn = t.sn; jr.cn = t.cn; jr.dn = t.dn;
         if (full) {
             E = fma(w(R_TH + TB_EOKM1), X, X) + t.Z;

@@ -114,6 +114,10 @@ static const double kc_host[32] = KG_SERIES_COEFFS;
 #define KC(i) kc_host[i]
 #endif
 
+}  // namespace kg
+#include "kg_math.cuh"
+namespace kg {
+
 // RC(1, b) with e = b - 1 given separately (both cancellation-free), e > -1:
 //   atan(sqrt e)/sqrt e   (e>0),   atanh(sqrt -e)/sqrt -e = log((1+s)/sqrt(b))/s, s = sqrt(-e)   (e<0)
 // closed forms (out of line: one copy serves every Pi track of the fused kernels)
@@ -357,7 +361,7 @@ KG_NOINLINE double pi_finish_pv(double s3n, double s, double c2, double y, doubl
     double q = -rho, xy = c2 * y, pq = p * q;
     double isq = frsqrt(xy + pq);                                  // xy + pq > 0 here
     double t = fsqrt(fmax(xy, 1.0e-300)) * isq;
-    double ath = 0.5 * log(fdiv(1.0 + t, 1.0 - t));                // = sqrt(xy) * RC(xy+pq, pq)
+    double ath = 0.5 * flog(fdiv(1.0 + t, 1.0 - t));                // = sqrt(xy) * RC(xy+pq, pq)
     double cpv = fdiv((p - 1.0) * rj - 3.0 * fdiv(F, s) + 3.0 * ath * isq, q + 1.0);
     return s3n * cpv;
 }
@@ -369,11 +373,12 @@ KG_HD double pi_finish(double n, double s, double c2, double y, double F, const 
 }
 
 // ---- complete integrals --------------------------------------------------------------------------------------
-KG_HD double ellip_K(double m) { return carlson_rf(0.0, 1.0 - m, 1.0); }
-KG_HD double ellip_RDc(double m) { return carlson_rd(0.0, 1.0 - m, 1.0); }         // (K-E)/m = RDc/3
+// complete integrals are setup-only: out of line, one copy per kernel (the setup code must stay inside the instruction cache)
+KG_NOINLINE double ellip_K(double m) { return carlson_rf(0.0, 1.0 - m, 1.0); }
+KG_NOINLINE double ellip_RDc(double m) { return carlson_rd(0.0, 1.0 - m, 1.0); }         // (K-E)/m = RDc/3
 KG_HD double ellip_Ec(double m) { return ellip_K(m) - (m * (1.0 / 3.0)) * ellip_RDc(m); }
 // Pi(n|m) - K(m); principal value for n > 1; n == 1 -> +inf
-KG_HD double ellip_PicTail(double n, double m) {
+KG_NOINLINE double ellip_PicTail(double n, double m) {
     double y = 1.0 - m;
     if (n == 1.0) return kInf;
     PiPrep pp = pi_prepare(n, 1.0, 0.0, y);
@@ -512,10 +517,21 @@ KG_HD void jacobi_sncndn(double u, double m, double* sn, double* cn, double* dn,
 // stores it once and every (ray, sample) evaluation skips the ~6 square roots of the descent.
 // Layout: L[0] = index of the last level (or -1 for m == 1), L[1] = c = last arithmetic mean,
 //         L[2+3i] = a_i, L[3+3i] = 1/a_i, L[4+3i] = g_i.
+// Pointer into a slot-major workspace: slot s of this ray lives at base[s * stride].  The per-ray setup is written against
+// a generic pointer type P (double* for a thread-local array, WsPtr for the [slot][ray] global workspace), so the setup
+// kernel stores every constant straight into HBM instead of staging ~2 KB per thread in local memory.
+struct WsPtr {
+    double* base;
+    size_t stride;
+    KG_HD double& operator[](int s) const { return base[(size_t)s * stride]; }
+    KG_HD WsPtr operator+(int s) const { return WsPtr{base + (size_t)s * stride, stride}; }
+};
+
 constexpr int kLadderLevels = 10;
 constexpr int kLadderSize = 2 + 3 * kLadderLevels;
 
-KG_HD void jacobi_make_ladder(double m, double* L) {
+template <class P>
+KG_NOINLINE void jacobi_make_ladder(double m, P L) {
     for (int i = 0; i < kLadderSize; ++i) L[i] = 0.0;
     double mc = 1.0 - m;
     if (!(mc > 0.0)) {
@@ -542,8 +558,8 @@ KG_HD void jacobi_make_ladder(double m, double* L) {
 
 // out-of-line libm calls shared by every call site of the fused kernels (code size: the track kernel must stay
 // inside the instruction cache)
-KG_NOINLINE double kg_log(double x) { return log(x); }
-KG_NOINLINE double kg_acos(double x) { return acos(x); }
+KG_NOINLINE double kg_log(double x) { return flog(x); }
+KG_NOINLINE double kg_acos(double x) { return facos(x); }
 
 struct SnCnDn {
     double sn, cn, dn;
@@ -567,12 +583,7 @@ KG_NOINLINE SnCnDn jacobi_from_ladder(const A L, double u) {
     }
     double uu = u * c;
     double s, co;
-#if defined(__CUDA_ARCH__)
-    sincos(uu, &s, &co);
-#else
-    s = sin(uu);
-    co = cos(uu);
-#endif
+    fsincos(uu, &s, &co);
     double d = 1.0;
     if (s != 0.0) {
         double aa = fdiv(co, s);

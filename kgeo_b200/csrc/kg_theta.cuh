@@ -23,7 +23,7 @@
 namespace kg {
 
 // F(psi|m) and D(psi|m) = (F - E)/m = s^3 RD / 3 for an amplitude given by (sin, cos) in the first quadrant
-KG_HD void legendre_F_D(double s, double c, double m, double* F, double* D) {
+KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D) {
     double c2 = c * c, y = fma(-m * s, s, 1.0);
     double rf, rd;
     carlson_bundle<0, true, true>(c2, y, nullptr, &rf, &rd, nullptr);
@@ -54,24 +54,40 @@ KG_HD ThetaRay theta_ray(double m) {
     return r;
 }
 
+// Powers of the nome by recurrence: q^((j+1)^2) = q^(j^2) q^(2j+1), q^((j+1/2)^2) = q^(1/4) q^(j^2+j); the relative error
+// grows like j eps, irrelevant for coefficients that are themselves < q^(j^2).
+struct NomePowers {
+    double q2, qe, qo, stepe, stepo;   // qe = q^((j+1)^2), qo = q^((j+1/2)^2) for the current j
+    KG_HD explicit NomePowers(double q) : q2(q * q), qe(q), qo(sqrt(sqrt(q))), stepe(q * q * q), stepo(q * q) {}
+    KG_HD void next() {
+        qe *= stepe; stepe *= q2;      // q^((j+2)^2) = q^((j+1)^2) q^(2j+3)
+        qo *= stepo; stepo *= q2;      // q^((j+3/2)^2) = q^((j+1/2)^2) q^(2j+2)
+    }
+};
+
 // base block of a motion; returns the number of harmonics needed by the base series
-KG_HD int theta_make_base(const ThetaRay& r, double* out) {
+template <class P>
+KG_HD int theta_make_base(const ThetaRay& r, P out) {
     for (int i = 0; i < TB_SIZE; ++i) out[i] = 0.0;
     if (!r.ok) return 0;
     out[TB_W] = kHalfPi / r.K;
     out[TB_EOKM1] = r.eokm1;
     double t2 = 0.0, t3 = 1.0, t4 = 1.0, sg = 1.0;
     int J = kThJM;
+    NomePowers np(r.q);
     for (int j = 0; j < kThJM; ++j) {
-        double qe = pow(r.q, (double)((j + 1) * (j + 1)));
-        double qo = pow(r.q, (j + 0.5) * (j + 0.5));
+        const double qe = np.qe, qo = np.qo;
+        if (qe < 1.0e-19 && qo < 1.0e-19) {     // harmonics 1..j (even) / 0..j-1 (odd) suffice
+            J = j;
+            break;
+        }
         out[TB_QO + j] = 2.0 * sg * qo;      // (-1)^j
         out[TB_QE + j] = -2.0 * sg * qe;     // (-1)^(j+1)
         t2 += 2.0 * qo;
         t3 += 2.0 * qe;
         t4 += -2.0 * sg * qe;
-        if (J == kThJM && qe < 1.0e-19 && qo < 1.0e-19) J = j;     // harmonics 1..j (even) / 0..j-1 (odd) suffice
         sg = -sg;
+        np.next();
     }
     if (J < 1) J = 1;
     out[TB_R1] = t3 / t2;
@@ -83,7 +99,8 @@ KG_HD int theta_make_base(const ThetaRay& r, double* out) {
 // one Pi block; returns the number of harmonics it needs, or -1 when the theta form is unusable for this (n, m)
 // nmm = n - m and omn = 1 - n are passed separately so that callers who know them without cancellation (the polar motion:
 // n' - m = n (1 - m), 1 - n' = (1 - n)(1 - m)) keep full accuracy next to the edges n -> m, n -> 1.
-KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, double* out) {
+template <class WP>
+KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, WP out) {
     for (int i = 0; i < TP_SIZE; ++i) out[i] = 0.0;
     out[TP_A] = 1.0;
     if (!r.ok || !(n == n)) return -1;
@@ -138,30 +155,54 @@ KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, dou
     out[TP_KIND] = (double)kind;
     out[TP_P] = P;
     out[TP_A] = fma(P, Zs, 1.0);
+    // harmonics of the shift by rotation (real shift) or by powers of e^(2 sh) (imaginary shift)
     int J = -1;
     double sg = 1.0;
+    NomePowers np(q);
+    double c1, s1, cj, sj, ep = 1.0, em = 1.0, e2p = 1.0, e2m = 1.0;
+    if (kind == 2) {
+        e2p = exp(2.0 * sh);
+        e2m = 1.0 / e2p;
+        ep = e2p; em = e2m;              // e^(+-2 (j+1) sh)
+        c1 = s1 = cj = sj = 0.0;
+    } else {
+        double ss = sin(sh), cs = cos(sh);
+        c1 = fma(cs, cs, -ss * ss); s1 = 2.0 * ss * cs;      // cos 2 sh, sin 2 sh
+        if (kind == 0) { cj = c1; sj = s1; }                   // (cos, sin)(2 (j+1) sh)
+        else { cj = cs; sj = ss; }                             // (cos, sin)((2j+1) sh)
+    }
     for (int j = 0; j < kThJM; ++j) {
         double cx, sy, mag;
         if (kind == 0) {                 // 2 (-1)^(j+1) q^((j+1)^2) {cos, sin}(2 (j+1) sh)
-            double qe = -2.0 * sg * pow(q, (double)((j + 1) * (j + 1)));
-            cx = qe * cos(2.0 * (j + 1) * sh);
-            sy = qe * sin(2.0 * (j + 1) * sh);
+            double qe = -2.0 * sg * np.qe;
+            cx = qe * cj;
+            sy = qe * sj;
             mag = fabs(qe);
-        } else if (kind == 1) {          // 2 (-1)^j q^((j+1/2)^2) {cos, sin}((2j+1) sh); th1(v -+ sh) = X -+ Y
-            double qo = 2.0 * sg * pow(q, (j + 0.5) * (j + 0.5));
-            cx = qo * cos((2.0 * j + 1.0) * sh);
-            sy = -qo * sin((2.0 * j + 1.0) * sh);             // th1(v -+ sh) = X +- Y: L = (1/2) ln|th1(v-sh)/th1(v+sh)| = (1/2) ln|(X+Y)/(X-Y)|
+        } else if (kind == 1) {          // 2 (-1)^j q^((j+1/2)^2) {cos, sin}((2j+1) sh); th1(v -+ sh) = X +- Y:
+            double qo = 2.0 * sg * np.qo; //   L = (1/2) ln|th1(v-sh)/th1(v+sh)| = (1/2) ln|(X+Y)/(X-Y)|
+            cx = qo * cj;
+            sy = -qo * sj;
             mag = fabs(qo);
         } else {                         // th4 (n<0): 2 (-1)^(j+1) q^(..) {cosh, sinh};  th3 (m<n<1): 2 q^(..) {cosh, sinh}
-            double qe = 2.0 * pow(q, (double)((j + 1) * (j + 1))) * ((n < 0.0) ? -sg : 1.0);
-            cx = qe * cosh(2.0 * (j + 1) * sh);
-            sy = qe * sinh(2.0 * (j + 1) * sh);
+            double qe = 2.0 * np.qe * ((n < 0.0) ? -sg : 1.0);
+            cx = qe * (0.5 * (ep + em));
+            sy = qe * (0.5 * (ep - em));
             mag = fabs(cx);
+        }
+        if (mag < 1.0e-19) {
+            J = j;
+            break;
         }
         out[TP_C + j] = cx;
         out[TP_S + j] = sy;
-        if (J < 0 && mag < 1.0e-19) J = j;
         sg = -sg;
+        np.next();
+        if (kind == 2) {
+            ep *= e2p; em *= e2m;
+        } else {
+            double cn_ = fma(cj, c1, -sj * s1), sn_ = fma(sj, c1, cj * s1);
+            cj = cn_; sj = sn_;
+        }
     }
     if (J < 0) {
         // not converged within the stored harmonics
@@ -179,36 +220,40 @@ struct ThetaOut {
     double sn, cn, dn, Z;
 };
 
-template <class W, int NP>
+// KINDS packs the kind (0, 1 or 2, see ThetaPiSlot) of Pi block i into bits [4i, 4i+3]; a nibble of 0xF means "read it from
+// the block" (generic).  The setup flags the rays whose pattern is one of the static ones (the polar block is always kind
+// 2; radial (1,0,0) = rays that turn outside the horizon, (1,1,1) = plunging rays), so the harmonic loop of almost every
+// warp has no selects.  The loop is fully unrolled (J <= kThJM, early exit): slot offsets become immediates and the
+// rotated harmonics stay in place.
+constexpr int kKindsGeneric = 0xFFF;
+template <class W, int NP, int KINDS>
 KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
     const int J = (int)w(base + TB_J);
     const double v = w(base + TB_W) * u;
     double sv, cv;
-#if defined(__CUDA_ARCH__)
-    sincos(v, &sv, &cv);
-#else
-    sv = sin(v);
-    cv = cos(v);
-#endif
+    fsincos(v, &sv, &cv);
     const double c1 = fma(cv, cv, -sv * sv), s1 = 2.0 * sv * cv;   // cos 2v, sin 2v
     // even harmonics (c_j, s_j) = (cos 2jv, sin 2jv) and odd ones (co_j, so_j) = (cos, sin)((2j+1)v) by rotation
     double ce = c1, se = s1;          // j = 1
     double co = cv, so = sv;          // j = 0
-    double th1 = 0.0, th2 = 0.0, th3 = 1.0, th4 = 1.0, dth4 = 0.0, sg = 1.0, jj = 1.0;
+    double th1 = 0.0, th2 = 0.0, th3 = 1.0, th4 = 1.0, dth4 = 0.0;
     double X[NP > 0 ? NP : 1], Y[NP > 0 ? NP : 1];
     int kind[NP > 0 ? NP : 1];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        kind[i] = (int)w(base + TB_SIZE + i * TP_SIZE + TP_KIND);
+        const int ks = (KINDS >> (4 * i)) & 0xF;
+        kind[i] = (ks == 0xF) ? (int)w(base + TB_SIZE + i * TP_SIZE + TP_KIND) : ks;
         X[i] = (kind[i] == 1) ? 0.0 : 1.0;
         Y[i] = 0.0;
     }
-#pragma unroll 1
-    for (int j = 0; j < J; ++j) {
+#pragma unroll
+    for (int j = 0; j < kThJM; ++j) {
+        if (j >= J) break;
         const double qe = w(base + TB_QE + j), qo = w(base + TB_QO + j);   // 2(-1)^(j+1) q^((j+1)^2), 2(-1)^j q^((j+1/2)^2)
+        const double sg = (j & 1) ? -1.0 : 1.0;
         th4 = fma(qe, ce, th4);
         th3 = fma(-sg * qe, ce, th3);            // 2 q^((j+1)^2) cos
-        dth4 = fma(-2.0 * jj * qe, se, dth4);
+        dth4 = fma(-2.0 * (double)(j + 1) * qe, se, dth4);
         th1 = fma(qo, so, th1);
         th2 = fma(sg * qo, co, th2);
 #pragma unroll
@@ -220,11 +265,9 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
             Y[i] = fma(w(pb + TP_S + j), hs, Y[i]);
         }
         // next harmonics: multiply by e^(2iv)
-        double cen = fma(ce, c1, -se * s1), sen = fma(se, c1, ce * s1);
-        double con = fma(co, c1, -so * s1), son = fma(so, c1, co * s1);
+        const double cen = fma(ce, c1, -se * s1), sen = fma(se, c1, ce * s1);
+        const double con = fma(co, c1, -so * s1), son = fma(so, c1, co * s1);
         ce = cen; se = sen; co = con; so = son;
-        sg = -sg;
-        jj += 1.0;
     }
     ThetaOut o;
     const double i4 = frcp(th4);
@@ -234,8 +277,8 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
     o.Z = w(base + TB_W) * dth4 * i4;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        if (kind[i] == 2) L[i] = atan2(Y[i], X[i]);
-        else L[i] = 0.5 * kg_log(fabs(fdiv(X[i] + Y[i], X[i] - Y[i])));
+        if (kind[i] == 2) L[i] = fatan2(Y[i], X[i]);
+        else L[i] = 0.5 * flog(fabs(fdiv(X[i] + Y[i], X[i] - Y[i])));
     }
     return o;
 }

@@ -132,11 +132,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) ray_setup_kernel(Observer o, si
                                                                   double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    double w[NW];
     int fl;
-    ray_setup<PHI_T>(o, alpha[i], beta[i], mode, w, &fl);
-#pragma unroll
-    for (int s = 0; s < NW; ++s) w_out[(size_t)s * npix + i] = w[s];
+    ray_setup<PHI_T>(o, alpha[i], beta[i], mode, WsPtr{w_out + i, npix}, &fl);   // constants go straight to the [slot][ray] workspace
     flags_out[i] = fl;
 }
 

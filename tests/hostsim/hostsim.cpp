@@ -11,6 +11,19 @@ using namespace kg;
 extern "C" {
 
 int hostsim_slots() { return NW; }
+// element-wise access to the hot-loop elementary functions of kg_math.cuh (which: 0 log, 1 sin, 2 cos, 3 atan2(x, y), 4 acos)
+void hostsim_math(int which, size_t n, const double* x, const double* y, double* out) {
+    for (size_t i = 0; i < n; ++i) {
+        double s, c;
+        switch (which) {
+            case 0: out[i] = flog(x[i]); break;
+            case 1: fsincos(x[i], &s, &c); out[i] = s; break;
+            case 2: fsincos(x[i], &s, &c); out[i] = c; break;
+            case 3: out[i] = fatan2(x[i], y[i]); break;
+            default: out[i] = facos(x[i]); break;
+        }
+    }
+}
 int hostsim_slot(int which) { const int v[] = {T_TH, R_TH, R_K, T_M, S_TAUTOT, TB_SIZE, TP_SIZE, R_N0}; return v[which]; }
 
 // tracks for npix rays, ntau samples each (numpy.linspace(0, maxtaufrac*tau_tot, ntau)); outputs [ntau][npix] row-major.
