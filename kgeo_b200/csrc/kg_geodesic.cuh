@@ -84,6 +84,8 @@ enum Slot {
     T_I2K, R_I2K,               // 1/(2 K(m)), 1/(2 K(k)) (0 when K is infinite)
     T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
     R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
+    // per-ray reciprocals / prefactors of the case-3 and case-4 algebra (see radial_eval): no per-sample division by a constant
+    R_C0, R_C1, R_C2, R_C3, R_C4, R_C5, R_C6, R_C7, R_C8, R_C9, R_C10, R_C11, R_C12,
     // theta-function path (kg_theta.cuh): polar block = base + 1 Pi, radial block = base + 3 Pi
     T_TH_G, T_TH_IM, T_TH_SLOPE, T_TH_COEF,       // 1 + (E/K - 1)/m, 1/m, G_phi slope and coefficient
     T_TH, T_TH_END = T_TH + TB_SIZE + TP_SIZE - 1,
@@ -609,6 +611,19 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
                 w[R_PO0 + i] = S1_of(al[i], p2, dno, Fo, Pio[i]);
             }
             w[R_EO] = S2_of(g0, k4, sa, ca, dno, Fo, Eo, w[R_PO0]);
+            // per-ray factors of the per-sample algebra (radial_eval, case 4)
+            for (int i = 0; i < 3; ++i) {
+                double p2 = w[R_Q5 + i];
+                w[R_C0 + i] = 1.0 / (1.0 + al[i] * al[i]);
+                w[R_C3 + i] = 0.5 * log(fabs((1.0 - p2) / (1.0 + p2)));
+            }
+            double a2g = a2 / g0, opg = 1.0 + g0 * g0;
+            w[R_C6] = a2g;
+            w[R_C7] = (pref * opg) / (g0 * g0 + g0 * x4rp);
+            w[R_C8] = (pref * opg) / (g0 * g0 + g0 * x4rm);
+            w[R_C9] = g0 / (a2 - a2 * g0 * x4rp);
+            w[R_C10] = g0 / (a2 - a2 * g0 * x4rm);
+            w[R_C11] = 1.0 / (1.0 - k4 + g0 * g0);
         }
         w[R_Q0] = a2; w[R_Q1] = b1; w[R_Q2] = g0; w[R_Q3] = gp; w[R_Q4] = gm;
         w[R_Q8] = pref; w[R_Q9] = x4rp; w[R_Q10] = x4rm;
@@ -658,6 +673,17 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
                 w[R_PO0 + i] = R1_of(al[i], p1[i], nn[i], sa, dno, Pio[i]);
             }
             w[R_EO] = R2_of(al[0], k3, nn[0], sa, ca, dno, Fo, Eo, w[R_PO0]);
+            // per-ray factors of the per-sample algebra (radial_eval, case 3)
+            for (int i = 0; i < 3; ++i) w[R_C0 + i] = 1.0 / (1.0 - al[i] * al[i]);
+            double fac = 2.0 * rr21 * sqAB;
+            w[R_C3] = fac / (BB * BB - AA * AA);
+            w[R_C4] = fac / (BB * rrp2 - AA * rrp1);
+            w[R_C5] = fac / (BB * rrm2 - AA * rrm1);
+            w[R_C6] = (BB * rr2 + AA * rr1) / (BB + AA);
+            w[R_C7] = -1.0 / (BB * rrp2 + AA * rrp1);
+            w[R_C8] = -1.0 / (BB * rrm2 + AA * rrm1);
+            w[R_C9] = 1.0 / (k3 + (1.0 - k3) * al[0] * al[0]);
+            w[R_C10] = 1.0 / (al[0] * al[0] - 1.0);
         }
         w[R_Q0] = rr1; w[R_Q1] = rr2; w[R_Q2] = AA; w[R_Q3] = BB; w[R_Q10] = sqAB;
         // tau_tot (utils :445-482): horizon amplitude acos(x3rp)
@@ -869,11 +895,12 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         double q1 = w(R_Q0), q2 = w(R_Q1), q3 = w(R_Q2), q4 = w(R_Q3), root = w(R_Q4);
         double rr31 = q3 - q1, rr41 = q4 - q1, rr43 = q4 - q3;
         double sn2 = sn * sn;
-        double den = rr31 - rr41 * sn2;
-        double rs = (q4 * rr31 - q3 * rr41 * sn2) / den;                      // :592-594
+        // explicit FMAs: r(tau) must not depend on how nvcc contracts the expression in the full / partial kernels
+        double den = fma(-rr41, sn2, rr31);
+        double iden = frcp(den);
+        double rs = fma(-(q3 * rr41), sn2, q4 * rr31) * iden;                 // :592-594
         *r_s = rs;
         if (full) {
-            double iden = frcp(den);
             double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) * (iden * iden);   // :600-603
             double H = fdiv(drs, rs - q3) - w(R_Q5);
             double Pi_1 = w(R_Q6) * (Pi[0] - w(R_PO0));
@@ -886,46 +913,62 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         }
     } else if (flags & F_CASE3) {
         double rr1 = w(R_Q0), rr2 = w(R_Q1), AA = w(R_Q2), BB = w(R_Q3), sqAB = w(R_Q10);
-        *r_s = ((BB * rr2 - AA * rr1) + (BB * rr2 + AA * rr1) * cn) / ((BB - AA) + (BB + AA) * cn);   // :516-519
+        const double b2 = BB * rr2, a1_ = AA * rr1;
+        *r_s = fdiv(fma(b2 + a1_, cn, b2 - a1_), fma(BB + AA, cn, BB - AA));   // :516-519
         if (full) {
-            double rr21 = rr2 - rr1, rrp1 = rp - rr1, rrp2 = rp - rr2, rrm1 = rm - rr1, rrm2 = rm - rr2;
+            // R1 = (Pi - al f1)/(1 - al^2), f1 = (p1/2) ln|(p1 dn + sn)/(p1 dn - sn)| (B62; :666-674); reciprocals per ray
             double R1a[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) R1a[i] = R1_of<true>(w(R_Q4 + i), w(R_Q7 + i), w(R_N0 + i), sn, dn, Pi[i]);
-            double R2a = R2_of<true>(w(R_Q4), k, w(R_N0), sn, cn, dn, X, E, R1a[0]);
+            for (int i = 0; i < 3; ++i) {
+                const double al = w(R_Q4 + i), p1 = w(R_Q7 + i);
+                const double f1 = p1 * atanh_ratio(p1 * dn, sn);
+                R1a[i] = (Pi[i] - al * f1) * w(R_C0 + i);
+            }
+            // R2 (B65; :675-683)
+            const double al0 = w(R_Q4), al2 = al0 * al0, iden = w(R_C9);
+            double R2a = (X - (al2 * iden) * (E - fdiv(al0 * sn * dn, 1.0 + al0 * cn))) * w(R_C10);
+            R2a += (2.0 * k - w(R_N0)) * R1a[0] * iden;
             double dm = (flags & F_LOWSPIN) ? 0.0 : (R1a[2] - w(R_PO2));      // :529-534
-            double fac = 2.0 * rr21 * sqAB;
-            double f0 = fdiv(fac, BB * BB - AA * AA);
+            double f0 = w(R_C3);
             double Pi_1 = f0 * (R1a[0] - w(R_PO0));
             double Pi_2 = sq(f0) * (R2a - w(R_EO));
-            double Pi_p = fdiv(fac, BB * rrp2 - AA * rrp1) * (R1a[1] - w(R_PO1));
-            double Pi_m = fdiv(fac, BB * rrm2 - AA * rrm1) * dm;
-            double pr = fdiv(BB * rr2 + AA * rr1, BB + AA);
+            double Pi_p = w(R_C4) * (R1a[1] - w(R_PO1));
+            double Pi_m = w(R_C5) * dm;
+            double pr = w(R_C6), bpa = BB + AA;
             I1 = pr * (-tau) + Pi_1;
             I2 = pr * pr * (-tau) + 2.0 * pr * Pi_1 + sqAB * Pi_2;
-            Ip = -fdiv((BB + AA) * (-tau) + Pi_p, BB * rrp2 + AA * rrp1);
-            Im = -fdiv((BB + AA) * (-tau) + Pi_m, BB * rrm2 + AA * rrm1);
+            Ip = (bpa * (-tau) + Pi_p) * w(R_C7);
+            Im = (bpa * (-tau) + Pi_m) * w(R_C8);
         }
     } else {  // case 4
         double a2 = w(R_Q0), b1 = w(R_Q1), g0 = w(R_Q2);
-        *r_s = -a2 * (g0 * cn - sn) / (cn + g0 * sn) - b1;                   // :441 with sc = sn/cn
+        *r_s = fma(-a2, fdiv(fma(g0, cn, -sn), fma(g0, sn, cn)), -b1);        // :441 with sc = sn/cn
         if (full) {
-            double pref = w(R_Q8), x4rp = w(R_Q9), x4rm = w(R_Q10);
+            // S1 = (F + al^2 Pi - al f2)/(1 + al^2), f2 = (p2/2) ln|(1-p2)(1+p2 dn)/((1+p2)(1-p2 dn))| (B92; :638-650): the
+            // dn-independent half of the logarithm is a per-ray constant
             double S1a[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) S1a[i] = S1_of<true>(w(R_Q2 + i), w(R_Q5 + i), dn, X, Pi[i]);
-            double S2a = S2_of<true>(g0, k, sn, cn, dn, X, E, S1a[0]);
-            double a2g = fdiv(a2, g0);
-            double aa0 = a2g * (1.0 + g0 * g0);
+            for (int i = 0; i < 3; ++i) {
+                const double al = w(R_Q2 + i), p2 = w(R_Q5 + i);
+                const double f2 = p2 * (atanh_ratio(1.0, p2 * dn) + w(R_C3 + i));
+                S1a[i] = (X + al * al * Pi[i] - al * f2) * w(R_C0 + i);
+            }
+            // S2 (B93; :651-663)
+            const double al2 = g0 * g0, i1 = w(R_C0), i2 = w(R_C11);
+            double S2a = (1.0 - k) * X + al2 * E + fdiv(al2 * dn * (g0 * cn - sn), cn + g0 * sn) - al2 * g0;
+            S2a = -S2a * (i1 * i2) + S1a[0] * (i1 + (1.0 - k) * i2);
+            double pref = w(R_Q8);
+            double a2g = w(R_C6);
+            double aa0 = a2g * (1.0 + al2);
             double Pi_1 = pref * aa0 * (S1a[0] - w(R_PO0));
             double Pi_2 = pref * (aa0 * aa0) * (S2a - w(R_EO));
-            double Pi_p = fdiv(pref * (1.0 + g0 * g0), g0 * g0 + g0 * x4rp) * (S1a[1] - w(R_PO1));
-            double Pi_m = fdiv(pref * (1.0 + g0 * g0), g0 * g0 + g0 * x4rm) * (S1a[2] - w(R_PO2));
+            double Pi_p = w(R_C7) * (S1a[1] - w(R_PO1));
+            double Pi_m = w(R_C8) * (S1a[2] - w(R_PO2));
             double aa1 = a2g - b1;
             I1 = aa1 * (-tau) - Pi_1;
             I2 = (aa1 * aa1) * (-tau) - 2.0 * aa1 * Pi_1 + Pi_2;
-            Ip = fdiv(g0, a2 - a2 * g0 * x4rp) * (-tau - Pi_p);
-            Im = fdiv(g0, a2 - a2 * g0 * x4rm) * (-tau - Pi_m);
+            Ip = w(R_C9) * (-tau - Pi_p);
+            Im = w(R_C10) * (-tau - Pi_m);
         }
     }
     if (!full) {

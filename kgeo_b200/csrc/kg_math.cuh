@@ -101,6 +101,48 @@ KG_HD double flog(double x) {
     return fma(de, kLn2Hi, fma(de, kLn2Lo, lm));
 }
 
+// (1/2) ln|a / b|, a and b finite and non-zero: the binary exponents of a and b are split off separately, so the only
+// division is the s = (ma - mb)/(ma + mb) of the atanh series (ma - mb is exact)
+KG_HD double half_log_ratio(double a, double b) {
+    const int ha = kg_hiint(a) & 0x7fffffff, hb = kg_hiint(b) & 0x7fffffff;
+    if ((unsigned)(ha - 0x00100000) >= 0x7fe00000u || (unsigned)(hb - 0x00100000) >= 0x7fe00000u)
+        return 0.5 * kg_log_cold(fabs(a / b));                                  // zero, subnormal, inf, NaN
+    int e = (ha >> 20) - (hb >> 20);
+    double ma = kg_sethi(a, (ha & 0x000fffff) | 0x3ff00000), mb = kg_sethi(b, (hb & 0x000fffff) | 0x3ff00000);   // in [1, 2)
+    if (ma > 1.4142135623730951 * mb) {            // ratio in (1/2, 2) -> [sqrt(1/2), sqrt(2)]
+        mb += mb;
+        e += 1;
+    } else if (mb > 1.4142135623730951 * ma) {
+        ma += ma;
+        e -= 1;
+    }
+    const double s = fdiv(ma - mb, ma + mb);
+    const double z = s * s;
+    double p = KM(KM_LOG + 6);
+#pragma unroll
+    for (int i = 5; i >= 0; --i) p = fma(p, z, KM(KM_LOG + i));
+    const double hl = fma(s * z, 0.5 * p, s);                                   // atanh(s) = (1/2) ln(ma/mb)
+    const double de = 0.5 * (double)e;
+    return fma(de, kLn2Hi, fma(de, kLn2Lo, hl));
+}
+
+// (1/2) ln|(X + Y)/(X - Y)| = atanh(Y/X) = atanh(X/Y): the Cauchy-principal-value logarithms of the third-kind integrals.
+// One division on either path: the atanh series directly when the ratio is small, otherwise half_log_ratio.
+KG_HD double atanh_ratio(double X, double Y) {
+    const double ax = fabs(X), ay = fabs(Y);
+    const bool swap = ay > ax;
+    const double num = swap ? X : Y, den = swap ? Y : X;
+    if (fabs(num) <= 0.17 * fabs(den)) {
+        const double t = fdiv(num, den);
+        const double z = t * t;
+        double p = KM(KM_LOG + 6);
+#pragma unroll
+        for (int i = 5; i >= 0; --i) p = fma(p, z, KM(KM_LOG + i));
+        return fma(t * z, 0.5 * p, t);
+    }
+    return half_log_ratio(X + Y, X - Y);
+}
+
 // sin and cos of v: Cody-Waite reduction by pi/2 (two FMAs: exact products), |v| < 1e6
 KG_HD void fsincos(double v, double* sv, double* cv) {
     if (!(fabs(v) < 1.0e6)) {

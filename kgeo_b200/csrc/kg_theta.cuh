@@ -31,6 +31,18 @@ KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D
     *D = cube(s) * rd * (1.0 / 3.0);
 }
 
+// Rays outside these bounds keep the Carlson path (decided once per ray in the setup):
+//   nome: the series need J = 7 harmonics at q = 0.4 (kThJM = 8 are stored); beyond that the ray is within ~1e-3 of the
+//   critical curve, where the reference itself loses digits (looser gate next to the critical curve);
+//   prefactor P = sn a/(cn a dn a) of Pi = A u + P L: A = 1 + P Z(a) is formed with an absolute error ~ P eps.
+#ifndef KG_THETA_QMAX
+#define KG_THETA_QMAX 0.4
+#endif
+#ifndef KG_THETA_PMAX
+#define KG_THETA_PMAX 3000.0
+#endif
+constexpr double kThetaQMax = KG_THETA_QMAX, kThetaPMax = KG_THETA_PMAX;
+
 struct ThetaRay {
     double m, K, Kp, q, eokm1, eokm1p;   // eokm1p = E(m')/K' - 1
     int ok;
@@ -50,7 +62,7 @@ KG_HD ThetaRay theta_ray(double m) {
     r.q = exp(-kPi * r.Kp / r.K);
     r.eokm1 = -m * ellip_RDc(m) / (3.0 * r.K);
     r.eokm1p = -mp * ellip_RDc(mp) / (3.0 * r.Kp);
-    if (!(r.q <= 0.3)) r.ok = 0;
+    if (!(r.q <= kThetaQMax)) r.ok = 0;
     return r;
 }
 
@@ -151,7 +163,7 @@ KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, WP 
         sh = kHalfPi * F / r.K;
         kind = 2;
     }
-    if (!(fabs(P) <= 300.0) || !(Zs == Zs)) return -1;
+    if (!(fabs(P) <= kThetaPMax) || !(Zs == Zs)) return -1;
     out[TP_KIND] = (double)kind;
     out[TP_P] = P;
     out[TP_A] = fma(P, Zs, 1.0);
@@ -233,9 +245,11 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
     double sv, cv;
     fsincos(v, &sv, &cv);
     const double c1 = fma(cv, cv, -sv * sv), s1 = 2.0 * sv * cv;   // cos 2v, sin 2v
-    // even harmonics (c_j, s_j) = (cos 2jv, sin 2jv) and odd ones (co_j, so_j) = (cos, sin)((2j+1)v) by rotation
-    double ce = c1, se = s1;          // j = 1
-    double co = cv, so = sv;          // j = 0
+    // even harmonics (ce, se) = (cos, sin)(2(j+1)v) and odd ones (co, so) = (cos, sin)((2j+1)v) by the three-term recurrence
+    // f_(j+1) = 2 cos(2v) f_j - f_(j-1): one FMA per sequence and harmonic (error ~ j^2 eps on terms that are < q^(j^2 - j))
+    const double tc = c1 + c1;
+    double ce = c1, se = s1, cep = 1.0, sep = 0.0;       // j = 0: 2v; previous: 0
+    double co = cv, so = sv, cop = cv, sop = -sv;        // j = 0: v;  previous: -v
     double th1 = 0.0, th2 = 0.0, th3 = 1.0, th4 = 1.0, dth4 = 0.0;
     double X[NP > 0 ? NP : 1], Y[NP > 0 ? NP : 1];
     int kind[NP > 0 ? NP : 1];
@@ -264,9 +278,10 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
             X[i] = fma(w(pb + TP_C + j), hc, X[i]);
             Y[i] = fma(w(pb + TP_S + j), hs, Y[i]);
         }
-        // next harmonics: multiply by e^(2iv)
-        const double cen = fma(ce, c1, -se * s1), sen = fma(se, c1, ce * s1);
-        const double con = fma(co, c1, -so * s1), son = fma(so, c1, co * s1);
+        // next harmonics
+        const double cen = fma(tc, ce, -cep), sen = fma(tc, se, -sep);
+        const double con = fma(tc, co, -cop), son = fma(tc, so, -sop);
+        cep = ce; sep = se; cop = co; sop = so;
         ce = cen; se = sen; co = con; so = son;
     }
     ThetaOut o;
@@ -278,7 +293,7 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         if (kind[i] == 2) L[i] = fatan2(Y[i], X[i]);
-        else L[i] = 0.5 * flog(fabs(fdiv(X[i] + Y[i], X[i] - Y[i])));
+        else L[i] = atanh_ratio(X[i], Y[i]);
     }
     return o;
 }

@@ -202,18 +202,31 @@ __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, s
 // 4 warps x 4 CTAs 93.5 ms; 8 x 2 87.3 ms) -- warps of one tile take the same root-class branches, so they share
 // instruction-cache lines (the "no instruction" stall per issue drops from 3.1 to 0.4), and 96 registers per thread
 // allow 20 resident warps.
-#ifndef KG_TRK_WARPS
-#define KG_TRK_WARPS 20
+// Mapping of the track kernel: ONE RAY PER WARP, lanes = 32 consecutive Mino-time samples.
+//  * every branch on the root class, the polar class, the theta-vs-Carlson choice and the number of harmonics is taken by
+//    the whole warp (they are properties of the ray): no intra-warp divergence, and a ray next to the critical curve costs
+//    only its own warp the Carlson path;
+//  * the ~90 per-ray constants a point reads are warp-uniform shared-memory broadcasts;
+//  * the outputs of a (32 samples x TRK_RAYS rays) block are transposed through shared memory (double-buffered, one barrier
+//    per block), so every store instruction still writes full 32-byte sectors: TRK_RAYS consecutive pixels of one sample row
+//    of the reference's (ngeo, npix) arrays.
+#ifndef KG_TRK_RAYS
+#define KG_TRK_RAYS 16
 #endif
 #ifndef KG_TRK_MINBLOCKS
 #define KG_TRK_MINBLOCKS 1
 #endif
-constexpr int TRK_WARPS = KG_TRK_WARPS;
-constexpr int TRK_THREADS = 32 * TRK_WARPS;
+constexpr int TRK_RAYS = KG_TRK_RAYS;               // rays (= warps) per CTA; multiple of 4 (32-byte sectors of doubles)
+constexpr int TRK_THREADS = 32 * TRK_RAYS;
+constexpr int TRK_TB_LD = TRK_RAYS + 1;             // padded row of the transpose buffer (conflict-free both ways)
+constexpr int TRK_NOUT = 6;                         // r, theta, t, phi, sigma, tau
+constexpr int TRK_TB_SIZE = TRK_NOUT * 32 * TRK_TB_LD;
+constexpr size_t TRK_SMEM = ((size_t)NW * TRK_RAYS + 2 * (size_t)TRK_TB_SIZE) * sizeof(double);
+static_assert(TRK_RAYS % 4 == 0 && TRK_RAYS <= 32, "TRK_RAYS must be a multiple of 4, at most 32");
 
 struct SmemW {
-    const double* p;   // &sw[0][lane]
-    __device__ __forceinline__ double operator()(int i) const { return p[i * 32]; }
+    const double* p;   // &sw[0][warp]: slot i of this warp's ray (a broadcast load)
+    __device__ __forceinline__ double operator()(int i) const { return p[i * TRK_RAYS]; }
 };
 
 struct TrackOut {
@@ -230,34 +243,61 @@ __global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS) track_kernel(Ob
                                                             const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
                                                             const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
                                                             size_t ld, int k_begin, int k_end, int chunk) {
-    extern __shared__ double sw_dyn[];                 // [NW][32] ray constants of this tile (61 KB: dynamic shared memory)
-    double (*sw)[32] = reinterpret_cast<double (*)[32]>(sw_dyn);
+    extern __shared__ double smem_dyn[];
+    double* sw = smem_dyn;                              // [NW][TRK_RAYS] ray constants of this tile
+    double* tb = smem_dyn + (size_t)NW * TRK_RAYS;      // [2][TRK_NOUT][32][TRK_TB_LD] transpose buffers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t pix = (size_t)blockIdx.x * 32 + lane;
+    const size_t pix0 = (size_t)blockIdx.x * TRK_RAYS;
+    const size_t pix = pix0 + warp;
     const bool live = pix < npix;
-    for (int s = warp; s < NW; s += TRK_WARPS) sw[s][lane] = live ? w_in[(size_t)s * npix + pix] : 0.0;
+    if (lane < TRK_RAYS) {
+        const bool ok = pix0 + lane < npix;
+        for (int s = warp; s < NW; s += TRK_RAYS) sw[s * TRK_RAYS + lane] = ok ? w_in[(size_t)s * npix + pix0 + lane] : 0.0;
+    }
     __syncthreads();
-    if (!live) return;
-    const int fl = flags_in[pix];
-    SmemW W{&sw[0][lane]};
-    // this launch covers samples [k_begin, k_end) of the ntau-sample track; output row = k - k_begin
+    const int fl = live ? flags_in[pix] : 0;
+    SmemW W{sw + warp};
+    // this CTA covers samples [k0, k1) of the ntau-sample track; output row = k - k_begin
     const int k0 = k_begin + blockIdx.y * chunk;
     const int k1 = min(k_end, k0 + chunk);
     // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
     const double stop = maxtaufrac * W(S_TAUTOT);
     const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
-    for (int k = k0 + warp; k < k1; k += TRK_WARPS) {
-        double tau;
-        if (tau_in) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
-        else tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
-        Point p = point_eval(W, o, fl, tau, FULL);
-        const size_t q = (size_t)(k - k_begin) * ld + pix;
-        if (out.r) __stcs(out.r + q, p.r);
-        if (out.th) __stcs(out.th + q, p.th);
-        if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
-        if (out.ph) __stcs(out.ph + q, FULL ? p.ph : 0.0);
-        if (out.sig) __stcs(out.sig + q, FULL ? p.sig : 0.0);
-        if (out.tau) __stcs(out.tau + q, tau);
+    // store role of this thread: sample row srow, ray column scol of the block
+    const int srow = threadIdx.x / TRK_RAYS, scol = threadIdx.x % TRK_RAYS;
+    const bool scol_ok = pix0 + scol < npix;
+    int buf = 0;
+    for (int kb = k0; kb < k1; kb += 32) {
+        const int k = kb + lane;
+        Point p;
+        p.t = p.r = p.th = p.ph = p.sig = 0.0;
+        double tau = 0.0;
+        if (live && k < k1) {
+            if (tau_in) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
+            else tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
+            p = point_eval(W, o, fl, tau, FULL);
+        }
+        double* b = tb + buf * TRK_TB_SIZE + lane * TRK_TB_LD + warp;
+        b[0 * 32 * TRK_TB_LD] = p.r;
+        b[1 * 32 * TRK_TB_LD] = p.th;
+        if (FULL) {
+            b[2 * 32 * TRK_TB_LD] = p.t;
+            b[3 * 32 * TRK_TB_LD] = p.ph;
+            b[4 * 32 * TRK_TB_LD] = p.sig;
+        }
+        b[5 * 32 * TRK_TB_LD] = tau;
+        __syncthreads();
+        if (scol_ok && kb + srow < k1) {
+            const double* c = tb + buf * TRK_TB_SIZE + srow * TRK_TB_LD + scol;
+            const size_t q = (size_t)(kb + srow - k_begin) * ld + pix0 + scol;
+            if (out.r) __stcs(out.r + q, c[0 * 32 * TRK_TB_LD]);
+            if (out.th) __stcs(out.th + q, c[1 * 32 * TRK_TB_LD]);
+            if (out.t) __stcs(out.t + q, FULL ? c[2 * 32 * TRK_TB_LD] : 0.0);
+            if (out.ph) __stcs(out.ph + q, FULL ? c[3 * 32 * TRK_TB_LD] : 0.0);
+            if (out.sig) __stcs(out.sig + q, FULL ? c[4 * 32 * TRK_TB_LD] : 0.0);
+            if (out.tau) __stcs(out.tau + q, c[5 * 32 * TRK_TB_LD]);
+        }
+        buf ^= 1;   // the next block fills the other buffer; this one is rewritten only after the next barrier
     }
 }
 
@@ -519,18 +559,17 @@ static int launch_tracks(const Observer& o, size_t npix, const double* w, const 
                          int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
                          cudaStream_t stream) {
     // samples [k_begin, k_end) of an ntau-sample track; output (and tau) rows are indexed by (k - k_begin)
-    const unsigned tiles = (unsigned)((npix + 31) / 32);
+    const unsigned tiles = (unsigned)((npix + TRK_RAYS - 1) / TRK_RAYS);
     const int ns = k_end - k_begin;
-    // enough CTAs to fill 148 SMs several times over even for a single image row
+    // enough CTAs to fill 148 SMs several times over even for a single image row; a CTA walks whole 32-sample blocks
     const int want = 148 * 8;
     int ychunks = (int)((want + tiles - 1) / tiles);
     int per = (ns + ychunks - 1) / ychunks;
-    per = ((per + TRK_WARPS - 1) / TRK_WARPS) * TRK_WARPS;
-    if (per < TRK_WARPS) per = TRK_WARPS;
+    per = ((per + 31) / 32) * 32;
     ychunks = (ns + per - 1) / per;
     if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
     dim3 grid(tiles, (unsigned)ychunks);
-    const size_t smem = (size_t)NW * 32 * sizeof(double);
+    const size_t smem = TRK_SMEM;
     if (full) {
         CU(cudaFuncSetAttribute(track_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         track_kernel<true><<<grid, TRK_THREADS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
@@ -702,9 +741,9 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
         CU(cudaStreamSynchronize(sp.compute));
         return 0;
     }
-    // slab = as many samples as fit ~256 MiB per output array (at least TRK_WARPS samples)
+    // slab = as many samples as fit ~256 MiB per output array (whole 32-sample blocks)
     size_t slab = (size_t)(256u << 20) / (npix * sizeof(double));
-    if (slab < (size_t)TRK_WARPS) slab = TRK_WARPS;
+    slab = (slab < 32) ? 32 : (slab / 32) * 32;
     if (slab > ngeo) slab = ngeo;
     DevBuf d_out[2][6];
     for (int b = 0; b < 2; ++b)

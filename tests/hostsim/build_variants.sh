@@ -1,0 +1,13 @@
+#!/bin/sh
+# developer tool: build launch-configuration variants of libkgeo_b200.so into kgeo_b200/lib/variants/ (timed on the GPU by
+# variant_bench.py).  usage: build_variants.sh "16 1" "20 1" "12 2" ...   (rays = warps per CTA, min CTAs per SM)
+R=$(cd "$(dirname "$0")/../.." && pwd)
+mkdir -p "$R/kgeo_b200/lib/variants"
+rm -f "$R"/kgeo_b200/lib/variants/*.so
+for v in "$@"; do
+  set -- $v
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=true -diag-suppress 177 -shared -Xcompiler -fPIC \
+       -DKG_TRK_RAYS=$1 -DKG_TRK_MINBLOCKS=$2 -o "$R/kgeo_b200/lib/variants/lib_r$1b$2.so" "$R/kgeo_b200/csrc/kgeo_b200.cu" &
+done
+wait
+ls -la "$R/kgeo_b200/lib/variants"
