@@ -108,7 +108,9 @@ enum Flag {
     F_TH_THETA = 1 << 14,                 // polar motion may use the theta-function path
     F_R_THETA = 1 << 15,                  // radial motion may use the theta-function path
     F_R_K100 = 1 << 16,                   // ... and its three Pi blocks have kinds (1, 0, 0): rays that turn outside the horizon
-    F_R_K111 = 1 << 17                    // ... kinds (1, 1, 1): plunging rays (see theta_eval_motion)
+    F_R_K111 = 1 << 17,                   // ... kinds (1, 1, 1): plunging rays (see theta_eval_motion)
+    F_TH_PENDING = 1 << 18,               // theta blocks still to be built by theta_setup (two-kernel setup)
+    F_R_PENDING = 1 << 19
 };
 
 struct Roots {
@@ -436,7 +438,8 @@ KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const doub
 //   Pi(n; phi | k) = sqrt(1-m) [ (m/n') w + (1 - m/n') Pi(n'; am w | m) ],  n' = m + n (1 - m)   (m < n' < 1: circular case)
 //   (F - E)(phi | k) / k = sqrt(1-m) [ (1 + (E/K - 1)/m) w + Z(w)/m - sn w cn w / dn w ]
 template <class WP>
-KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double Km, double n, double D3, WP w, int* flags) {
+KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double n, double D3, WP w, int* flags) {
+    const double Km = ellip_K(m);
     const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
     bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, w + T_TH);
     const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
@@ -448,15 +451,26 @@ KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, dou
     if (ok && !o.lowspin && m > 1.0e-6 && w[T_TH + TB_SIZE + TP_KIND] == 2.0) *flags |= F_TH_THETA;
 }
 
+template <class WP>
+KG_HD void radial_theta_setup(double k, const double* n, WP w, int* flags) {
+    if (!theta_make_motion(3, k, n, nullptr, nullptr, w + R_TH)) return;
+    *flags |= F_R_THETA;
+    const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
+                 k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
+    if (k0 == 1.0 && k1 == 0.0 && k2 == 0.0) *flags |= F_R_K100;
+    if (k0 == 1.0 && k1 == 1.0 && k2 == 1.0) *flags |= F_R_K111;
+}
+
 // ---- ray setup -------------------------------------------------------------------------------------------------------
 // any_eta_pos / any_eta_nonpos reproduce the reference's whole-array guards `np.any(eta>0)` / `np.any(eta<=0)`
 // (kgeo/kerr_raytracing_ana.py:217,300): they are properties of the CALL, computed once by the host wrapper.
 enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 4, M_INPUT_LAM_ETA = 8, M_POLISH_ROOTS = 16, M_CARLSON_ONLY = 32 };
+// DEFER = true leaves the theta-function blocks to theta_setup (second kernel of the two-kernel setup).
 // PHI_T = false skips every constant that only the phi / t / sigma integrals need (image and lensing paths).
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
 // AGM descent inline instead.
-template <bool PHI_T, bool LADDER = true, class P = double*>
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     for (int i = 0; i < NW; ++i) w[i] = 0.0;
@@ -515,7 +529,10 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         }
         w[T_F0] = F0;
         w[T_KC] = Kk;
-        if (PHI_T && LADDER) polar_theta_setup(o, m, sq1m, Km, up, pref, w, &flags);
+        if (PHI_T && LADDER) {
+            if (DEFER) { w[T_TH_SLOPE] = up; w[T_TH_COEF] = pref; flags |= F_TH_PENDING; }
+            else polar_theta_setup(o, m, sq1m, up, pref, w, &flags);
+        }
     } else if (any_eta_nonpos && eta < 0.0) {
         flags |= F_TH_VORT;
         double h = (o.th_o <= kHalfPi) ? 1.0 : -1.0;
@@ -554,7 +571,10 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[T_C2] = 2.0 * prefC * (Ek - Kk);
         w[T_C3] = prefC;
         w[T_GT0] = s_o * (-h * prefC * E0);
-        if (PHI_T && LADDER) polar_theta_setup(o, m, sq1m, Km, nch, prefB, w, &flags);
+        if (PHI_T && LADDER) {
+            if (DEFER) { w[T_TH_SLOPE] = nch; w[T_TH_COEF] = prefB; flags |= F_TH_PENDING; }
+            else polar_theta_setup(o, m, sq1m, nch, prefB, w, &flags);
+        }
     }
 
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
@@ -741,15 +761,30 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         }
     }
     w[S_TAUTOT] = tau_tot;
-    if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0 && theta_make_motion(3, th_k, th_n, nullptr, nullptr, w + R_TH)) {
-        flags |= F_R_THETA;
-        const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
-                     k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
-        if (k0 == 1.0 && k1 == 0.0 && k2 == 0.0) flags |= F_R_K100;
-        if (k0 == 1.0 && k1 == 1.0 && k2 == 1.0) flags |= F_R_K111;
+    if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0) {
+        if (DEFER) flags |= F_R_PENDING;            // k and the characteristics are in w[R_K], w[R_N0..2]
+        else radial_theta_setup(th_k, th_n, w, &flags);
     }
-    if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA);
+    if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA | F_TH_PENDING | F_R_PENDING);
     *flags_out = flags;
+}
+
+// Second half of the two-kernel setup: builds the theta blocks ray_setup<.., DEFER = true> left pending.  Splitting the
+// setup keeps each kernel's code small enough for the instruction caches (every warp walks the setup code once, front to
+// back: with everything in one 16 k-instruction kernel the dominant stall was instruction fetch).
+template <class P>
+KG_HD void theta_setup(const Observer& o, P w, int* flags_io) {
+    int flags = *flags_io;
+    if (flags & F_TH_PENDING) {
+        flags &= ~F_TH_PENDING;
+        polar_theta_setup(o, w[T_M], w[T_SQ], w[T_TH_SLOPE], w[T_TH_COEF], w, &flags);
+    }
+    if (flags & F_R_PENDING) {
+        flags &= ~F_R_PENDING;
+        const double n[3] = {w[R_N0], w[R_N1], w[R_N2]};
+        radial_theta_setup(w[R_K], n, w, &flags);
+    }
+    *flags_io = flags;
 }
 
 // view of the workspace starting at a base slot (used for the ladders)

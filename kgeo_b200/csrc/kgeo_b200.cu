@@ -15,6 +15,7 @@
 //
 // FP64 vector pipe bound; no tensor cores (there is no contraction in this path).
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
@@ -133,8 +134,19 @@ __global__ void __launch_bounds__(SETUP_THREADS) ray_setup_kernel(Observer o, si
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     int fl;
-    ray_setup<PHI_T>(o, alpha[i], beta[i], mode, WsPtr{w_out + i, npix}, &fl);   // constants go straight to the [slot][ray] workspace
+    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, WsPtr{w_out + i, npix}, &fl);   // constants go straight to the [slot][ray] workspace
     flags_out[i] = fl;
+}
+
+// second setup kernel: theta-function blocks of the rays ray_setup_kernel left pending (see theta_setup)
+__global__ void __launch_bounds__(SETUP_THREADS) theta_setup_kernel(Observer o, size_t npix, double* __restrict__ w_io,
+                                                                    int32_t* __restrict__ flags_io) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    int fl = flags_io[i];
+    if (!(fl & (F_TH_PENDING | F_R_PENDING))) return;
+    theta_setup(o, WsPtr{w_io + i, npix}, &fl);
+    flags_io[i] = fl;
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) ray_summary_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
@@ -202,31 +214,34 @@ __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, s
 // 4 warps x 4 CTAs 93.5 ms; 8 x 2 87.3 ms) -- warps of one tile take the same root-class branches, so they share
 // instruction-cache lines (the "no instruction" stall per issue drops from 3.1 to 0.4), and 96 registers per thread
 // allow 20 resident warps.
-// Mapping of the track kernel: ONE RAY PER WARP, lanes = 32 consecutive Mino-time samples.
-//  * every branch on the root class, the polar class, the theta-vs-Carlson choice and the number of harmonics is taken by
-//    the whole warp (they are properties of the ray): no intra-warp divergence, and a ray next to the critical curve costs
-//    only its own warp the Carlson path;
-//  * the ~90 per-ray constants a point reads are warp-uniform shared-memory broadcasts;
-//  * the outputs of a (32 samples x TRK_RAYS rays) block are transposed through shared memory (double-buffered, one barrier
-//    per block), so every store instruction still writes full 32-byte sectors: TRK_RAYS consecutive pixels of one sample row
-//    of the reference's (ngeo, npix) arrays.
-#ifndef KG_TRK_RAYS
-#define KG_TRK_RAYS 16
+// Mapping of the track kernel: a CTA owns FOUR CONSECUTIVE RAYS and all its warps walk their Mino-time samples together:
+// lane = 4 * (sample within the warp's 8-sample block) + (ray within the group); warp w takes blocks w, w + TRK_WARPS, ...
+//  * the four lanes of one sample write four consecutive pixels of one row of the reference's (ngeo, npix) arrays = one full
+//    32-byte sector, so every store instruction writes 8 whole sectors and DRAM never sees a partial one;
+//  * branches on the root class, the polar class, the theta-vs-Carlson choice and the number of harmonics are properties of
+//    the ray: a warp diverges only where its 4 neighbouring pixels straddle a class boundary (the first mapping, 32
+//    neighbouring pixels per warp, paid the Carlson path for 32 rays whenever one of them needed it);
+//  * all warps of the CTA evaluate the SAME rays at different Mino times, i.e. they run the same code at the same time:
+//    the ~8 k-instruction kernel stays hot in the instruction caches (one-ray-group-per-warp variants lost 20 % to
+//    instruction fetch stalls, profiles/);
+//  * the ~90 per-ray constants a point reads come from a [slot][4] shared-memory block (4 distinct addresses per load:
+//    one wavefront), staged once per CTA.
+#ifndef KG_TRK_WARPS
+#define KG_TRK_WARPS 8
 #endif
 #ifndef KG_TRK_MINBLOCKS
-#define KG_TRK_MINBLOCKS 1
+#define KG_TRK_MINBLOCKS 2
 #endif
-constexpr int TRK_RAYS = KG_TRK_RAYS;               // rays (= warps) per CTA; multiple of 4 (32-byte sectors of doubles)
-constexpr int TRK_THREADS = 32 * TRK_RAYS;
-constexpr int TRK_TB_LD = TRK_RAYS + 1;             // padded row of the transpose buffer (conflict-free both ways)
-constexpr int TRK_NOUT = 6;                         // r, theta, t, phi, sigma, tau
-constexpr int TRK_TB_SIZE = TRK_NOUT * 32 * TRK_TB_LD;
-constexpr size_t TRK_SMEM = ((size_t)NW * TRK_RAYS + 2 * (size_t)TRK_TB_SIZE) * sizeof(double);
-static_assert(TRK_RAYS % 4 == 0 && TRK_RAYS <= 32, "TRK_RAYS must be a multiple of 4, at most 32");
+constexpr int TRK_WARPS = KG_TRK_WARPS;             // warps per CTA
+constexpr int TRK_THREADS = 32 * TRK_WARPS;
+constexpr int TRK_RPW = 4;                          // rays per warp = doubles per 32-byte sector
+constexpr int TRK_XS = 1;                           // extra per-ray slot staged behind the workspace: flags
+constexpr int TRK_WSLOTS = NW + TRK_XS;
+constexpr size_t TRK_SMEM = (size_t)TRK_WSLOTS * TRK_RPW * sizeof(double);
 
 struct SmemW {
-    const double* p;   // &sw[0][warp]: slot i of this warp's ray (a broadcast load)
-    __device__ __forceinline__ double operator()(int i) const { return p[i * TRK_RAYS]; }
+    const double* p;   // &sw[0][j]: slot i of ray j of this warp (a broadcast load)
+    __device__ __forceinline__ double operator()(int i) const { return p[i * TRK_RPW]; }
 };
 
 struct TrackOut {
@@ -238,66 +253,54 @@ struct TrackOut {
     double* tau;
 };
 
+#ifndef KG_TRK_GROUPS
+#define KG_TRK_GROUPS 8
+#endif
+constexpr int TRK_GROUPS = KG_TRK_GROUPS;           // 4-ray groups a CTA works through one after the other
+
 template <bool FULL>
 __global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS) track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
                                                             const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
                                                             const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
                                                             size_t ld, int k_begin, int k_end, int chunk) {
-    extern __shared__ double smem_dyn[];
-    double* sw = smem_dyn;                              // [NW][TRK_RAYS] ray constants of this tile
-    double* tb = smem_dyn + (size_t)NW * TRK_RAYS;      // [2][TRK_NOUT][32][TRK_TB_LD] transpose buffers
+    extern __shared__ double sw[];                                      // [TRK_WSLOTS][4] constants of the current ray group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t pix0 = (size_t)blockIdx.x * TRK_RAYS;
-    const size_t pix = pix0 + warp;
-    const bool live = pix < npix;
-    if (lane < TRK_RAYS) {
-        const bool ok = pix0 + lane < npix;
-        for (int s = warp; s < NW; s += TRK_RAYS) sw[s * TRK_RAYS + lane] = ok ? w_in[(size_t)s * npix + pix0 + lane] : 0.0;
-    }
-    __syncthreads();
-    const int fl = live ? flags_in[pix] : 0;
-    SmemW W{sw + warp};
+    const int j = lane & (TRK_RPW - 1), ks = lane / TRK_RPW;
     // this CTA covers samples [k0, k1) of the ntau-sample track; output row = k - k_begin
     const int k0 = k_begin + blockIdx.y * chunk;
     const int k1 = min(k_end, k0 + chunk);
-    // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
-    const double stop = maxtaufrac * W(S_TAUTOT);
-    const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
-    // store role of this thread: sample row srow, ray column scol of the block
-    const int srow = threadIdx.x / TRK_RAYS, scol = threadIdx.x % TRK_RAYS;
-    const bool scol_ok = pix0 + scol < npix;
-    int buf = 0;
-    for (int kb = k0; kb < k1; kb += 32) {
-        const int k = kb + lane;
-        Point p;
-        p.t = p.r = p.th = p.ph = p.sig = 0.0;
-        double tau = 0.0;
-        if (live && k < k1) {
+    for (int g = 0; g < TRK_GROUPS; ++g) {
+        const size_t pix0 = ((size_t)blockIdx.x * TRK_GROUPS + g) * TRK_RPW;
+        if (pix0 >= npix) break;                                        // uniform over the CTA
+        const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
+        if (g) __syncthreads();                                         // everyone is done with the previous group's constants
+        for (int i = threadIdx.x; i < NW * TRK_RPW; i += TRK_THREADS) {
+            const int s = i / TRK_RPW, jj = i % TRK_RPW;
+            sw[i] = (jj < nvalid) ? w_in[(size_t)s * npix + pix0 + jj] : 0.0;
+        }
+        if (threadIdx.x < TRK_RPW)
+            sw[NW * TRK_RPW + threadIdx.x] = (threadIdx.x < nvalid) ? (double)flags_in[pix0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        if (j >= nvalid) continue;
+        const size_t pix = pix0 + j;
+        SmemW W{sw + j};
+        const int fl = (int)W(NW);
+        // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
+        const double stop = maxtaufrac * W(S_TAUTOT);
+        const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+        for (int k = k0 + warp * (32 / TRK_RPW) + ks; k < k1; k += TRK_WARPS * (32 / TRK_RPW)) {
+            double tau;
             if (tau_in) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
             else tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
-            p = point_eval(W, o, fl, tau, FULL);
+            const Point p = point_eval(W, o, fl, tau, FULL);
+            const size_t q = (size_t)(k - k_begin) * ld + pix;
+            if (out.r) __stcs(out.r + q, p.r);
+            if (out.th) __stcs(out.th + q, p.th);
+            if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
+            if (out.ph) __stcs(out.ph + q, FULL ? p.ph : 0.0);
+            if (out.sig) __stcs(out.sig + q, FULL ? p.sig : 0.0);
+            if (out.tau) __stcs(out.tau + q, tau);
         }
-        double* b = tb + buf * TRK_TB_SIZE + lane * TRK_TB_LD + warp;
-        b[0 * 32 * TRK_TB_LD] = p.r;
-        b[1 * 32 * TRK_TB_LD] = p.th;
-        if (FULL) {
-            b[2 * 32 * TRK_TB_LD] = p.t;
-            b[3 * 32 * TRK_TB_LD] = p.ph;
-            b[4 * 32 * TRK_TB_LD] = p.sig;
-        }
-        b[5 * 32 * TRK_TB_LD] = tau;
-        __syncthreads();
-        if (scol_ok && kb + srow < k1) {
-            const double* c = tb + buf * TRK_TB_SIZE + srow * TRK_TB_LD + scol;
-            const size_t q = (size_t)(kb + srow - k_begin) * ld + pix0 + scol;
-            if (out.r) __stcs(out.r + q, c[0 * 32 * TRK_TB_LD]);
-            if (out.th) __stcs(out.th + q, c[1 * 32 * TRK_TB_LD]);
-            if (out.t) __stcs(out.t + q, FULL ? c[2 * 32 * TRK_TB_LD] : 0.0);
-            if (out.ph) __stcs(out.ph + q, FULL ? c[3 * 32 * TRK_TB_LD] : 0.0);
-            if (out.sig) __stcs(out.sig + q, FULL ? c[4 * 32 * TRK_TB_LD] : 0.0);
-            if (out.tau) __stcs(out.tau + q, c[5 * 32 * TRK_TB_LD]);
-        }
-        buf ^= 1;   // the next block fills the other buffer; this one is rewritten only after the next barrier
     }
 }
 
@@ -517,6 +520,20 @@ int kgeo_special_ellipj(size_t n, const double* u, const double* m, double* sn, 
     EW_ENTRY(ew_jacobi_kernel, n, u, m, sn, cn, dn, am)
 }
 
+// per-ray setup = two kernels on one stream: ray_setup_kernel (roots, classes, observer-side integrals; theta blocks left
+// pending) and theta_setup_kernel (the theta-function blocks); see theta_setup in kg_geodesic.cuh
+static int launch_setup(const Observer& o, size_t npix, const double* alpha, const double* beta, int mode, double* w,
+                         int32_t* flags, cudaStream_t stream) {
+    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, alpha, beta,
+                                                                                      mode, w, flags);
+    LAUNCHED("ray_setup_kernel");
+    if (!(mode & M_CARLSON_ONLY)) {
+        theta_setup_kernel<<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, w, flags);
+        LAUNCHED("theta_setup_kernel");
+    }
+    return 0;
+}
+
 int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* w,
                    int32_t* flags, void* stream) {
     int rc = check_observer(obs, true);
@@ -524,10 +541,7 @@ int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha, c
     if (npix && (!alpha || !beta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_setup: NULL pointer");
     if (npix == 0) return 0;
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
-    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, (cudaStream_t)stream>>>(o, npix, alpha, beta,
-                                                                                                    mode, w, flags);
-    LAUNCHED("ray_setup_kernel");
-    return 0;
+    return launch_setup(o, npix, alpha, beta, mode, w, flags, (cudaStream_t)stream);
 }
 
 int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* roots,
@@ -559,13 +573,16 @@ static int launch_tracks(const Observer& o, size_t npix, const double* w, const 
                          int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
                          cudaStream_t stream) {
     // samples [k_begin, k_end) of an ntau-sample track; output (and tau) rows are indexed by (k - k_begin)
-    const unsigned tiles = (unsigned)((npix + TRK_RAYS - 1) / TRK_RAYS);
+    const size_t tiles_ = (npix + TRK_RPW * TRK_GROUPS - 1) / (TRK_RPW * TRK_GROUPS);
+    if (tiles_ > 0x7fffffffu) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many rays in one launch");
+    const unsigned tiles = (unsigned)tiles_;
     const int ns = k_end - k_begin;
-    // enough CTAs to fill 148 SMs several times over even for a single image row; a CTA walks whole 32-sample blocks
+    // enough CTAs to fill 148 SMs several times over even for a single image row; a CTA walks whole 8-sample blocks
     const int want = 148 * 8;
     int ychunks = (int)((want + tiles - 1) / tiles);
     int per = (ns + ychunks - 1) / ychunks;
-    per = ((per + 31) / 32) * 32;
+    const int blk = TRK_WARPS * (32 / TRK_RPW);       // samples one CTA-wide pass covers
+    per = ((per + blk - 1) / blk) * blk;
     ychunks = (ns + per - 1) / per;
     if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
     dim3 grid(tiles, (unsigned)ychunks);
@@ -734,9 +751,8 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     CU(d_flags.alloc(npix * sizeof(int32_t)));
     CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
     CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
-    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, sp.compute>>>(
-        o, npix, d_alpha.as<double>(), d_beta.as<double>(), mode, d_w.as<double>(), d_flags.as<int32_t>());
-    LAUNCHED("ray_setup_kernel");
+    rc = launch_setup(o, npix, d_alpha.as<double>(), d_beta.as<double>(), mode, d_w.as<double>(), d_flags.as<int32_t>(), sp.compute);
+    if (rc) return rc;
     if (nout == 0) {
         CU(cudaStreamSynchronize(sp.compute));
         return 0;

@@ -7,7 +7,7 @@ rm -f "$R"/kgeo_b200/lib/variants/*.so
 for v in "$@"; do
   set -- $v
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=true -diag-suppress 177 -shared -Xcompiler -fPIC \
-       -DKG_TRK_RAYS=$1 -DKG_TRK_MINBLOCKS=$2 -o "$R/kgeo_b200/lib/variants/lib_r$1b$2.so" "$R/kgeo_b200/csrc/kgeo_b200.cu" &
+       -DKG_TRK_WARPS=$1 -DKG_TRK_MINBLOCKS=$2 -DKG_TRK_GROUPS=${3:-8} -o "$R/kgeo_b200/lib/variants/lib_w$1b$2g${3:-8}.so" "$R/kgeo_b200/csrc/kgeo_b200.cu" &
 done
 wait
 ls -la "$R/kgeo_b200/lib/variants"
