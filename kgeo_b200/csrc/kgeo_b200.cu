@@ -126,9 +126,12 @@ __global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const d
 // per-ray setup
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SETUP_THREADS = 64;
+#ifndef KG_SETUP_MINBLOCKS
+#define KG_SETUP_MINBLOCKS 8          // 64-thread CTAs per SM the two setup kernels are compiled for (register cap = 65536/(64*n))
+#endif
 
 template <bool PHI_T>
-__global__ void __launch_bounds__(SETUP_THREADS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
+__global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                   const double* __restrict__ beta, int mode,
                                                                   double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) ray_setup_kernel(Observer o, si
 }
 
 // second setup kernel: theta-function blocks of the rays ray_setup_kernel left pending (see theta_setup)
-__global__ void __launch_bounds__(SETUP_THREADS) theta_setup_kernel(Observer o, size_t npix, double* __restrict__ w_io,
+__global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) theta_setup_kernel(Observer o, size_t npix, double* __restrict__ w_io,
                                                                     int32_t* __restrict__ flags_io) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;

@@ -31,3 +31,12 @@ for v in (0.0, 1.0, -1.0, 0.5, -0.5): print("acos(%g) = %r vs %r" % (v, call(4, 
 print("special: log(0)=%r log(inf)=%r log(-1)=%r atan2(0,1)=%r atan2(0,-1)=%r atan2(1,0)=%r acos(1.0000001)=%r" % (
     call(0, np.array([0.0]))[0], call(0, np.array([np.inf]))[0], call(0, np.array([-1.0]))[0], call(3, np.array([0.0]), np.array([1.0]))[0],
     call(3, np.array([0.0]), np.array([-1.0]))[0], call(3, np.array([1.0]), np.array([0.0]))[0], call(4, np.array([1.0000001]))[0]))
+
+import mpmath as mp
+mp.mp.dps = 40
+for scale in (1.0, 1e-3, 1e-8):
+    X = rng.normal(size=200000); Y = rng.normal(size=200000) * scale
+    got = call(5, X, Y); ref = 0.5 * np.log(np.abs((X + Y) / (X - Y)))
+    # the float64 reference itself loses eps * X / Y for small ratios: compare against atanh in extended precision there
+    refx = np.array([float(mp.atanh(mp.mpf(float(y)) / mp.mpf(float(x)))) if abs(y) < abs(x) else float(mp.atanh(mp.mpf(float(x)) / mp.mpf(float(y)))) for x, y in zip(X[:20000], Y[:20000])])
+    print("atanh_ratio scale %g: max abs err vs mp %.2e, max rel %.2e" % (scale, np.abs(got[:20000] - refx).max(), (np.abs(got[:20000] - refx) / np.abs(refx)).max()))

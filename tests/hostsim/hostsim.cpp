@@ -11,7 +11,7 @@ using namespace kg;
 extern "C" {
 
 int hostsim_slots() { return NW; }
-// element-wise access to the hot-loop elementary functions of kg_math.cuh (which: 0 log, 1 sin, 2 cos, 3 atan2(x, y), 4 acos)
+// element-wise access to the hot-loop elementary functions of kg_math.cuh (which: 0 log, 1 sin, 2 cos, 3 atan2(x, y), 4 acos, 5 atanh_ratio(x, y))
 void hostsim_math(int which, size_t n, const double* x, const double* y, double* out) {
     for (size_t i = 0; i < n; ++i) {
         double s, c;
@@ -20,6 +20,7 @@ void hostsim_math(int which, size_t n, const double* x, const double* y, double*
             case 1: fsincos(x[i], &s, &c); out[i] = s; break;
             case 2: fsincos(x[i], &s, &c); out[i] = c; break;
             case 3: out[i] = fatan2(x[i], y[i]); break;
+            case 5: out[i] = atanh_ratio(x[i], y[i]); break;
             default: out[i] = facos(x[i]); break;
         }
     }
