@@ -1,0 +1,18 @@
+"""Developer tool (GPU): small calls of every kernel family, meant to run under compute-sanitizer (memcheck / racecheck).
+Odd sizes on purpose: 41 x 37 rays (not a multiple of 4 or 32), 21 samples, plus a single-ray call."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import kgeo_b200 as kg
+a, th_o = 0.94, 17 * np.pi / 180
+x = np.linspace(-8, 8, 41); y = np.linspace(-8, 8, 37)
+A, B = [v.flatten() for v in np.meshgrid(x, y)]
+g = kg.raytrace_ana(a, [0, 1000., th_o, 0], [A, B], ngeo=21, plotdata=False)
+assert np.isfinite(g.geo_coords[1][:-1]).all()
+g1 = kg.raytrace_ana(a, [0, 1000., th_o, 0], [A[:1], B[:1]], ngeo=7, plotdata=False)
+sig, (t, r, th, ph) = kg.coords_at_tau(a, [0, 1000., th_o, 0], [A, B], g.tausteps[:5], do_phi_and_t=False)
+img = kg.make_image(a, np.inf, th_o, 2, -10., 10., -10., 10., 20. / 50, emissivity=kg.Emissivity('ring'),
+                    velocity=kg.Velocity('general', fac_subkep=0.7, beta_phi=0.7, beta_r=0.7), bfield=kg.Bfield('bz_guess', C=1.),
+                    polarization=True, specind=1., pathlength=True)
+rs = kg.r_equatorial(a, np.inf, th_o, 1, A, B)
+print("sanitize_case ok", g.geo_coords[1].shape, img[0].shape)
