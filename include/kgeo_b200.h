@@ -167,6 +167,24 @@ int kgeo_r_equatorial(const kgeo_observer* obs, size_t npix, const double* alpha
                       int mbar_lo, int mbar_hi, double* rs_dev, double* Ir_dev, double* Nmax_dev, double* Imax_dev,
                       double* npol_dev, void* stream);
 
+/* ---- inverse lensing (kgeo/equatorial_lensing.py:197-298) -----------------------------------------------------------
+ * rho_of_req: for every image-plane polar angle varphi_dev[i] the radius rho at which the mbar-th equatorial crossing of the
+ * ray (alpha, beta) = rho (cos varphi, sin varphi) happens at r = req, observer at infinity (the reference's R0).  One thread
+ * per angle runs the bracketed root find the reference runs serially: SciPy's brentq (scipy/optimize/Zeros/brentq.c, SciPy
+ * 1.18: inverse quadratic interpolation / secant / bisection, tolerance (xtol + rtol |x|)/2) on r_equatorial2(rho) - req with
+ * the reference's sign-definite patches (r <= 0 -> 1e50 outside the critical curve, 1 inside; :208-215).
+ * status_dev[i]: 0 converged, -1 f(rho_min) and f(rho_max) have the same sign (SciPy raises ValueError), -2 not converged
+ * after maxiter iterations (SciPy raises RuntimeError).  rho/alpha/beta outputs may be NULL.  r_o of obs is ignored. */
+int kgeo_rho_of_req(const kgeo_observer* obs, size_t n, const double* varphi_dev, double req, int mbar, double rho_min,
+                    double rho_max, double xtol, double rtol, int maxiter, double* rho_dev, double* alpha_dev,
+                    double* beta_dev, int32_t* status_dev, void* stream);
+
+/* critical_curve (:268-298, GL19 eqs 38-40): (alpha, beta) of the n photon-orbit radii r = linspace(r_minus, r_plus, n);
+ * the caller passes the scalars the reference computes with NumPy (r_minus, r_plus, sin/cos/tan th_0) so that the NaN mask
+ * next to the end points is the reference's.  Outputs [n]; NaN entries are dropped and the curve mirrored by the caller. */
+int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0, double cos_th0, double tan_th0, size_t n,
+                        double* alpha_dev, double* beta_dev, void* stream);
+
 /* ---- equatorial image (kgeo/equatorial_images.py:23-544) -------------------------------------------------------
  * Fused n = mbar_min..mbar_max image: per pixel one setup, then per order the crossing radius, redshift, (polarization,)
  * emissivity and Stokes I,Q,U.  Planes are [mbar_max-mbar_min+1, npix] (order-major); the Python wrapper exposes them with the

@@ -67,6 +67,9 @@ SIGNATURES = {
                                           _P, _P, _P, _P, _P, _P, ctypes.c_int]),
     "kgeo_crossing_counts": (ctypes.c_int, [_OBS, _S, _P, _P, c_int32_p, _S, _P, _P, _P, _V]),
     "kgeo_r_equatorial": (ctypes.c_int, [_OBS, _S, _P, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P, _V]),
+    "kgeo_rho_of_req": (ctypes.c_int, [_OBS, _S, _P, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_double, ctypes.c_int, _P, _P, _P, c_int32_p, _V]),
+    "kgeo_critical_curve": (ctypes.c_int, [ctypes.c_double] * 6 + [_S, _P, _P, _V]),
     "kgeo_equatorial_image": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [_V]),
     "kgeo_equatorial_image_host": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [ctypes.c_int]),
     "kgeo_velocity_u_lab": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, _P, _V]),

@@ -365,6 +365,110 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_ke
     }
 }
 
+// ---- inverse lensing: rho_of_req (kgeo/equatorial_lensing.py:197-266) ----------------------------------------------------
+// objective of the root find: r_equatorial2(rho, varphi) - req (:197-224), observer at infinity
+__device__ __noinline__ double req_objective(const Observer& o, double rho, double cv, double sv, int mbar, double req) {
+    double w[NW];
+    int fl;
+    const double al = cv * rho, be = sv * rho;
+    ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
+    ArrayW W{w};
+    double rs = -1.0;
+    if (w[S_ETA] > 0.0) {
+        double Ir, Nmax, d0, d1, d2;
+        crossing_time(W, o, be, mbar, &Ir, &Nmax);
+        radial_eval<ArrayW, false>(W, o, fl, Ir, false, &rs, &d0, &d1, &d2);
+        if (Nmax < (double)mbar) rs = 0.0;
+    }
+    if (rs <= 0.0) rs = (fl & F_OUTSIDE) ? 1.0e50 : 1.0;     // :208-215 ("fudge to make things continuous")
+    return rs - req;
+}
+
+// SciPy's brentq (scipy/optimize/Zeros/brentq.c), statement for statement, one thread per angle
+__global__ void __launch_bounds__(32) rho_of_req_kernel(Observer o, size_t n, const double* __restrict__ varphi, double req, int mbar,
+                                                        double xa, double xb, double xtol, double rtol, int maxiter,
+                                                        double* rho_out, double* alpha_out, double* beta_out,
+                                                        int32_t* status_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cv = cos(varphi[i]), sv = sin(varphi[i]);
+    double xpre = xa, xcur = xb, xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+    double fpre = req_objective(o, xpre, cv, sv, mbar, req);
+    double fcur = req_objective(o, xcur, cv, sv, mbar, req);
+    int status = -2;
+    double root = 0.0;
+    bool done = false;
+    if (fpre == 0.0) { root = xpre; status = 0; done = true; }
+    else if (fcur == 0.0) { root = xcur; status = 0; done = true; }
+    else if (signbit(fpre) == signbit(fcur)) { root = 0.0; status = -1; done = true; }
+    for (int it = 0; it < maxiter && !done; ++it) {
+        if (fpre != 0.0 && fcur != 0.0 && (signbit(fpre) != signbit(fcur))) {
+            xblk = xpre;
+            fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        const double delta = (xtol + rtol * fabs(xcur)) / 2;
+        const double sbis = (xblk - xcur) / 2;
+        if (fcur == 0.0 || fabs(sbis) < delta) {
+            root = xcur; status = 0; done = true;
+            break;
+        }
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);                      // interpolate
+            } else {
+                const double dpre = (fpre - fcur) / (xpre - xcur);                  // extrapolate
+                const double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) {
+                spre = scur;                                                       // good short step
+                scur = stry;
+            } else {
+                spre = sbis;                                                       // bisect
+                scur = sbis;
+            }
+        } else {
+            spre = sbis;                                                           // bisect
+            scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = req_objective(o, xcur, cv, sv, mbar, req);
+    }
+    if (!done) root = xcur;
+    if (rho_out) rho_out[i] = root;
+    if (alpha_out) alpha_out[i] = cv * root;
+    if (beta_out) beta_out[i] = sv * root;
+    if (status_out) status_out[i] = status;
+}
+
+// critical curve (kgeo/equatorial_lensing.py:268-290): NumPy's operation order with individually rounded operations (the
+// square root of a difference that vanishes at both end points decides which entries are NaN)
+__global__ void critical_curve_kernel(double a, double rminus, double rplus, double sth, double cth, double tth, size_t n,
+                                      double* alpha, double* beta) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double step = (n > 1) ? div_rn(add_rn(rplus, -rminus), (double)(n - 1)) : 0.0;
+    const double r = (i == n - 1 && n > 1) ? rplus : add_rn(rminus, mul_rn((double)i, step));     // numpy.linspace
+    const double a2 = mul_rn(a, a), r2 = mul_rn(r, r);
+    // r**3 as NumPy computes it (libm pow, correctly rounded in practice): r2 * r with the rounding error of r2 carried along
+    const double r3 = fma(fma(r, r, -r2), r, mul_rn(r2, r)) ;
+    const double num = add_rn(add_rn(add_rn(r3, a2), mul_rn(r, a2)), -mul_rn(3.0, r2));
+    const double lam = div_rn(-num, add_rn(mul_rn(a, r), -a));
+    const double eta = div_rn(mul_rn(r2, add_rn(add_rn(mul_rn(3.0, r2), a2), -mul_rn(lam, lam))), add_rn(r2, -a2));
+    const double ac = mul_rn(a, cth), lt = div_rn(lam, tth);
+    alpha[i] = div_rn(-lam, sth);
+    beta[i] = sqrt_rn(add_rn(add_rn(eta, mul_rn(ac, ac)), -mul_rn(lt, lt)));
+}
+
 struct ImageOut {
     double *I, *Q, *U, *r, *Ir, *g, *sinthb, *nmax, *npol, *imax, *lp, *Ie;
 };
@@ -651,6 +755,34 @@ int kgeo_r_equatorial(const kgeo_observer* obs, size_t npix, const double* alpha
     r_equatorial_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, npix, alpha, beta, mbar_lo,
                                                                                               mbar_hi, rs, Ir, Nmax, Imax, npol);
     LAUNCHED("r_equatorial_kernel");
+    return 0;
+}
+
+int kgeo_rho_of_req(const kgeo_observer* obs, size_t n, const double* varphi, double req, int mbar, double rho_min, double rho_max,
+                    double xtol, double rtol, int maxiter, double* rho, double* alpha, double* beta, int32_t* status,
+                    void* stream) {
+    if (!obs) return fail_arg(KGEO_E_BADARG, "kgeo_rho_of_req: obs is NULL");
+    kgeo_observer oinf = *obs;
+    oinf.r_o = KG_INF;                                       // R0 = inf (kgeo/equatorial_lensing.py:19)
+    int rc = check_observer(&oinf, true);
+    if (rc) return rc;
+    if (n && !varphi) return fail_arg(KGEO_E_BADARG, "kgeo_rho_of_req: NULL pointer");
+    if (mbar < 0 || maxiter < 0 || !(xtol > 0.0)) return fail_arg(KGEO_E_BADARG, "kgeo_rho_of_req: bad mbar / tolerance");
+    if (n == 0) return 0;
+    Observer o = make_observer(oinf.a, oinf.r_o, oinf.th_o);
+    rho_of_req_kernel<<<grid_for(n, 32), 32, 0, (cudaStream_t)stream>>>(o, n, varphi, req, mbar, rho_min, rho_max, xtol, rtol,
+                                                                       maxiter, rho, alpha, beta, status);
+    LAUNCHED("rho_of_req_kernel");
+    return 0;
+}
+
+int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0, double cos_th0, double tan_th0, size_t n,
+                        double* alpha, double* beta, void* stream) {
+    if (n && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_critical_curve: NULL pointer");
+    if (n == 0) return 0;
+    critical_curve_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(a, r_minus, r_plus, sin_th0, cos_th0, tan_th0, n,
+                                                                             alpha, beta);
+    LAUNCHED("critical_curve_kernel");
     return 0;
 }
 

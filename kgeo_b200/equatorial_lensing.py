@@ -1,7 +1,8 @@
-"""Drop-in for the hot-path part of kgeo/equatorial_lensing.py: r_equatorial (:85-196), nmax_equatorial (:22-51),
-nmax_poloidal (:53-82), computed by libkgeo_b200.so.
+"""Drop-in for kgeo/equatorial_lensing.py: r_equatorial (:85-196), nmax_equatorial (:22-51), nmax_poloidal (:53-82) and the
+inverse lensing of SURVEY 8(f2) -- rho_of_req (:226-247), rho_of_req_single (:249-266), critical_curve (:268-298) --
+computed by libkgeo_b200.so (the root find runs on the GPU, one thread per image-plane angle).
 
-Out of scope: rho_of_req*, critical_curve, plot_curves, generate_library (serial Brent root-finding callers).
+Out of scope: plot_curves, generate_library (matplotlib / file output around rho_of_req).
 """
 import ctypes
 
@@ -11,6 +12,10 @@ from . import _checks, _engine, _lib
 from ._engine import dptr
 
 RMAX = np.inf  # kgeo/equatorial_lensing.py:19
+INF = 1.e50    # :18
+R0 = np.inf    # :19
+# scipy.optimize.brentq defaults, which the reference relies on (:243, :264)
+BRENTQ_XTOL, BRENTQ_RTOL, BRENTQ_MAXITER = 2e-12, 4 * np.finfo(float).eps, 100
 
 
 def _r_equatorial_device(a, r_o, th_o, mbar_lo, mbar_hi, alpha, beta, want=("rs", "Ir", "Nmax", "Imax", "npol")):
@@ -71,3 +76,70 @@ def r_equatorial_orders(a, r_o, th_o, mbar_max, alpha, beta):
     alpha, beta = _checks.pixel_arrays(alpha, beta)
     out = _r_equatorial_device(a, r_o, th_o, 0, int(mbar_max), alpha, beta, want=("rs", "Ir", "Nmax", "Imax"))
     return tuple(out[k].cpu().numpy() for k in ("rs", "Ir", "Nmax", "Imax"))
+
+
+def _rho_bracket(req, mbar):
+    # bounding ranges eyeballed from Gralla+Lupsasca Fig 6 (kgeo/equatorial_lensing.py:232-241)
+    if mbar == 0:
+        return 0, req + 5
+    elif mbar == 1:
+        return 0, 100
+    return 1, 10
+
+
+def _rho_of_req_device(a, th0, req, mbar, varphis):
+    L = _lib.lib()
+    _engine.require_cuda()
+    t = _engine.torch()
+    dev = _engine.device()
+    obs = _engine.observer_struct(a, np.inf, th0)
+    vp = _engine.to_device(np.atleast_1d(np.asarray(varphis, dtype=np.float64)), dev)
+    n = int(vp.numel())
+    rho, al, be = (_engine.empty((n,), dev) for _ in range(3))
+    status = _engine.empty((n,), dev, dtype=t.int32)
+    rhomin, rhomax = _rho_bracket(req, mbar)
+    _lib.check(L.kgeo_rho_of_req(ctypes.byref(obs), n, dptr(vp), float(req), int(mbar), float(rhomin), float(rhomax),
+                                 BRENTQ_XTOL, BRENTQ_RTOL, BRENTQ_MAXITER, dptr(rho), dptr(al), dptr(be),
+                                 _engine.iptr(status), _engine.stream_ptr()))
+    st = status.cpu().numpy()
+    if (st == -1).any():      # what scipy.optimize.brentq raises inside the reference's list comprehension
+        raise ValueError("f(a) and f(b) must have different signs")
+    if (st == -2).any():
+        raise RuntimeError("Failed to converge after %d iterations." % BRENTQ_MAXITER)
+    return rho.cpu().numpy(), al.cpu().numpy(), be.cpu().numpy()
+
+
+def rho_of_req(a, th0, req, mbar=0, varphis=None):
+    """Image-plane curve (varphis, rhos, alphas, betas) of the mbar-th image of the equatorial ring r = req
+    (kgeo/equatorial_lensing.py:226-247)"""
+    if varphis is None:
+        varphis = np.linspace(-180, 179, 360) * np.pi / 180.
+    rhos, alphas, betas = _rho_of_req_device(a, th0, req, mbar, varphis)
+    return (varphis, rhos, alphas, betas)
+
+
+def rho_of_req_single(a, th0, req, varphi, mbar=0):
+    """rho of one image-plane angle (kgeo/equatorial_lensing.py:249-266)"""
+    rhos, _, _ = _rho_of_req_device(a, th0, req, mbar, [varphi])
+    return float(rhos[0])
+
+
+def critical_curve(a, th0, n=100000):
+    """returns parametrized critical curve (alpha,beta) array with n points
+       won't work for a=0 exactly"""
+    L = _lib.lib()
+    _engine.require_cuda()
+    t = _engine.torch()
+    dev = _engine.device()
+    # beginning and ending points, Eq 40 (scalars, exactly as the reference forms them: :275-276, :288-289)
+    rminus = 2 * (1 + np.cos(2. * np.arccos(-a) / 3.))
+    rplus = 2 * (1 + np.cos(2. * np.arccos(a) / 3.))
+    n = int(n)
+    alpha, beta = _engine.empty((n,), dev), _engine.empty((n,), dev)
+    _lib.check(L.kgeo_critical_curve(float(a), float(rminus), float(rplus), float(np.sin(th0)), float(np.cos(th0)),
+                                     float(np.tan(th0)), n, dptr(alpha), dptr(beta), _engine.stream_ptr()))
+    keep = ~(t.isnan(alpha) | t.isnan(beta))          # "fails a lot..." (:292-295): drop NaNs, then mirror
+    alpha, beta = alpha[keep], beta[keep]
+    alpha = t.cat((alpha, t.flip(alpha, (0,))))
+    beta = t.cat((beta, -t.flip(beta, (0,))))
+    return (alpha.cpu().numpy(), beta.cpu().numpy())

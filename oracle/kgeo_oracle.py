@@ -655,6 +655,64 @@ def r_equatorial(a, r_o, th_o, mbar, alpha, beta):
     return r_s, Ir, Imax, Nmax
 
 
+INF_LENS = 1.0e50     # kgeo/equatorial_lensing.py:18
+R0_LENS = np.inf      # kgeo/equatorial_lensing.py:19
+
+
+def r_equatorial2(rho, varphi, a, th0, mbar=0):
+    """Crossing radius along a polar ray of the image plane, made sign-definite for the root find
+    (equatorial_lensing.py:197-217)."""
+    alpha = np.cos(varphi) * rho
+    beta = np.sin(varphi) * rho
+    r = r_equatorial(a, R0_LENS, th0, mbar, np.array([alpha]), np.array([beta]))[0][0]
+    oc = outside_crit(a, th0, np.array([alpha]), np.array([beta]))[0]
+    if r <= 0 and oc == 1:
+        r = INF_LENS
+    elif r <= 0:
+        r = 1
+    return r
+
+
+def _rho_bracket(req, mbar):
+    """equatorial_lensing.py:232-241 (bounding ranges eyeballed from Gralla+Lupsasca Fig 6)"""
+    if mbar == 0:
+        return 0, req + 5
+    if mbar == 1:
+        return 0, 100
+    return 1, 10
+
+
+def rho_of_req_single(a, th0, req, varphi, mbar=0):
+    """equatorial_lensing.py:249-266: scipy.optimize.brentq (default xtol=2e-12, rtol=4 eps, maxiter=100) on
+    r_equatorial2(rho) - req."""
+    from scipy.optimize import brentq
+    rhomin, rhomax = _rho_bracket(req, mbar)
+    return brentq(lambda rho: r_equatorial2(rho, varphi, a, th0, mbar) - req, rhomin, rhomax)
+
+
+def rho_of_req(a, th0, req, mbar=0, varphis=None):
+    """equatorial_lensing.py:226-247"""
+    if varphis is None:
+        varphis = np.linspace(-180, 179, 360) * np.pi / 180.
+    rhos = np.array([rho_of_req_single(a, th0, req, v, mbar) for v in varphis])
+    return varphis, rhos, np.cos(varphis) * rhos, np.sin(varphis) * rhos
+
+
+def critical_curve(a, th0, n=100000):
+    """equatorial_lensing.py:268-298 (GL19 eqs 38-40)"""
+    rminus = 2 * (1 + np.cos(2. * np.arccos(-a) / 3.))
+    rplus = 2 * (1 + np.cos(2. * np.arccos(a) / 3.))
+    r = np.linspace(rminus, rplus, n)
+    lam = -(r ** 3 + a ** 2 + r * (a ** 2) - 3 * r ** 2) / (a * r - a)
+    eta = (r ** 2) * (3 * r ** 2 + a ** 2 - lam ** 2) / (r ** 2 - a ** 2)
+    alpha = -lam / np.sin(th0)
+    beta = np.sqrt(eta + (a * np.cos(th0)) ** 2 - (lam / np.tan(th0)) ** 2)
+    mask = np.isnan(alpha) + np.isnan(beta)
+    alpha = alpha[~mask]
+    beta = beta[~mask]
+    return np.hstack((alpha, np.flip(alpha))), np.hstack((beta, -np.flip(beta)))
+
+
 def nmax_equatorial(a, r_o, th_o, alpha, beta):
     """equatorial_lensing.py:22-51"""
     alpha, beta = _arr(alpha), _arr(beta)

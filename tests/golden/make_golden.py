@@ -24,7 +24,8 @@ import scipy  # noqa: E402
 from kgeo.bfields import Bfield  # noqa: E402
 from kgeo.emissivities import Emissivity  # noqa: E402
 from kgeo.equatorial_images import make_image  # noqa: E402
-from kgeo.equatorial_lensing import nmax_equatorial, nmax_poloidal, r_equatorial  # noqa: E402
+from kgeo.equatorial_lensing import (critical_curve, nmax_equatorial, nmax_poloidal, r_equatorial,  # noqa: E402
+                                     rho_of_req, rho_of_req_single)
 from kgeo.kerr_raytracing_ana import coords_at_tau, raytrace_ana  # noqa: E402
 from kgeo.kerr_raytracing_utils import (is_outside_crit, mino_total, n_equatorial_crossings,  # noqa: E402
                                          n_poloidal_orbits, radial_roots, uplus_uminus)
@@ -256,8 +257,32 @@ def counts():
          neq=n_equatorial_crossings(a, th_o, A, B, tau), npol=n_poloidal_orbits(a, th_o, A, B, tau))
 
 
+def inverse_lensing():
+    """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
+    out = {}
+    cases = [(0.94, 17 * DEG, 6.0), (0.5, 60 * DEG, 4.0), (0.99, 80 * DEG, 3.0)]
+    varphis = np.linspace(-180, 165, 24) * np.pi / 180.
+    out['cases'] = np.array(cases)
+    out['varphis'] = varphis
+    for ic, (a, th0, req) in enumerate(cases):
+        for mbar in (0, 1, 2):
+            vp, rho, al, be = quiet(rho_of_req, a, th0, req, mbar=mbar, varphis=varphis)
+            out['rho_%d_%d' % (ic, mbar)] = rho
+            out['alpha_%d_%d' % (ic, mbar)] = al
+            out['beta_%d_%d' % (ic, mbar)] = be
+    out['single'] = np.array([rho_of_req_single(0.94, 17 * DEG, 5.0, 0.3, mbar=m) for m in (0, 1, 2)])
+    for ic, (a, th0, req) in enumerate(cases):
+        al, be = critical_curve(a, th0, n=2001)
+        out['crit_alpha_%d' % ic] = al
+        out['crit_beta_%d' % ic] = be
+    save('inverse_lensing', **out)
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
+    if len(sys.argv) > 1 and sys.argv[1] == 'inverse_lensing':     # add this fixture without touching the others
+        inverse_lensing()
+        sys.exit(0)
     special()
     setup()
     tracks()
@@ -265,5 +290,6 @@ if __name__ == '__main__':
     images()
     models()
     counts()
+    inverse_lensing()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

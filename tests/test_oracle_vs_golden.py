@@ -174,3 +174,18 @@ def test_ipole_midplane_rays():
         if z[0] > z[1]:
             x, y, z = x[::-1], y[::-1], z[::-1]
         assert np.allclose([np.interp(0, z, x), np.interp(0, z, y)], want, rtol=1e-3)
+
+
+def test_inverse_lensing_oracle_matches_reference(golden):
+    """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298): same SciPy brentq, same objective."""
+    g = golden('inverse_lensing')
+    vp = g['varphis'][::4]
+    for ic, (a, th0, req) in enumerate(g['cases']):
+        for mbar in (0, 1, 2):
+            _, rho, al, be = ko.rho_of_req(float(a), float(th0), float(req), mbar, vp)
+            assert np.max(np.abs(rho - g['rho_%d_%d' % (ic, mbar)][::4])) <= 1e-12
+            assert np.max(np.abs(al - g['alpha_%d_%d' % (ic, mbar)][::4])) <= 1e-12
+        al, be = ko.critical_curve(float(a), float(th0), 2001)
+        assert np.array_equal(al, g['crit_alpha_%d' % ic]) and np.array_equal(be, g['crit_beta_%d' % ic])
+    for m in (0, 1, 2):
+        assert abs(ko.rho_of_req_single(0.94, 17 * np.pi / 180, 5.0, 0.3, mbar=m) - g['single'][m]) <= 1e-12
