@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KGEO_B200_ABI_VERSION 1
+#define KGEO_B200_ABI_VERSION 2
 
 #define KGEO_E_BADARG (-1)   /* NULL pointer, negative size, inconsistent shapes */
 #define KGEO_E_RANGE (-2)    /* |a| >= 1, r_o < 100, th_o outside (0,pi) or == pi/2 (the reference's own checks) */
@@ -53,8 +53,9 @@ typedef struct kgeo_observer {
 
 /* ---- physics models of the equatorial image (kgeo/velocities.py, kgeo/bfields.py, kgeo/emissivities.py) ---- */
 enum kgeo_velocity_type { KGEO_VEL_ZAMO = 0, KGEO_VEL_INFALL, KGEO_VEL_KEP, KGEO_VEL_SUBKEP, KGEO_VEL_GENERAL,
-                          KGEO_VEL_GELLES, KGEO_VEL_SIMFIT };
-enum kgeo_bfield_type { KGEO_B_SIMPLE = 0, KGEO_B_SIMPLE_RM1, KGEO_B_BZ_GUESS, KGEO_B_GEN_POWER, KGEO_B_MONOPOLE_A };
+                          KGEO_VEL_GELLES, KGEO_VEL_SIMFIT, KGEO_VEL_FROMFILE };
+enum kgeo_bfield_type { KGEO_B_SIMPLE = 0, KGEO_B_SIMPLE_RM1, KGEO_B_BZ_GUESS, KGEO_B_GEN_POWER, KGEO_B_MONOPOLE_A,
+                        KGEO_B_FROMFILE };
 enum kgeo_emissivity_type { KGEO_EM_CONSTANT = 0, KGEO_EM_BPL, KGEO_EM_GLM, KGEO_EM_RING, KGEO_EM_THERMAL };
 
 /* Parameter meaning per type (defaults as in the reference constructors):
@@ -78,6 +79,13 @@ typedef struct kgeo_models {
     double emissivity_p[8];
     double emiscut_in;
     double emiscut_out;
+    /* 'fromfile' models (kgeo/velocities.py:626-698, kgeo/bfields.py:749-806): DEVICE tables of 4 rows x table_n doubles,
+     * row 0 = radii (increasing), rows 1..3 = U1,U2,U3 resp. Br,Btheta,Bphi, evaluated with numpy.interp semantics
+     * (linear, clamped to the end values).  NULL / 0 for every other model. */
+    const double* velocity_table_dev;
+    const double* bfield_table_dev;
+    int64_t velocity_table_n;
+    int64_t bfield_table_n;
 } kgeo_models;
 
 /* Image options = keyword arguments of Iobs / make_image (kgeo/equatorial_images.py:23-32,124-127). */

@@ -23,7 +23,9 @@ class Observer(ctypes.Structure):
 class Models(ctypes.Structure):
     _fields_ = [("velocity_type", ctypes.c_int32), ("bfield_type", ctypes.c_int32), ("emissivity_type", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("velocity_p", ctypes.c_double * 8), ("bfield_p", ctypes.c_double * 8),
-                ("emissivity_p", ctypes.c_double * 8), ("emiscut_in", ctypes.c_double), ("emiscut_out", ctypes.c_double)]
+                ("emissivity_p", ctypes.c_double * 8), ("emiscut_in", ctypes.c_double), ("emiscut_out", ctypes.c_double),
+                ("velocity_table_dev", ctypes.c_void_p), ("bfield_table_dev", ctypes.c_void_p),
+                ("velocity_table_n", ctypes.c_int64), ("bfield_table_n", ctypes.c_int64)]
 
 
 class ImageOpts(ctypes.Structure):
@@ -32,8 +34,8 @@ class ImageOpts(ctypes.Structure):
                 ("nu_obs", ctypes.c_double)]
 
 
-VEL = dict(zamo=0, infall=1, kep=2, subkep=3, general=4, gelles=5, simfit=6)
-BF = dict(simple=0, simple_rm1=1, bz_guess=2, gen_power=3, monopoleA=4)
+VEL = dict(zamo=0, infall=1, kep=2, subkep=3, general=4, gelles=5, simfit=6, fromfile=7)
+BF = dict(simple=0, simple_rm1=1, bz_guess=2, gen_power=3, monopoleA=4, fromfile=5)
 EM = dict(constant=0, bpl=1, glm=2, ring=3, thermal=4)
 
 _P, _S, _V = c_double_p, ctypes.c_size_t, ctypes.c_void_p
@@ -104,7 +106,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.kgeo_abi_version() != 1:
+        if L.kgeo_abi_version() != 2:
             raise ImportError("kgeo_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -1,6 +1,6 @@
 """Magnetic field model descriptor with the constructor / bfield_lab / bsq interface of kgeo/bfields.py:33-131,365-396.
-Closed-form models run on the device; 'bz_monopole', 'bz_para', 'power', 'fromfile', 'const_comoving' are outside the
-accelerated path (tables / Lambert W)."""
+Closed-form models and the tabulated 'fromfile' model run on the device; 'bz_monopole', 'bz_para', 'power',
+'const_comoving' are outside the accelerated path (a data file the reference does not ship / Lambert W)."""
 import ctypes
 
 import numpy as np
@@ -13,9 +13,9 @@ class Bfield(object):
 
     def __init__(self, fieldtype="rad", **kwargs):
         self.fieldtype = fieldtype
-        if self.fieldtype in ['rad', 'vert', 'tor', 'simple', 'simple_rm1', 'monopoleA', 'bz_guess', 'gen_power']:
+        if self.fieldtype in ['rad', 'vert', 'tor', 'simple', 'simple_rm1', 'monopoleA', 'bz_guess', 'gen_power', 'fromfile']:
             self.fieldframe = 'lab'
-        elif self.fieldtype in ['bz_monopole', 'bz_para', 'power', 'fromfile', 'const_comoving']:
+        elif self.fieldtype in ['bz_monopole', 'bz_para', 'power', 'const_comoving']:
             raise NotImplementedError("Bfield(%r) is outside the accelerated path (SURVEY 8f)" % self.fieldtype)
         else:
             raise Exception("fieldtype %s not recognized in Bfield!" % self.fieldtype)
@@ -33,6 +33,12 @@ class Bfield(object):
             self.Cr, self.Cvert, self.Cph = 0, 1, 0
         elif self.fieldtype == 'tor':
             self.Cr, self.Cvert, self.Cph = 0, 0, 1
+        elif self.fieldtype == 'fromfile':
+            from .models import load_cache_from_file
+            self.filename = self.kwargs.get('file', None)
+            radii, Br, Bth, Bph = load_cache_from_file(self.filename, ('Br', 'Btheta', 'Bphi'))
+            self.cached_data = dict(radii=radii, Br=Br, Bth=Bth, Bph=Bph)
+            self._table = None
         elif self.fieldtype == 'gen_power':
             self.n_I = self.kwargs.get('n_I', 0)
             self.p_val = self.kwargs.get('p_val', 1)
@@ -44,8 +50,20 @@ class Bfield(object):
             if self.Cr == self.Cvert == self.Cph == 0.:
                 raise Exception("all field coefficients are 0!")
 
+    def table(self):
+        """device table of the 'fromfile' model (None for the closed forms)"""
+        if self.fieldtype != 'fromfile':
+            return None
+        if self._table is None:
+            from .models import device_table
+            c = self.cached_data
+            self._table = device_table((c['radii'], c['Br'], c['Bth'], c['Bph']))
+        return self._table
+
     def descriptor(self):
         f = self.fieldtype
+        if f == 'fromfile':
+            return _lib.BF['fromfile'], []
         if f in ('rad', 'vert', 'tor', 'simple'):
             return _lib.BF['simple'], [float(self.Cr), float(self.Cvert), float(self.Cph)]
         if f == 'simple_rm1':

@@ -146,6 +146,39 @@ KG_HD U4 u_general(double a, double r, bool retro, double fac, double beta_phi, 
     u0 /= sqrt(1.0 - (r * r + a * a) * Omega * Omega - (2.0 / r) * sq(1.0 - a * Omega));
     return U4{u0, u1, 0.0, u0 * Omega};
 }
+// numpy.interp(x, xp, fp) for one x: linear between the bracketing samples, clamped to fp[0] / fp[n-1] outside, NaN -> NaN
+// (numpy/core/src/multiarray/compiled_base.c: slope * (x - xp[j]) + fp[j])
+KG_HD double interp_table(const double* xp, const double* fp, long long n, double x) {
+    if (!(x == x)) return x;
+    if (x <= xp[0]) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    long long lo = 0, hi = n - 1;          // xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (x >= xp[mid]) lo = mid;
+        else hi = mid;
+    }
+    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    return slope * (x - xp[lo]) + fp[lo];
+}
+
+// four-velocity from tabulated primitives U1, U2, U3 (kgeo/velocities.py:659-698), equatorial plane
+KG_HD U4 u_fromfile(const kgeo_models& M, double a, double r) {
+    const double* tab = M.velocity_table_dev;
+    const long long n = M.velocity_table_n;
+    double u1 = interp_table(tab, tab + n, n, r);
+    double u2 = interp_table(tab, tab + 2 * n, n, r);
+    double u3 = interp_table(tab, tab + 3 * n, n, r);
+    double r2 = r * r, a2 = a * a;
+    double Delta = r2 - 2.0 * r + a2, Sigma = r2;
+    double g11 = Sigma / Delta, g22 = Sigma, g33 = r2 + a2 + 2.0 * r * a2 / Sigma;
+    double gcon00 = -(r2 + a2 + 2.0 * r * a2 / Sigma) / Delta;
+    double gcon03 = -2.0 * r * a / Sigma / Delta;
+    double alpha = 1.0 / sqrt(-gcon00);
+    double gamma = sqrt(1.0 + g11 * u1 * u1 + g22 * u2 * u2 + g33 * u3 * u3);
+    return U4{gamma / alpha, u1, u2, u3 - gamma * alpha * gcon03};
+}
+
 KG_HD U4 velocity_u_lab(const kgeo_models& M, double a, double r) {   // velocities.py:70-96
     const double* p = M.velocity_p;
     switch (M.velocity_type) {
@@ -155,6 +188,7 @@ KG_HD U4 velocity_u_lab(const kgeo_models& M, double a, double r) {   // velocit
         case KGEO_VEL_SUBKEP: return u_subkep(a, r, p[0] != 0.0, p[1]);
         case KGEO_VEL_GENERAL: return u_general(a, r, p[0] != 0.0, p[1], p[2], p[3]);
         case KGEO_VEL_GELLES: return u_gelles(a, r, p[0], p[1]);
+        case KGEO_VEL_FROMFILE: return u_fromfile(M, a, r);
         default: return u_simfit(a, r, p[0], p[1], p[2], p[3], p[4]);
     }
 }
@@ -202,6 +236,14 @@ KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, doub
             *B1 = dpsidtheta / gdet;
             *B2 = -1.0 * (dpsidr / gdet);
             *B3 = I / (2.0 * kPi * Delta);
+            return;
+        }
+        case KGEO_B_FROMFILE: {   // bfields.py:790-806
+            const double* tab = M.bfield_table_dev;
+            const long long n = M.bfield_table_n;
+            *B1 = interp_table(tab, tab + n, n, r);
+            *B2 = interp_table(tab, tab + 2 * n, n, r);
+            *B3 = interp_table(tab, tab + 3 * n, n, r);
             return;
         }
         default: {   // KGEO_B_MONOPOLE_A, bfields.py:480-501

@@ -62,8 +62,12 @@ static int check_observer(const kgeo_observer* obs, bool allow_inf) {
 }
 static int check_models(const kgeo_models* m) {
     if (!m) return fail_arg(KGEO_E_BADARG, "models is NULL");
-    if (m->velocity_type < 0 || m->velocity_type > KGEO_VEL_SIMFIT) return fail_arg(KGEO_E_MODEL, "unknown velocity model");
-    if (m->bfield_type < 0 || m->bfield_type > KGEO_B_MONOPOLE_A) return fail_arg(KGEO_E_MODEL, "unknown bfield model");
+    if (m->velocity_type < 0 || m->velocity_type > KGEO_VEL_FROMFILE) return fail_arg(KGEO_E_MODEL, "unknown velocity model");
+    if (m->bfield_type < 0 || m->bfield_type > KGEO_B_FROMFILE) return fail_arg(KGEO_E_MODEL, "unknown bfield model");
+    if (m->velocity_type == KGEO_VEL_FROMFILE && (!m->velocity_table_dev || m->velocity_table_n < 1))
+        return fail_arg(KGEO_E_MODEL, "velocity 'fromfile' needs a device table (velocity_table_dev, velocity_table_n)");
+    if (m->bfield_type == KGEO_B_FROMFILE && (!m->bfield_table_dev || m->bfield_table_n < 1))
+        return fail_arg(KGEO_E_MODEL, "bfield 'fromfile' needs a device table (bfield_table_dev, bfield_table_n)");
     if (m->emissivity_type < 0 || m->emissivity_type > KGEO_EM_THERMAL) return fail_arg(KGEO_E_MODEL, "unknown emissivity model");
     return 0;
 }

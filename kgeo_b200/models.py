@@ -1,5 +1,27 @@
 """Pack Velocity / Bfield / Emissivity objects into the POD kgeo_models descriptor of the C ABI."""
+import numpy as np
+
 from . import _lib
+
+
+def load_cache_from_file(filename, columns):
+    """The reference's CSV reader of the 'fromfile' models (kgeo/velocities.py:626-657, kgeo/bfields.py:749-787): a '#'
+    header line naming the columns, then comma-separated rows; missing columns are zero.  Returns (radii, c1, c2, c3)."""
+    with open(filename, 'r') as f:
+        header = f.readline().strip()
+        if header[0] != '#':
+            raise Exception("file %s does not have a header!" % filename)
+        header = [x.strip() for x in header[1:].split(',')]
+    data = np.loadtxt(filename, delimiter=',', skiprows=1)
+    radii = data[:, header.index('r')]
+    cols = [data[:, header.index(c)] if c in header else np.zeros_like(radii) for c in columns]
+    return (radii,) + tuple(cols)
+
+
+def device_table(rows):
+    """4 x n float64 device table (row 0 = radii) for kgeo_models.*_table_dev"""
+    from . import _engine
+    return _engine.to_device(np.ascontiguousarray(np.vstack(rows), dtype=np.float64))
 
 
 def pack_models(emissivity=None, velocity=None, bfield=None):
@@ -18,4 +40,10 @@ def pack_models(emissivity=None, velocity=None, bfield=None):
     if emissivity is not None:
         M.emiscut_in = float(emissivity.emiscut_in)
         M.emiscut_out = float(emissivity.emiscut_out)
+    # 'fromfile' models: device tables owned by the model objects (kept alive by them)
+    for obj, prefix in ((velocity, "velocity"), (bfield, "bfield")):
+        tab = obj.table() if (obj is not None and hasattr(obj, "table")) else None
+        if tab is not None:
+            setattr(M, prefix + "_table_dev", tab.data_ptr())
+            setattr(M, prefix + "_table_n", int(tab.shape[1]))
     return M

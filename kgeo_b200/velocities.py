@@ -1,5 +1,6 @@
 """Velocity model descriptor with the constructor and u_lab interface of kgeo/velocities.py:23-96.
-The closed forms run on the device (kg_image.cuh); 'fromfile' and 'driftframe' are outside the accelerated path."""
+The closed forms and the tabulated 'fromfile' model run on the device (kg_image.cuh); 'driftframe' is outside the
+accelerated path."""
 import ctypes
 
 import numpy as np
@@ -43,15 +44,33 @@ class Velocity(object):
             self.p1 = self.kwargs.get('p1', P1)
             self.p2 = self.kwargs.get('p2', P2)
             self.dd = self.kwargs.get('dd', DD)
-        elif self.veltype in ('fromfile', 'driftframe'):
-            raise NotImplementedError("Velocity(%r) needs host tables / root finds and is outside the accelerated path "
+        elif self.veltype == 'fromfile':
+            from .models import load_cache_from_file
+            self.filename = self.kwargs.get('file', None)
+            radii, U1, U2, U3 = load_cache_from_file(self.filename, ('U1', 'U2', 'U3'))
+            self.cached_data = dict(radii=radii, U1=U1, U2=U2, U3=U3)
+            self._table = None
+        elif self.veltype == 'driftframe':
+            raise NotImplementedError("Velocity(%r) needs a B-field root find and is outside the accelerated path "
                                       "(SURVEY 8f)" % self.veltype)
         else:
             raise Exception("veltype %s not recognized in Velocity!" % self.veltype)
 
+    def table(self):
+        """device table of the 'fromfile' model (None for the closed forms)"""
+        if self.veltype != 'fromfile':
+            return None
+        if self._table is None:
+            from .models import device_table
+            c = self.cached_data
+            self._table = device_table((c['radii'], c['U1'], c['U2'], c['U3']))
+        return self._table
+
     def descriptor(self):
         """(type id, parameter list) for kgeo_models.velocity_*"""
         v = self.veltype
+        if v == 'fromfile':
+            return _lib.VEL['fromfile'], []
         if v == 'zamo':
             return _lib.VEL['zamo'], []
         if v == 'infall':

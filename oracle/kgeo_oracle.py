@@ -883,7 +883,39 @@ def velocity_u_lab(vel, a, r):
     if t == 'simfit':
         return u_simfit(a, r, vel.get('ell_isco', 1.), vel.get('vr_isco', 2.), vel.get('p1', 6.), vel.get('p2', 2.),
                         vel.get('dd', 0.2))
+    if t == 'fromfile':
+        return u_from_table(a, r, load_table(vel['file'], ('U1', 'U2', 'U3')))
     raise Exception("veltype %s not in oracle" % t)
+
+
+def load_table(filename, columns):
+    """CSV reader of the 'fromfile' models (kgeo/velocities.py:626-657, kgeo/bfields.py:749-787)."""
+    with open(filename, 'r') as f:
+        header = [x.strip() for x in f.readline().strip()[1:].split(',')]
+    data = np.loadtxt(filename, delimiter=',', skiprows=1)
+    radii = data[:, header.index('r')]
+    return [radii] + [data[:, header.index(c)] if c in header else np.zeros_like(radii) for c in columns]
+
+
+def u_from_table(a, r, tab):
+    """u_from_u123 (kgeo/velocities.py:659-698): np.interp of the primitives, then normalisation."""
+    radii, U1, U2, U3 = tab
+    u1 = np.interp(r, radii, U1)
+    u2 = np.interp(r, radii, U2)
+    u3 = np.interp(r, radii, U3)
+    r2 = r * r
+    a2 = a * a
+    th = np.pi / 2.
+    Delta = r2 - 2 * r + a2
+    Sigma = r2 + a2 * np.cos(th) ** 2
+    g11 = Sigma / Delta
+    g22 = Sigma
+    g33 = (r2 + a2 + 2 * r * (a * np.sin(th)) ** 2 / Sigma) * np.sin(th) ** 2
+    gcon00 = - (r2 + a2 + 2 * r * a2 / Sigma * np.sin(th) ** 2) / Delta
+    gcon03 = -2 * r * a / Sigma / Delta
+    alpha = 1. / np.sqrt(-gcon00)
+    gamma = np.sqrt(1. + g11 * u1 * u1 + g22 * u2 * u2 + g33 * u3 * u3)
+    return gamma / alpha, u1, u2, u3 - gamma * alpha * gcon03
 
 
 def _metric_eq(a, r):
@@ -931,6 +963,9 @@ def bfield_lab(bf, a, r):
     r = _arr(r)
     t = bf['type']
     th = np.pi / 2
+    if t == 'fromfile':                                            # bfields.py:790-806
+        radii, Br, Bth, Bph = load_table(bf['file'], ('Br', 'Btheta', 'Bphi'))
+        return np.interp(r, radii, Br), np.interp(r, radii, Bth), np.interp(r, radii, Bph)
     if t in ('simple', 'rad', 'vert', 'tor', 'simple_rm1'):
         if t == 'rad':
             cr, cv, cp = 1, 0, 0

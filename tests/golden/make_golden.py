@@ -257,6 +257,30 @@ def counts():
          neq=n_equatorial_crossings(a, th_o, A, B, tau), npol=n_poloidal_orbits(a, th_o, A, B, tau))
 
 
+TABLE_FILE = '/root/reference/tests/data/a0p6_inflow.csv'      # committed copy: tests/golden/a0p6_inflow.csv
+
+
+def fromfile_models():
+    """Velocity('fromfile') / Bfield('fromfile') (np.interp tables; kgeo/velocities.py:626-698, kgeo/bfields.py:749-806):
+    element-wise values on a radius grid that extends beyond both ends of the table, and one polarized image."""
+    a = 0.6
+    r = np.concatenate((np.linspace(1.81, 5.2, 150), [1.827254825200443022, 2.5, 6.0, 30.0]))
+    v = Velocity('fromfile', file=TABLE_FILE)
+    b = Bfield('fromfile', file=TABLE_FILE)
+    out = dict(a=np.array(a), r=r)
+    out['u'] = np.array([np.broadcast_to(c, r.shape) for c in v.u_lab(a, r)], dtype=float)
+    out['B'] = np.array([np.broadcast_to(c, r.shape) for c in b.bfield_lab(a, r)], dtype=float)
+    out['bsq'] = b.bsq(a, r, v)
+    half, npx = 8., 40
+    with np.errstate(all='ignore'):
+        img = quiet(make_image, a, np.inf, 30 * DEG, 1, -half, half, -half, half, 2 * half / npx,
+                    emissivity=Emissivity('ring', r_ring=3.5, sigma=0.6), velocity=v, bfield=b, polarization=True, specind=1.)
+    out['par'] = np.array([a, np.inf, 30 * DEG, 1, half, npx])
+    for k, val in zip(['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np'], img):
+        out['img_' + k] = val
+    save('fromfile_models', **out)
+
+
 def inverse_lensing():
     """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
     out = {}
@@ -280,8 +304,8 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] == 'inverse_lensing':     # add this fixture without touching the others
-        inverse_lensing()
+    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models'):     # add one fixture without touching the others
+        globals()[sys.argv[1]]()
         sys.exit(0)
     special()
     setup()
@@ -291,5 +315,6 @@ if __name__ == '__main__':
     models()
     counts()
     inverse_lensing()
+    fromfile_models()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

@@ -297,3 +297,52 @@ def test_spin_inclination_sweep_against_oracle(kg):
                 tol = TRACK_RTOL if key in ('r', 't') else IMAGE_RTOL
                 assert e <= tol, "a=%g inc=%g %s: %.2e" % (a, inc, key, e)
     print("sweep worst rel errors", worst)
+
+
+# ---- tabulated 'fromfile' models -----------------------------------------------------------------
+TABLE = None
+
+
+def _table_file():
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'a0p6_inflow.csv')
+
+
+def test_fromfile_models_against_reference(golden, kg):
+    """Velocity('fromfile') / Bfield('fromfile'): element-wise u^mu, B^i, b^2 (incl. radii beyond both table ends) and one
+    polarized image vs the unmodified reference (tests/golden/fromfile_models.npz)."""
+    g = golden('fromfile_models')
+    a, r = float(g['a']), g['r']
+    v = kg.Velocity('fromfile', file=_table_file())
+    b = kg.Bfield('fromfile', file=_table_file())
+    assert_close(np.array(v.u_lab(a, r)), g['u'], 1e-12, what='fromfile u_lab')
+    assert_close(np.array(b.bfield_lab(a, r)), g['B'], 1e-12, what='fromfile bfield_lab')
+    assert_close(b.bsq(a, r, v), g['bsq'], 1e-11, what='fromfile bsq')
+    a_, r_o, th_o, mbar_max, half, npx = [float(x) for x in g['par']]
+    out = kg.make_image(a_, r_o, th_o, int(mbar_max), -half, half, -half, half, 2 * half / npx,
+                        emissivity=kg.Emissivity('ring', r_ring=3.5, sigma=0.6), velocity=v, bfield=b, polarization=True,
+                        specind=1.)
+    ref_I = g['img_I']
+    for got, key in zip(out, ['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np']):
+        ref = g['img_' + key]
+        assert got.shape == ref.shape and np.array_equal(got == 0, ref == 0), key
+        if key in ('Q', 'U'):
+            den = np.where(ref_I != 0, np.abs(ref_I), 1.0)
+            assert np.nanmax(np.abs(got - ref) / den) <= IMAGE_RTOL, key
+        elif key == 'n':
+            assert np.array_equal(got, ref)
+        else:
+            assert_close(got, ref, IMAGE_RTOL if key in ('I', 'g', 'sinthb', 'np') else TRACK_RTOL, floor=1e-300,
+                         what='fromfile image %s' % key)
+
+
+def test_fromfile_known_answers_of_the_reference_tests(kg):
+    """tests/test_velocities.py:56-74 and tests/test_bfields.py:29-44 of the reference (same data file, same numbers)."""
+    v = kg.Velocity('fromfile', file=_table_file())
+    for radius, want in {2.15708: [5.0056, -0.54416, 0.0, 0.75899], 2.5: [3.0016, -0.45323831, 0.0, 0.41926807],
+                         3.58635: [1.7755, -0.22549, 0.0, 0.19684], 4.90566: [1.4859, -0.021582, 0.0, 0.12754]}.items():
+        assert np.allclose(np.squeeze(v.u_lab(0.6, np.array(radius))), want, rtol=1.e-4)
+    b = kg.Bfield('fromfile', file=_table_file())
+    for radius, want in {2.15708: [0.84877, 0.0, -0.53419], 2.5: [0.63206, 0.0, -0.23666],
+                         3.58635: [0.30706, 0.0, -0.066873], 4.90566: [0.16411, 0.0, -0.029673]}.items():
+        assert np.allclose(np.squeeze(b.bfield_lab(0.6, radius)), want, rtol=1.e-4)

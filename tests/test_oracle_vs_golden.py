@@ -189,3 +189,20 @@ def test_inverse_lensing_oracle_matches_reference(golden):
         assert np.array_equal(al, g['crit_alpha_%d' % ic]) and np.array_equal(be, g['crit_beta_%d' % ic])
     for m in (0, 1, 2):
         assert abs(ko.rho_of_req_single(0.94, 17 * np.pi / 180, 5.0, 0.3, mbar=m) - g['single'][m]) <= 1e-12
+
+
+def test_fromfile_models_oracle_matches_reference(golden):
+    """np.interp table models (kgeo/velocities.py:626-698, kgeo/bfields.py:749-806) incl. one polarized image."""
+    import os
+    g = golden('fromfile_models')
+    F = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'a0p6_inflow.csv')
+    a, r = float(g['a']), g['r']
+    vel, bf = dict(type='fromfile', file=F), dict(type='fromfile', file=F)
+    assert_close(np.array(ko.velocity_u_lab(vel, a, r)), g['u'], 1e-14, what='fromfile u')
+    assert_close(np.array(ko.bfield_lab(bf, a, r)), g['B'], 1e-14, what='fromfile B')
+    assert_close(ko.bfield_bsq(bf, vel, a, r), g['bsq'], 1e-13, what='fromfile bsq')
+    a_, ro, th, mb, half, npx = g['par']
+    img = ko.make_image(a_, ro, th, int(mb), -half, half, -half, half, 2 * half / npx, dict(type='ring', r_ring=3.5, sigma=0.6),
+                        vel, bf, polarization=True, specind=1.)
+    for k, val in zip(['I', 'Q', 'U', 'r', 't', 'g', 'sinthb'], img):
+        assert_close(val, g['img_' + k], 1e-12, floor=1e-300, what='fromfile image ' + k)
