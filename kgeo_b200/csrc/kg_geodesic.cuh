@@ -419,12 +419,12 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 // ---- theta blocks of a motion (setup) -------------------------------------------------------------------------------------
 // Builds base + NP Pi blocks at w[slot...]; returns true when the theta path is usable for every integral of the motion.
 template <class P>
-KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, P blk) {
+KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double pmax, P blk) {
     ThetaRay r = theta_ray(m);
     int J = theta_make_base(r, blk);
     bool ok = r.ok != 0;
     for (int i = 0; i < NP; ++i) {
-        int Ji = theta_make_pi(r, n[i], nmm ? nmm[i] : n[i] - m, omn ? omn[i] : 1.0 - n[i], blk + TB_SIZE + i * TP_SIZE);
+        int Ji = theta_make_pi(r, n[i], nmm ? nmm[i] : n[i] - m, omn ? omn[i] : 1.0 - n[i], pmax, blk + TB_SIZE + i * TP_SIZE);
         if (Ji < 0) ok = false;
         else if (Ji > J) J = Ji;
     }
@@ -441,7 +441,7 @@ template <class WP>
 KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double n, double D3, WP w, int* flags) {
     const double Km = ellip_K(m);
     const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
-    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, w + T_TH);
+    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, kThetaPMaxPolar, w + T_TH);
     const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
     const double mn = m / npr;
     w[T_TH_SLOPE] = D3 * sq1m * fma(1.0 - mn, A, mn);
@@ -453,7 +453,7 @@ KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, dou
 
 template <class WP>
 KG_HD void radial_theta_setup(double k, const double* n, WP w, int* flags) {
-    if (!theta_make_motion(3, k, n, nullptr, nullptr, w + R_TH)) return;
+    if (!theta_make_motion(3, k, n, nullptr, nullptr, kThetaPMax, w + R_TH)) return;
     *flags |= F_R_THETA;
     const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
                  k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
@@ -817,8 +817,9 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
         const double sq1m_ = w(T_SQ), ua = snarg * w(T_ISQ);
         double L = 0.0;
         const ThetaOut t = full ? theta_eval_motion<W, 1, 0x2>(w, T_TH, ua, &L) : theta_eval_motion<W, 0, 0>(w, T_TH, ua, &L);
-        const double idn_ = frcp(t.dn);
-        const double sinA_ = sq1m_ * t.sn * idn_;
+        // sn/dn = (R1/R3) th1/th3, sn cn/dn = (R1 R2/R3) th1 th2/(th3 th4), Z = W th4'/th4: one reciprocal for all three
+        const double inv34 = frcp(t.th3 * t.th4);
+        const double sinA_ = sq1m_ * (w(T_TH + TB_R13) * t.th1 * (inv34 * t.th4));
         if (flags & F_TH_ORD) {
             *th = kg_acos(w(T_A) * sinA_);
         } else {
@@ -827,7 +828,8 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
         }
         if (!full) return;
         *Gph = fma(w(T_TH_SLOPE), ua, w(T_TH_COEF) * L) - w(T_GPH0);
-        const double Dtot = sq1m_ * (fma(w(T_TH_G), ua, t.Z * w(T_TH_IM)) - t.sn * t.cn * idn_);
+        const double Z_ = w(T_TH + TB_W) * t.dth4 * (inv34 * t.th3);
+        const double Dtot = sq1m_ * (fma(w(T_TH_G), ua, Z_ * w(T_TH_IM)) - w(T_TH + TB_R123) * (t.th1 * t.th2) * inv34);
         *Gt = fma(w(T_C3), snarg, 3.0 * w(T_C1) * Dtot) - w(T_GT0);
         return;
     }
@@ -900,6 +902,8 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     double I1 = 0.0, I2 = 0.0, Ip = 0.0, Im = 0.0;
     // E and the three Pi's at am(X|k), shared by every radial case
     double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
+    bool th_case2 = false;           // theta path of case 2: r(tau) and 1/den come out of the merged reciprocal below
+    double rs2 = 0.0, iden2 = 0.0;
     if (LADDER && (flags & F_R_THETA)) {   // theta-function path (kg_theta.cuh)
         double L[3] = {0.0, 0.0, 0.0};
         ThetaOut t;
@@ -907,9 +911,30 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
         else if (flags & F_R_K100) t = theta_eval_motion<W, 3, 0x001>(w, R_TH, X, L);
         else if (flags & F_R_K111) t = theta_eval_motion<W, 3, 0x111>(w, R_TH, X, L);
         else t = theta_eval_motion<W, 3, kKindsGeneric>(w, R_TH, X, L);
-        jr.sn = t.sn; jr.cn = t.cn; jr.dn = t.dn;
+        double Z;
+        if (flags & F_CASE2) {
+            // r = (r4 r31 - r3 r41 sn^2)/(r31 - r41 sn^2) with sn = R1 th1/th4: numerator and denominator times th4^2, and
+            // ONE reciprocal 1/(th4 D) gives both 1/th4 (for sn, cn, dn, Z) and 1/D
+            th_case2 = true;
+            const double q1 = w(R_Q0), q3 = w(R_Q2), q4 = w(R_Q3);
+            const double rr31 = q3 - q1, rr41 = q4 - q1;
+            const double s1 = w(R_TH + TB_R1) * t.th1, s2 = s1 * s1, t42 = t.th4 * t.th4;
+            const double D = fma(-rr41, s2, rr31 * t42);
+            const double inv = frcp(t.th4 * D);
+            const double i4 = inv * D, iD = inv * t.th4;
+            rs2 = fma(-(q3 * rr41), s2, (q4 * rr31) * t42) * iD;
+            iden2 = t42 * iD;
+            jr.sn = s1 * i4;
+            jr.cn = w(R_TH + TB_R2) * t.th2 * i4;
+            jr.dn = w(R_TH + TB_R3) * t.th3 * i4;
+            Z = w(R_TH + TB_W) * t.dth4 * i4;
+        } else {
+            const ThetaJac j = theta_ratios(w, R_TH, t);
+            jr.sn = j.sn; jr.cn = j.cn; jr.dn = j.dn;
+            Z = j.Z;
+        }
         if (full) {
-            E = fma(w(R_TH + TB_EOKM1), X, X) + t.Z;
+            E = fma(w(R_TH + TB_EOKM1), X, X) + Z;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 Pi[i] = fma(w(R_TH + TB_SIZE + i * TP_SIZE + TP_A), X, w(R_TH + TB_SIZE + i * TP_SIZE + TP_P) * L[i]);
@@ -929,15 +954,21 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     if (flags & F_CASE2) {
         double q1 = w(R_Q0), q2 = w(R_Q1), q3 = w(R_Q2), q4 = w(R_Q3), root = w(R_Q4);
         double rr31 = q3 - q1, rr41 = q4 - q1, rr43 = q4 - q3;
-        double sn2 = sn * sn;
-        // explicit FMAs: r(tau) must not depend on how nvcc contracts the expression in the full / partial kernels
-        double den = fma(-rr41, sn2, rr31);
-        double iden = frcp(den);
-        double rs = fma(-(q3 * rr41), sn2, q4 * rr31) * iden;                 // :592-594
+        double rs, iden;
+        if (th_case2) {
+            rs = rs2;
+            iden = iden2;
+        } else {
+            double sn2 = sn * sn;
+            // explicit FMAs: r(tau) must not depend on how nvcc contracts the expression in the full / partial kernels
+            double den = fma(-rr41, sn2, rr31);
+            iden = frcp(den);
+            rs = fma(-(q3 * rr41), sn2, q4 * rr31) * iden;                    // :592-594
+        }
         *r_s = rs;
         if (full) {
-            double drs = rr31 * rr43 * rr41 * (sn * cn * dn * root) * (iden * iden);   // :600-603
-            double H = fdiv(drs, rs - q3) - w(R_Q5);
+            // H = (dr/dtau)/(r - r3) (:600-606) with dr/dtau = r31 r43 r41 sn cn dn root/den^2 and r - r3 = r31 r43/den
+            double H = rr41 * (sn * cn * dn * root) * iden - w(R_Q5);
             double Pi_1 = w(R_Q6) * (Pi[0] - w(R_PO0));
             double Pi_p = w(R_Q7) * (Pi[1] - w(R_PO1));
             double Pi_m = w(R_Q8) * (Pi[2] - w(R_PO2));

@@ -34,14 +34,19 @@ KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D
 // Rays outside these bounds keep the Carlson path (decided once per ray in the setup):
 //   nome: the series need J = 7 harmonics at q = 0.4 (kThJM = 8 are stored); beyond that the ray is within ~1e-3 of the
 //   critical curve, where the reference itself loses digits (looser gate next to the critical curve);
-//   prefactor P = sn a/(cn a dn a) of Pi = A u + P L: A = 1 + P Z(a) is formed with an absolute error ~ P eps.
+//   prefactor P = sn a/(cn a dn a) of Pi = A u + P L: A = 1 + P Z(a) is formed with an absolute error ~ P eps (radial bound);
+//   for the polar motion (kind 2, L = arg theta3(v - i beta)) a ray that passes next to the rotation axis drives theta3 to
+//   within ~1/P of its zero, so L carries eps P and Pi eps P^2 there (measured 9e-11 at P = 780): polar bound 300.
 #ifndef KG_THETA_QMAX
 #define KG_THETA_QMAX 0.4
 #endif
 #ifndef KG_THETA_PMAX
 #define KG_THETA_PMAX 3000.0
 #endif
-constexpr double kThetaQMax = KG_THETA_QMAX, kThetaPMax = KG_THETA_PMAX;
+#ifndef KG_THETA_PMAX_POLAR
+#define KG_THETA_PMAX_POLAR 300.0
+#endif
+constexpr double kThetaQMax = KG_THETA_QMAX, kThetaPMax = KG_THETA_PMAX, kThetaPMaxPolar = KG_THETA_PMAX_POLAR;
 
 struct ThetaRay {
     double m, K, Kp, q, eokm1, eokm1p;   // eokm1p = E(m')/K' - 1
@@ -105,6 +110,8 @@ KG_HD int theta_make_base(const ThetaRay& r, P out) {
     out[TB_R1] = t3 / t2;
     out[TB_R2] = t4 / t2;
     out[TB_R3] = t4 / t3;
+    out[TB_R13] = (t3 * t3) / (t2 * t4);
+    out[TB_R123] = (t3 * t3) / (t2 * t2);
     return J;
 }
 
@@ -112,7 +119,7 @@ KG_HD int theta_make_base(const ThetaRay& r, P out) {
 // nmm = n - m and omn = 1 - n are passed separately so that callers who know them without cancellation (the polar motion:
 // n' - m = n (1 - m), 1 - n' = (1 - n)(1 - m)) keep full accuracy next to the edges n -> m, n -> 1.
 template <class WP>
-KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, WP out) {
+KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, double pmax, WP out) {
     for (int i = 0; i < TP_SIZE; ++i) out[i] = 0.0;
     out[TP_A] = 1.0;
     if (!r.ok || !(n == n)) return -1;
@@ -163,7 +170,7 @@ KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, WP 
         sh = kHalfPi * F / r.K;
         kind = 2;
     }
-    if (!(fabs(P) <= kThetaPMax) || !(Zs == Zs)) return -1;
+    if (!(fabs(P) <= pmax) || !(Zs == Zs)) return -1;
     out[TP_KIND] = (double)kind;
     out[TP_P] = P;
     out[TP_A] = fma(P, Zs, 1.0);
@@ -227,10 +234,21 @@ KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, WP 
 }
 
 // ---- per-sample evaluation ------------------------------------------------------------------------------------------
-// Out: sn, cn, dn, Z(u) and L_i (i < NP) of the motion whose base block starts at slot `base`; Pi blocks follow the base block.
+// Out: the theta sums (-> sn, cn, dn, Z(u) by theta_ratios) and L_i (i < NP) of the motion whose base block starts at slot `base`; Pi blocks follow the base block.
 struct ThetaOut {
+    double th1, th2, th3, th4, dth4;   // theta1..4(v) (up to the constant factors folded into TB_R*) and d theta4/dv
+};
+// sn, cn, dn, Z from the raw sums with one reciprocal (callers that need further quotients merge their own, see
+// theta_eval / radial_eval)
+struct ThetaJac {
     double sn, cn, dn, Z;
 };
+template <class W>
+KG_HD ThetaJac theta_ratios(const W& w, int base, const ThetaOut& t) {
+    const double i4 = frcp(t.th4);
+    return ThetaJac{w(base + TB_R1) * t.th1 * i4, w(base + TB_R2) * t.th2 * i4, w(base + TB_R3) * t.th3 * i4,
+                    w(base + TB_W) * t.dth4 * i4};
+}
 
 // KINDS packs the kind (0, 1 or 2, see ThetaPiSlot) of Pi block i into bits [4i, 4i+3]; a nibble of 0xF means "read it from
 // the block" (generic).  The setup flags the rays whose pattern is one of the static ones (the polar block is always kind
@@ -284,12 +302,7 @@ KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
         cep = ce; sep = se; cop = co; sop = so;
         ce = cen; se = sen; co = con; so = son;
     }
-    ThetaOut o;
-    const double i4 = frcp(th4);
-    o.sn = w(base + TB_R1) * th1 * i4;
-    o.cn = w(base + TB_R2) * th2 * i4;
-    o.dn = w(base + TB_R3) * th3 * i4;
-    o.Z = w(base + TB_W) * dth4 * i4;
+    const ThetaOut o{th1, th2, th3, th4, dth4};
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         if (kind[i] == 2) L[i] = fatan2(Y[i], X[i]);

@@ -11,6 +11,7 @@ enum ThetaBaseSlot {
     TB_EOKM1,      // E/K - 1  (accurate for m -> 0)
     TB_J,          // number of harmonics to sum
     TB_R1, TB_R2, TB_R3,                 // th3(0)/th2(0), th4(0)/th2(0), th4(0)/th3(0)
+    TB_R13, TB_R123,                     // R1/R3, R1 R2/R3 (polar motion: sn/dn and sn cn/dn with one reciprocal)
     TB_QE,                               // 2 (-1)^j q^(j^2), j = 1..JM
     TB_QO = TB_QE + kThJM,               // 2 (-1)^j q^((j+1/2)^2), j = 0..JM-1
     TB_SIZE = TB_QO + kThJM

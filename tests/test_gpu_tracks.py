@@ -146,6 +146,36 @@ def test_invariants_at_baseline_size(kg):
     assert np.max(np.abs(rr[0] / rs[ok] - 1)) < 1e-12
 
 
+def test_theta_path_agrees_with_duplication_path_on_a_dense_grid(kg, monkeypatch):
+    """The shipped per-ray theta-function evaluation vs the reference's algorithm (Carlson duplication per sample, selected
+    with KGEO_B200_CARLSON_ONLY) over 512 x 512 rays x 40 samples of the BASELINE cfg 3 view and of an edge-on view: the
+    two must agree to the parity gate on every sample that is not a removable singularity of the reference's formulas
+    (see helpers.removable_singularity_mask), for all four coordinates."""
+    from helpers import removable_singularity_mask, track_errors, TRACK_RTOL, PV_RTOL
+    for a, inc, half in ((0.94, 17.0, 10.0), (0.7, 80.0, 8.0)):
+        th_o, r_o = inc * np.pi / 180, 1000.
+        x = np.linspace(-half, half, 512)
+        A, B = [v.flatten() for v in np.meshgrid(x, x)]
+        monkeypatch.delenv("KGEO_B200_CARLSON_ONLY", raising=False)
+        g1 = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=40, plotdata=False)
+        monkeypatch.setenv("KGEO_B200_CARLSON_ONLY", "1")
+        g0 = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=40, plotdata=False)
+        monkeypatch.delenv("KGEO_B200_CARLSON_ONLY", raising=False)
+        assert np.array_equal(g0.tausteps, g1.tausteps)
+        rplus = 1 + np.sqrt(1 - a * a)
+        pv = removable_singularity_mask(a, r_o, th_o, A, B, g0.geo_coords[1])
+        assert pv.mean() < 0.01
+        for key, got, ref, floor in (('r', g1.geo_coords[1], g0.geo_coords[1], 1e-3), ('th', g1.geo_coords[2], g0.geo_coords[2], 1.0),
+                                     ('ph', g1.geo_coords[3], g0.geo_coords[3], 1.0), ('t', g1.geo_coords[0], g0.geo_coords[0], r_o)):
+            if key in ('ph', 't'):
+                core, _ = track_errors(np.where(pv, got, ref), ref, g0.tausteps, g0.geo_coords[1], floor, rplus)
+                assert core <= PV_RTOL, "a=%g inc=%g %s on removable singularities: %.3e" % (a, inc, key, core)
+                got = np.where(pv, ref, got)
+            core, tail = track_errors(got, ref, g0.tausteps, g0.geo_coords[1], floor, rplus)
+            assert core <= TRACK_RTOL, "a=%g inc=%g %s: theta vs duplication path %.3e" % (a, inc, key, core)
+            assert tail <= 1e-2
+
+
 def test_row_shards_equal_single_launch_bitwise(kg):
     """Multi-GPU check of SURVEY 8e runnable on one GPU: tracing row blocks separately == tracing the whole plane."""
     from kgeo_b200 import sharding
