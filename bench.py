@@ -122,7 +122,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -281,7 +281,7 @@ def run_ours(args):
     if os.environ.get("KGEO_BENCH_PROFILE"):      # under ncu: kernels only, no e2e / CPU legs, no JSON claim
         if rank == 0:
             sampler.stop()
-            print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "track_kernel_ms": float(np.median(track_ms))}))
+            emit({"profile_only": True, "ms_per_step": ms_per_step, "track_kernel_ms": float(np.median(track_ms))})
         return
 
     # ---- e2e through the host-buffer C ABI ----
@@ -432,12 +432,31 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "secondary": secondary,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (see main: libraries print to stderr meanwhile)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints (e.g. "NCCL version ..." on communicator creation)
+    # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
