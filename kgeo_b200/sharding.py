@@ -134,3 +134,80 @@ def raytrace_sharded(a, observer_coords, image_coords, ncols, ngeo, maxtaufrac=1
     geos = raytrace_ana(a, observer_coords, [np.ascontiguousarray(al), np.ascontiguousarray(be)], ngeo=ngeo,
                         maxtaufrac=maxtaufrac, plotdata=False)
     return geos, rows
+
+
+# ---- BASELINE cfg 5: a sweep of whole images, partitioned by CONFIG ------------------------------------
+def config_indices(nconf, rank, world):
+    """Configurations owned by `rank`: every world-th one (cost grows with spin and inclination along the usual sweep
+    order, so a round-robin split balances better than blocks)."""
+    return list(range(rank, nconf, world))
+
+
+def gather_configs(local, nconf, dst=0, group=None):
+    """Gather per-configuration tensors to rank `dst`.
+
+    local: tensor [nconf_local, ...] holding this rank's configurations in the order of config_indices.  Returns the
+    [nconf, ...] tensor in sweep order on `dst`, None elsewhere (equal-size padded buffers, one gather)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    owned = [config_indices(nconf, r, world) for r in range(world)]
+    maxn = max(len(ix) for ix in owned)
+    tail = tuple(local.shape[1:])
+    buf = torch.zeros((maxn,) + tail, dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, gather_list=parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty((nconf,) + tail, dtype=local.dtype, device=local.device)
+    for ix, p in zip(owned, parts):
+        if len(ix):
+            out[torch.as_tensor(ix, device=local.device)] = p[:len(ix)]
+    return out
+
+
+def make_image_sweep_sharded(configs, r_o, mbar_max, alpha_min, alpha_max, beta_min, beta_max, psize, dst=0, group=None,
+                             **kwargs):
+    """Images of a list of (a, th_o) configurations (BASELINE cfg 5: 64 spin x inclination configs of 512 x 512 pixels over
+    8 GPUs), one whole image per fused kernel launch, configurations dealt round-robin to the ranks of `group`; rank `dst`
+    returns a list of make_image-shaped tuples in the order of `configs`, other ranks None.  Works without a process group
+    (single GPU: every configuration is local)."""
+    import torch
+    import torch.distributed as dist
+    from . import equatorial_images as ei
+    have_pg = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if have_pg else 1
+    rank = dist.get_rank(group) if have_pg else 0
+    alpha_arr, beta_arr = ei.pixel_grid(alpha_min, alpha_max, beta_min, beta_max, psize)
+    pathlength = bool(kwargs.get("pathlength", False))
+    names = ["I", "Q", "U", "r", "Ir", "g", "sinthb"] + (["lp", "Ie"] if pathlength else [])
+    planes, scal = [], []
+    for i in config_indices(len(configs), rank, world):
+        a, th_o = configs[i]
+        out = ei.image_device(float(a), r_o, float(th_o), 0, mbar_max, alpha_arr, beta_arr,
+                              kwargs.get("emissivity", ei.emis_default), kwargs.get("velocity", ei.vel_default),
+                              kwargs.get("bfield", ei.bfield_default), kwargs.get("polarization", False), pathlength,
+                              kwargs.get("specind", ei.SPECIND), kwargs.get("diskangle", ei.DISKANGLE),
+                              kwargs.get("nu_obs", ei.OBSFREQ))
+        planes.append(torch.stack([out[k] for k in names]))              # [nplane, norder, npix]
+        scal.append(torch.stack([out["nmax"], out["npol"]]))             # [2, npix]
+    from . import _engine
+    dev = _engine.device()
+    npix, norder = alpha_arr.size, mbar_max + 1
+    P = torch.stack(planes) if planes else torch.zeros((0, len(names), norder, npix), dtype=torch.float64, device=dev)
+    S = torch.stack(scal) if scal else torch.zeros((0, 2, npix), dtype=torch.float64, device=dev)
+    if have_pg and world > 1:
+        P = gather_configs(P, len(configs), dst, group)
+        S = gather_configs(S, len(configs), dst, group)
+        if rank != dst:
+            return None
+    P, S = P.cpu().numpy(), S.cpu().numpy()
+    res = []
+    for c in range(len(configs)):
+        tup = tuple(P[c, i].T for i in range(7)) + (S[c, 0], S[c, 1])
+        if pathlength:
+            tup = tup + (P[c, 7].T, P[c, 8].T)
+        res.append(tup)
+    return res

@@ -28,6 +28,9 @@ def main():
     geos, (r0, r1) = sharding.raytrace_sharded(a, [0, 1000., th_o, 0], [A, B], 120, ngeo=50)
     whole = kg.raytrace_ana(a, [0, 1000., th_o, 0], [A, B], ngeo=50, plotdata=False)
     ok = all(np.array_equal(w[:, r0 * 120:r1 * 120], p, equal_nan=True) for w, p in zip(whole.geo_coords, geos.geo_coords))
+    # BASELINE cfg 5 partition: whole images dealt round-robin to the ranks, gathered in sweep order
+    cfgs = [(aa, tt * np.pi / 180) for aa in (0.0, 0.5, 0.99) for tt in (5.0, 45.0, 85.0)]
+    sweep = sharding.make_image_sweep_sharded(cfgs, np.inf, 2, -10., 10., -10., 10., 20. / 64, dst=0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -35,7 +38,10 @@ def main():
         for got, want in zip(res, single):
             assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True), "sharded image differs"
         assert int(flag.item()) == 1, "a track shard differs from the whole-plane trace"
-        print("dist_check ok: world %d, image %s, track shards bitwise equal" % (world, res[0].shape))
+        for (aa, tt), got in zip(cfgs, sweep):
+            want = kg.make_image(aa, np.inf, tt, 2, -10., 10., -10., 10., 20. / 64)
+            assert all(np.array_equal(g_, w_, equal_nan=True) for g_, w_ in zip(got, want)), "sweep image differs"
+        print("dist_check ok: world %d, image %s, track shards bitwise equal, %d-config sweep equal" % (world, res[0].shape, len(cfgs)))
     dist.destroy_process_group()
 
 

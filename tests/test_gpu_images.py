@@ -346,3 +346,16 @@ def test_fromfile_known_answers_of_the_reference_tests(kg):
     for radius, want in {2.15708: [0.84877, 0.0, -0.53419], 2.5: [0.63206, 0.0, -0.23666],
                          3.58635: [0.30706, 0.0, -0.066873], 4.90566: [0.16411, 0.0, -0.029673]}.items():
         assert np.allclose(np.squeeze(b.bfield_lab(0.6, radius)), want, rtol=1.e-4)
+
+
+def test_image_sweep_matches_single_images(kg):
+    """BASELINE cfg 5 entry point without a process group (one GPU): every configuration's image == make_image."""
+    from kgeo_b200 import sharding
+    cfgs = [(0.0, 5 * np.pi / 180), (0.42, 45 * np.pi / 180), (0.99, 85 * np.pi / 180)]
+    res = sharding.make_image_sweep_sharded(cfgs, np.inf, 2, -10., 10., -10., 10., 20. / 48)
+    assert len(res) == 3
+    for (a, th), got in zip(cfgs, res):
+        want = kg.make_image(a, np.inf, th, 2, -10., 10., -10., 10., 20. / 48)
+        assert len(got) == len(want)
+        for g_, w_ in zip(got, want):
+            assert g_.shape == w_.shape and np.array_equal(g_, w_, equal_nan=True)

@@ -65,3 +65,46 @@ def test_gather_rows_gloo(world, nrows, ncols):
     want = np.stack([np.stack([A + 10 * B, A * B]), np.stack([A - B, A + B])])
     assert np.array_equal(out, want)
     assert np.array_equal(vec, A)
+
+
+def _worker_cfg(rank, world, port, nconf, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from kgeo_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = sharding.config_indices(nconf, rank, world)
+        # stand-in for one fused image per configuration: planes that encode the configuration index
+        local = torch.tensor([[[10.0 * c + p + 0.25 * k for k in range(3)] for p in range(2)] for c in mine],
+                             dtype=torch.float64).reshape(len(mine), 2, 3)
+        out = sharding.gather_configs(local, nconf, dst=0)
+        if rank == 0:
+            q.put(out.numpy())
+        else:
+            assert out is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nconf", [(2, 8), (2, 5), (3, 7)])
+def test_gather_configs_gloo(world, nconf):
+    """BASELINE cfg 5 partition (whole images dealt round-robin to ranks) and its gather, on gloo."""
+    import torch.multiprocessing as mp
+    from kgeo_b200 import sharding
+    assert sorted(sum((sharding.config_indices(nconf, r, world) for r in range(world)), [])) == list(range(nconf))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_cfg, args=(r, world, port, nconf, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = np.array([[[10.0 * c + p + 0.25 * k for k in range(3)] for p in range(2)] for c in range(nconf)])
+    assert np.array_equal(out, want)
