@@ -244,7 +244,10 @@ constexpr int TRK_THREADS = 32 * TRK_WARPS;
 constexpr int TRK_RPW = 4;                          // rays per warp = doubles per 32-byte sector
 constexpr int TRK_XS = 1;                           // extra per-ray slot staged behind the workspace: flags
 constexpr int TRK_WSLOTS = NW + TRK_XS;
-constexpr size_t TRK_SMEM = (size_t)TRK_WSLOTS * TRK_RPW * sizeof(double);
+#ifndef KG_TRK_PAD_SMEM
+#define KG_TRK_PAD_SMEM 0               // experiments only: unused shared memory that limits the CTAs per SM
+#endif
+constexpr size_t TRK_SMEM = (size_t)TRK_WSLOTS * TRK_RPW * sizeof(double) + KG_TRK_PAD_SMEM;
 
 struct SmemW {
     const double* p;   // &sw[0][j]: slot i of ray j of this warp (a broadcast load)
