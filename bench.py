@@ -9,7 +9,7 @@ theta_o=17 deg, r_o=1000, +-10 M).  With N>1 ranks (one process per GPU under to
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      FP64-pipe roofline of the track kernel: achieved = FP64 flops the kernel executes per point (631: the
+  roofline      FP64-pipe roofline of the track kernel: achieved = FP64 flops the kernel executes per point (607: the
                 DFMA/DMUL/DADD mix of the committed ncu capture, profiles/) x points per launch / CUDA-event duration;
                 peak = DFMA-chain rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry).  "canonical"
                 restates the same launch in SURVEY 8(d)'s work model (2400 flop/point for Carlson duplication): the kernel
@@ -39,9 +39,9 @@ NPIX_SIDE, NGEO = 1024, 500
 MAXTAUFRAC = 1.0 - 1.0e-10
 CANONICAL_FLOP_PER_POINT = 2400.0   # SURVEY.md 8(d) work model: Carlson duplication, the reference's algorithm
 # FP64 flops track_kernel<true> executes per point on this workload (thread-level, predicated-on, ncu --set full of this
-# command: 238 DFMA x 2 + 114 DMUL + 41 DADD; profiles/r01_final_ncu_full_subset.csv)
-EXECUTED_FLOP_PER_POINT = 631.0
-FP64_PIPE_ACTIVE_NCU = 0.504        # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
+# command: 227 DFMA x 2 + 114 DMUL + 39 DADD; profiles/r01_final_ncu_full_subset.csv)
+EXECUTED_FLOP_PER_POINT = 607.0
+FP64_PIPE_ACTIVE_NCU = 0.492        # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the same capture
 BYTES_PER_POINT = 32.0      # r, theta, phi, t written once
 
 
@@ -356,15 +356,15 @@ def run_ours(args):
         "bound": "fp64", "kernel": "track_kernel<true>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": (ach_tf / peak_tf) if peak_tf else None,
         "flop_per_point": EXECUTED_FLOP_PER_POINT,
-        "flop_source": "FP64 flops executed per point (ncu: 238 DFMA + 114 DMUL + 41 DADD thread instructions)",
+        "flop_source": "FP64 flops executed per point (ncu: 227 DFMA + 114 DMUL + 39 DADD thread instructions)",
         "fp64_pipe_active_ncu": FP64_PIPE_ACTIVE_NCU,
         "canonical": {"flop_per_point": CANONICAL_FLOP_PER_POINT, "achieved": canon_tf,
                       "frac": (canon_tf / peak_tf) if peak_tf else None,
                       "note": "SURVEY 8(d) work model of the reference's algorithm (Carlson duplication per sample); this "
                               "kernel computes the same values with per-ray theta-function series, ~4x fewer flops"},
         # dram__bytes_read.sum + dram__bytes_write.sum of one track_kernel launch on this workload, from the committed
-        # ncu --set full capture (profiles/r01_final_ncu_full_subset.csv): 2.15 GB + 16.77 GB; algorithmic 16.78 GB
-        "traffic": 18.92e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/launch",
+        # ncu --set full capture (profiles/r01_final_ncu_full_subset.csv): 2.18 GB + 16.76 GB; algorithmic 16.78 GB
+        "traffic": 18.95e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/launch",
         "peak_source": "DFMA-chain probe (kgeo_fp64_peak_probe) measured live on this GPU; MEASURED_PEAKS.json has no "
                        "FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s" % nominal_tf,
         "points_per_launch": npts_rank, "kernel_ms": tk * 1e3,

@@ -268,8 +268,13 @@ struct TrackOut {
 #endif
 constexpr int TRK_GROUPS = KG_TRK_GROUPS;           // 4-ray groups a CTA works through one after the other
 
+#ifdef KG_TRK_MAXNREG
+#define KG_TRK_BOUNDS __maxnreg__(KG_TRK_MAXNREG)     // experiments: explicit register cap
+#else
+#define KG_TRK_BOUNDS __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS)
+#endif
 template <bool FULL>
-__global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS) track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
+__global__ void KG_TRK_BOUNDS track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
                                                             const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
                                                             const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
                                                             size_t ld, int k_begin, int k_end, int chunk) {
