@@ -92,6 +92,9 @@ enum Slot {
     R_TH, R_TH_END = R_TH + TB_SIZE + 3 * TP_SIZE - 1,
     NW
 };
+// ray_setup<.., LADDER = false> (image / lensing kernels: register- or local-memory workspace) touches only the slots below
+// the ladders; those kernels size their per-thread workspace with NW_LITE instead of NW
+constexpr int NW_LITE = T_LAD;
 // case-specific meaning of the R_Q* slots
 //  case 2: Q0..Q3 = r1..r4, Q4 = sqrt(r31 r42), Q5 = H_o
 //  case 3: Q0 = r1, Q1 = r2, Q2 = A, Q3 = B, Q4..Q6 = al0, alp, alm, Q7..Q9 = p1(al_i), Q10 = sqrt(AB)
@@ -473,7 +476,7 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
-    for (int i = 0; i < NW; ++i) w[i] = 0.0;
+    for (int i = 0; i < (LADDER ? NW : NW_LITE); ++i) w[i] = 0.0;
     int flags = 0;
     double lam = -alpha * o.sth;
     double eta = conserved_eta(o, alpha, beta);

@@ -129,9 +129,12 @@ __global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const d
 // ---------------------------------------------------------------------------------------------------------------------
 // per-ray setup
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SETUP_THREADS = 64;
+#ifndef KG_SETUP_THREADS
+#define KG_SETUP_THREADS 256
+#endif
+constexpr int SETUP_THREADS = KG_SETUP_THREADS;
 #ifndef KG_SETUP_MINBLOCKS
-#define KG_SETUP_MINBLOCKS 8          // 64-thread CTAs per SM the two setup kernels are compiled for (register cap = 65536/(64*n))
+#define KG_SETUP_MINBLOCKS 2          // CTAs per SM the two setup kernels are compiled for (register cap = 65536/(threads*n))
 #endif
 
 template <bool PHI_T>
@@ -341,10 +344,10 @@ __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o
 // equatorial lensing / image
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef KG_IMG_THREADS
-#define KG_IMG_THREADS 64
+#define KG_IMG_THREADS 256
 #endif
 #ifndef KG_IMG_MINBLOCKS
-#define KG_IMG_MINBLOCKS 16
+#define KG_IMG_MINBLOCKS 3
 #endif
 constexpr int IMG_THREADS = KG_IMG_THREADS;
 
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_ke
                                                                    double* Imax_out, double* npol_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    double w[NW];
+    double w[NW_LITE];
     int fl;
     double be = beta[i];
     ray_setup<false, false>(o, alpha[i], be, M_ANY_ETA_POS, w, &fl);
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_ke
 // ---- inverse lensing: rho_of_req (kgeo/equatorial_lensing.py:197-266) ----------------------------------------------------
 // objective of the root find: r_equatorial2(rho, varphi) - req (:197-224), observer at infinity
 __device__ __noinline__ double req_objective(const Observer& o, double rho, double cv, double sv, int mbar, double req) {
-    double w[NW];
+    double w[NW_LITE];
     int fl;
     const double al = cv * rho, be = sv * rho;
     ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Ob
                                                             ImageOut out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    double w[NW];
+    double w[NW_LITE];
     int fl;
     double al = alpha[i], be = beta[i];
     ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
