@@ -811,12 +811,14 @@ KG_HD double reduce_half_periods(double u, double K, double i2K, double* ur, dou
     return j;
 }
 
-template <class W>
+// THETA_ONLY: the caller guarantees F_TH_THETA / F_R_THETA (hot track kernels: the Carlson fallback is compiled out, which
+// takes 30-60 registers off the kernel; rays without the flag are traced by the fix-up launch with the complete code)
+template <class W, bool THETA_ONLY = false>
 KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, double* Gph, double* Gt) {
     *th = 0.0; *Gph = 0.0; *Gt = 0.0;
     if (!(flags & (F_TH_ORD | F_TH_VORT))) return;
     double snarg = fma(-w(T_W), tau, w(T_X0));
-    if (flags & F_TH_THETA) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
+    if (THETA_ONLY || (flags & F_TH_THETA)) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
         const double sq1m_ = w(T_SQ), ua = snarg * w(T_ISQ);
         double L = 0.0;
         const ThetaOut t = full ? theta_eval_motion<W, 1, 0x2>(w, T_TH, ua, &L) : theta_eval_motion<W, 0, 0>(w, T_TH, ua, &L);
@@ -836,6 +838,7 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
         *Gt = fma(w(T_C3), snarg, 3.0 * w(T_C1) * Dtot) - w(T_GT0);
         return;
     }
+    if (THETA_ONLY) return;
     double sq1m = w(T_SQ);
     const double uarg = snarg * w(T_ISQ);
     const SnCnDn jt = jacobi_from_ladder(SlotView<W>{w, T_LAD}, uarg);
@@ -896,7 +899,7 @@ KG_HD void radial_legendre(const W& w, double X, double Kc, double sn, double cn
     }
 }
 
-template <class W, bool LADDER = true>
+template <class W, bool LADDER = true, bool THETA_ONLY = false>
 KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, bool full, double* r_s, double* Iph,
                        double* It, double* Isig) {
     double X = fma(-w(R_SC), tau, w(R_X0));
@@ -907,7 +910,7 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
     bool th_case2 = false;           // theta path of case 2: r(tau) and 1/den come out of the merged reciprocal below
     double rs2 = 0.0, iden2 = 0.0;
-    if (LADDER && (flags & F_R_THETA)) {   // theta-function path (kg_theta.cuh)
+    if (LADDER && (THETA_ONLY || (flags & F_R_THETA))) {   // theta-function path (kg_theta.cuh)
         double L[3] = {0.0, 0.0, 0.0};
         ThetaOut t;
         if (!full) t = theta_eval_motion<W, 0, 0>(w, R_TH, X, L);
@@ -942,7 +945,7 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
             for (int i = 0; i < 3; ++i)
                 Pi[i] = fma(w(R_TH + TB_SIZE + i * TP_SIZE + TP_A), X, w(R_TH + TB_SIZE + i * TP_SIZE + TP_P) * L[i]);
         }
-    } else {
+    } else if (!THETA_ONLY) {
         if (LADDER) {
             jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
         } else {
@@ -1053,12 +1056,12 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
 }
 
 // one full point (kgeo/kerr_raytracing_ana.py:172-188)
-template <class W>
+template <class W, bool THETA_ONLY = false>
 KG_HD Point point_eval(const W& w, const Observer& o, int flags, double tau, bool full) {
     Point p;
     double Gph, Gt, Iph, It, Isig;
-    theta_eval(w, flags, tau, full, &p.th, &Gph, &Gt);
-    radial_eval(w, o, flags, tau, full, &p.r, &Iph, &It, &Isig);
+    theta_eval<W, THETA_ONLY>(w, flags, tau, full, &p.th, &Gph, &Gt);
+    radial_eval<W, true, THETA_ONLY>(w, o, flags, tau, full, &p.r, &Iph, &It, &Isig);
     p.sig = Isig + o.a2 * Gt;
     p.t = It + o.a2 * Gt;
     p.ph = Iph + w(S_LAM) * Gph;

@@ -258,7 +258,9 @@ KG_HD ThetaJac theta_ratios(const W& w, int base, const ThetaOut& t) {
 constexpr int kKindsGeneric = 0xFFF;
 template <class W, int NP, int KINDS>
 KG_HD ThetaOut theta_eval_motion(const W& w, int base, double u, double* L) {
-    const int J = (int)w(base + TB_J);
+    // J >= 1 (theta_block_build): saying so lets the compiler drop the exit in front of the first harmonic, and with it the
+    // 11-16 instructions that would materialise the initial values of the sums (they fold into the first FMAs instead)
+    const int Jw = (int)w(base + TB_J), J = (Jw < 1) ? 1 : Jw;
     const double v = w(base + TB_W) * u;
     double sv, cv;
     fsincos(v, &sv, &cv);

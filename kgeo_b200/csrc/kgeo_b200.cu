@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -271,47 +272,93 @@ struct TrackOut {
 #endif
 constexpr int TRK_GROUPS = KG_TRK_GROUPS;           // 4-ray groups a CTA works through one after the other
 
-#ifdef KG_TRK_MAXNREG
-#define KG_TRK_BOUNDS __maxnreg__(KG_TRK_MAXNREG)     // experiments: explicit register cap
-#else
-#define KG_TRK_BOUNDS __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS)
+// Passes of a full (r, theta, phi, t) trace.  The Carlson-duplication fallback (0.3 % of the rays of BASELINE cfg 3) costs
+// every thread 50-60 registers whether it runs or not (ptxas wants 154 for the complete per-point code, 64-80 without the
+// fallback), so a full trace is two launches:
+//   P_HOT      theta-function code only, for the rays that are `hot` (F_TH_THETA and F_R_THETA): 64 registers, 32 warps / SM
+//   P_FIXUP    the complete code (theta or Carlson per motion) for the other rays; CTAs whose rays are all hot exit
+//              after reading their flags
+//   P_ALL      every ray through the complete code in one pass: do_phi_and_t = False, caller-supplied Mino times
+//              (coords_at_tau) and KGEO_B200_TRK_PASSES=fused
+// (A third variant -- polar and radial motion as separate passes of 61 / 79 registers that hand lam*G_phi, a^2 G_t over
+// through the output arrays -- was measured and is slower: 9.2 + 18.8 ms against 22.1 ms, profiles/r01_pass_variants.txt.)
+enum TrkPass { P_ALL = 0, P_HOT = 1, P_FIXUP = 2 };
+#ifndef KG_TRK_HOT_MINBLOCKS
+#define KG_TRK_HOT_MINBLOCKS 4
 #endif
-template <bool FULL>
-__global__ void KG_TRK_BOUNDS track_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
-                                                            const int32_t* __restrict__ flags_in, int ntau, double maxtaufrac,
-                                                            const double* __restrict__ tau_in, size_t tau_ld, TrackOut out,
-                                                            size_t ld, int k_begin, int k_end, int chunk) {
+template <int PASS> struct TrkCfg { static constexpr int warps = TRK_WARPS, minblocks = KG_TRK_MINBLOCKS; };
+template <> struct TrkCfg<P_HOT> { static constexpr int warps = TRK_WARPS, minblocks = KG_TRK_HOT_MINBLOCKS; };
+
+__device__ __forceinline__ bool trk_hot(int fl) { return (fl & (F_TH_THETA | F_R_THETA)) == (F_TH_THETA | F_R_THETA); }
+// does this pass trace the ray with these flags?
+template <int PASS>
+__device__ __forceinline__ bool trk_mine(int fl) {
+    return PASS == P_ALL ? true : (PASS == P_FIXUP ? !trk_hot(fl) : trk_hot(fl));
+}
+
+template <bool FULL, int PASS, bool HAS_TAU>
+__global__ void __launch_bounds__(32 * TrkCfg<PASS>::warps, TrkCfg<PASS>::minblocks)
+track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int32_t* __restrict__ flags_in, int ntau,
+             double maxtaufrac, const double* __restrict__ tau_in, size_t tau_ld, TrackOut out, size_t ld, int k_begin,
+             int k_end, int chunk) {
+    constexpr int WARPS = TrkCfg<PASS>::warps, THREADS = 32 * WARPS;
+    constexpr bool THETA_ONLY = (PASS == P_HOT);
+    constexpr int KSTEP = WARPS * (32 / TRK_RPW);                        // samples one CTA-wide pass covers
     extern __shared__ double sw[];                                      // [TRK_WSLOTS][4] constants of the current ray group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = lane & (TRK_RPW - 1), ks = lane / TRK_RPW;
+#ifndef KG_TRK_NO_OPAQUE
+    // byte offset of this thread's ray column, passed through a shuffle: ptxas otherwise re-derives it from %tid (S2R, LOP3,
+    // LEA: ~50 instructions per point) in front of the constant loads instead of keeping one register alive
+    const unsigned joff = __shfl_sync(0xffffffffu, (unsigned)j * (unsigned)sizeof(double), lane);
+#else
+    const unsigned joff = (unsigned)j * (unsigned)sizeof(double);
+#endif
     // this CTA covers samples [k0, k1) of the ntau-sample track; output row = k - k_begin
     const int k0 = k_begin + blockIdx.y * chunk;
     const int k1 = min(k_end, k0 + chunk);
+    const int kfirst = k0 + warp * (32 / TRK_RPW) + ks;
+    const int klast = (ntau > 1) ? ntau - 1 : -1;                        // numpy.linspace: the last sample is `stop` exactly
+    bool staged = false;
     for (int g = 0; g < TRK_GROUPS; ++g) {
         const size_t pix0 = ((size_t)blockIdx.x * TRK_GROUPS + g) * TRK_RPW;
         if (pix0 >= npix) break;                                        // uniform over the CTA
         const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
-        if (g) __syncthreads();                                         // everyone is done with the previous group's constants
-        for (int i = threadIdx.x; i < NW * TRK_RPW; i += TRK_THREADS) {
+        int fl = 0;
+        if (PASS != P_ALL) {                                            // is any ray of the group traced by this pass?
+            bool any = false;
+#pragma unroll
+            for (int jj = 0; jj < TRK_RPW; ++jj) {
+                const int f = (jj < nvalid) ? __ldg(flags_in + pix0 + jj) : 0;
+                any = any || (jj < nvalid && trk_mine<PASS>(f));
+                if (jj == j) fl = f;
+            }
+            if (!any) continue;                                         // uniform over the CTA
+        }
+        if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
+        staged = true;
+        for (int i = threadIdx.x; i < NW * TRK_RPW; i += THREADS) {
             const int s = i / TRK_RPW, jj = i % TRK_RPW;
             sw[i] = (jj < nvalid) ? w_in[(size_t)s * npix + pix0 + jj] : 0.0;
         }
-        if (threadIdx.x < TRK_RPW)
+        if (PASS == P_ALL && threadIdx.x < TRK_RPW)
             sw[NW * TRK_RPW + threadIdx.x] = (threadIdx.x < nvalid) ? (double)flags_in[pix0 + threadIdx.x] : 0.0;
         __syncthreads();
         if (j >= nvalid) continue;
         const size_t pix = pix0 + j;
-        SmemW W{sw + j};
-        const int fl = (int)W(NW);
+        SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(sw) + joff)};
+        if (PASS == P_ALL) fl = (int)W(NW);
+        else if (!trk_mine<PASS>(fl)) continue;
         // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
         const double stop = maxtaufrac * W(S_TAUTOT);
         const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
-        for (int k = k0 + warp * (32 / TRK_RPW) + ks; k < k1; k += TRK_WARPS * (32 / TRK_RPW)) {
+        size_t q = (size_t)(kfirst - k_begin) * ld + pix;              // output index, advanced by KSTEP rows per sample
+        const size_t qstep = (size_t)KSTEP * ld;
+        for (int k = kfirst; k < k1; k += KSTEP, q += qstep) {
             double tau;
-            if (tau_in) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
-            else tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
-            const Point p = point_eval(W, o, fl, tau, FULL);
-            const size_t q = (size_t)(k - k_begin) * ld + pix;
+            if (HAS_TAU) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
+            else tau = (k == klast) ? stop : (double)k * step;
+            const Point p = point_eval<SmemW, THETA_ONLY>(W, o, fl, tau, FULL);
             if (out.r) __stcs(out.r + q, p.r);
             if (out.th) __stcs(out.th + q, p.th);
             if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
@@ -691,9 +738,12 @@ int kgeo_mino_total(const kgeo_observer* obs, size_t n, const double* roots, dou
     return 0;
 }
 
-static int launch_tracks(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
-                         int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
-                         cudaStream_t stream) {
+extern "C++" {
+template <bool FULL, int PASS, bool HAS_TAU>
+static int launch_track_pass(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
+                             int k_end, double maxtaufrac, const double* tau, size_t tau_ld, TrackOut out, size_t ld,
+                             cudaStream_t stream) {
+    constexpr int WARPS = TrkCfg<PASS>::warps;
     // samples [k_begin, k_end) of an ntau-sample track; output (and tau) rows are indexed by (k - k_begin)
     const size_t tiles_ = (npix + TRK_RPW * TRK_GROUPS - 1) / (TRK_RPW * TRK_GROUPS);
     if (tiles_ > 0x7fffffffu) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many rays in one launch");
@@ -703,24 +753,41 @@ static int launch_tracks(const Observer& o, size_t npix, const double* w, const 
     const int want = 148 * 8;
     int ychunks = (int)((want + tiles - 1) / tiles);
     int per = (ns + ychunks - 1) / ychunks;
-    const int blk = TRK_WARPS * (32 / TRK_RPW);       // samples one CTA-wide pass covers
+    const int blk = WARPS * (32 / TRK_RPW);           // samples one CTA-wide pass covers
     per = ((per + blk - 1) / blk) * blk;
     ychunks = (ns + per - 1) / per;
     if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
     dim3 grid(tiles, (unsigned)ychunks);
     const size_t smem = TRK_SMEM;
-    if (full) {
-        CU(cudaFuncSetAttribute(track_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<true><<<grid, TRK_THREADS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
-                                                                k_begin, k_end, per);
-    } else {
-        CU(cudaFuncSetAttribute(track_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        track_kernel<false><<<grid, TRK_THREADS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld, out, ld,
-                                                                 k_begin, k_end, per);
-    }
+    CU(cudaFuncSetAttribute(track_kernel<FULL, PASS, HAS_TAU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    track_kernel<FULL, PASS, HAS_TAU><<<grid, 32 * WARPS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, tau, tau_ld,
+                                                                           out, ld, k_begin, k_end, per);
     LAUNCHED("track_kernel");
     return 0;
 }
+}  // extern "C++"
+
+// KGEO_B200_TRK_PASSES=fused (developer A/B switch, read once): trace every ray with the complete code in a single pass
+static bool track_single_pass() {
+    static const bool fused = [] {
+        const char* e = getenv("KGEO_B200_TRK_PASSES");
+        return e && !strcmp(e, "fused");
+    }();
+    return fused;
+}
+
+#define TRK_ARGS o, npix, w, flags, ntau, k_begin, k_end, maxtaufrac, tau, tau_ld, out, ld, stream
+static int launch_tracks(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
+                         int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
+                         cudaStream_t stream) {
+    if (tau) return full ? launch_track_pass<true, P_ALL, true>(TRK_ARGS) : launch_track_pass<false, P_ALL, true>(TRK_ARGS);
+    if (!full) return launch_track_pass<false, P_ALL, false>(TRK_ARGS);
+    if (track_single_pass()) return launch_track_pass<true, P_ALL, false>(TRK_ARGS);
+    const int rc = launch_track_pass<true, P_HOT, false>(TRK_ARGS);
+    if (rc) return rc;
+    return launch_track_pass<true, P_FIXUP, false>(TRK_ARGS);
+}
+#undef TRK_ARGS
 
 int kgeo_tracks(const kgeo_observer* obs, size_t npix, const double* w, const int32_t* flags, size_t ntau, double maxtaufrac,
                 const double* tau, size_t tau_ld, int full, double* t, double* r, double* th, double* ph, double* sig,
