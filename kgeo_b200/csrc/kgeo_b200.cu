@@ -306,7 +306,16 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
     constexpr int KSTEP = WARPS * (32 / TRK_RPW);                        // samples one CTA-wide pass covers
     extern __shared__ double sw[];                                      // [TRK_WSLOTS][4] constants of the current ray group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // lane = 4 * (sample of the warp's 8-sample block) + ray.  A 64-bit shared-memory load with 4 distinct addresses per half
+    // warp costs two wavefronts, with <= 2 per half warp one (research/ubench/lds_wavefronts.cu: 2.01 against 1.03 cycles per
+    // warp-wide load); the mapping that exploits this (KG_TRK_LANES_HALFWARP: rays (0,1) in lanes 0-15, (2,3) in 16-31,
+    // same full-sector stores) halves the constant-load wavefronts but measured 20.44 against 20.29 ms: the LSU data pipe
+    // (72 % busy) is not what the kernel waits for.
+#ifdef KG_TRK_LANES_HALFWARP
+    const int j = ((lane >> 4) << 1) | (lane & 1), ks = (lane >> 1) & 7;
+#else
     const int j = lane & (TRK_RPW - 1), ks = lane / TRK_RPW;
+#endif
 #ifndef KG_TRK_NO_OPAQUE
     // byte offset of this thread's ray column, passed through a shuffle: ptxas otherwise re-derives it from %tid (S2R, LOP3,
     // LEA: ~50 instructions per point) in front of the constant loads instead of keeping one register alive
@@ -319,21 +328,29 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
     const int k1 = min(k_end, k0 + chunk);
     const int kfirst = k0 + warp * (32 / TRK_RPW) + ks;
     const int klast = (ntau > 1) ? ntau - 1 : -1;                        // numpy.linspace: the last sample is `stop` exactly
+    // flags of the CTA's 32 rays: one coalesced load per warp, and a ballot of the rays this pass traces (every warp gets the
+    // same mask).  A CTA without such rays exits after this single load -- the fix-up pass is thousands of those.
+    static_assert(TRK_GROUPS * TRK_RPW <= 32, "one flag per lane");
+    int tile_flag = 0;
+    unsigned mine_mask = 0xffffffffu;
+    if (PASS != P_ALL) {
+        const size_t p = (size_t)blockIdx.x * (TRK_GROUPS * TRK_RPW) + lane;
+        const bool inside = lane < TRK_GROUPS * TRK_RPW && p < npix;
+        tile_flag = inside ? __ldg(flags_in + p) : 0;
+        mine_mask = __ballot_sync(0xffffffffu, inside && trk_mine<PASS>(tile_flag));
+        if (mine_mask == 0) return;                                     // uniform over the CTA
+    }
+    // (Staging the next group's constants with cp.async into a second buffer while the current group is traced was
+    // measured: 20.25 against 19.99 ms -- with four CTAs per SM the other CTAs already cover the staging latency.)
     bool staged = false;
     for (int g = 0; g < TRK_GROUPS; ++g) {
         const size_t pix0 = ((size_t)blockIdx.x * TRK_GROUPS + g) * TRK_RPW;
         if (pix0 >= npix) break;                                        // uniform over the CTA
         const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
         int fl = 0;
-        if (PASS != P_ALL) {                                            // is any ray of the group traced by this pass?
-            bool any = false;
-#pragma unroll
-            for (int jj = 0; jj < TRK_RPW; ++jj) {
-                const int f = (jj < nvalid) ? __ldg(flags_in + pix0 + jj) : 0;
-                any = any || (jj < nvalid && trk_mine<PASS>(f));
-                if (jj == j) fl = f;
-            }
-            if (!any) continue;                                         // uniform over the CTA
+        if (PASS != P_ALL) {
+            fl = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + j);
+            if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // uniform over the CTA
         }
         if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
         staged = true;
@@ -776,6 +793,8 @@ static bool track_single_pass() {
     return fused;
 }
 
+// (Forking the fix-up pass onto a side stream so that its few long-running CTAs overlap the hot pass was measured: 20.02
+// against 20.08 ms -- not worth a second stream inside the library.)
 #define TRK_ARGS o, npix, w, flags, ntau, k_begin, k_end, maxtaufrac, tau, tau_ld, out, ld, stream
 static int launch_tracks(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
                          int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
