@@ -3,11 +3,11 @@
 // Kernels
 //   ray_setup_kernel   one thread per ray: conserved quantities, quartic roots, root class, tau_tot, observer-side
 //                      antiderivatives and complete integrals -> slot-major SoA workspace (coalesced in the ray index).
-//   track_kernel       the hot kernel.  A CTA owns a tile of 32 consecutive rays; their constants are staged once in
-//                      shared memory ([slot][lane], conflict free), then each warp walks Mino-time samples: one thread
-//                      per (ray, sample), lanes = consecutive rays of one sample, so every store instruction writes one
-//                      contiguous 256-byte row segment of the reference's (ngeo, npix) arrays and every branch on the
-//                      root class is taken by 32 neighbouring pixels together.
+//   track_kernel       the hot kernel: one thread per (ray, Mino-time sample).  A CTA works through 8 groups of 4 consecutive
+//                      rays; a group's constants are staged in shared memory ([slot][4]) and all warps of the CTA walk
+//                      the group's samples together (lane = 4 * sample + ray: every store instruction writes 8 full
+//                      32-byte sectors of the reference's (ngeo, npix) arrays).  A full trace is two launches: a hot
+//                      pass without the Carlson fallback (64 registers) and a fix-up pass for the fallback rays.
 //   image_kernel       fused equatorial image: per pixel one setup in registers/local memory, then all orders
 //                      mbar_min..mbar_max (crossing time, crossing radius, redshift, polarization, emissivity); no
 //                      geodesic array ever goes through HBM.
@@ -221,10 +221,6 @@ __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, s
 // ---------------------------------------------------------------------------------------------------------------------
 // the track kernel
 // ---------------------------------------------------------------------------------------------------------------------
-// 20 warps on one 32-ray tile, one CTA per SM: measured fastest on B200 for BASELINE cfg 3 (78.7 ms; 16 warps 82.7 ms;
-// 4 warps x 4 CTAs 93.5 ms; 8 x 2 87.3 ms) -- warps of one tile take the same root-class branches, so they share
-// instruction-cache lines (the "no instruction" stall per issue drops from 3.1 to 0.4), and 96 registers per thread
-// allow 20 resident warps.
 // Mapping of the track kernel: a CTA owns FOUR CONSECUTIVE RAYS and all its warps walk their Mino-time samples together:
 // lane = 4 * (sample within the warp's 8-sample block) + (ray within the group); warp w takes blocks w, w + TRK_WARPS, ...
 //  * the four lanes of one sample write four consecutive pixels of one row of the reference's (ngeo, npix) arrays = one full
