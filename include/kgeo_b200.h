@@ -53,17 +53,23 @@ typedef struct kgeo_observer {
 
 /* ---- physics models of the equatorial image (kgeo/velocities.py, kgeo/bfields.py, kgeo/emissivities.py) ---- */
 enum kgeo_velocity_type { KGEO_VEL_ZAMO = 0, KGEO_VEL_INFALL, KGEO_VEL_KEP, KGEO_VEL_SUBKEP, KGEO_VEL_GENERAL,
-                          KGEO_VEL_GELLES, KGEO_VEL_SIMFIT, KGEO_VEL_FROMFILE };
+                          KGEO_VEL_GELLES, KGEO_VEL_SIMFIT, KGEO_VEL_FROMFILE, KGEO_VEL_DRIFTFRAME };
 enum kgeo_bfield_type { KGEO_B_SIMPLE = 0, KGEO_B_SIMPLE_RM1, KGEO_B_BZ_GUESS, KGEO_B_GEN_POWER, KGEO_B_MONOPOLE_A,
-                        KGEO_B_FROMFILE };
+                        KGEO_B_FROMFILE, KGEO_B_BZ_MONOPOLE, KGEO_B_BZ_PARA, KGEO_B_POWER };
 enum kgeo_emissivity_type { KGEO_EM_CONSTANT = 0, KGEO_EM_BPL, KGEO_EM_GLM, KGEO_EM_RING, KGEO_EM_THERMAL };
 
 /* Parameter meaning per type (defaults as in the reference constructors):
  *  velocity: ZAMO/INFALL: none.  KEP: p[0]=retrograde.  SUBKEP: p[0]=retrograde, p[1]=fac_subkep.
  *            GENERAL: p[0]=retrograde, p[1]=fac_subkep, p[2]=beta_phi, p[3]=beta_r.  GELLES: p[0]=beta, p[1]=chi.
  *            SIMFIT: p[0]=ell_isco, p[1]=vr_isco, p[2]=p1, p[3]=p2, p[4]=dd.                 (velocities.py:26-68)
+ *            DRIFTFRAME: p[0]=nu_parallel (numeric, no gammamax); the E x B drift of THIS struct's bfield model, which
+ *            must be one with a field-line angular speed (velocities.py:487-623).
  *  bfield:   SIMPLE/SIMPLE_RM1: p[0]=Cr, p[1]=Cvert, p[2]=Cph ('rad','vert','tor' are SIMPLE with unit coefficients).
  *            BZ_GUESS: p[0]=C.  GEN_POWER: p[0]=n_I, p[1]=p_val, p[2]=isAbove.  MONOPOLE_A: p[0]=C, p[1]=omegafac.
+ *            BZ_MONOPOLE: p[0]=C, p[1]=secondorder_only; bfield_table_dev = 2 rows x table_n doubles (r, f(r)), the
+ *            reference's bz_fr_data.dat, evaluated as a linear spline with linear extrapolation (bfields.py:23-30,545-592).
+ *            BZ_PARA: p[0]=C (Lambert-W field-line speed, bfields.py:609-673).  POWER: p[0]=p, p[1]=C, p[2]=usemono
+ *            (bfields.py:618-625,676-709).
  *                                                                                            (bfields.py:36-91)
  *  emissivity: BPL: p[0]=p1, p[1]=p2.  GLM: p[0]=gamma_off, p[1]=sigma.  RING: p[0]=r_ring, p[1]=gamma_off, p[2]=sigma.
  *            THERMAL: p[0]=Rb, p[1]=ne0, p[2]=Te0, p[3]=B0, p[4]=alpha_n, p[5]=alpha_T, p[6]=alpha_B, p[7]=bfield_model.
@@ -215,6 +221,9 @@ int kgeo_velocity_u_lab(const kgeo_models* models, double a, size_t n, const dou
                         double* u1_dev, double* u2_dev, double* u3_dev, void* stream);
 int kgeo_bfield_lab(const kgeo_models* models, double a, size_t n, const double* r_dev, double* B1_dev, double* B2_dev,
                     double* B3_dev, double* bsq_dev, void* stream);
+/* Bfield.omega_field (kgeo/bfields.py:175-197): field-line angular speed of the models that define one (bz_monopole,
+ * monopoleA, bz_guess, bz_para, power, gen_power); NaN for the others. */
+int kgeo_bfield_omega(const kgeo_models* models, double a, size_t n, const double* r_dev, double* omega_dev, void* stream);
 int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const double* r_dev, const double* g_dev,
                           const double* sinthb_dev, const double* Bmag_dev, double nu_obs, double specind,
                           double* j_dev, void* stream);

@@ -34,8 +34,8 @@ class ImageOpts(ctypes.Structure):
                 ("nu_obs", ctypes.c_double)]
 
 
-VEL = dict(zamo=0, infall=1, kep=2, subkep=3, general=4, gelles=5, simfit=6, fromfile=7)
-BF = dict(simple=0, simple_rm1=1, bz_guess=2, gen_power=3, monopoleA=4, fromfile=5)
+VEL = dict(zamo=0, infall=1, kep=2, subkep=3, general=4, gelles=5, simfit=6, fromfile=7, driftframe=8)
+BF = dict(simple=0, simple_rm1=1, bz_guess=2, gen_power=3, monopoleA=4, fromfile=5, bz_monopole=6, bz_para=7, power=8)
 EM = dict(constant=0, bpl=1, glm=2, ring=3, thermal=4)
 
 _P, _S, _V = c_double_p, ctypes.c_size_t, ctypes.c_void_p
@@ -76,6 +76,7 @@ SIGNATURES = {
     "kgeo_equatorial_image_host": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [ctypes.c_int]),
     "kgeo_velocity_u_lab": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, _P, _V]),
     "kgeo_bfield_lab": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, _P, _V]),
+    "kgeo_bfield_omega": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _V]),
     "kgeo_emissivity_jrest": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, ctypes.c_double,
                                              ctypes.c_double, _P, _V]),
     "kgeo_fp64_peak_probe": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_float), _V]),

@@ -1,11 +1,56 @@
-"""Magnetic field model descriptor with the constructor / bfield_lab / bsq interface of kgeo/bfields.py:33-131,365-396.
-Closed-form models and the tabulated 'fromfile' model run on the device; 'bz_monopole', 'bz_para', 'power',
-'const_comoving' are outside the accelerated path (a data file the reference does not ship / Lambert W)."""
+"""Magnetic field model descriptor with the constructor / bfield_lab / omega_field / efield_lab / bsq interface of
+kgeo/bfields.py:33-131,175-235,365-396.  Every lab-frame model runs on the device (kg_image.cuh), including the perturbative
+BZ monopole (linear spline of f(r)), the BZ paraboloid (Lambert W) and the power-law stream functions.  'const_comoving' is
+not offered: in the reference itself every image path raises for it (bfield_lab refuses comoving fields and
+calc_polquantities uses `norm_x` before assignment, kgeo/equatorial_images.py:422-436)."""
 import ctypes
 
 import numpy as np
 
 from . import _engine, _lib
+
+RMAXINTERP = 100       # kgeo/bfields.py:16-20: bz_fr_data.dat holds f(r) on linspace(1, RMAXINTERP, NINTERP)
+NINTERP = 100000
+_FR_TABLE = None
+
+
+def _li2_unit(x):
+    """Real dilogarithm Li2(x) for 0 <= x <= 1 (power series below 1/2, Euler's reflection above)."""
+    x = np.asarray(x, dtype=np.float64)
+    small = np.where(x <= 0.5, x, 1.0 - x)
+    k = np.arange(1, 61, dtype=np.float64)
+    ser = np.zeros_like(small)
+    term = np.ones_like(small)
+    for kk in k:
+        term = term * small
+        ser = ser + term / (kk * kk)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        refl = np.pi ** 2 / 6. - np.where((x > 0) & (x < 1), np.log(x) * np.log1p(-x), 0.0) - ser
+    return np.where(x <= 0.5, ser, refl)
+
+
+def bz_fr(r):
+    """f(r) of the perturbative BZ monopole: the real part of the reference's complex formula (kgeo/bfields.py:7-13),
+    with Re Li2(x) = pi^2/3 - ln^2(x)/2 - Li2(1/x) and Re ln(1 - x) = ln|1 - x| for x = 2/r > 1."""
+    r = np.asarray(r, dtype=np.float64)
+    x = 2. / r
+    with np.errstate(divide='ignore', invalid='ignore'):
+        li = np.where(x <= 1, _li2_unit(np.minimum(x, 1.0)),
+                      np.pi ** 2 / 3. - 0.5 * np.log(x) ** 2 - _li2_unit(np.minimum(1. / x, 1.0)))
+        out = (li - np.log(np.abs(1 - x)) * np.log(r / 2.)) * r * r * (2 * r - 3) / 8.
+        out += (1 + 3 * r - 6 * r * r) * np.log(r / 2.) / 12.
+        out += 11. / 72. + 1. / (3. * r) + r / 2. - r * r / 2.
+    return out
+
+
+def bz_fr_table():
+    """(rsinterp, fsinterp) of the reference's bz_fr_data.dat, rebuilt from its generating formula (the reference tree
+    does not ship the file; kgeo/bfields.py:15-24 shows how it was made)."""
+    global _FR_TABLE
+    if _FR_TABLE is None:
+        rs = np.linspace(1, RMAXINTERP, NINTERP)
+        _FR_TABLE = (rs, bz_fr(rs))
+    return _FR_TABLE
 
 
 class Bfield(object):
@@ -13,17 +58,28 @@ class Bfield(object):
 
     def __init__(self, fieldtype="rad", **kwargs):
         self.fieldtype = fieldtype
-        if self.fieldtype in ['rad', 'vert', 'tor', 'simple', 'simple_rm1', 'monopoleA', 'bz_guess', 'gen_power', 'fromfile']:
+        if self.fieldtype in ['rad', 'vert', 'tor', 'simple', 'simple_rm1', 'monopoleA', 'bz_monopole', 'bz_guess',
+                              'bz_para', 'power', 'fromfile', 'gen_power']:
             self.fieldframe = 'lab'
-        elif self.fieldtype in ['bz_monopole', 'bz_para', 'power', 'const_comoving']:
-            raise NotImplementedError("Bfield(%r) is outside the accelerated path (SURVEY 8f)" % self.fieldtype)
+        elif self.fieldtype in ['const_comoving']:
+            raise NotImplementedError("Bfield('const_comoving'): every image path of the reference raises for comoving "
+                                      "fields (kgeo/bfields.py:100-101, kgeo/equatorial_images.py:422-436)")
         else:
             raise Exception("fieldtype %s not recognized in Bfield!" % self.fieldtype)
         self.kwargs = kwargs
 
-        if self.fieldtype in ['bz_guess']:
+        self._table = None
+        if self.fieldtype in ['bz_monopole', 'bz_guess', 'bz_para']:
             self.secondorder_only = self.kwargs.get('secondorder_only', False)
             self.C = self.kwargs.get('C', 1)
+            if self.fieldtype == 'bz_monopole':
+                # extension: fr_table=(r, f) replaces the rebuilt bz_fr_data.dat (e.g. the original file, if at hand)
+                self.fr_table = self.kwargs.get('fr_table', None)
+        elif self.fieldtype == 'power':
+            self.secondorder_only = self.kwargs.get('secondorder_only', False)
+            self.C = self.kwargs.get('C', 1)
+            self.pval = self.kwargs.get('p', 1)
+            self.usemono = self.kwargs.get('usemono', False)
         elif self.fieldtype in ['monopoleA']:
             self.omegafac = self.kwargs.get('omegafac', 0.5)
             self.C = self.kwargs.get('C', 1)
@@ -51,19 +107,29 @@ class Bfield(object):
                 raise Exception("all field coefficients are 0!")
 
     def table(self):
-        """device table of the 'fromfile' model (None for the closed forms)"""
-        if self.fieldtype != 'fromfile':
+        """device table of the 'fromfile' and 'bz_monopole' models (None for the closed forms)"""
+        if self.fieldtype not in ('fromfile', 'bz_monopole'):
             return None
         if self._table is None:
             from .models import device_table
-            c = self.cached_data
-            self._table = device_table((c['radii'], c['Br'], c['Bth'], c['Bph']))
+            if self.fieldtype == 'bz_monopole':
+                rs, fs = self.fr_table if self.fr_table is not None else bz_fr_table()
+                self._table = device_table((np.asarray(rs, dtype=np.float64), np.asarray(fs, dtype=np.float64)))
+            else:
+                c = self.cached_data
+                self._table = device_table((c['radii'], c['Br'], c['Bth'], c['Bph']))
         return self._table
 
     def descriptor(self):
         f = self.fieldtype
         if f == 'fromfile':
             return _lib.BF['fromfile'], []
+        if f == 'bz_monopole':
+            return _lib.BF['bz_monopole'], [float(self.C), float(bool(self.secondorder_only))]
+        if f == 'bz_para':
+            return _lib.BF['bz_para'], [float(self.C)]
+        if f == 'power':
+            return _lib.BF['power'], [float(self.pval), float(self.C), float(bool(self.usemono))]
         if f in ('rad', 'vert', 'tor', 'simple'):
             return _lib.BF['simple'], [float(self.Cr), float(self.Cvert), float(self.Cph)]
         if f == 'simple_rm1':
@@ -94,6 +160,41 @@ class Bfield(object):
     def bfield_lab(self, a, r, th=np.pi / 2):
         """lab frame b field starF^i0 = (B1, B2, B3)"""
         return self._run(a, r, None, False)
+
+    def omega_field(self, a, r, th=np.pi / 2):
+        """fieldline angular speed (kgeo/bfields.py:175-197)"""
+        if self.fieldtype not in ('bz_monopole', 'monopoleA', 'bz_guess', 'bz_para', 'power', 'gen_power'):
+            raise Exception("self.omega_field not implemented for fieldtype %s'!" % self.fieldtype)
+        from .models import pack_models
+        if not isinstance(r, np.ndarray):
+            r = np.array([r]).flatten()
+        L = _lib.lib()
+        M = pack_models(bfield=self)
+        dev = _engine.device()
+        dr = _engine.to_device(r.ravel(), dev)
+        n = int(dr.numel())
+        out = _engine.empty((n,), dev)
+        _lib.check(L.kgeo_bfield_omega(ctypes.byref(M), float(a), n, _engine.dptr(dr), _engine.dptr(out), _engine.stream_ptr()))
+        return out.cpu().numpy().reshape(r.shape)
+
+    def efield_lab(self, a, r, th=np.pi / 2):
+        """lab frame electric field F^{0i} of a stationary, axisymmetric field (kgeo/bfields.py:199-235), in the
+        equatorial plane: assembled from the device's B^i and omega"""
+        if not isinstance(r, np.ndarray):
+            r = np.array([r]).flatten()
+        if self.fieldtype == 'bz_monopole' and self.secondorder_only:   # Efield_BZmonopole, kgeo/bfields.py:595-606
+            return (0, a * np.sin(th) * (-1. / 8. + 2. / r ** 3) / (r ** 2 - 2 * r), 0)
+        omega = self.omega_field(a, r, th=th)
+        B1, B2, B3 = self.bfield_lab(a, r, th=th)
+        a2, r2 = a ** 2, r ** 2
+        cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
+        Delta = r2 - 2 * r + a2
+        Sigma = r2 + a2 * cth2
+        Pi = (r2 + a2) ** 2 - a2 * Delta * sth2
+        omegaz = 2 * a * r / Pi
+        E1 = (omega - omegaz) * Pi * np.sin(th) * B2 / Sigma
+        E2 = -(omega - omegaz) * Pi * np.sin(th) * B1 / (Sigma * Delta)
+        return (E1, E2, np.zeros_like(E2))
 
     def bsq(self, a, r, velocity, th=np.pi / 2.):
         """b^2 in the frame u^mu of `velocity`, ideal MHD"""

@@ -179,26 +179,136 @@ KG_HD U4 u_fromfile(const kgeo_models& M, double a, double r) {
     return U4{gamma / alpha, u1, u2, u3 - gamma * alpha * gcon03};
 }
 
-KG_HD U4 velocity_u_lab(const kgeo_models& M, double a, double r) {   // velocities.py:70-96
-    const double* p = M.velocity_p;
-    switch (M.velocity_type) {
-        case KGEO_VEL_ZAMO: return u_zamo(a, r);
-        case KGEO_VEL_INFALL: return u_infall(a, r);
-        case KGEO_VEL_KEP: return u_kep(a, r, p[0] != 0.0);
-        case KGEO_VEL_SUBKEP: return u_subkep(a, r, p[0] != 0.0, p[1]);
-        case KGEO_VEL_GENERAL: return u_general(a, r, p[0] != 0.0, p[1], p[2], p[3]);
-        case KGEO_VEL_GELLES: return u_gelles(a, r, p[0], p[1]);
-        case KGEO_VEL_FROMFILE: return u_fromfile(M, a, r);
-        default: return u_simfit(a, r, p[0], p[1], p[2], p[3], p[4]);
+// Principal branch of the Lambert W function for real x >= -1/e (scipy.special.lambertw(x, k=0) on that range): series
+// about the branch point or a logarithmic / rational start, then Fritsch's iteration (quartic convergence, stable next to
+// W = -1 because it works with ln(x/w) - w instead of w e^w - x)
+KG_HD double lambertw0(double x) {
+    const double em1 = 0.36787944117144233;   // 1/e
+    if (!(x >= -em1)) return kg_nan();
+    if (x == 0.0) return 0.0;
+    double w;
+    const double pp = 2.0 * (2.718281828459045 * x + 1.0);
+    if (x < -0.25) {
+        const double q = sqrt(pp > 0.0 ? pp : 0.0);
+        w = -1.0 + q * (1.0 + q * (-1.0 / 3.0 + q * (11.0 / 72.0 + q * (-43.0 / 540.0 + q * (769.0 / 17280.0 + q * (-221.0 / 8505.0))))));
+        if (q < 1.0e-6) return w;
+    } else if (x < 3.0) {
+        w = x * (1.0 + (4.0 / 3.0) * x) / (1.0 + x * (7.0 / 3.0 + (5.0 / 6.0) * x));   // Pade start about 0
+    } else {
+        const double l1 = log(x), l2 = log(l1);
+        w = l1 - l2 + l2 / l1;
     }
+    for (int it = 0; it < 4; ++it) {
+        const double z = log(x / w) - w;
+        const double w1 = 1.0 + w;
+        const double q = 2.0 * w1 * (w1 + (2.0 / 3.0) * z);
+        const double e = (z / w1) * ((q - z) / (q - 2.0 * z));
+        w = w * (1.0 + e);
+        if (fabs(e) < 1.0e-16) break;
+    }
+    return w;
 }
 
-// lab-frame B^i at theta = pi/2 (kgeo/bfields.py:93-131 and the model functions)
-KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, double* B2, double* B3) {
+// piecewise-linear table f(x) with FITPACK's k=1, ext=0 semantics (scipy UnivariateSpline(k=1, s=0): linear extrapolation
+// with the end segments) and its derivative (slope of the segment holding x; right-continuous at the knots)
+KG_HD void linear_spline(const double* xp, const double* fp, long long n, double x, double* f, double* fprime) {
+    long long lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (x >= xp[mid]) lo = mid; else hi = mid;
+    }
+    const double h = xp[lo + 1] - xp[lo];
+    *f = (fp[lo] * (xp[lo + 1] - x) + fp[lo + 1] * (x - xp[lo])) / h;
+    *fprime = (fp[lo + 1] - fp[lo]) / h;
+}
+
+// lab-frame B^i at theta = pi/2 and the field-line angular speed (kgeo/bfields.py:93-131,175-197 and the model functions);
+// omega = NaN for the models the reference's omega_field does not cover
+KG_HD void bfield_lab_omega(const kgeo_models& M, double a, double r, double* B1, double* B2, double* B3, double* omega) {
     const double* p = M.bfield_p;
     double a2 = a * a, r2 = r * r;
     double Delta = r2 - 2.0 * r + a2;
+    *omega = kg_nan();
     switch (M.bfield_type) {
+        case KGEO_B_BZ_MONOPOLE: {   // bfields.py:545-592; cos(pi/2) = 6.1e-17 kept as in the reference
+            const double C = p[0];
+            const bool second = p[1] != 0.0;
+            const double* tab = M.bfield_table_dev;
+            const long long n = M.bfield_table_n;
+            double fr, frp;
+            linear_spline(tab, tab + n, n, r, &fr, &frp);
+            if (r > tab[n - 1]) {   // RMAXINTERP
+                fr = 1.0 / (4.0 * r);
+                frp = -1.0 / (4.0 * r2);
+            }
+            const double cth = kCosHalfPi, cth2 = cth * cth;
+            const double gdet = r2 + a2 * cth2;
+            const double cos2th = -1.0;
+            const double dphidtheta = C * (1.0 + 0.5 * a2 * fr * (1.0 + 3.0 * cos2th));
+            const double dphidr = C * a2 * cth * frp;
+            const double f2 = (6.0 * kPi * kPi - 49.0) / 72.0;
+            const double omega2 = 1.0 / 32.0 - (4.0 * f2 - 1.0) / 64.0;
+            const double I = -1.0 * C * 2.0 * kPi * (a / 8.0 + (a * a * a) * (omega2 + 0.25 * fr * cth2));
+            double Br = dphidtheta / gdet, Bth = -dphidr / gdet, Bph = I / (2.0 * kPi * Delta);
+            if (second) {
+                const double rr = r2 - 2.0 * r;
+                Br = C / r2 + C * a2 * (-cth2 / (r2 * r2) + fr * (0.5 + 1.5 * cos2th) / r2);
+                Bth = -C * a2 * frp * cth / r2;
+                Bph = -C * 0.125 * a / rr + C * (a * a * a) * (0.125 / (rr * rr) - (omega2 + 0.25 * cth2 * fr) / rr);
+            }
+            const double spin = fabs(a);
+            double Om = spin / 8.0 + (spin * spin * spin) * omega2;
+            if (a < 0.0) Om = -Om;
+            *B1 = Br; *B2 = Bth; *B3 = Bph; *omega = Om;
+            return;
+        }
+        case KGEO_B_BZ_PARA: {   // bfields.py:609-673 (array branch: omega carries the factor C and the argvals mask)
+            const double C = p[0];
+            const double rp = 1.0 + sqrt(1.0 - a2);
+            const double c = kCosHalfPi;
+            const double gdet = r2 + a2 * c * c;
+            const double psi = r * (1.0 - c) + rp * (1.0 + c) * (1.0 - log(1.0 + c)) - 2.0 * rp * (1.0 - 0.6931471805599453);
+            const double dpsidtheta = r + rp * log(1.0 + c);
+            const double dpsidr = 1.0 - c;
+            const double arg = -psi / rp + 1.3862943611198906;   // + log(4)
+            double Om = 0.0;
+            if (arg >= -0.36787944117144233) {
+                const double wf = lambertw0(arg);
+                const double xf = exp(wf);
+                const double yf = 1.0 + psi / (1.0 + wf) / (xf * (2.0 - xf));
+                Om = C * (a / 4.0 / yf);
+            }
+            const double I = -4.0 * kPi * psi * Om;
+            *B1 = C * dpsidtheta / gdet;
+            *B2 = -C * dpsidr / gdet;
+            *B3 = I / (2.0 * kPi * Delta);
+            *omega = Om;
+            return;
+        }
+        case KGEO_B_POWER: {   // bfields.py:618-625,676-709
+            const double pv = p[0], C = p[1];
+            const bool usemono = p[2] != 0.0;
+            const double rp = 1.0 + sqrt(1.0 - a2);
+            const double c = kCosHalfPi;
+            const double gdet = r2 + a2 * c * c;
+            const double rpw = pow(r, pv);
+            const double psi = rpw * (1.0 - c);
+            const double dpsidtheta = rpw;
+            const double dpsidr = pv * psi / r;
+            double Om;
+            if (usemono || pv == 0.0) {
+                Om = a / 8.0;
+            } else {
+                const double cthh = 1.0 - psi * pow(rp, -pv);
+                Om = a / (4.0 + 8.0 / (1.0 + cthh));
+            }
+            const double I = (pv > 0.0) ? (-4.0 * kPi * psi * Om) : (-2.0 * kPi * psi * (2.0 - psi) * Om);
+            *B1 = C * dpsidtheta / gdet;
+            *B2 = -C * dpsidr / gdet;
+            *B3 = I / (2.0 * kPi * Delta);
+            *omega = Om;
+            return;
+        }
         case KGEO_B_SIMPLE:
         case KGEO_B_SIMPLE_RM1: {   // bfields.py:429-477
             double gdet = r2;
@@ -222,6 +332,7 @@ KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, doub
             *B1 = Br;
             *B2 = 0.0 * Br;
             *B3 = ratio * Br;
+            *omega = OmegaBZ;
             return;
         }
         case KGEO_B_GEN_POWER: {   // bfields.py:712-746
@@ -236,6 +347,7 @@ KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, doub
             *B1 = dpsidtheta / gdet;
             *B2 = -1.0 * (dpsidr / gdet);
             *B3 = I / (2.0 * kPi * Delta);
+            *omega = 0.5 * (a / (2.0 * rp));
             return;
         }
         case KGEO_B_FROMFILE: {   // bfields.py:790-806
@@ -256,10 +368,66 @@ KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, doub
             *B1 = (phih / (4.0 * kPi)) / r2;
             *B2 = 0.0;
             *B3 = I / (2.0 * kPi * Delta);
+            *omega = omegaf;
             return;
         }
     }
 }
+KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, double* B2, double* B3) {
+    double omega;
+    bfield_lab_omega(M, a, r, B1, B2, B3, &omega);
+}
+
+// drift-frame velocity of the image's B-field model (kgeo/velocities.py:487-623 with a numeric nu_parallel and no gammamax)
+KG_HD U4 u_driftframe(const kgeo_models& M, double a, double r, double nu_parallel) {
+    const double a2 = a * a, r2 = r * r;
+    const double cth = kCosHalfPi, cth2 = cth * cth;
+    const double Delta = r2 - 2.0 * r + a2;
+    const double Sigma = r2 + a2 * cth2;
+    const double Xi = sq(r2 + a2) - Delta * a2;
+    const double omegaz = 2.0 * a * r / Xi;
+    const double gdet = Sigma;
+    const double g11 = Sigma / Delta, g22 = Sigma, g33 = Xi / Sigma;
+    const double alpha = sqrt(Delta * Sigma / Xi);
+    const double eta3 = 2.0 * a * r / sqrt(Delta * Sigma * Xi);
+    double B1, B2, B3, omegaf;
+    bfield_lab_omega(M, a, r, &B1, &B2, &B3, &omegaf);
+    const double E1 = (omegaf - omegaz) * Xi * B2 / Sigma;
+    const double E2 = -(omegaf - omegaz) * Xi * B1 / (Sigma * Delta);
+    const double E3 = 0.0;
+    const double Bsq = g11 * B1 * B1 + g22 * B2 * B2 + g33 * B3 * B3;
+    const double Esq = g11 * E1 * E1 + g22 * E2 * E2 + g33 * E3 * E3;
+    const double B1c = g11 * B1, B2c = g22 * B2, B3c = g33 * B3;
+    const double E1c = g11 * E1, E2c = g22 * E2, E3c = g33 * E3;
+    const double pre = alpha / (Bsq * gdet);
+    const double vperp1 = pre * (E2c * B3c - B2c * E3c);
+    const double vperp2 = pre * (E3c * B1c - B3c * E1c);
+    const double vperp3 = pre * (E1c * B2c - B1c * E2c);
+    const double vpar_max = sqrt(1.0 - Esq / Bsq);
+    const double sB = sqrt(Bsq);
+    const double v1 = vperp1 + nu_parallel * vpar_max * B1 / sB;
+    const double v2 = vperp2 + nu_parallel * vpar_max * B2 / sB;
+    const double v3 = vperp3 + nu_parallel * vpar_max * B3 / sB;
+    const double vsq = g11 * v1 * v1 + g22 * v2 * v2 + g33 * v3 * v3;
+    const double gamma = 1.0 / sqrt(1.0 - vsq);
+    return U4{gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)};
+}
+
+KG_HD U4 velocity_u_lab(const kgeo_models& M, double a, double r) {   // velocities.py:70-96
+    const double* p = M.velocity_p;
+    switch (M.velocity_type) {
+        case KGEO_VEL_ZAMO: return u_zamo(a, r);
+        case KGEO_VEL_INFALL: return u_infall(a, r);
+        case KGEO_VEL_KEP: return u_kep(a, r, p[0] != 0.0);
+        case KGEO_VEL_SUBKEP: return u_subkep(a, r, p[0] != 0.0, p[1]);
+        case KGEO_VEL_GENERAL: return u_general(a, r, p[0] != 0.0, p[1], p[2], p[3]);
+        case KGEO_VEL_GELLES: return u_gelles(a, r, p[0], p[1]);
+        case KGEO_VEL_FROMFILE: return u_fromfile(M, a, r);
+        case KGEO_VEL_DRIFTFRAME: return u_driftframe(M, a, r, p[0]);
+        default: return u_simfit(a, r, p[0], p[1], p[2], p[3], p[4]);
+    }
+}
+
 
 // b^2 in the fluid frame, ideal MHD (kgeo/bfields.py:330-396)
 KG_HD double bfield_bsq(const kgeo_models& M, double a, double r, const U4& u) {

@@ -63,10 +63,12 @@ static int check_observer(const kgeo_observer* obs, bool allow_inf) {
 }
 static int check_models(const kgeo_models* m) {
     if (!m) return fail_arg(KGEO_E_BADARG, "models is NULL");
-    if (m->velocity_type < 0 || m->velocity_type > KGEO_VEL_FROMFILE) return fail_arg(KGEO_E_MODEL, "unknown velocity model");
-    if (m->bfield_type < 0 || m->bfield_type > KGEO_B_FROMFILE) return fail_arg(KGEO_E_MODEL, "unknown bfield model");
+    if (m->velocity_type < 0 || m->velocity_type > KGEO_VEL_DRIFTFRAME) return fail_arg(KGEO_E_MODEL, "unknown velocity model");
+    if (m->bfield_type < 0 || m->bfield_type > KGEO_B_POWER) return fail_arg(KGEO_E_MODEL, "unknown bfield model");
     if (m->velocity_type == KGEO_VEL_FROMFILE && (!m->velocity_table_dev || m->velocity_table_n < 1))
         return fail_arg(KGEO_E_MODEL, "velocity 'fromfile' needs a device table (velocity_table_dev, velocity_table_n)");
+    if (m->bfield_type == KGEO_B_BZ_MONOPOLE && (!m->bfield_table_dev || m->bfield_table_n < 2))
+        return fail_arg(KGEO_E_MODEL, "bfield model 'bz_monopole' needs the device table of f(r)");
     if (m->bfield_type == KGEO_B_FROMFILE && (!m->bfield_table_dev || m->bfield_table_n < 1))
         return fail_arg(KGEO_E_MODEL, "bfield 'fromfile' needs a device table (bfield_table_dev, bfield_table_n)");
     if (m->emissivity_type < 0 || m->emissivity_type > KGEO_EM_THERMAL) return fail_arg(KGEO_E_MODEL, "unknown emissivity model");
@@ -598,6 +600,12 @@ __global__ void __launch_bounds__(EW_THREADS) ew_bfield_kernel(kgeo_models M, do
     if (B3) B3[i] = b3;
     if (bsq) bsq[i] = bfield_bsq(M, a, r[i], velocity_u_lab(M, a, r[i]));
 }
+__global__ void __launch_bounds__(EW_THREADS) ew_bfield_omega_kernel(kgeo_models M, double a, size_t n, const double* r, double* omega) {
+    EW_INDEX
+    double b1, b2, b3, om;
+    bfield_lab_omega(M, a, r[i], &b1, &b2, &b3, &om);
+    omega[i] = om;
+}
 __global__ void __launch_bounds__(EW_THREADS) ew_emissivity_kernel(kgeo_models M, double a, size_t n, const double* r,
                                                                    const double* g, const double* sinthb, const double* Bmag,
                                                                    double nu_obs, double specind, double* j) {
@@ -915,6 +923,12 @@ int kgeo_bfield_lab(const kgeo_models* models, double a, size_t n, const double*
     if (rc) return rc;
     if (n && !r) return fail_arg(KGEO_E_BADARG, "kgeo_bfield_lab: NULL pointer");
     EW_ENTRY(ew_bfield_kernel, *models, a, n, r, B1, B2, B3, bsq)
+}
+int kgeo_bfield_omega(const kgeo_models* models, double a, size_t n, const double* r, double* omega, void* stream) {
+    int rc = check_models(models);
+    if (rc) return rc;
+    if (n && (!r || !omega)) return fail_arg(KGEO_E_BADARG, "kgeo_bfield_omega: NULL pointer");
+    EW_ENTRY(ew_bfield_omega_kernel, *models, a, n, r, omega)
 }
 int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const double* r, const double* g, const double* sinthb,
                           const double* Bmag, double nu_obs, double specind, double* j, void* stream) {

@@ -25,6 +25,13 @@ def device_table(rows):
 
 
 def pack_models(emissivity=None, velocity=None, bfield=None):
+    if velocity is not None and getattr(velocity, 'veltype', None) == 'driftframe':
+        # the drift frame is the E x B drift of ONE field model: kgeo_models carries a single bfield descriptor
+        vb = velocity.bfield
+        if bfield is None:
+            bfield = vb
+        elif bfield is not vb and (bfield.descriptor() != vb.descriptor() or bfield.table() is not vb.table()):
+            raise NotImplementedError("Velocity('driftframe', bfield=X) is accelerated only together with bfield=X")
     M = _lib.Models()
     M.velocity_type, M.bfield_type, M.emissivity_type = _lib.VEL['zamo'], _lib.BF['simple'], _lib.EM['constant']
     M.bfield_p[0] = 1.0

@@ -1,6 +1,6 @@
 """Velocity model descriptor with the constructor and u_lab interface of kgeo/velocities.py:23-96.
-The closed forms and the tabulated 'fromfile' model run on the device (kg_image.cuh); 'driftframe' is outside the
-accelerated path."""
+The closed forms, the tabulated 'fromfile' model and the E x B 'driftframe' of a B-field model (numeric nu_parallel) run on
+the device (kg_image.cuh)."""
 import ctypes
 
 import numpy as np
@@ -51,8 +51,17 @@ class Velocity(object):
             self.cached_data = dict(radii=radii, U1=U1, U2=U2, U3=U3)
             self._table = None
         elif self.veltype == 'driftframe':
-            raise NotImplementedError("Velocity(%r) needs a B-field root find and is outside the accelerated path "
-                                      "(SURVEY 8f)" % self.veltype)
+            from .bfields import Bfield
+            self.bfield = self.kwargs.get('bfield', None)
+            if self.bfield is None:
+                self.bfield = Bfield('bz_para')                       # BFIELD_DEFAULT, kgeo/velocities.py:14
+            self.nu_parallel = self.kwargs.get('nu_parallel', 0)
+            self.gammamax = self.kwargs.get('gammamax', None)
+            if isinstance(self.nu_parallel, str) or self.gammamax:
+                raise NotImplementedError("Velocity('driftframe') with nu_parallel='FF' or a gammamax needs the jet "
+                                          "model's stagnation-surface root finds (kgeo/ff_boost.py; SURVEY 8 f4)")
+            if not -1 <= self.nu_parallel <= 1:
+                raise Exception("nu_parallel should be in the range (-1,1)")
         else:
             raise Exception("veltype %s not recognized in Velocity!" % self.veltype)
 
@@ -71,6 +80,8 @@ class Velocity(object):
         v = self.veltype
         if v == 'fromfile':
             return _lib.VEL['fromfile'], []
+        if v == 'driftframe':
+            return _lib.VEL['driftframe'], [float(self.nu_parallel)]
         if v == 'zamo':
             return _lib.VEL['zamo'], []
         if v == 'infall':
@@ -93,7 +104,7 @@ class Velocity(object):
         if not isinstance(r, np.ndarray):
             r = np.array([r]).flatten()
         L = _lib.lib()
-        M = pack_models(velocity=self)
+        M = pack_models(velocity=self, bfield=getattr(self, 'bfield', None))
         dev = _engine.device()
         dr = _engine.to_device(r.ravel(), dev)
         n = int(dr.numel())

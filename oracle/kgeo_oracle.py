@@ -885,6 +885,8 @@ def velocity_u_lab(vel, a, r):
                         vel.get('dd', 0.2))
     if t == 'fromfile':
         return u_from_table(a, r, load_table(vel['file'], ('U1', 'U2', 'U3')))
+    if t == 'driftframe':
+        return u_driftframe(a, r, vel['bfield'], vel.get('nu_parallel', 0))
     raise Exception("veltype %s not in oracle" % t)
 
 
@@ -1021,7 +1023,144 @@ def bfield_lab(bf, a, r):
         omegaf = omegafac * omegah
         I = phih * (np.sin(th) ** 2) * rh * (omegaf - omegah) / (rh ** 2 + a ** 2 * cth ** 2)
         return (phih / (4 * np.pi)) / Sigma, 0 * r, I / (2 * np.pi * Delta * (np.sin(th) ** 2))
+    if t in ('bz_monopole', 'bz_para', 'power'):
+        return bfield_lab_omega(bf, a, r)[:3]
     raise Exception("fieldtype %s not in oracle" % t)
+
+
+_BZ_FR = None
+
+
+def bz_fr_table():
+    """The reference's bz_fr_data.dat rebuilt from its recipe (kgeo/bfields.py:7-20): f(r) on linspace(1, 100, 100000); real
+    part of the complex formula, Li2(x) = spence(1 - x) and Re Li2(x) = pi^2/3 - ln^2(x)/2 - Li2(1/x) for x > 1."""
+    global _BZ_FR
+    if _BZ_FR is None:
+        r = np.linspace(1.0, 100.0, 100000)
+        x = 2.0 / r
+        with np.errstate(all="ignore"):
+            li = np.where(x <= 1, sp.spence(1 - np.minimum(x, 1.0)),
+                          np.pi ** 2 / 3.0 - 0.5 * np.log(x) ** 2 - sp.spence(1 - np.minimum(1.0 / x, 1.0)))
+            f = (li - np.log(np.abs(1 - x)) * np.log(r / 2.0)) * r * r * (2 * r - 3) / 8.0
+            f += (1 + 3 * r - 6 * r * r) * np.log(r / 2.0) / 12.0
+            f += 11.0 / 72.0 + 1.0 / (3.0 * r) + r / 2.0 - r * r / 2.0
+        _BZ_FR = (r, f)
+    return _BZ_FR
+
+
+def _linear_spline(xp, fp, x):
+    """UnivariateSpline(k=1, s=0, ext=0) and its derivative (kgeo/bfields.py:27-30): linear interpolation, linear
+    extrapolation with the end segments, slope of the segment holding x."""
+    i = np.clip(np.searchsorted(xp, x, side='right') - 1, 0, len(xp) - 2)
+    h = xp[i + 1] - xp[i]
+    return (fp[i] * (xp[i + 1] - x) + fp[i + 1] * (x - xp[i])) / h, (fp[i + 1] - fp[i]) / h
+
+
+def bfield_lab_omega(bf, a, r):
+    """(B1, B2, B3, omega) of the models with a field-line angular speed (kgeo/bfields.py:175-197 and the model functions);
+    theta = pi/2 with the reference's cos(pi/2) = 6e-17."""
+    r = _arr(r)
+    t = bf['type']
+    th = np.pi / 2
+    a2, r2 = a ** 2, r ** 2
+    sth, cth = np.sin(th), np.cos(th)
+    abscth, cth2, sth2 = np.abs(cth), cth ** 2, sth ** 2
+    Delta = r2 - 2 * r + a2
+    Sigma = r2 + a2 * cth2
+    gdet = sth * Sigma
+    rp = 1 + np.sqrt(1 - a2)
+    if t == 'bz_monopole':                                                                # bfields.py:545-592
+        C, second = bf.get('C', 1), bf.get('secondorder_only', False)
+        xs, fs = bf['fr_table'] if bf.get('fr_table') is not None else bz_fr_table()
+        fr, frp = _linear_spline(xs, fs, r)
+        far = r > np.max(xs)
+        fr = np.where(far, 1. / (4. * r), fr)
+        frp = np.where(far, -1. / (4. * r2), frp)
+        dphidtheta = C * sth * (1 + 0.5 * a2 * fr * (1 + 3 * np.cos(2 * th)))
+        dphidr = C * a2 * sth2 * cth * frp
+        f2 = (6 * np.pi * np.pi - 49.) / 72.
+        omega2 = 1. / 32. - sth2 * (4 * f2 - 1) / 64.
+        I = -1 * C * 2 * np.pi * sth2 * (a / 8. + (a ** 3) * (omega2 + 0.25 * fr * cth2))
+        Br, Bth, Bph = dphidtheta / gdet, -dphidr / gdet, I / (2 * np.pi * Delta * sth2)
+        if second:
+            Br = C / r2 + C * a2 * (-cth2 / (r2 * r2) + fr * (0.5 + 1.5 * np.cos(2 * th)) / r2)
+            Bth = -C * a2 * frp * cth * sth / r2
+            Bph = -C * 0.125 * a / (r2 - 2 * r) + C * (a ** 3) * (0.125 / ((r2 - 2 * r) ** 2) - (omega2 + 0.25 * cth2 * fr) / ((r2 - 2 * r)))
+        spin = np.abs(a)
+        Om = spin / 8. + spin ** 3 * omega2
+        if a < 0:
+            Om *= -1
+        return Br, Bth, Bph, Om + 0 * r
+    if t == 'bz_para':                                                                    # bfields.py:609-673
+        C = bf.get('C', 1)
+        psi = r * (1 - abscth) + rp * (1 + abscth) * (1 - np.log(1 + abscth)) - 2 * rp * (1 - np.log(2))
+        dpsidtheta = np.sign(cth) * sth * (r + rp * np.log(1 + abscth))
+        dpsidr = 1 - abscth
+        argvals = -psi / rp + np.log(4)
+        ok = argvals >= -1 / np.e
+        w = np.real(sp.lambertw(np.where(ok, argvals, 0.0), k=0))
+        x = np.exp(w)
+        y = 1 + psi / (1 + w) / (x * (2 - x))
+        Om = np.where(ok, C * (a / 4 / y), 0.0)        # the reference's complex value times the mask, real part
+        I = -4 * np.pi * psi * Om * np.sign(cth)
+        return C * dpsidtheta / gdet, -C * dpsidr / gdet, I / (2 * np.pi * Delta * sth2), Om
+    if t == 'power':                                                                      # bfields.py:618-625,676-709
+        p, C, usemono = bf.get('p', 1), bf.get('C', 1), bf.get('usemono', False)
+        psi = r ** p * (1 - abscth)
+        dpsidtheta = np.sign(cth) * sth * (r ** p)
+        dpsidr = p * psi / r
+        if usemono or p == 0:
+            Om = a / 8 + 0 * r
+        else:
+            cthh = 1 - psi * rp ** (-p)
+            Om = a / (4 + 8 / (1 + cthh))
+        I = -4 * np.pi * psi * Om * np.sign(cth) if p > 0 else -2 * np.pi * psi * (2 - psi) * Om * np.sign(cth)
+        return C * dpsidtheta / gdet, -C * dpsidr / gdet, I / (2 * np.pi * Delta * sth2), Om
+    B1, B2, B3 = bfield_lab(bf, a, r)
+    if t == 'bz_guess':
+        spin = np.abs(a)
+        f2 = (6 * np.pi * np.pi - 49.) / 72.
+        Om = spin / 8. + (spin ** 3) * (1. / 32. - (4 * f2 - 1) * sth2 / 64.)
+        return B1, B2, B3, (-Om if a < 0 else Om) + 0 * r
+    if t == 'monopoleA':
+        return B1, B2, B3, bf.get('omegafac', 0.5) * a / (2 * rp) + 0 * r
+    if t == 'gen_power':
+        return B1, B2, B3, 0.5 * a / (2 * rp) + 0 * r
+    raise Exception("self.omega_field not implemented for fieldtype %s'!" % t)
+
+
+def u_driftframe(a, r, bf, nu_parallel=0):
+    """kgeo/velocities.py:487-623 with a numeric nu_parallel and gammamax=None, theta = pi/2."""
+    r = _arr(r)
+    th = np.pi / 2
+    a2, r2 = a ** 2, r ** 2
+    cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
+    Delta = r2 - 2 * r + a2
+    Sigma = r2 + a2 * cth2
+    Xi = (r2 + a2) ** 2 - Delta * a2 * sth2
+    omegaz = 2 * a * r / Xi
+    gdet = Sigma * np.sin(th)
+    g11, g22, g33 = Sigma / Delta, Sigma, Xi * sth2 / Sigma
+    alpha = np.sqrt(Delta * Sigma / Xi)
+    eta3 = 2 * a * r / np.sqrt(Delta * Sigma * Xi)
+    B1, B2, B3, omegaf = bfield_lab_omega(bf, a, r)
+    E1 = (omegaf - omegaz) * Xi * np.sin(th) * B2 / Sigma
+    E2 = -(omegaf - omegaz) * Xi * np.sin(th) * B1 / (Sigma * Delta)
+    E3 = 0
+    Bsq = g11 * B1 * B1 + g22 * B2 * B2 + g33 * B3 * B3
+    Esq = g11 * E1 * E1 + g22 * E2 * E2 + g33 * E3 * E3
+    B1c, B2c, B3c = g11 * B1, g22 * B2, g33 * B3
+    E1c, E2c, E3c = g11 * E1, g22 * E2, g33 * E3
+    vperp1 = (alpha / (Bsq * gdet)) * (E2c * B3c - B2c * E3c)
+    vperp2 = (alpha / (Bsq * gdet)) * (E3c * B1c - B3c * E1c)
+    vperp3 = (alpha / (Bsq * gdet)) * (E1c * B2c - B1c * E2c)
+    vpar_max = np.sqrt(1 - Esq / Bsq)
+    v1 = vperp1 + nu_parallel * vpar_max * B1 / np.sqrt(Bsq)
+    v2 = vperp2 + nu_parallel * vpar_max * B2 / np.sqrt(Bsq)
+    v3 = vperp3 + nu_parallel * vpar_max * B3 / np.sqrt(Bsq)
+    vsq = g11 * v1 * v1 + g22 * v2 * v2 + g33 * v3 * v3
+    gamma = 1. / np.sqrt(1 - vsq)
+    return gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)
 
 
 def bfield_fluid(bf, vel, a, r):

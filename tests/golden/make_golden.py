@@ -281,6 +281,54 @@ def fromfile_models():
     save('fromfile_models', **out)
 
 
+def bz_models():
+    """Bfield('bz_monopole' | 'bz_para' | 'power') with omega_field, and Velocity('driftframe') on them (kgeo/bfields.py:
+    545-709, kgeo/velocities.py:487-623): element-wise values and two polarized images.  The f(r) table the reference
+    loads is the one tests/golden/ref_shim.py rebuilds; a decimated copy of what the reference interpolates is not needed
+    because the fixture stores the table's generating grid parameters and the product rebuilds the same table."""
+    from ref_shim import bz_fr_table
+    rs, fs = bz_fr_table()
+    out = dict(fr_r=rs[::250].copy(), fr_f=fs[::250].copy())
+    bfs = [('bz_monopole', {}), ('bz_monopole', dict(C=-1.)), ('bz_monopole', dict(secondorder_only=True)), ('bz_para', {}),
+           ('bz_para', dict(C=-1.)), ('power', dict(p=1)), ('power', dict(p=0.75, C=2.)), ('power', dict(p=0.75, usemono=True)),
+           ('power', dict(p=0)), ('bz_guess', dict(C=1.)), ('monopoleA', dict(C=1.)), ('gen_power', dict(n_I=0.5, p_val=1.0))]
+    nus = [0.0, 0.5, -0.3]
+    spins = [0.3, 0.94, -0.5]
+    out['spins'] = np.array(spins)
+    out['nus'] = np.array(nus)
+    out['spec'] = np.array(json.dumps(dict(bfs=bfs)))
+    rgrid = np.concatenate((np.linspace(1.05, 12., 140), [1.9, 2.0, 2.5, 30., 99.5, 150.]))
+    for ia, a in enumerate(spins):
+        rp = 1 + np.sqrt(1 - a * a)
+        rr = rgrid[rgrid > rp + 0.02]
+        out['a%d_r' % ia] = rr
+        with np.errstate(all='ignore'):
+            for ib, (bt, kw) in enumerate(bfs):
+                b = Bfield(bt, **kw)
+                out['a%d_b%d' % (ia, ib)] = np.array([np.real(np.broadcast_to(c, rr.shape)) for c in b.bfield_lab(float(a), rr)], dtype=float)
+                out['a%d_om%d' % (ia, ib)] = np.real(np.broadcast_to(b.omega_field(float(a), rr), rr.shape)).astype(float)
+                out['a%d_bsq%d' % (ia, ib)] = np.real(b.bsq(float(a), rr, Velocity('general', fac_subkep=0.6, beta_phi=0.8, beta_r=0.7))).astype(float)
+                for inu, nu in enumerate(nus):
+                    v = Velocity('driftframe', bfield=b, nu_parallel=nu)
+                    u = [np.broadcast_to(c, rr.shape) for c in v.u_lab(float(a), rr)]
+                    out['a%d_u%d_%d' % (ia, ib, inu)] = np.array([np.real(c) for c in u], dtype=float)
+                    # bz_para is complex-valued in the reference (scipy's lambertw): where E^2 > B^2 its square roots turn
+                    # imaginary instead of NaN; record where the reference's result is genuinely real
+                    out['a%d_ureal%d_%d' % (ia, ib, inu)] = np.all([np.imag(c) == 0 for c in u], axis=0)
+    half, npx = 8., 36
+    # (no bz_para image: scipy's lambertw makes that field complex-valued and the reference's Iobs cannot cast it)
+    imgs = [('mono', 0.5, Bfield('bz_monopole'), 0.0), ('power', 0.7, Bfield('power', p=0.75), 0.3)]
+    for name, a, b, nu in imgs:
+        with np.errstate(all='ignore'):
+            img = quiet(make_image, a, np.inf, 30 * DEG, 1, -half, half, -half, half, 2 * half / npx,
+                        emissivity=Emissivity('ring', r_ring=3.5, sigma=0.8), velocity=Velocity('driftframe', bfield=b, nu_parallel=nu),
+                        bfield=b, polarization=True, specind=1.)
+        out['img_%s_par' % name] = np.array([a, 30 * DEG, 1, half, npx, nu])
+        for k, val in zip(['I', 'Q', 'U', 'r', 't', 'g', 'sinthb', 'n', 'np'], img):
+            out['img_%s_%s' % (name, k)] = np.real(val).astype(float)
+    save('bz_models', **out)
+
+
 def inverse_lensing():
     """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
     out = {}
@@ -304,7 +352,7 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -316,5 +364,6 @@ if __name__ == '__main__':
     counts()
     inverse_lensing()
     fromfile_models()
+    bz_models()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

@@ -32,6 +32,20 @@ def _stub(name, **attrs):
     return mod
 
 
+def bz_fr_table():
+    """(r, f(r)) of the reference's missing bz_fr_data.dat, from the formula in kgeo/bfields.py:7-13 (SciPy dilogarithm)."""
+    from scipy.special import spence
+    r = np.linspace(1.0, 100.0, 100000)
+    x = 2.0 / r
+    with np.errstate(all="ignore"):
+        li = np.where(x <= 1, spence(1 - np.minimum(x, 1.0)),
+                      np.pi ** 2 / 3.0 - 0.5 * np.log(x) ** 2 - spence(1 - np.minimum(1.0 / x, 1.0)))
+        f = (li - np.log(np.abs(1 - x)) * np.log(r / 2.0)) * r * r * (2 * r - 3) / 8.0
+        f += (1 + 3 * r - 6 * r * r) * np.log(r / 2.0) / 12.0
+        f += 11.0 / 72.0 + 1.0 / (3.0 * r) + r / 2.0 - r * r / 2.0
+    return r, f
+
+
 def install():
     """Install the shims and return the imported reference package."""
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "kgeo")):
@@ -53,15 +67,16 @@ def install():
     sys.modules["ehtim"].parloop = sys.modules["ehtim.parloop"]
     sys.modules["ehtim.observing"].obs_helpers = sys.modules["ehtim.observing.obs_helpers"]
 
-    # (3) synthetic BZ-monopole table: 2 rows x N, r in [1,100]; the asymptotic
-    # f(r) ~ 1/(4r) is good enough because no golden vector uses bz_monopole.
+    # (3) synthetic BZ-monopole table: the reference's own generating recipe (kgeo/bfields.py:7-20: f(r) on
+    # linspace(1, 100, 100000), stored as 2 rows x N), with the real part of its complex mpmath formula written with
+    # scipy.special.spence (Li2(x) = spence(1 - x); Re Li2(x) = pi^2/3 - ln^2(x)/2 - Li2(1/x) for x > 1).
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         import pkg_resources
-    rs = np.linspace(1.0, 100.0, 2000)
+    rs, fs = bz_fr_table()
     buf = io.StringIO()
-    np.savetxt(buf, np.vstack((rs, 0.25 / rs)))
+    np.savetxt(buf, np.vstack((rs, fs)), fmt="%.18e")
     payload = buf.getvalue().encode()
     _orig_stream = pkg_resources.resource_stream
 

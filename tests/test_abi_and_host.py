@@ -156,10 +156,21 @@ def test_model_packing():
     assert list(M.emissivity_p)[:2] == [-1.5, 0.5] and M.velocity_p[0] == 1.0 and list(M.bfield_p)[:3] == [0., 1., 0.]
     M = pack_models(kg.Emissivity('thermal', ne0=1e5, Te0=1e11, B0=5., bfield_model=True))
     assert list(M.emissivity_p) == [5.0, 1e5, 1e11, 5.0, 0.7, 1.0, 1.5, 1.0]
+    b = kg.Bfield('power', p=0.75, C=2., usemono=True)
+    assert b.descriptor() == (_lib.BF['power'], [0.75, 2.0, 1.0])
+    assert kg.Bfield('bz_monopole', secondorder_only=True).descriptor() == (_lib.BF['bz_monopole'], [1.0, 1.0])
+    v = kg.Velocity('driftframe', bfield=b, nu_parallel=0.25)
+    assert v.descriptor() == (_lib.VEL['driftframe'], [0.25]) and kg.Velocity('driftframe').bfield.fieldtype == 'bz_para'
+    M = pack_models(velocity=v)                       # the drift frame brings its own field model along
+    assert M.bfield_type == _lib.BF['power'] and list(M.bfield_p)[:3] == [0.75, 2.0, 1.0]
     with pytest.raises(NotImplementedError):
-        kg.Bfield('bz_monopole')
+        pack_models(velocity=v, bfield=kg.Bfield('bz_para'))
     with pytest.raises(NotImplementedError):
-        kg.Velocity('driftframe')
+        kg.Bfield('const_comoving')
+    with pytest.raises(NotImplementedError):
+        kg.Velocity('driftframe', nu_parallel='FF')
+    with pytest.raises(Exception, match="nu_parallel should be in the range"):
+        kg.Velocity('driftframe', nu_parallel=1.5)
 
 
 def test_row_ranges():

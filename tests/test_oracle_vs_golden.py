@@ -206,3 +206,66 @@ def test_fromfile_models_oracle_matches_reference(golden):
                         vel, bf, polarization=True, specind=1.)
     for k, val in zip(['I', 'Q', 'U', 'r', 't', 'g', 'sinthb'], img):
         assert_close(val, g['img_' + k], 1e-12, floor=1e-300, what='fromfile image ' + k)
+
+
+# ---- BZ field models and the drift-frame velocity ---------------------------------------------------
+def _bz_cases(g):
+    import json
+    spec = json.loads(str(g['spec']))
+    for ia, a in enumerate(g['spins']):
+        for ib, (bt, kw) in enumerate(spec['bfs']):
+            yield ia, float(a), ib, dict(type=bt, **kw)
+
+
+def test_bz_models_oracle_against_reference(golden):
+    """Bfield('bz_monopole' | 'bz_para' | 'power' | ...) B^i, omega_field, b^2 and Velocity('driftframe') u^mu of the oracle
+    vs the unmodified reference (tests/golden/bz_models.npz).  bz_para is complex-valued in the reference (scipy's
+    lambertw): u^mu is compared where the reference's result is real (the fixture records that)."""
+    g = golden('bz_models')
+    vel = dict(type='general', fac_subkep=0.6, beta_phi=0.8, beta_r=0.7)
+    with np.errstate(all='ignore'):
+        for ia, a, ib, bf in _bz_cases(g):
+            r = g['a%d_r' % ia]
+            B1, B2, B3, om = ko.bfield_lab_omega(bf, a, r)
+            ref = g['a%d_b%d' % (ia, ib)]
+            for got, want in zip((B1, B2, B3), ref):
+                assert_close(np.broadcast_to(got, r.shape), want, 1e-12, floor=1e-6 * np.max(np.abs(ref[np.isfinite(ref)])), what='B %s' % bf)
+            assert_close(np.broadcast_to(om, r.shape), g['a%d_om%d' % (ia, ib)], 1e-12, floor=1e-9, what='omega %s' % bf)
+            assert_close(ko.bfield_bsq(bf, vel, a, r), g['a%d_bsq%d' % (ia, ib)], 1e-11, what='bsq %s' % bf)
+            for inu, nu in enumerate(g['nus']):
+                u = np.array([np.broadcast_to(c, r.shape) for c in
+                              ko.velocity_u_lab(dict(type='driftframe', bfield=bf, nu_parallel=float(nu)), a, r)])
+                want = g['a%d_u%d_%d' % (ia, ib, inu)]
+                # r = 2 with omega = 0 is the static limit: the drift speed is 1 +- eps there (gamma 1e8 or NaN)
+                ok = g['a%d_ureal%d_%d' % (ia, ib, inu)] & ~(np.abs(want[0]) > 1e6)
+                assert_close(u[:, ok], want[:, ok], 1e-11, floor=1.0, what='u %s nu=%g' % (bf, nu))
+
+
+def test_bz_monopole_images_oracle(golden):
+    g = golden('bz_models')
+    cases = dict(mono=dict(type='bz_monopole'), power=dict(type='power', p=0.75))
+    for name, bf in cases.items():
+        a, th_o, mbar_max, half, npx, nu = [float(x) for x in g['img_%s_par' % name]]
+        with np.errstate(all='ignore'):
+            out = ko.make_image(a, np.inf, th_o, int(mbar_max), -half, half, -half, half, 2 * half / npx,
+                                dict(type='ring', r_ring=3.5, sigma=0.8), dict(type='driftframe', bfield=bf, nu_parallel=nu), bf,
+                                polarization=True, specind=1.)
+        for got, key in zip(out, ['I', 'Q', 'U', 'r', 't', 'g', 'sinthb']):
+            ref = g['img_%s_%s' % (name, key)]
+            if key in ('Q', 'U'):
+                den = np.where(g['img_%s_I' % name] != 0, np.abs(g['img_%s_I' % name]), 1.0)
+                assert np.nanmax(np.abs(got - ref) / den) <= 1e-10, (name, key)
+            else:
+                assert_close(got, ref, 1e-10, floor=1e-300, what='%s image %s' % (name, key))
+
+
+def test_product_fr_table_matches_the_reference_recipe(golden):
+    """kgeo_b200.bfields.bz_fr_table (NumPy dilogarithm; no SciPy in the product) vs the table the reference was run with.
+    f(r) is a difference of terms ~r^3/4 that cancel to ~1/(4r): both sides carry ~r^3 eps of rounding noise."""
+    from kgeo_b200.bfields import bz_fr_table
+    g = golden('bz_models')
+    rs, fs = bz_fr_table()
+    assert rs.shape == (100000,) and rs[0] == 1.0 and rs[-1] == 100.0
+    assert np.array_equal(rs[::250], g['fr_r'])
+    d = np.abs(fs[::250] - g['fr_f'])
+    assert np.all(d <= 1e-15 * g["fr_r"] ** 3 + 1e-15), float(np.max(d / (g['fr_r'] ** 3)))
