@@ -15,4 +15,10 @@ img = kg.make_image(a, np.inf, th_o, 2, -10., 10., -10., 10., 20. / 50, emissivi
                     velocity=kg.Velocity('general', fac_subkep=0.7, beta_phi=0.7, beta_r=0.7), bfield=kg.Bfield('bz_guess', C=1.),
                     polarization=True, specind=1., pathlength=True)
 rs = kg.r_equatorial(a, np.inf, th_o, 1, A, B)
+bm = kg.Bfield('bz_monopole')
+img2 = kg.make_image(0.5, np.inf, 0.5, 1, -8., 8., -8., 8., 16. / 37, emissivity=kg.Emissivity('ring'),
+                     velocity=kg.Velocity('driftframe', bfield=bm, nu_parallel=0.3), bfield=bm, polarization=True, specind=1.)
+rr = np.linspace(1.9, 120., 333)
+for bf in (bm, kg.Bfield('bz_para'), kg.Bfield('power', p=0.75)):
+    bf.bfield_lab(0.5, rr); bf.omega_field(0.5, rr); kg.Velocity('driftframe', bfield=bf).u_lab(0.5, rr)
 print("sanitize_case ok", g.geo_coords[1].shape, img[0].shape)
