@@ -228,6 +228,26 @@ int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const d
                           const double* sinthb_dev, const double* Bmag_dev, double nu_obs, double specind,
                           double* j_dev, void* stream);
 
+/* ---- field-line crossings of the jet models (kgeo/solver.py:98-207: getguesses / findroot) --------------------------
+ * psi models: 0 = BZ paraboloid, 1 = monopole, 2 = power law r^pval (1 - |cos theta|), 3 = none (psi = 0).
+ * kgeo_fieldline_guesses, maxlen <= 0: per ray the number of starting guesses the reference's sign-change scan over the
+ *   (ngeo, npix) track arrays r, theta, tau yields (>= 1: a ray without crossing holds the single guess -1) -> count_dev,
+ *   their maximum -> maxcount_dev, the search limit of get_maxtau_forwardjet -> taumax_dev (optional); neqmax < 0 = None.
+ *   maxlen > 0: the guesses themselves, guesses_dev[m * npix + ray], padded with -1 (makegoodarray + transpose).
+ * kgeo_fieldline_solve: scipy.optimize.newton's vectorised secant iteration on psi(r(tau), theta(tau)) - psitarget for the
+ *   nguess x npix guesses (all elements iterate until every one has converged, as in the reference), then r, theta at the
+ *   roots, the signs of p^r and p^theta and the crossing count of getneq; elements whose guess is -1 come back as zeros.
+ *   Blocks until done (the iteration count depends on device-side convergence flags).  iterations / nfailed: host ints. */
+int kgeo_fieldline_guesses(const kgeo_observer* obs, size_t npix, size_t ngeo, const double* r_dev, const double* th_dev,
+                           const double* tau_dev, size_t ld, const double* alpha_dev, const double* beta_dev, const double* w,
+                           const int32_t* flags, int model, double pval, double psitarget, int neqmax, double maxtaufrac,
+                           int maxlen, int32_t* count_dev, int32_t* maxcount_dev, double* guesses_dev, double* taumax_dev,
+                           void* stream);
+int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, const double* beta_dev, const double* w,
+                         const int32_t* flags, int model, double pval, double psitarget, const double* guesses_dev, double tol,
+                         int maxiter, double* tau_dev, double* r_dev, double* th_dev, double* signpr_dev, double* signpth_dev,
+                         double* neq_dev, int32_t* iterations, int32_t* nfailed, void* stream);
+
 /* ---- measurement helper: sustained DFMA rate of the device (the measured FP64 roofline denominator) ------------ */
 int kgeo_fp64_peak_probe(int iters, double* flops_per_launch, float* ms, void* stream);
 

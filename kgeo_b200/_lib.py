@@ -79,6 +79,11 @@ SIGNATURES = {
     "kgeo_bfield_omega": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _V]),
     "kgeo_emissivity_jrest": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, ctypes.c_double,
                                              ctypes.c_double, _P, _V]),
+    "kgeo_fieldline_guesses": (ctypes.c_int, [_OBS, _S, _S, _P, _P, _P, _S, _P, _P, _P, c_int32_p, ctypes.c_int, ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_int32_p, c_int32_p,
+                                              _P, _P, _V]),
+    "kgeo_fieldline_solve": (ctypes.c_int, [_OBS, _S, _S, _P, _P, c_int32_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P,
+                                            ctypes.c_double, ctypes.c_int, _P, _P, _P, _P, _P, _P, c_int32_p, c_int32_p, _V]),
     "kgeo_fp64_peak_probe": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_float), _V]),
 }
 

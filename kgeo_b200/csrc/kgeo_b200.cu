@@ -23,6 +23,7 @@
 
 #include "../../include/kgeo_b200.h"
 #include "kg_image.cuh"
+#include "kg_fieldline.cuh"
 
 using namespace kg;
 
@@ -400,6 +401,172 @@ __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o
         if (neq) neq[q] = n_equatorial_at(W, o, fl, b, tau);
         if (npol) npol[q] = n_poloidal_at(W, tau);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// field-line crossings (kgeo/solver.py: getguesses / findroot)
+// ---------------------------------------------------------------------------------------------------------------------
+struct PsiSpec {
+    int model;
+    double pval, psitarget;
+};
+
+// getguesses (kgeo/solver.py:98-137), one thread per ray.  PASS 0 counts the ray's guesses (and takes the maximum over the
+// rays), PASS 1 writes them into guesses[m * npix + ray] (padded with -1: makegoodarray + transpose).
+template <int PASS>
+__global__ void __launch_bounds__(256) fieldline_guess_kernel(Observer o, PsiSpec ps, size_t npix, int ngeo,
+                                                              const double* __restrict__ r, const double* __restrict__ th,
+                                                              const double* __restrict__ tau, size_t ld,
+                                                              const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                              const double* __restrict__ w_in, const int32_t* __restrict__ flags_in,
+                                                              int neqmax, double maxtaufrac, int32_t* count, int32_t* maxcount,
+                                                              int maxlen, double* guesses, double* taumax_out) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    StridedW W{w_in + pix, (long long)npix};
+    const int fl = flags_in[pix];
+    const double al = alpha[pix], be = beta[pix];
+    const double taumax = maxtau_forwardjet(W, fl, be, neqmax, maxtaufrac);
+    if (PASS == 0 && taumax_out) taumax_out[pix] = taumax;
+    int n = 0;
+    auto emit = [&](double g) {
+        if (PASS == 1 && n < maxlen) guesses[(size_t)n * npix + pix] = g;
+        ++n;
+    };
+    const double impact = sqrt(al * al + be * be);
+    bool flat = false;
+    if (fabs(o.sth) < 0.1 && impact > 100.0) {                          // flat-space face-on guesses
+        double rparam = 0.0;
+        if (ps.model == PSI_POWER && ps.pval > 0.0) {
+            rparam = pow(impact * impact / (2.0 * ps.psitarget), 1.0 / (2.0 - ps.pval));
+            flat = true;
+        } else if (ps.model == PSI_PARA) {
+            rparam = (impact * impact + ps.psitarget * ps.psitarget) / (2.0 * ps.psitarget);
+            flat = true;
+        }
+        if (flat) {
+            emit(1.0 / rparam);
+            emit(2.0 / impact - 1.0 / rparam);
+        }
+    }
+    if (!flat) {
+        // indmax = argmin_k |tau_k - taumax| (first minimum; NaN distances never win, all-NaN gives 0 as np.argmin does)
+        int indmax = 0;
+        double best = fabs(tau[pix] - taumax);
+        for (int k = 1; k < ngeo; ++k) {
+            const double d = fabs(tau[(size_t)k * ld + pix] - taumax);
+            if (best != best) {
+                // np.argmin returns the first NaN: keep index of the first NaN
+            } else if (d != d || d < best) {
+                best = d;
+                indmax = k;
+                if (d != d) break;
+            }
+        }
+        // minfunc[k] = psi[k+1] psi[k] on k = 1 .. indmax-2 ("don't trust left or right endpoint")
+        double pk = 0.0;
+        bool have = false;
+        for (int k = 1; k <= indmax - 2; ++k) {
+            const size_t q = (size_t)k * ld + pix;
+            if (!have) pk = psi_value(ps.model, ps.pval, o.a, r[q], th[q]) - ps.psitarget;
+            const size_t q1 = (size_t)((k + 1) % ngeo) * ld + pix;
+            const double pn = psi_value(ps.model, ps.pval, o.a, r[q1], th[q1]) - ps.psitarget;
+            if (pn * pk < 0.0) emit(0.5 * (tau[q] + tau[q1]));
+            pk = pn;
+            have = true;
+        }
+        if (n == 0) emit(-1.0);
+    }
+    if (PASS == 0) {
+        count[pix] = n;
+        atomicMax(maxcount, n);
+    } else {
+        for (int m = n; m < maxlen; ++m) guesses[(size_t)m * npix + pix] = -1.0;
+    }
+}
+
+// state of scipy.optimize.newton's vectorised secant iteration (_array_newton), element e = m * npix + ray
+struct SecantState {
+    double *p, *p1, *q0, *q1, *pnew;
+    int32_t *active, *fail;
+    int32_t* gflags;    // [0] any(q1 != q0), [1] any(failures[nz_der])
+};
+
+__global__ void __launch_bounds__(256) fieldline_eval_kernel(Observer o, PsiSpec ps, size_t npix, size_t n,
+                                                             const double* __restrict__ w_in, const int32_t* __restrict__ flags_in,
+                                                             const double* __restrict__ guesses, const double* __restrict__ tau,
+                                                             double* q, double* r_out, double* th_out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t pix = e % npix;
+    StridedW W{w_in + pix, (long long)npix};
+    double rr, tt;
+    double v = psi_residual(W, o, flags_in[pix], ps.model, ps.pval, ps.psitarget, tau[e], &rr, &tt);
+    if (guesses[e] == -1.0) v = 0.0;                                    // arrhere[guesses == -1] = 0
+    if (q) q[e] = v;
+    if (r_out) r_out[e] = rr;
+    if (th_out) th_out[e] = tt;
+}
+
+__global__ void __launch_bounds__(256) fieldline_secant_start_kernel(size_t n, const double* __restrict__ guesses, SecantState st) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double dx = 6.828499381469512e-06;                            // np.finfo(float).eps ** 0.33
+    const double p = guesses[e];
+    st.p[e] = p;
+    st.p1[e] = p * (1.0 + dx) + ((p >= 0.0) ? dx : -dx);
+    st.active[e] = 1;
+    st.fail[e] = 1;
+}
+
+__global__ void __launch_bounds__(256) fieldline_secant_step_kernel(size_t n, double tol, SecantState st) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double p = st.p[e], p1 = st.p1[e], q0 = st.q0[e], q1 = st.q1[e];
+    const bool nz = (q1 != q0);
+    double pn = p;
+    int act = st.active[e], fail = st.fail[e];
+    if (nz) {
+        const double dp = (q1 * (p1 - p)) / (q1 - q0);
+        pn = p1 - dp;
+        fail = (fabs(dp) >= tol) ? 1 : 0;
+        if (fail) atomicOr(st.gflags + 1, 1);
+        atomicOr(st.gflags + 0, 1);
+    } else if (act) {
+        pn = (p1 + p) / 2.0;
+    }
+    act = act && nz;
+    st.pnew[e] = pn;
+    st.active[e] = act;
+    st.fail[e] = fail;
+}
+
+__global__ void __launch_bounds__(256) fieldline_average_kernel(size_t n, const double* p, const double* p1, double* out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = (p1[e] + p[e]) / 2.0;
+}
+
+// tail of findroot (kgeo/solver.py:181-207): coordinates at the root and at (1 + 1e-5) times it, momentum signs, crossing count
+__global__ void __launch_bounds__(256) fieldline_finish_kernel(Observer o, size_t npix, size_t n, const double* __restrict__ w_in,
+                                                               const int32_t* __restrict__ flags_in, const double* __restrict__ beta,
+                                                               const double* __restrict__ guesses, const double* __restrict__ root,
+                                                               double* tau_out, double* r_out, double* th_out, double* signpr,
+                                                               double* signpth, double* neq) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t pix = e % npix;
+    StridedW W{w_in + pix, (long long)npix};
+    const int fl = flags_in[pix];
+    const double tau = root[e];
+    const Point a = point_eval(W, o, fl, tau, false);
+    const Point b = point_eval(W, o, fl, tau * (1.0 + 1.0e-5), false);
+    const bool none = (guesses[e] == -1.0);
+    if (neq) neq[e] = neq_of_tau(W, fl, beta[pix], tau);
+    tau_out[e] = none ? 0.0 : tau;
+    r_out[e] = none ? 0.0 : a.r;
+    th_out[e] = none ? 0.0 : a.th;
+    signpr[e] = none ? 0.0 : np_sign(a.r - b.r);
+    signpth[e] = none ? 0.0 : np_sign(a.th - b.th);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -834,6 +1001,117 @@ int kgeo_raytrace(const kgeo_observer* obs, size_t npix, const double* alpha, co
     rc = kgeo_ray_setup(obs, npix, alpha, beta, mode, w, flags, stream);
     if (rc) return rc;
     return kgeo_tracks(obs, npix, w, flags, ngeo, maxtaufrac, nullptr, 0, 1, t, r, th, ph, sig, tau_out, ld, stream);
+}
+
+int kgeo_fieldline_guesses(const kgeo_observer* obs, size_t npix, size_t ngeo, const double* r, const double* th, const double* tau,
+                           size_t ld, const double* alpha, const double* beta, const double* w, const int32_t* flags, int model,
+                           double pval, double psitarget, int neqmax, double maxtaufrac, int maxlen, int32_t* count,
+                           int32_t* maxcount, double* guesses, double* taumax, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!r || !th || !tau || !alpha || !beta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: NULL pointer");
+    if (ld < npix || ngeo > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: bad leading dimension / ngeo");
+    if (model < PSI_PARA || model > PSI_NONE) return fail_arg(KGEO_E_MODEL, "kgeo_fieldline_guesses: unknown psi model");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    PsiSpec ps{model, pval, psitarget};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxlen <= 0) {            // pass 0: counts per ray and their maximum
+        if (!count || !maxcount) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: count / maxcount missing");
+        CU(cudaMemsetAsync(maxcount, 0, sizeof(int32_t), st));
+        fieldline_guess_kernel<0><<<grid_for(npix, 256), 256, 0, st>>>(o, ps, npix, (int)ngeo, r, th, tau, ld, alpha, beta, w, flags,
+                                                                      neqmax, maxtaufrac, count, maxcount, 0, nullptr, taumax);
+    } else {
+        if (!guesses) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: guesses missing");
+        fieldline_guess_kernel<1><<<grid_for(npix, 256), 256, 0, st>>>(o, ps, npix, (int)ngeo, r, th, tau, ld, alpha, beta, w, flags,
+                                                                      neqmax, maxtaufrac, nullptr, nullptr, maxlen, guesses, nullptr);
+    }
+    LAUNCHED("fieldline_guess_kernel");
+    return 0;
+}
+
+int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, const double* beta, const double* w,
+                         const int32_t* flags, int model, double pval, double psitarget, const double* guesses, double tol,
+                         int maxiter, double* tau_out, double* r_out, double* th_out, double* signpr, double* signpth, double* neq,
+                         int32_t* iterations, int32_t* nfailed, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    const size_t n = npix * nguess;
+    if (n && (!beta || !w || !flags || !guesses || !tau_out || !r_out || !th_out || !signpr || !signpth))
+        return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_solve: NULL pointer");
+    if (model < PSI_PARA || model > PSI_NONE) return fail_arg(KGEO_E_MODEL, "kgeo_fieldline_solve: unknown psi model");
+    if (iterations) *iterations = 0;
+    if (nfailed) *nfailed = 0;
+    if (n == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    PsiSpec ps{model, pval, psitarget};
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf dbl, ints;
+    CU(dbl.alloc(5 * n * sizeof(double)));
+    CU(ints.alloc((2 * n + 2) * sizeof(int32_t)));
+    SecantState S;
+    S.p = dbl.as<double>();
+    S.p1 = S.p + n;
+    S.q0 = S.p1 + n;
+    S.q1 = S.q0 + n;
+    S.pnew = S.q1 + n;
+    S.active = ints.as<int32_t>();
+    S.fail = S.active + n;
+    S.gflags = S.fail + n;
+    const unsigned grid = grid_for(n, 256);
+    fieldline_secant_start_kernel<<<grid, 256, 0, st>>>(n, guesses, S);
+    LAUNCHED("fieldline_secant_start_kernel");
+    fieldline_eval_kernel<<<grid, 256, 0, st>>>(o, ps, npix, n, w, flags, guesses, S.p, S.q0, nullptr, nullptr);
+    LAUNCHED("fieldline_eval_kernel");
+    fieldline_eval_kernel<<<grid, 256, 0, st>>>(o, ps, npix, n, w, flags, guesses, S.p1, S.q1, nullptr, nullptr);
+    LAUNCHED("fieldline_eval_kernel");
+    int it = 0;
+    bool converged = false;
+    const double* result = S.p;
+    for (; it < maxiter; ++it) {      // scipy.optimize.newton's secant loop: every element iterates until ALL have converged
+        int32_t g[2] = {0, 0};
+        CU(cudaMemsetAsync(S.gflags, 0, 2 * sizeof(int32_t), st));
+        fieldline_secant_step_kernel<<<grid, 256, 0, st>>>(n, tol, S);
+        LAUNCHED("fieldline_secant_step_kernel");
+        CU(cudaMemcpyAsync(g, S.gflags, sizeof(g), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!g[0]) {                  // all derivatives zero: p = (p1 + p) / 2 for every element, without this step's update
+            fieldline_average_kernel<<<grid, 256, 0, st>>>(n, S.p, S.p1, S.pnew);
+            LAUNCHED("fieldline_average_kernel");
+            result = S.pnew;
+            converged = true;
+            ++it;
+            break;
+        }
+        double* t = S.p;              // p <- updated p
+        S.p = S.pnew;
+        S.pnew = t;
+        result = S.p;
+        if (!g[1]) {
+            converged = true;
+            ++it;
+            break;
+        }
+        t = S.p1;                     // p1, p = p, p1 ; q0 = q1 ; q1 = func(p1)
+        S.p1 = S.p;
+        S.p = t;
+        t = S.q0;
+        S.q0 = S.q1;
+        S.q1 = t;
+        fieldline_eval_kernel<<<grid, 256, 0, st>>>(o, ps, npix, n, w, flags, guesses, S.p1, S.q1, nullptr, nullptr);
+        LAUNCHED("fieldline_eval_kernel");
+        result = S.p;
+    }
+    if (iterations) *iterations = it;
+    if (!converged && nfailed) {      // count the elements scipy would report as not converged
+        // (failures & nz_der are not distinguished here: the caller only needs all / some / none)
+        *nfailed = 1;
+    }
+    fieldline_finish_kernel<<<grid, 256, 0, st>>>(o, npix, n, w, flags, beta, guesses, result, tau_out, r_out, th_out, signpr,
+                                                  signpth, neq);
+    LAUNCHED("fieldline_finish_kernel");
+    CU(cudaStreamSynchronize(st));    // the state buffers are freed on return
+    return 0;
 }
 
 int kgeo_crossing_counts(const kgeo_observer* obs, size_t npix, const double* beta, const double* w, const int32_t* flags,

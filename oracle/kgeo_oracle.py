@@ -1395,3 +1395,126 @@ def make_image(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, beta_max,
     if pathlength:
         out = out + (planes['lp'], planes['Ie'])
     return out
+
+
+# ---- field-line crossings (kgeo/solver.py) --------------------------------------------------------------------------
+def psifunc(r, theta, a, model='para', pval=1):
+    """kgeo/solver.py:13-37"""
+    abscth = np.abs(np.cos(theta))
+    if model == 'para':
+        rp = 1 + np.sqrt(1 - a ** 2)
+        return r * (1 - abscth) + rp * (1 + abscth) * (1 - np.log(1 + abscth)) - 2 * rp * (1 - np.log(2))
+    if model == 'mono':
+        return 1 - abscth
+    if model == 'power':
+        return r ** pval * (1 - abscth)
+    return 0 * r
+
+
+def maxtau_forwardjet(a, r_o, th_o, alpha, beta, neqmax=1, maxtaufrac=1.0 - 1.0e-10):
+    """get_maxtau_forwardjet, kgeo/solver.py:57-88"""
+    lam, eta = conserved(a, th_o, alpha, beta)
+    r1, r2, r3, r4, _ = quartic_roots(a, lam, eta)
+    tt2 = mino_total(a, r_o, eta, r1, r2, r3, r4) * maxtaufrac
+    if neqmax is None:
+        return tt2
+    up, um, uratio, a2um = angular_consts(a, th_o, lam, eta)
+    F0 = sp.ellipkinc(np.arcsin(np.cos(th_o) / np.sqrt(up)), uratio)
+    K = sp.ellipkinc(0.5 * np.pi, uratio)
+    mmax = neqmax - 1 + np.heaviside(beta, 0)
+    taumax = (2 * mmax * K - np.sign(beta) * F0) / np.sqrt(-um * a ** 2)
+    taumax = np.where(eta <= 0, tt2, taumax)
+    return np.min(np.array([taumax, tt2]), axis=0)
+
+
+def fieldline_guesses(r_s, th_s, tau_s, a, r_o, th_o, alpha, beta, psitarget, neqmax=1, model='para', pval=1):
+    """getguesses, kgeo/solver.py:98-137, on (ngeo, npix) track arrays"""
+    taumaxes = maxtau_forwardjet(a, r_o, th_o, alpha, beta, neqmax)
+    psig = psifunc(r_s, th_s, a, model, pval) - psitarget
+    out = []
+    for i in range(len(alpha)):
+        impact = np.sqrt(alpha[i] ** 2 + beta[i] ** 2)
+        if np.abs(np.sin(th_o)) < .1 and impact > 100:
+            if model == 'power' and pval > 0:
+                rparam = (impact ** 2 / (2 * psitarget)) ** (1 / (2 - pval))
+                out.append(np.array([1 / rparam, 2 / impact - 1 / rparam]))
+                continue
+            elif model == 'para':
+                rparam = (impact ** 2 + psitarget ** 2) / (2 * psitarget)
+                out.append(np.array([1 / rparam, 2 / impact - 1 / rparam]))
+                continue
+        minfunc = np.roll(psig[:, i], -1) * psig[:, i]
+        indmax = np.argmin(np.abs(tau_s[:, i] - taumaxes[i]))
+        minfunc = minfunc[:indmax + 1][1:-2]
+        idx = np.where(minfunc < 0)[0] + 1
+        if len(idx) == 0:
+            out.append(np.array([-1]))
+            continue
+        out.append(np.array([(tau_s[k, i] + tau_s[k + 1, i]) / 2 for k in idx]))
+    m = max(len(x) for x in out)
+    res = -np.ones((len(out), m))
+    for i, x in enumerate(out):
+        res[i, :len(x)] = x
+    return np.transpose(res.copy())
+
+
+def _secant_all(func, x0, tol, maxiter=500):
+    """scipy.optimize.newton(func, x0) for arrays without a derivative (scipy/optimize/_zeros_py.py::_array_newton, secant
+    branch): every element keeps iterating until all have converged."""
+    p = np.array(x0, copy=True)
+    failures = np.ones_like(p, dtype=bool)
+    dx = np.finfo(float).eps ** 0.33
+    p1 = p * (1 + dx) + np.where(p >= 0, dx, -dx)
+    q0, q1 = np.asarray(func(p)), np.asarray(func(p1))
+    active = np.ones_like(p, dtype=bool)
+    for _ in range(maxiter):
+        nz = (q1 != q0)
+        if not nz.any():
+            p = (p1 + p) / 2.0
+            break
+        dp = (q1 * (p1 - p))[nz] / (q1 - q0)[nz]
+        p[nz] = p1[nz] - dp
+        azd = ~nz & active
+        p[azd] = (p1 + p)[azd] / 2.0
+        active &= nz
+        failures[nz] = np.abs(dp) >= tol
+        if not failures[nz].any():
+            break
+        p1, p = p, p1
+        q0 = q1
+        q1 = np.asarray(func(p1))
+    return p
+
+
+def findroot(r_s, th_s, tau_s, psitarget, alpha, beta, r_o, th_o, a, model='para', neqmax=1, tol=1e-8, pval=1):
+    """findroot, kgeo/solver.py:142-207, on the (ngeo, npix) tracks of raytrace()"""
+    guesses = fieldline_guesses(r_s, th_s, tau_s, a, r_o, th_o, alpha, beta, psitarget, neqmax, model, pval)
+    shape = guesses.shape
+    nrep = len(guesses)
+    al, be = np.tile(alpha, nrep), np.tile(beta, nrep)
+    g = guesses.flatten()
+    obs = [0, r_o, th_o, 0]
+
+    def coords(tau):
+        _, (_, r, th, _) = coords_at_tau(a, obs, [al, be], tau.reshape(1, -1), full=False)
+        return r[0], th[0]
+
+    def func(tau):
+        r, th = coords(tau)
+        v = psifunc(r, th, a, model, pval) - psitarget
+        v[g == -1] = 0
+        return v
+
+    root = _secant_all(func, g, tol)
+    r0, t0 = coords(root)
+    r1, t1 = coords(root * (1 + 1e-5))
+    signpr, signpth = np.sign(r0 - r1), np.sign(t0 - t1)
+    lam, eta = conserved(a, th_o, al, be)
+    up, um, uratio, _ = angular_consts(a, th_o, lam, eta)
+    F0 = sp.ellipkinc(np.arcsin(np.cos(th_o) / np.sqrt(up)), uratio)
+    K = sp.ellipkinc(0.5 * np.pi, uratio)
+    mbar = (np.sqrt(-um * a ** 2) * root + np.sign(be) * F0) / (2 * K) - np.heaviside(be, 0)
+    neq = np.ceil(np.nan_to_num(mbar))
+    none = (g == -1)
+    root, r0, t0, signpr, signpth = [np.where(none, 0.0, x) for x in (root, r0, t0, signpr, signpth)]
+    return root, r0, t0, signpr, signpth, neq, shape

@@ -329,6 +329,33 @@ def bz_models():
     save('bz_models', **out)
 
 
+def fieldline_crossings():
+    """solver.getguesses / solver.findroot / solver.get_maxtau_forwardjet (kgeo/solver.py:57-207) on small ray grids: the three
+    stream functions, neqmax 1 / 2 / None, a face-on distant-ray case that takes the flat-space guesses."""
+    from kgeo.solver import findroot, getguesses, get_maxtau_forwardjet
+    cases = [('para_n1', 0.5, 1000., 20 * DEG, grid(13, 9.), 2.0, 'para', 1, 1, 120),
+             ('para_n2', 0.94, 1000., 60 * DEG, grid(11, 7.), 1.5, 'para', 1, 2, 150),
+             ('mono_nall', 0.7, 500., 40 * DEG, grid(11, 8.), 0.3, 'mono', 1, None, 120),
+             ('power_n1', 0.3, 1000., 163 * DEG, grid(11, 8.), 1.2, 'power', 0.75, 1, 120),
+             ('para_flat', 0.5, 1.e4, 3 * DEG, grid(7, 300.), 40.0, 'para', 1, 1, 100)]
+    out = dict(names=np.array(json.dumps([c[0] for c in cases])))
+    for name, a, r_o, th_o, (A, B), psit, model, pval, neqmax, ngeo in cases:
+        with np.errstate(all='ignore'):
+            geo = quiet(raytrace_ana, a, [0, r_o, th_o, 0], [A, B], ngeo, plotdata=False)
+            g = quiet(getguesses, geo, a, r_o, th_o, A, B, psit, ngeo, neqmax=neqmax, model=model, pval=pval)
+            res = quiet(findroot, geo, psit, A, B, r_o, th_o, a, ngeo, model=model, neqmax=neqmax, tol=1e-8, pval=pval)
+            tm = get_maxtau_forwardjet(a, r_o, th_o, A, B, neqmax=neqmax)
+        out[name + '_par'] = np.array([a, r_o, th_o, psit, pval, -1 if neqmax is None else neqmax, ngeo])
+        out[name + '_model'] = np.array(model)
+        out[name + '_alpha'], out[name + '_beta'] = A, B
+        out[name + '_guesses'] = g
+        out[name + '_taumax'] = tm
+        for k, v in zip(['tau', 'r', 'th', 'signpr', 'signpth', 'neq'], res[:6]):
+            out[name + '_' + k] = np.asarray(v, dtype=float)
+        out[name + '_shape'] = np.array(res[6])
+    save('fieldline', **out)
+
+
 def inverse_lensing():
     """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
     out = {}
@@ -352,7 +379,7 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -365,5 +392,6 @@ if __name__ == '__main__':
     inverse_lensing()
     fromfile_models()
     bz_models()
+    fieldline_crossings()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

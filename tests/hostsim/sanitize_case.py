@@ -21,4 +21,7 @@ img2 = kg.make_image(0.5, np.inf, 0.5, 1, -8., 8., -8., 8., 16. / 37, emissivity
 rr = np.linspace(1.9, 120., 333)
 for bf in (bm, kg.Bfield('bz_para'), kg.Bfield('power', p=0.75)):
     bf.bfield_lab(0.5, rr); bf.omega_field(0.5, rr); kg.Velocity('driftframe', bfield=bf).u_lab(0.5, rr)
+from kgeo_b200 import solver
+gg = kg.raytrace_ana(0.5, [0, 1000., 20 * np.pi / 180, 0], [A[:333], B[:333]], ngeo=60, plotdata=False)
+fr = solver.findroot(gg, 2.0, A[:333], B[:333], 1000., 20 * np.pi / 180, 0.5, 60, model='para', neqmax=2)
 print("sanitize_case ok", g.geo_coords[1].shape, img[0].shape)

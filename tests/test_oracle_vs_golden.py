@@ -269,3 +269,30 @@ def test_product_fr_table_matches_the_reference_recipe(golden):
     assert np.array_equal(rs[::250], g['fr_r'])
     d = np.abs(fs[::250] - g['fr_f'])
     assert np.all(d <= 1e-15 * g["fr_r"] ** 3 + 1e-15), float(np.max(d / (g['fr_r'] ** 3)))
+
+
+# ---- field-line crossings of the jet models (kgeo/solver.py) -----------------------------------------
+def _fieldline_case(g, name):
+    a, r_o, th_o, psit, pval, neqmax, ngeo = [float(x) for x in g[name + '_par']]
+    return (a, r_o, th_o, psit, pval, None if neqmax < 0 else int(neqmax), int(ngeo), str(g[name + '_model']),
+            g[name + '_alpha'], g[name + '_beta'])
+
+
+def test_fieldline_crossings_oracle_against_reference(golden):
+    """getguesses / findroot / get_maxtau_forwardjet of the oracle (incl. SciPy's all-elements secant loop) vs the unmodified
+    reference: identical guesses, and roots / coordinates / signs / crossing counts to 1e-12."""
+    import warnings
+    g = golden('fieldline')
+    for name in json.loads(str(g['names'])):
+        a, r_o, th_o, psit, pval, neqmax, ngeo, model, A, B = _fieldline_case(g, name)
+        with np.errstate(all='ignore'), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            tau, _, (_, r, th, _) = ko.raytrace(a, [0, r_o, th_o, 0], [A, B], ngeo)
+            guesses = ko.fieldline_guesses(r, th, tau, a, r_o, th_o, A, B, psit, neqmax, model, pval)
+            res = ko.findroot(r, th, tau, psit, A, B, r_o, th_o, a, model, neqmax, 1e-8, pval)
+            tm = ko.maxtau_forwardjet(a, r_o, th_o, A, B, neqmax)
+        assert guesses.shape == g[name + '_guesses'].shape == tuple(g[name + '_shape'])
+        assert_close(guesses, g[name + '_guesses'], 1e-13, what=name + ' guesses')
+        assert_close(tm, g[name + '_taumax'], 1e-13, what=name + ' taumax')
+        for k, v in zip(['tau', 'r', 'th', 'signpr', 'signpth', 'neq'], res[:6]):
+            assert_close(v, g[name + '_' + k], 1e-12, what='%s %s' % (name, k))
