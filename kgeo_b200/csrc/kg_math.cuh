@@ -145,7 +145,8 @@ KG_HD double atanh_ratio(double X, double Y) {
 
 // sin and cos of v: Cody-Waite reduction by pi/2 (two FMAs: exact products), |v| < 1e6
 KG_HD void fsincos(double v, double* sv, double* cv) {
-    if (!(fabs(v) < 1.0e6)) {
+    // |v| < 2^19 (and not NaN / inf): compared on the exponent field (integer pipe instead of an FP64-pipe DSETP)
+    if ((unsigned)(kg_hiint(v) & 0x7fffffff) >= 0x41200000u) {
         kg_sincos_cold(v, sv, cv);
         return;
     }
@@ -162,16 +163,21 @@ KG_HD void fsincos(double v, double* sv, double* cv) {
     const double s = fma(r * z, ps, r);
     const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
     const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;       // quadrant 1, 3: swap
-    *sv = (n & 2) ? -a : a;
-    *cv = ((n + 1) & 2) ? -b : b;
+    // quadrants 2, 3 negate the sine, 1, 2 the cosine: flip the sign bit (the same value as -a / -b, without the
+    // select on both register halves)
+    *sv = kg_sethi(a, kg_hiint(a) ^ (int)(((unsigned)n & 2u) << 30));
+    *cv = kg_sethi(b, kg_hiint(b) ^ (int)(((unsigned)(n + 1) & 2u) << 30));
 }
 
 // atan2(y, x), result in [-pi, pi]: one division; the octant angle is atan(c) + atan((a - c)/(1 + a c)) with
 // c in {0, tan(pi/8), 1} chosen so that |t| <= tan(pi/16)
 KG_HD double fatan2(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
-    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
-    if (!(mx < 1.0e150) || !(mx > 1.0e-150)) return kg_atan2_cold(y, x);   // zeros, inf, NaN, extreme scales
+    const bool swapped = ay > ax;
+    const double mx = swapped ? ay : ax, mn = swapped ? ax : ay;
+    // zeros, inf, NaN, extreme scales (either argument outside 2^-500 .. 2^500) go to libm; tested on the exponent fields
+    if ((unsigned)((kg_hiint(ax) >> 20) - 523) > 1000u || (unsigned)((kg_hiint(ay) >> 20) - 523) > 1000u)
+        return kg_atan2_cold(y, x);
     double c = 0.0, base = 0.0;
     if (mn > kTanPio16 * mx) {
         c = kTanPio8;
@@ -187,7 +193,7 @@ KG_HD double fatan2(double y, double x) {
 #pragma unroll
     for (int i = 6; i >= 0; --i) p = fma(p, z, KM(KM_ATAN + i));
     double r = base + fma(t * z, p, t);
-    if (ay > ax) r = (kPio2Hi - r) + kPio2Lo;
+    if (swapped) r = (kPio2Hi - r) + kPio2Lo;
     if (x < 0.0) r = (kPiHi - r) + kPiLo;
     return (y < 0.0) ? -r : r;
 }
