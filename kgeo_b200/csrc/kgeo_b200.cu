@@ -360,6 +360,32 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
         if (PASS == P_ALL && threadIdx.x < TRK_RPW)
             sw[NW * TRK_RPW + threadIdx.x] = (threadIdx.x < nvalid) ? (double)flags_in[pix0 + threadIdx.x] : 0.0;
         __syncthreads();
+        if (PASS == P_FIXUP) {
+            // Fix-up rays are isolated (1-3 of a group's 4 are typical), so lane = 4 ks + ray would leave most lanes idle (17 of
+            // 32 active, measured): here a warp takes ONE ray at a time and its lanes 32 consecutive samples.  The stores are
+            // then 8-byte pieces of 32 different rows -- partial sectors, but only for the 0.3 % of the rays traced here.
+            const unsigned gm = (mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u);
+            for (int jr = 0; jr < nvalid; ++jr) {
+                if (!((gm >> jr) & 1u)) continue;                       // uniform over the CTA
+                const int flr = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + jr);
+                const size_t pixr = pix0 + jr;
+                SmemW Wr{sw + jr};
+                const double stop = maxtaufrac * Wr(S_TAUTOT);
+                const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+                for (int k = k0 + warp * 32 + lane; k < k1; k += WARPS * 32) {
+                    const double tau = (k == klast) ? stop : (double)k * step;
+                    const Point p = point_eval<SmemW, false>(Wr, o, flr, tau, FULL);
+                    const size_t q = (size_t)(k - k_begin) * ld + pixr;
+                    if (out.r) __stcs(out.r + q, p.r);
+                    if (out.th) __stcs(out.th + q, p.th);
+                    if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
+                    if (out.ph) __stcs(out.ph + q, FULL ? p.ph : 0.0);
+                    if (out.sig) __stcs(out.sig + q, FULL ? p.sig : 0.0);
+                    if (out.tau) __stcs(out.tau + q, tau);
+                }
+            }
+            continue;
+        }
         if (j >= nvalid) continue;
         const size_t pix = pix0 + j;
         SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(sw) + joff)};
