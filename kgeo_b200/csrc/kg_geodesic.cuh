@@ -476,7 +476,15 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
-    for (int i = 0; i < (LADDER ? NW : NW_LITE); ++i) w[i] = 0.0;
+    // Two-kernel setup (DEFER): the AGM ladders are only read by the Carlson fallback, so they are built where the theta path
+    // is turned down (theta_setup, or at the end of this function for motions that never were candidates) instead of for every
+    // ray, and neither they nor the theta blocks are zero-filled first: 190 of the 257 slots, which the first version
+    // wrote twice (ncu: 3.1 GB of DRAM writes for a 2.15 GB workspace).  Slots a ray does not use stay undefined.
+    const bool defer_ladders = DEFER && !(mode & M_CARLSON_ONLY);
+    for (int i = 0; i < (LADDER ? NW : NW_LITE); ++i) {
+        if (DEFER && ((i >= T_LAD && i <= R_LAD_END) || (i >= T_TH && i <= R_TH_END))) continue;
+        w[i] = 0.0;
+    }
     int flags = 0;
     double lam = -alpha * o.sth;
     double eta = conserved_eta(o, alpha, beta);
@@ -513,7 +521,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        if (LADDER) jacobi_make_ladder(m, w + T_LAD);
+        if (LADDER && !defer_ladders) jacobi_make_ladder(m, w + T_LAD);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = -s_o * sqrt(up);
@@ -561,7 +569,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[T_SQ] = sq1m;
         w[T_ISQ] = 1.0 / sq1m;
         w[T_I2K] = (Km < kInf) ? 0.5 / Km : 0.0;
-        if (LADDER) jacobi_make_ladder(m, w + T_LAD);
+        if (LADDER && !defer_ladders) jacobi_make_ladder(m, w + T_LAD);
         w[T_K] = Km;
         w[T_KPAR] = k;
         w[T_A] = um;
@@ -617,7 +625,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         if (PHI_T) legendre_sc<3>(sa, ca, k4, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k4);
         w[R_K] = k4;
-        if (LADDER) jacobi_make_ladder(k4, w + R_LAD);
+        if (LADDER && !defer_ladders) jacobi_make_ladder(k4, w + R_LAD);
         th_k = k4; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 1.0 / pref;
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
@@ -679,7 +687,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         if (PHI_T) legendre_sc<3>(sa, ca, k3, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k3);
         w[R_K] = k3;
-        if (LADDER) jacobi_make_ladder(k3, w + R_LAD);
+        if (LADDER && !defer_ladders) jacobi_make_ladder(k3, w + R_LAD);
         th_k = k3; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = sqAB;
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
@@ -727,7 +735,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         if (PHI_T) legendre_sc<3>(sa, ca, k2, nn, &Fo, &Eo, Pio);
         else Fo = legendre_F_sc(sa, ca, k2);
         w[R_K] = k2;
-        if (LADDER) jacobi_make_ladder(k2, w + R_LAD);
+        if (LADDER && !defer_ladders) jacobi_make_ladder(k2, w + R_LAD);
         th_k = k2; th_n[0] = nn[0]; th_n[1] = nn[1]; th_n[2] = nn[2];
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
@@ -769,6 +777,10 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         else radial_theta_setup(th_k, th_n, w, &flags);
     }
     if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA | F_TH_PENDING | F_R_PENDING);
+    if (LADDER && defer_ladders) {      // motions theta_setup will not visit keep the Carlson path: their ladders are built here
+        if (!(flags & F_TH_PENDING) && (flags & (F_TH_ORD | F_TH_VORT))) jacobi_make_ladder(w[T_M], w + T_LAD);
+        if (!(flags & F_R_PENDING)) jacobi_make_ladder(w[R_K], w + R_LAD);
+    }
     *flags_out = flags;
 }
 
@@ -781,11 +793,13 @@ KG_HD void theta_setup(const Observer& o, P w, int* flags_io) {
     if (flags & F_TH_PENDING) {
         flags &= ~F_TH_PENDING;
         polar_theta_setup(o, w[T_M], w[T_SQ], w[T_TH_SLOPE], w[T_TH_COEF], w, &flags);
+        if (!(flags & F_TH_THETA)) jacobi_make_ladder(w[T_M], w + T_LAD);      // Carlson fallback: needs the AGM ladder
     }
     if (flags & F_R_PENDING) {
         flags &= ~F_R_PENDING;
         const double n[3] = {w[R_N0], w[R_N1], w[R_N2]};
         radial_theta_setup(w[R_K], n, w, &flags);
+        if (!(flags & F_R_THETA)) jacobi_make_ladder(w[R_K], w + R_LAD);
     }
     *flags_io = flags;
 }

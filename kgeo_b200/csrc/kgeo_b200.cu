@@ -355,6 +355,7 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
         staged = true;
         for (int i = threadIdx.x; i < NW * TRK_RPW; i += THREADS) {
             const int s = i / TRK_RPW, jj = i % TRK_RPW;
+            if (PASS == P_HOT && s >= T_LAD && s <= R_LAD_END) continue;       // AGM ladders: Carlson fallback only
             sw[i] = (jj < nvalid) ? w_in[(size_t)s * npix + pix0 + jj] : 0.0;
         }
         if (PASS == P_ALL && threadIdx.x < TRK_RPW)
