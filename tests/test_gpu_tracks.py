@@ -176,6 +176,37 @@ def test_theta_path_agrees_with_duplication_path_on_a_dense_grid(kg, monkeypatch
             assert tail <= 1e-2
 
 
+def test_two_launch_pass_equals_the_single_pass_kernel(kg, tmp_path):
+    """A full trace is a hot launch (theta-function code only) plus a fix-up launch (Carlson-fallback rays).  Against the one-pass
+    kernel with the complete per-point code (KGEO_B200_TRK_PASSES=fused, read once per process, hence the subprocess): every ray
+    is written exactly once (no NaN holes, no ray traced twice differently), r and theta are bit-identical, phi and t agree to the
+    last bits away from the horizon (ptxas contracts the final sums differently under the hot kernel's register cap)."""
+    import os
+    import subprocess
+    import sys
+    from helpers import track_errors
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a, r_o, th_o, n, ngeo = 0.94, 1000., 17 * np.pi / 180, 203, 57      # 203^2 rays: not a multiple of the 32-ray tile
+    script = ("import sys, numpy as np; sys.path.insert(0, %r); import kgeo_b200 as kg; x = np.linspace(-9, 9, %d); "
+              "A, B = [v.flatten() for v in np.meshgrid(x, x)]; g = kg.raytrace_ana(%r, [0, %r, %r, 0], [A, B], ngeo=%d, plotdata=False); "
+              "np.savez(%r, t=g.geo_coords[0], r=g.geo_coords[1], th=g.geo_coords[2], ph=g.geo_coords[3], sig=g.affine_times, tau=g.mino_times)"
+              % (root, n, a, r_o, th_o, ngeo, str(tmp_path / "fused.npz")))
+    env = dict(os.environ, KGEO_B200_TRK_PASSES="fused")
+    subprocess.run([sys.executable, "-c", script], env=env, check=True, capture_output=True, timeout=300)
+    ref = np.load(str(tmp_path / "fused.npz"))
+    x = np.linspace(-9, 9, n)
+    A, B = [v.flatten() for v in np.meshgrid(x, x)]
+    g = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=ngeo, plotdata=False)
+    t, r, th, ph = g.geo_coords
+    assert np.array_equal(g.mino_times, ref['tau'])
+    assert np.array_equal(r, ref['r'], equal_nan=True) and np.array_equal(th, ref['th'], equal_nan=True)
+    rplus = 1 + np.sqrt(1 - a * a)
+    for key, got, floor in (('ph', ph, 1.0), ('t', t, r_o), ('sig', g.affine_times, r_o)):
+        assert np.array_equal(np.isnan(got), np.isnan(ref[key])), key
+        core, tail = track_errors(got, ref[key], g.mino_times, r, floor, rplus)
+        assert core <= 1e-11 and tail <= 1e-5, (key, core, tail)
+
+
 def test_row_shards_equal_single_launch_bitwise(kg):
     """Multi-GPU check of SURVEY 8e runnable on one GPU: tracing row blocks separately == tracing the whole plane."""
     from kgeo_b200 import sharding
