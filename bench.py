@@ -40,10 +40,10 @@ NPIX_SIDE, NGEO = 1024, 500
 MAXTAUFRAC = 1.0 - 1.0e-10
 CANONICAL_FLOP_PER_POINT = 2400.0   # SURVEY.md 8(d) work model: Carlson duplication, the reference's algorithm
 # FP64 flops the track pass executes per point on this workload (thread-level, predicated-on, ncu --set full of this
-# command, profiles/r01_final3_ncu_full_subset.csv): hot kernel 223.9 DFMA x 2 + 113.2 DMUL + 35.0 DADD = 596.1, fix-up
+# command, profiles/r01_final4_ncu_full_subset.csv): hot kernel 223.9 DFMA x 2 + 113.2 DMUL + 35.0 DADD = 596.1, fix-up
 # kernel (the 0.3 % Carlson-fallback rays, spread over all points) 12.3
 EXECUTED_FLOP_PER_POINT = 608.0
-FP64_PIPE_ACTIVE_NCU = 0.608        # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the hot kernel, same capture
+FP64_PIPE_ACTIVE_NCU = 0.609        # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the hot kernel, same capture
 BYTES_PER_POINT = 32.0      # r, theta, phi, t written once
 
 
@@ -367,9 +367,9 @@ def run_ours(args):
                       "note": "SURVEY 8(d) work model of the reference's algorithm (Carlson duplication per sample); this "
                               "kernel computes the same values with per-ray theta-function series, ~4x fewer flops"},
         # dram__bytes_read.sum + dram__bytes_write.sum of one track pass on this workload, from the committed ncu --set full
-        # capture (profiles/r01_final3_ncu_full_subset.csv): hot 3.29 + 16.97 GB, fix-up 0.33 + 0.26 GB; algorithmic 16.78 GB
-        # of results + 2.16 GB of ray constants
-        "traffic": 20.85e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/pass",
+        # capture (profiles/r01_final4_ncu_full_subset.csv): hot 2.19 + 16.92 GB, fix-up 0.39 + 0.45 GB; algorithmic 16.78 GB
+        # of results + 1.62 GB of ray constants (2.16 GB workspace less the AGM ladders the hot pass does not stage)
+        "traffic": 19.95e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/pass",
         "peak_source": "DFMA-chain probe (kgeo_fp64_peak_probe) measured live on this GPU; MEASURED_PEAKS.json has no "
                        "FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s" % nominal_tf,
         "points_per_launch": npts_rank, "kernel_ms": tk * 1e3,
