@@ -233,6 +233,7 @@ int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const d
  * kgeo_fieldline_guesses, maxlen <= 0: per ray the number of starting guesses the reference's sign-change scan over the
  *   (ngeo, npix) track arrays r, theta, tau yields (>= 1: a ray without crossing holds the single guess -1) -> count_dev,
  *   their maximum -> maxcount_dev, the search limit of get_maxtau_forwardjet -> taumax_dev (optional); neqmax < 0 = None.
+ *   ngeo = 0 (track pointers may be NULL) skips the scan: only taumax_dev is of interest then.
  *   maxlen > 0: the guesses themselves, guesses_dev[m * npix + ray], padded with -1 (makegoodarray + transpose).
  * kgeo_fieldline_solve: scipy.optimize.newton's vectorised secant iteration on psi(r(tau), theta(tau)) - psitarget for the
  *   nguess x npix guesses (all elements iterate until every one has converged, as in the reference), then r, theta at the

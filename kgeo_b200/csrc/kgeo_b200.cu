@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) fieldline_guess_kernel(Observer o, PsiSpe
             emit(2.0 / impact - 1.0 / rparam);
         }
     }
-    if (!flat) {
+    if (!flat && ngeo > 0) {
         // indmax = argmin_k |tau_k - taumax| (first minimum; NaN distances never win, all-NaN gives 0 as np.argmin does)
         int indmax = 0;
         double best = fabs(tau[pix] - taumax);
@@ -502,8 +502,8 @@ __global__ void __launch_bounds__(256) fieldline_guess_kernel(Observer o, PsiSpe
             pk = pn;
             have = true;
         }
-        if (n == 0) emit(-1.0);
     }
+    if (n == 0) emit(-1.0);
     if (PASS == 0) {
         count[pix] = n;
         atomicMax(maxcount, n);
@@ -1036,7 +1036,8 @@ int kgeo_fieldline_guesses(const kgeo_observer* obs, size_t npix, size_t ngeo, c
                            int32_t* maxcount, double* guesses, double* taumax, void* stream) {
     int rc = check_observer(obs, true);
     if (rc) return rc;
-    if (npix && (!r || !th || !tau || !alpha || !beta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: NULL pointer");
+    if (npix && (!alpha || !beta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: NULL pointer");
+    if (npix && ngeo && (!r || !th || !tau)) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: NULL track arrays");
     if (ld < npix || ngeo > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_guesses: bad leading dimension / ngeo");
     if (model < PSI_PARA || model > PSI_NONE) return fail_arg(KGEO_E_MODEL, "kgeo_fieldline_guesses: unknown psi model");
     if (npix == 0) return 0;

@@ -60,8 +60,12 @@ def _bundle_of(outgeo, a, r_o, th_o, alpha, beta):
 
 def _guess_call(bundle, outgeo, psitarget, neqmax, model, pval, maxlen, count=None, maxcount=None, guesses=None, taumax=None):
     L = _lib.lib()
-    r, th, tau = [_engine.to_device(outgeo.device_array(k), bundle.dev) for k in ('r', 'th', 'tau')]
-    ngeo = int(r.shape[0])
+    if outgeo is None:                       # no tracks: only the search limit (get_maxtau_forwardjet)
+        r = th = tau = None
+        ngeo = 0
+    else:
+        r, th, tau = [_engine.to_device(outgeo.device_array(k), bundle.dev) for k in ('r', 'th', 'tau')]
+        ngeo = int(r.shape[0])
     _lib.check(L.kgeo_fieldline_guesses(ctypes.byref(bundle.obs), bundle.npix, ngeo, _engine.dptr(r), _engine.dptr(th),
                                         _engine.dptr(tau), bundle.npix, _engine.dptr(bundle.alpha), _engine.dptr(bundle.beta),
                                         _engine.dptr(bundle.w), _engine.iptr(bundle.flags), _model_id(model), float(pval),
@@ -75,16 +79,10 @@ def get_maxtau_forwardjet(a, r_o, th_o, alpha, beta, neqmax=1):
     alpha, beta = np.asarray(alpha, dtype=np.float64), np.asarray(beta, dtype=np.float64)
     bundle = _engine.RayBundle(a, r_o, th_o, alpha, beta, clamp_lowspin=False)
     t = _engine.torch()
-    dummy = _engine.empty((4, bundle.npix), bundle.dev)
-    dummy.zero_()
-
-    class _G(object):
-        def device_array(self, k):
-            return dummy
     taumax = _engine.empty((bundle.npix,), bundle.dev)
     count = _engine.empty((bundle.npix,), bundle.dev, t.int32)
     maxcount = _engine.empty((1,), bundle.dev, t.int32)
-    _guess_call(bundle, _G(), 1.0, neqmax, 'none', 1, 0, count=count, maxcount=maxcount, taumax=taumax)
+    _guess_call(bundle, None, 1.0, neqmax, 'none', 1, 0, count=count, maxcount=maxcount, taumax=taumax)
     return taumax.cpu().numpy()
 
 

@@ -187,3 +187,15 @@ def test_row_ranges():
     assert (r0, r1) == (3, 5) and np.array_equal(np.unique(be), [3., 4.]) and al.size == 10
     with pytest.raises(ValueError):
         sharding.row_range(10, 3, 3)
+
+
+def test_solver_host_side():
+    """kgeo_b200.solver: stream-function closed forms (host helpers, as in kgeo/solver.py:13-37) and the model ids of the ABI"""
+    from kgeo_b200 import solver
+    from oracle import kgeo_oracle as ko
+    r, th = np.linspace(1.5, 40., 50), np.linspace(0.05, 3.1, 50)
+    for model, pval in (('para', 1), ('mono', 1), ('power', 0.75)):
+        assert np.allclose(solver.psifunc(r, th, 0.7, model=model, pval=pval), ko.psifunc(r, th, 0.7, model, pval), rtol=1e-15)
+    assert solver.psifunc(r, th, 0.7, model='nonsense') == 0
+    assert [solver._model_id(m) for m in ('para', 'mono', 'power', 'nonsense')] == [0, 1, 2, 3]
+    assert solver.MAXTAUFRAC == 1. - 1.e-10
