@@ -228,6 +228,11 @@ int kgeo_emissivity_jrest(const kgeo_models* models, double a, size_t n, const d
                           const double* sinthb_dev, const double* Bmag_dev, double nu_obs, double specind,
                           double* j_dev, void* stream);
 
+/* The host-buffer entry points take their device scratch from the device's default memory pool and leave it cached there
+ * between calls (a cfg 3 trace uses ~4 GB; returning it to the driver cost up to 200 ms per call).  kgeo_trim_memory gives
+ * the cached blocks back (synchronises the device). */
+int kgeo_trim_memory(int device);
+
 /* ---- field-line crossings of the jet models (kgeo/solver.py:98-207: getguesses / findroot) --------------------------
  * psi models: 0 = BZ paraboloid, 1 = monopole, 2 = power law r^pval (1 - |cos theta|), 3 = none (psi = 0).
  * kgeo_fieldline_guesses, maxlen <= 0: per ray the number of starting guesses the reference's sign-change scan over the

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <chrono>
 
 #include "../../include/kgeo_b200.h"
 #include "kg_image.cuh"
@@ -830,6 +831,34 @@ struct DevBuf {
     template <class T>
     T* as() const { return (T*)p; }
 };
+// Stream-ordered scratch of the host-buffer entry points.  cudaFree of the ~4 GB a BASELINE cfg 3 call uses took up to 200 ms
+// per call (measured: 305 ms to the last byte on the host, 490-515 ms until the call returned), so the scratch comes from the
+// device's default memory pool, whose release threshold is raised once: freed blocks stay in the pool and the next call gets
+// them back without a trip to the driver.  kgeo_trim_memory() hands the cached blocks back.
+struct PoolBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~PoolBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        st = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 8, stream);
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+static cudaError_t keep_pool_memory(int device) {
+    static std::atomic<unsigned long long> done{0};
+    if (device < 0 || device >= 64 || (done.load() >> device) & 1ULL) return cudaSuccess;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e != cudaSuccess) return e;
+    unsigned long long thr = ~0ULL;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (e == cudaSuccess) done.fetch_or(1ULL << device);
+    return e;
+}
 struct StreamPair {
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
@@ -1285,10 +1314,19 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     if (ngeo > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_raytrace_host: ngeo too large");
     if (npix == 0 || ngeo == 0) return 0;
     CU(cudaSetDevice(device));
+    // KGEO_B200_TRACE_HOST=1 (developer): wall-clock phases of this call on stderr
+    static const bool trace = getenv("KGEO_B200_TRACE_HOST") != nullptr;
+    const auto tc0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace)
+            fprintf(stderr, "kgeo_raytrace_host: %-28s %8.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+    };
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
     double* host[6] = {t, r, th, ph, sig, tau_out};
     int nout = 0;
     for (int i = 0; i < 6; ++i) nout += host[i] != nullptr;
+    CU(keep_pool_memory(device));
     StreamPair sp;
     CU(cudaStreamCreateWithFlags(&sp.compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&sp.copy, cudaStreamNonBlocking));
@@ -1296,13 +1334,14 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
         CU(cudaEventCreateWithFlags(&sp.done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sp.drained[i], cudaEventDisableTiming));
     }
-    DevBuf d_alpha, d_beta, d_w, d_flags;
-    CU(d_alpha.alloc(npix * sizeof(double)));
-    CU(d_beta.alloc(npix * sizeof(double)));
-    CU(d_w.alloc((size_t)NW * npix * sizeof(double)));
-    CU(d_flags.alloc(npix * sizeof(int32_t)));
+    PoolBuf d_alpha, d_beta, d_w, d_flags;            // freed (stream-ordered, on sp.compute) before sp goes out of scope
+    CU(d_alpha.alloc(npix * sizeof(double), sp.compute));
+    CU(d_beta.alloc(npix * sizeof(double), sp.compute));
+    CU(d_w.alloc((size_t)NW * npix * sizeof(double), sp.compute));
+    CU(d_flags.alloc(npix * sizeof(int32_t), sp.compute));
     CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
     CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
+    lap("streams, workspace alloc");
     rc = launch_setup(o, npix, d_alpha.as<double>(), d_beta.as<double>(), mode, d_w.as<double>(), d_flags.as<int32_t>(), sp.compute);
     if (rc) return rc;
     if (nout == 0) {
@@ -1313,10 +1352,11 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     size_t slab = (size_t)(256u << 20) / (npix * sizeof(double));
     slab = (slab < 32) ? 32 : (slab / 32) * 32;
     if (slab > ngeo) slab = ngeo;
-    DevBuf d_out[2][6];
+    PoolBuf d_out[2][6];
     for (int b = 0; b < 2; ++b)
         for (int i = 0; i < 6; ++i)
-            if (host[i]) CU(d_out[b][i].alloc(slab * npix * sizeof(double)));
+            if (host[i]) CU(d_out[b][i].alloc(slab * npix * sizeof(double), sp.compute));
+    lap("slab alloc");
     int nslab = (int)((ngeo + slab - 1) / slab);
     for (int s = 0; s < nslab; ++s) {
         int b = s & 1;
@@ -1336,8 +1376,19 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
                                    sp.copy));
         CU(cudaEventRecord(sp.drained[b], sp.copy));
     }
+    lap("all slabs enqueued");
     CU(cudaStreamSynchronize(sp.copy));
     CU(cudaStreamSynchronize(sp.compute));
+    lap("copies drained");
+    return 0;
+}
+
+int kgeo_trim_memory(int device) {
+    cudaMemPool_t pool;
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    CU(cudaMemPoolTrimTo(pool, 0));
     return 0;
 }
 
