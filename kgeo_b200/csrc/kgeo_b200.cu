@@ -1416,11 +1416,12 @@ int kgeo_equatorial_image_host(const kgeo_observer* obs, const kgeo_models* mode
     double* host[NOUT] = {I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr,
                           opts->pathlength ? Ie : nullptr};
     const size_t planes[NOUT] = {norder, norder, norder, norder, norder, norder, norder, 1, 1, 1, norder, norder};
-    DevBuf d_alpha, d_beta, d_out[NOUT];
-    CU(d_alpha.alloc(npix * sizeof(double)));
-    CU(d_beta.alloc(npix * sizeof(double)));
+    CU(keep_pool_memory(device));
+    PoolBuf d_alpha, d_beta, d_out[NOUT];             // pool-backed scratch (see PoolBuf), freed stream-ordered before `guard`
+    CU(d_alpha.alloc(npix * sizeof(double), st));
+    CU(d_beta.alloc(npix * sizeof(double), st));
     for (int i = 0; i < NOUT; ++i)
-        if (host[i]) CU(d_out[i].alloc(planes[i] * npix * sizeof(double)));
+        if (host[i]) CU(d_out[i].alloc(planes[i] * npix * sizeof(double), st));
     CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, st));
     rc = kgeo_equatorial_image(obs, models, opts, npix, d_alpha.as<double>(), d_beta.as<double>(), d_out[0].as<double>(),
