@@ -356,6 +356,48 @@ def fieldline_crossings():
     save('fieldline', **out)
 
 
+def jet_pipeline():
+    """Pinned targets for the rest of SURVEY 8 f4 (NOT built yet): off_eq.getstokes of the unmodified reference for the monopole and
+    power-law jet models on small grids, with the intermediate quantities a device implementation has to reproduce: findroot's
+    crossings, the densities of densityfuncs.density_*_all, the raw per-crossing Stokes parameters (sumsubring=False) and the
+    sorted images.  The paraboloid model is absent: in this environment the reference's own pipeline fails for it
+    (densityfuncs.eta_para: float() of a complex number -- SciPy's lambertw makes the field-line quantities complex)."""
+    import contextlib
+    import io
+    from kgeo.off_eq import getstokes
+    from kgeo.solver import findroot
+    from kgeo.densityfuncs import density_mono_all, density_power_all
+    out = dict(names=np.array(json.dumps(['mono', 'power'])))
+    cases = [('mono', 0.5, 1000., 20 * DEG, 0.3, 1, 1), ('power', 0.7, 1000., 30 * DEG, 1.5, 0.75, 2)]
+    for name, a, r_o, th_o, psit, pval, neqmax in cases:
+        x = np.linspace(-8, 8, 11)
+        A2, B2 = np.meshgrid(x, x)
+        A, B = A2.flatten(), B2.flatten()
+        ngeo = 100
+        with np.errstate(all='ignore'), contextlib.redirect_stdout(io.StringIO()):
+            geo = raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo, plotdata=False)
+            fr = findroot(geo, psit, A, B, r_o, th_o, a, ngeo, model=name, neqmax=neqmax, tol=1e-8, pval=pval)
+            if name == 'mono':
+                dens = density_mono_all(fr[1], fr[2], fr[6], psit, a, 0, 2, neqmax=neqmax, gammamax=None)
+            else:
+                dens = density_power_all(fr[1], fr[2], fr[6], psit, a, 0, 2, neqmax=neqmax, gammamax=None, pval=pval)
+            raw = getstokes(psit, A2, B2, r_o, th_o, a, ngeo, neqmax=neqmax, outgeo=geo, model=name, pval=pval, nu_parallel=0,
+                            sigma=2, sumsubring=False)
+            img = getstokes(psit, A2, B2, r_o, th_o, a, ngeo, neqmax=neqmax, outgeo=geo, model=name, pval=pval, nu_parallel=0,
+                            sigma=2, retvals=True, retsin=True)
+        out[name + '_par'] = np.array([a, r_o, th_o, psit, pval, neqmax, ngeo])
+        out[name + '_alpha'], out[name + '_beta'] = A2, B2
+        for k, v in zip(['tau', 'r', 'th', 'signpr', 'signpth', 'neq'], fr[:6]):
+            out[name + '_root_' + k] = np.asarray(v, dtype=float)
+        out[name + '_shape'] = np.array(fr[6])
+        out[name + '_density'] = np.asarray(dens, dtype=float)
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            out[name + '_raw_' + k] = np.real(np.asarray(v)).astype(float)
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            out[name + '_img_' + k] = np.real(np.asarray(v)).astype(float)
+    save('jet_pipeline', **out)
+
+
 def inverse_lensing():
     """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
     out = {}
@@ -379,7 +421,7 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -393,5 +435,6 @@ if __name__ == '__main__':
     fromfile_models()
     bz_models()
     fieldline_crossings()
+    jet_pipeline()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

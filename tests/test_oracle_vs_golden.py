@@ -296,3 +296,23 @@ def test_fieldline_crossings_oracle_against_reference(golden):
         assert_close(tm, g[name + '_taumax'], 1e-13, what=name + ' taumax')
         for k, v in zip(['tau', 'r', 'th', 'signpr', 'signpth', 'neq'], res[:6]):
             assert_close(v, g[name + '_' + k], 1e-12, what='%s %s' % (name, k))
+
+
+def test_jet_pipeline_fixture_crossings(golden):
+    """tests/golden/jet_pipeline.npz pins the targets of the rest of SURVEY 8 f4 (off_eq.getstokes of the unmodified reference:
+    crossings, densities, per-crossing and sorted Stokes parameters), which is not built yet.  What IS built -- the crossings
+    of solver.findroot -- is checked against it here, so the fixture and the oracle stay tied together."""
+    import warnings
+    g = golden('jet_pipeline')
+    for name in json.loads(str(g['names'])):
+        a, r_o, th_o, psit, pval, neqmax, ngeo = [float(x) for x in g[name + '_par']]
+        A, B = g[name + '_alpha'].flatten(), g[name + '_beta'].flatten()
+        with np.errstate(all='ignore'), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            tau, _, (_, r, th, _) = ko.raytrace(a, [0, r_o, th_o, 0], [A, B], int(ngeo))
+            res = ko.findroot(r, th, tau, psit, A, B, r_o, th_o, a, name, int(neqmax), 1e-8, pval)
+        assert tuple(res[6]) == tuple(g[name + '_shape'])
+        for k, v in zip(['tau', 'r', 'th', 'signpr', 'signpth', 'neq'], res[:6]):
+            assert_close(v, g[name + '_root_' + k], 1e-12, what='%s %s' % (name, k))
+        n = len(g[name + '_density'])
+        assert n == res[0].size and g[name + '_raw_i'].size == n and g[name + '_img_I'].shape[-2:] == g[name + '_alpha'].shape
