@@ -863,8 +863,8 @@ def u_general(a, r, fac_subkep=1, beta_phi=1, beta_r=1, retrograde=False):
     return u0, u1, 0 * r, u0 * Omega
 
 
-def velocity_u_lab(vel, a, r):
-    """Dispatch of Velocity.u_lab (kgeo/velocities.py:70-96)."""
+def velocity_u_lab(vel, a, r, th=np.pi / 2):
+    """Dispatch of Velocity.u_lab (kgeo/velocities.py:70-96); th is only honoured by the drift frame (jet models)."""
     r = _arr(r)
     t = vel['type']
     if t == 'zamo':
@@ -886,7 +886,7 @@ def velocity_u_lab(vel, a, r):
     if t == 'fromfile':
         return u_from_table(a, r, load_table(vel['file'], ('U1', 'U2', 'U3')))
     if t == 'driftframe':
-        return u_driftframe(a, r, vel['bfield'], vel.get('nu_parallel', 0))
+        return u_driftframe(a, r, vel['bfield'], vel.get('nu_parallel', 0), th)
     raise Exception("veltype %s not in oracle" % t)
 
 
@@ -920,10 +920,9 @@ def u_from_table(a, r, tab):
     return gamma / alpha, u1, u2, u3 - gamma * alpha * gcon03
 
 
-def _metric_eq(a, r):
-    """Covariant BL metric at theta=pi/2 with the reference's cos(pi/2)=6e-17 kept
+def _metric_eq(a, r, th=np.pi / 2):
+    """Covariant BL metric, by default at theta=pi/2 with the reference's cos(pi/2)=6e-17 kept
     (kgeo/velocities.py:102-114)."""
-    th = np.pi / 2
     a2, r2 = a ** 2, r ** 2
     cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
     Delta = r2 - 2 * r + a2
@@ -936,20 +935,19 @@ def _metric_eq(a, r):
     return Delta, Sigma, g00, g11, g22, g33, g03
 
 
-def velocity_u_cov(vel, a, r):
+def velocity_u_cov(vel, a, r, th=np.pi / 2):
     """kgeo/velocities.py:98-122."""
-    u0, u1, u2, u3 = velocity_u_lab(vel, a, r)
-    _, _, g00, g11, g22, g33, g03 = _metric_eq(a, r)
+    u0, u1, u2, u3 = velocity_u_lab(vel, a, r, th)
+    _, _, g00, g11, g22, g33, g03 = _metric_eq(a, r, th)
     return g00 * u0 + g03 * u3, g11 * u1, g22 * u2, g33 * u3 + g03 * u0
 
 
-def velocity_tetrads(vel, a, r):
+def velocity_tetrads(vel, a, r, th=np.pi / 2):
     """kgeo/velocities.py:124-176."""
-    th = np.pi / 2
     sth2 = np.sin(th) ** 2
-    Delta, Sigma, g00, g11, g22, g33, g03 = _metric_eq(a, r)
-    u0, u1, u2, u3 = velocity_u_lab(vel, a, r)
-    l0, l1, l2, l3 = velocity_u_cov(vel, a, r)
+    Delta, Sigma, g00, g11, g22, g33, g03 = _metric_eq(a, r, th)
+    u0, u1, u2, u3 = velocity_u_lab(vel, a, r, th)
+    l0, l1, l2, l3 = velocity_u_cov(vel, a, r, th)
     Nr = np.sqrt(-g11 * (l0 * u0 + l3 * u3) * (1 + l2 * u2))
     Nth = np.sqrt(g22 * (1 + l2 * u2))
     Nph = np.sqrt(-Delta * sth2 * (l0 * u0 + l3 * u3))
@@ -1056,12 +1054,11 @@ def _linear_spline(xp, fp, x):
     return (fp[i] * (xp[i + 1] - x) + fp[i + 1] * (x - xp[i])) / h, (fp[i + 1] - fp[i]) / h
 
 
-def bfield_lab_omega(bf, a, r):
+def bfield_lab_omega(bf, a, r, th=np.pi / 2):
     """(B1, B2, B3, omega) of the models with a field-line angular speed (kgeo/bfields.py:175-197 and the model functions);
-    theta = pi/2 with the reference's cos(pi/2) = 6e-17."""
+    by default theta = pi/2 with the reference's cos(pi/2) = 6e-17; the jet models pass the polar angle of the crossing."""
     r = _arr(r)
     t = bf['type']
-    th = np.pi / 2
     a2, r2 = a ** 2, r ** 2
     sth, cth = np.sin(th), np.cos(th)
     abscth, cth2, sth2 = np.abs(cth), cth ** 2, sth ** 2
@@ -1116,6 +1113,8 @@ def bfield_lab_omega(bf, a, r):
             Om = a / (4 + 8 / (1 + cthh))
         I = -4 * np.pi * psi * Om * np.sign(cth) if p > 0 else -2 * np.pi * psi * (2 - psi) * Om * np.sign(cth)
         return C * dpsidtheta / gdet, -C * dpsidr / gdet, I / (2 * np.pi * Delta * sth2), Om
+    if np.any(np.asarray(th) != np.pi / 2):
+        raise Exception("fieldtype %s: only the equatorial plane is restated" % t)
     B1, B2, B3 = bfield_lab(bf, a, r)
     if t == 'bz_guess':
         spin = np.abs(a)
@@ -1129,10 +1128,9 @@ def bfield_lab_omega(bf, a, r):
     raise Exception("self.omega_field not implemented for fieldtype %s'!" % t)
 
 
-def u_driftframe(a, r, bf, nu_parallel=0):
-    """kgeo/velocities.py:487-623 with a numeric nu_parallel and gammamax=None, theta = pi/2."""
+def u_driftframe(a, r, bf, nu_parallel=0, th=np.pi / 2):
+    """kgeo/velocities.py:487-623 with a numeric nu_parallel and gammamax=None (theta = pi/2 unless given)."""
     r = _arr(r)
-    th = np.pi / 2
     a2, r2 = a ** 2, r ** 2
     cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
     Delta = r2 - 2 * r + a2
@@ -1143,7 +1141,7 @@ def u_driftframe(a, r, bf, nu_parallel=0):
     g11, g22, g33 = Sigma / Delta, Sigma, Xi * sth2 / Sigma
     alpha = np.sqrt(Delta * Sigma / Xi)
     eta3 = 2 * a * r / np.sqrt(Delta * Sigma * Xi)
-    B1, B2, B3, omegaf = bfield_lab_omega(bf, a, r)
+    B1, B2, B3, omegaf = bfield_lab_omega(bf, a, r, th)
     E1 = (omegaf - omegaz) * Xi * np.sin(th) * B2 / Sigma
     E2 = -(omegaf - omegaz) * Xi * np.sin(th) * B1 / (Sigma * Delta)
     E3 = 0
@@ -1225,8 +1223,7 @@ def emissivity_jrest(em, a, r, g=None, sinthb=None, Bmag=None, nu_obs=230.e9, sp
 # --------------------------------------------------------------------------------------
 # equatorial image pipeline                          (kgeo/equatorial_images.py)
 # --------------------------------------------------------------------------------------
-def _photon_potentials(a, r, lam, eta):
-    th = np.pi / 2
+def _photon_potentials(a, r, lam, eta, th=np.pi / 2):
     a2, r2 = a ** 2, r ** 2
     cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
     Delta = r2 - 2 * r + a2
@@ -1235,31 +1232,30 @@ def _photon_potentials(a, r, lam, eta):
     return Delta, R, TH
 
 
-def redshift(a, r, lam, eta, kr_sign, kth_sign, u0, u1, u2, u3):
+def redshift(a, r, lam, eta, kr_sign, kth_sign, u0, u1, u2, u3, th=np.pi / 2):
     """kgeo/equatorial_images.py:307-334."""
-    Delta, R, TH = _photon_potentials(a, r, lam, eta)
+    Delta, R, TH = _photon_potentials(a, r, lam, eta, th)
     return 1 / (u0 - lam * u3 - np.sign(kth_sign) * u2 * np.sqrt(TH) - np.sign(kr_sign) * u1 * np.sqrt(R) / Delta)
 
 
-def pol_quantities(a, r, lam, eta, kr_sign, kth_sign, vel, bf):
+def pol_quantities(a, r, lam, eta, kr_sign, kth_sign, vel, bf, th=np.pi / 2):
     """sin(theta_b), Penrose-Walker kappa, path length, b^2 (kgeo/equatorial_images.py:336-487)."""
-    th = np.pi / 2
     a2, r2 = a ** 2, r ** 2
     cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
-    Delta, Sigma, g00, g11, g22, g33, g03 = _metric_eq(a, r)
+    Delta, Sigma, g00, g11, g22, g33, g03 = _metric_eq(a, r, th)
     gdet = Sigma * np.sqrt(sth2)
     g00u = -(r2 + a2 + 2 * r * a2 * sth2 / Sigma) / Delta
     g11u = Delta / Sigma
     g22u = 1. / Sigma
     g33u = (Delta - a2 * sth2) / (Sigma * Delta * sth2)
     g03u = -(2 * a * r) / (Sigma * Delta)
-    u0, u1, u2, u3 = velocity_u_lab(vel, a, r)
+    u0, u1, u2, u3 = velocity_u_lab(vel, a, r, th)
     l0, l1, l2, l3 = g00 * u0 + g03 * u3, g11 * u1, g22 * u2, g33 * u3 + g03 * u0
-    (_, ex, ey, ez) = velocity_tetrads(vel, a, r)
+    (_, ex, ey, ez) = velocity_tetrads(vel, a, r, th)
     if bf['type'] == 'const_comoving':
         # the reference's comoving branch never defines norm_x (equatorial_images.py:422-436) and fails
         raise Exception("const_comoving is not usable through Iobs in the reference")
-    B1, B2, B3 = bfield_lab(bf, a, r)
+    B1, B2, B3 = bfield_lab(bf, a, r) if np.all(np.asarray(th) == np.pi / 2) else bfield_lab_omega(bf, a, r, th)[:3]
     n_l = (0, -B2 * gdet, B1 * gdet, 0)
     b0 = B1 * l1 + B2 * l2 + B3 * l3
     b1, b2, b3 = (B1 + b0 * u1) / u0, (B2 + b0 * u2) / u0, (B3 + b0 * u3) / u0
@@ -1273,7 +1269,7 @@ def pol_quantities(a, r, lam, eta, kr_sign, kth_sign, vel, bf):
     Bmag = np.sqrt(Bx ** 2 + By ** 2 + Bz ** 2)
     bsq = Bmag ** 2
     nmag = np.sqrt(nx ** 2 + ny ** 2 + nz ** 2)
-    _, R, TH = _photon_potentials(a, r, lam, eta)
+    _, R, TH = _photon_potentials(a, r, lam, eta, th)
     kl = (-1, kr_sign * np.sqrt(R) / Delta, kth_sign * np.sqrt(TH), lam)
     k0 = g00u * kl[0] + g03u * kl[3]
     k1 = g11u * kl[1]
@@ -1518,3 +1514,168 @@ def findroot(r_s, th_s, tau_s, psitarget, alpha, beta, r_o, th_o, a, model='para
     none = (g == -1)
     root, r0, t0, signpr, signpth = [np.where(none, 0.0, x) for x in (root, r0, t0, signpr, signpth)]
     return root, r0, t0, signpr, signpth, neq, shape
+
+
+# ---- jet-model densities (kgeo/densityfuncs.py, kgeo/ff_boost.py) -- groundwork for the rest of SURVEY 8 f4 ---------------
+def r0min_mono(theta, Omegaf, spin, M=1.0):
+    """stagnation surface of the monopole: largest-index root of the quintic of kgeo/ff_boost.py:8-19"""
+    theta = np.arccos(np.abs(np.cos(theta)))
+    c2t = np.cos(2 * theta)
+    fac = (2 - spin * Omegaf + spin * Omegaf * c2t) ** 2
+    coefs = [-spin ** 2 / 2 * M * np.cos(theta) ** 2 * fac, -2 * spin ** 4 * Omegaf ** 2 * np.cos(theta) ** 4 * np.sin(theta) ** 2,
+             M / 2 * fac, -spin ** 2 * Omegaf ** 2 * np.sin(2 * theta) ** 2, 0.0, -2 * Omegaf ** 2 * np.sin(theta) ** 2]
+    return np.real(np.polynomial.polynomial.Polynomial(coefs).roots()[4])
+
+
+def eta_mono(rvals, theta, r0, spin, sigma):
+    """mass loading of the monopole jet: Gaussian source integrated in closed form (kgeo/densityfuncs.py:31-41)"""
+    if sigma == 0:
+        return np.sign(rvals - r0)
+    cth = np.cos(theta)
+    s2pi = np.sqrt(2 * np.pi)
+    num1 = 2 * sigma * (2 * r0 - (rvals + r0) * np.exp(-(rvals - r0) ** 2 / (2 * sigma ** 2)))
+    num2 = s2pi * sp.erf((rvals - r0) / (np.sqrt(2) * sigma)) * (r0 ** 2 + sigma ** 2 + spin ** 2 * cth ** 2)
+    return (num1 + num2) / (4 * r0 * sigma + s2pi * sigma ** 2 + s2pi * (r0 ** 2 + spin ** 2 * cth ** 2))
+
+
+def density_mono_all(rvals, thvals, shape, spin, nu_parallel, sigma):
+    """density_mono_all, kgeo/densityfuncs.py:44-79: rho = eta B^r / u^r per crossing, crossings reflected to the north"""
+    bf = dict(type='bz_monopole')
+    rnew = np.reshape(rvals, shape)
+    thnew = np.arccos(np.abs(np.cos(np.reshape(thvals, shape))))
+    i0 = np.where(rnew[0] != 0)[0][0]
+    omega = bfield_lab_omega(bf, spin, rnew[0][i0:i0 + 1], thnew[0][i0])[3][0]
+    r0 = r0min_mono(thnew[0][i0], omega, spin, 1.0)
+    rho = []
+    for ind in range(len(rnew)):
+        B1 = bfield_lab_omega(bf, spin, rnew[ind], thnew[ind])[0]
+        u1 = u_driftframe(spin, rnew[ind], bf, nu_parallel, thnew[ind])[1]
+        rho.append(eta_mono(rnew[ind], thnew[ind], r0, spin, sigma) * B1 / u1)
+    return np.nan_to_num(np.array(rho).flatten(), nan=0.0)
+
+
+def _nderiv(r, theta, a, Omegaf, M, bf):
+    """B . grad N along the field line (kgeo/ff_boost.py:85-99)"""
+    cth, sth = np.cos(theta), np.sin(theta)
+    Sigma = r ** 2 + a ** 2 * cth ** 2
+    dNdr = (a ** 4 * Omegaf ** 2 * r * cth ** 4 * sth ** 2
+            + r ** 2 * (-M + Omegaf * sth ** 2 * (2 * a * M + Omegaf * r ** 3 - a ** 2 * M * Omegaf * sth ** 2))
+            + a ** 2 * cth ** 2 * (M + Omegaf * sth ** 2 * (-2 * a * M + 2 * Omegaf * r ** 3 + a ** 2 * M * Omegaf * sth ** 2)))
+    dNdr /= Sigma ** 2 / 2
+    den = a ** 2 + 2 * r ** 2 + a ** 2 * np.cos(2 * theta) ** 2
+    dNdth = Omegaf ** 2 * (a ** 2 + r * (r - 2 * M)) + 8 * M * r * (a * (a * Omegaf - 1) + Omegaf * r ** 2) ** 2 / den ** 2
+    dNdth *= np.sin(2 * theta)
+    B = bfield_lab_omega(bf, a, np.array([r]).flatten(), theta)
+    return (B[0] * dNdr + B[1] * dNdth)[0]
+
+
+def _rfromR_power(R, psi0, p):
+    """kgeo/ff_boost.py:74-83 (SciPy's scalar secant, as in the reference)"""
+    import scipy.optimize as opt
+
+    def f(Z):
+        return np.sqrt(R ** 2 + Z ** 2) ** p * (1 - np.abs(np.cos(np.arctan(R / Z)))) - psi0
+    try:
+        Z = opt.newton(f, 4.0)
+    except Exception:
+        Z = opt.newton(f, 0)
+    return np.sqrt(Z ** 2 + R ** 2)
+
+
+def r0min_power(psi, Omegaf, spin, p, M=1.0, usemono=False):
+    """stagnation surface of the power-law jet (kgeo/ff_boost.py:34-45)"""
+    import scipy.optimize as opt
+    bf = dict(type='power', p=p, usemono=usemono)
+
+    def f(R):
+        rs = _rfromR_power(R, psi, p)
+        return _nderiv(rs, np.arcsin(R / rs), spin, Omegaf, M, bf)
+    Rt = opt.newton(f, 4)
+    rt = _rfromR_power(Rt, psi, p)
+    return rt, np.arcsin(Rt / rt)
+
+
+def eta_power(rvals, r0, spin, pval, psi, sigma):
+    """mass loading of the power-law jet by quadrature of the Gaussian source (kgeo/densityfuncs.py:24-28,155-183)"""
+    import scipy.integrate as scint
+    if sigma == 0:
+        return np.sign(rvals - r0)
+
+    def src(r):
+        return np.exp(-(r - r0) ** 2 / (2 * sigma ** 2)) * (r ** 2 + spin ** 2 * (1 - psi / r ** pval) ** 2)
+    norm = scint.quad(src, r0, np.inf, epsabs=1e-13, epsrel=1e-13)[0]
+    i0 = np.where(rvals != 1)[0][0]
+    vals = [0.0] * i0
+    for i in range(i0, len(rvals)):
+        vals.append(0 if rvals[i] == 0 else scint.quad(src, r0, rvals[i], epsabs=1e-13, epsrel=1e-13)[0])
+    return np.array(vals) / norm
+
+
+def density_power_all(rvals, thvals, shape, psitarget, spin, nu_parallel, sigma, pval=1.0, usemono=False):
+    """density_power_all, kgeo/densityfuncs.py:186-219"""
+    bf = dict(type='power', p=pval, usemono=usemono)
+    rnew = np.reshape(rvals, shape)
+    thnew = np.arccos(np.abs(np.cos(np.reshape(thvals, shape))))
+    i0 = np.where(np.nan_to_num(rnew)[0] != 0)[0][0]
+    omega = np.broadcast_to(bfield_lab_omega(bf, spin, rnew[0][i0:i0 + 1], thnew[0][i0])[3], (1,))[0]
+    r0, _ = r0min_power(psitarget, omega, spin, pval, 1.0, usemono)
+    rho = []
+    for ind in range(len(rnew)):
+        B1 = bfield_lab_omega(bf, spin, rnew[ind], thnew[ind])[0]
+        u1 = u_driftframe(spin, rnew[ind], bf, nu_parallel, thnew[ind])[1]
+        rho.append(eta_power(rnew[ind], r0, spin, pval, psitarget, sigma) * B1 / u1)
+    return np.nan_to_num(np.array(rho).flatten(), nan=0.0)
+
+
+def iobs_off(a, r_o, r_s, th_o, alpha, beta, kr_sign, kth_sign, vel, bf, th_s, density=1, specind=1):
+    """Iobs_off with Emissivity('constant') and polarization=True as getstokes calls it (kgeo/off_eq.py:15-121):
+    (I, Q, U, sin theta_b) per crossing."""
+    alpha, beta, r_s = _arr(alpha), _arr(beta), _arr(r_s)
+    rh = 1 + np.sqrt(1 - a ** 2)
+    lam, eta = conserved(a, th_o, alpha, beta)
+    u0, u1, u2, u3 = velocity_u_lab(vel, a, r_s, th_s)
+    gg = redshift(a, r_s, lam, eta, kr_sign, kth_sign, u0, u1, u2, u3, th_s)
+    Iemis = emissivity_jrest(dict(type='constant'), a, r_s) * density
+    sinthb, kappa, pathlength, bsq = pol_quantities(a, r_s, lam, eta, kr_sign, kth_sign, vel, bf, th_s)
+    c2, s2 = evpa_terms(a, th_o, alpha, beta, kappa)
+    Iemis = Iemis * bsq ** ((1 + specind) / 2)
+    I = (gg ** 3) * (gg ** specind) * pathlength * Iemis * (sinthb ** (1 + specind))
+    Q, U = c2 * I, s2 * I
+    inside = r_s <= rh
+    I, Q, U = [np.where(inside, 0, x) for x in (I, Q, U)]
+    return I, Q, U, sinthb
+
+
+def sort_image(iobs, qobs, uobs, neqvals, shape, ashape, neqmax):
+    """geometry.sort_image (kgeo/geometry.py:38-62): one image per crossing order, the total last"""
+    out = []
+    for arr in (iobs, qobs, uobs):
+        planes = [np.reshape(np.sum(np.reshape(np.where(neqvals != neq, 0, arr), shape), axis=0), ashape) for neq in range(neqmax)]
+        planes.append(np.reshape(np.sum(np.reshape(arr, shape), axis=0), ashape))
+        out.append(np.array(planes))
+    return out
+
+
+def getstokes(psitarget, alphavals, betavals, r_o, th_o, a, ngeo, neqmax=1, tol=1e-8, model='mono', pval=1, nu_parallel=0, sigma=2,
+              sumsubring=True):
+    """off_eq.getstokes for the monopole and power-law jets (kgeo/off_eq.py:124-233; nu_parallel numeric, gammamax None)"""
+    ashape = alphavals.shape
+    A, B = alphavals.flatten(), betavals.flatten()
+    tau_s, _, (_, r_t, th_t, _) = raytrace(a, [0, r_o, th_o, 0], [A, B], ngeo)
+    tau, rvals, thvals, signpr, signpth, neqvals, shape = findroot(r_t, th_t, tau_s, psitarget, A, B, r_o, th_o, a, model, neqmax,
+                                                                   tol, pval)
+    At, Bt = np.tile(A, shape[0]), np.tile(B, shape[0])
+    if model == 'mono' or (model == 'power' and pval == 0):
+        bf = dict(type='bz_monopole')
+        dvals = density_mono_all(rvals, thvals, shape, a, nu_parallel, sigma)
+    else:
+        bf = dict(type='power', p=pval)
+        dvals = density_power_all(rvals, thvals, shape, psitarget, a, nu_parallel, sigma, pval)
+    vel = dict(type='driftframe', bfield=bf, nu_parallel=nu_parallel)
+    I, Q, U, sinthb = iobs_off(a, r_o, rvals, th_o, At, Bt, signpr, signpth, vel, bf, thvals, dvals, 1)
+    none = (rvals == 0)
+    I, Q, U = [np.real(np.nan_to_num(np.where(none, 0, x))) for x in (I, Q, U)]
+    if not sumsubring:
+        return I, Q, U, neqvals, np.nan_to_num(rvals), np.nan_to_num(thvals), shape
+    iv, qv, uv = sort_image(I, Q, U, neqvals, shape, ashape, neqmax)
+    return iv, qv, uv, np.nan_to_num(0.5 * np.arctan2(uv, qv)), np.nan_to_num(rvals), np.nan_to_num(thvals), np.nan_to_num(sinthb)

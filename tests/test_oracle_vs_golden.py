@@ -316,3 +316,31 @@ def test_jet_pipeline_fixture_crossings(golden):
             assert_close(v, g[name + '_root_' + k], 1e-12, what='%s %s' % (name, k))
         n = len(g[name + '_density'])
         assert n == res[0].size and g[name + '_raw_i'].size == n and g[name + '_img_I'].shape[-2:] == g[name + '_alpha'].shape
+
+
+def test_jet_pipeline_oracle_against_reference(golden):
+    """The oracle's restatement of the whole off-equatorial jet pipeline -- crossings, stagnation surface (ff_boost), mass loading
+    and density (densityfuncs), drift frame / field / redshift / Penrose-Walker transport off the equator (Iobs_off), subring
+    sorting (geometry.sort_image) -- vs off_eq.getstokes of the unmodified reference for the monopole and power-law jets.
+    This is the checker the device implementation of the rest of SURVEY 8 f4 will be held against."""
+    import warnings
+    g = golden('jet_pipeline')
+    for name in json.loads(str(g['names'])):
+        a, r_o, th_o, psit, pval, neqmax, ngeo = [float(x) for x in g[name + '_par']]
+        A, B = g[name + '_alpha'], g[name + '_beta']
+        shape = tuple(g[name + '_shape'])
+        with np.errstate(all='ignore'), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            if name == 'mono':
+                dens = ko.density_mono_all(g[name + '_root_r'], g[name + '_root_th'], shape, a, 0, 2)
+            else:
+                dens = ko.density_power_all(g[name + '_root_r'], g[name + '_root_th'], shape, psit, a, 0, 2, pval)
+            raw = ko.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), int(neqmax), 1e-8, name, pval, 0, 2, sumsubring=False)
+            img = ko.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), int(neqmax), 1e-8, name, pval, 0, 2)
+        assert_close(dens, g[name + '_density'], 1e-12, what=name + ' density')
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            ref = g[name + '_raw_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            ref = g[name + '_img_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
