@@ -3,7 +3,7 @@
 // tetrad, Penrose-Walker transport -- per-crossing device functions for the rest of SURVEY 8 f4.
 //
 // STATUS: verified on the CPU only (tests/hostsim/check_offeq.py compiles this header for the host and compares every output
-// with the pinned oracle on the crossings of tests/golden/jet_pipeline.npz); no kernel uses it yet and nothing here has run on a
+// with the reference-pinned CPU checker on the crossings of tests/golden/jet_pipeline.npz); no kernel uses it yet and nothing here has run on a
 // GPU.  The equatorial image kernel keeps its own plane-specialised versions (kg_image.cuh).
 #pragma once
 #include "kg_image.cuh"
