@@ -254,6 +254,22 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
                          int maxiter, double* tau_dev, double* r_dev, double* th_dev, double* signpr_dev, double* signpth_dev,
                          double* neq_dev, int32_t* iterations, int32_t* nfailed, void* stream);
 
+/* ---- off-equatorial jet emission (kgeo/off_eq.py:124-233 getstokes, kgeo/densityfuncs.py, kgeo/geometry.py:38-62) -------------
+ * STATUS: the device functions behind these two entry points are verified on the CPU; the entry points themselves have not run
+ * on a GPU yet (tests marked gpu_unverified).
+ * kgeo_jet_stokes: for the nguess x npix crossings of kgeo_fieldline_solve (r, theta, sign p^r, sign p^theta; r = 0 = none) the
+ *   density of the jet model (field 0 = BZ monopole with its f(r) table of 2 x fr_n doubles, 1 = power law r^pval; r0 =
+ *   stagnation radius, norm = source integral from r0 to infinity for the power law) and Iobs_off's polarized Stokes parameters
+ *   with Emissivity('constant') in the drift frame of the field; NaN -> 0 as in getstokes.
+ * kgeo_jet_sort: geometry.sort_image: (neqmax + 1) x npix planes, plane k < neqmax = crossings of order k, last plane = all. */
+int kgeo_jet_stokes(const kgeo_observer* obs, size_t npix, size_t nguess, const double* alpha_dev, const double* beta_dev,
+                    const double* r_dev, const double* th_dev, const double* signpr_dev, const double* signpth_dev, int field, double C,
+                    double pval, int usemono, const double* fr_table_dev, int64_t fr_n, double nu_parallel, double sigma, double r0,
+                    double norm, double psitarget, double specind, double* I_dev, double* Q_dev, double* U_dev, double* sinthb_dev,
+                    double* density_dev, void* stream);
+int kgeo_jet_sort(size_t npix, size_t nguess, int neqmax, const double* I_dev, const double* Q_dev, const double* U_dev,
+                  const double* neq_dev, double* out_I_dev, double* out_Q_dev, double* out_U_dev, void* stream);
+
 /* ---- measurement helper: sustained DFMA rate of the device (the measured FP64 roofline denominator) ------------ */
 int kgeo_fp64_peak_probe(int iters, double* flops_per_launch, float* ms, void* stream);
 

@@ -194,3 +194,64 @@ KG_HD StokesOut iobs_off_point(const JetSpec& J, double a, double th_o, double a
 }
 
 }  // namespace kg
+
+// ---- mass loading and density of the jet models (kgeo/densityfuncs.py) ----------------------------------------------------
+namespace kg {
+
+// eta of the monopole jet: Gaussian source integrated in closed form (kgeo/densityfuncs.py:31-41)
+KG_HD double eta_mono(double r, double th, double r0, double a, double sigma) {
+    if (sigma == 0.0) return sgn0(r - r0);
+    const double cth = cos(th), s2pi = 2.5066282746310002;   // sqrt(2 pi)
+    const double d = r - r0;
+    const double num1 = 2.0 * sigma * (2.0 * r0 - (r + r0) * exp(-d * d / (2.0 * sigma * sigma)));
+    const double num2 = s2pi * erf(d / (1.4142135623730951 * sigma)) * (r0 * r0 + sigma * sigma + a * a * cth * cth);
+    return (num1 + num2) / (4.0 * r0 * sigma + s2pi * sigma * sigma + s2pi * (r0 * r0 + a * a * cth * cth));
+}
+
+// integral of the power-law jet's source exp(-(x - r0)^2 / 2 sigma^2) (x^2 + a^2 (1 - psi / x^p)^2) from r0 to r
+// (kgeo/densityfuncs.py:24-28; the reference uses QUADPACK at 1e-13): 16-point Gauss-Legendre on panels one sigma wide; the
+// Gaussian makes everything beyond 40 sigma vanish in double precision
+KG_HD double power_source_integral(double r, double r0, double a, double sigma, double psi, double pval) {
+    const double xg[8] = {0.0950125098376374402, 0.2816035507792589132, 0.4580167776572273863, 0.6178762444026437484,
+                          0.7554044083550030339, 0.8656312023878317439, 0.9445750230732325761, 0.9894009349916499326};
+    const double wg[8] = {0.1894506104550684963, 0.1826034150449235888, 0.1691565193950025382, 0.1495959888165767321,
+                          0.1246289712555338720, 0.0951585116824927848, 0.0622535239386478929, 0.0271524594117540949};
+    const double dir = (r >= r0) ? 1.0 : -1.0;
+    double span = fabs(r - r0);
+    if (span > 40.0 * sigma) span = 40.0 * sigma;
+    const int npanel = (int)ceil(span / sigma);
+    double total = 0.0;
+    for (int k = 0; k < npanel; ++k) {
+        const double lo = k * sigma, hi = ((k + 1) * sigma < span) ? (k + 1) * sigma : span;
+        const double c = 0.5 * (lo + hi), h = 0.5 * (hi - lo);
+        double acc = 0.0;
+        for (int i = 0; i < 8; ++i) {
+            for (int s = -1; s <= 1; s += 2) {
+                const double t = c + s * h * xg[i];           // distance from r0
+                const double x = r0 + dir * t;
+                const double q = 1.0 - psi / pow(x, pval);
+                acc += wg[i] * exp(-t * t / (2.0 * sigma * sigma)) * (x * x + a * a * q * q);
+            }
+        }
+        total += acc * h;
+    }
+    return dir * total;
+}
+
+// rho = eta B^r / u^r at a crossing reflected into the northern hemisphere (density_mono_all / density_power_all,
+// kgeo/densityfuncs.py:44-79,186-219); r0 = stagnation radius, norm = source integral from r0 to infinity (power law)
+KG_HD double jet_density(const JetSpec& J, double a, double r, double th, double nu_parallel, double sigma, double r0, double norm,
+                         double psitarget) {
+    const double thn = acos(fabs(cos(th)));
+    double B1, B2, B3, om;
+    jet_field(J, a, r, thn, &B1, &B2, &B3, &om);
+    const U4 u = jet_driftframe(J, a, r, thn, nu_parallel);
+    double eta;
+    if (J.field == JET_MONO) eta = eta_mono(r, thn, r0, a, sigma);
+    else if (sigma == 0.0) eta = sgn0(r - r0);
+    else eta = (r == 0.0) ? 0.0 : power_source_integral(r, r0, a, sigma, psitarget, J.pval) / norm;
+    const double rho = eta * B1 / u.u1;
+    return (rho == rho) ? rho : 0.0;                          // nan_to_num(nan = 0)
+}
+
+}  // namespace kg

@@ -25,6 +25,7 @@
 #include "../../include/kgeo_b200.h"
 #include "kg_image.cuh"
 #include "kg_fieldline.cuh"
+#include "kg_offeq.cuh"
 
 using namespace kg;
 
@@ -598,6 +599,62 @@ __global__ void __launch_bounds__(256) fieldline_finish_kernel(Observer o, size_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// off-equatorial jet emission (kgeo/off_eq.py getstokes: density + Iobs_off per crossing, geometry.sort_image)
+// NOT YET RUN ON A GPU: the per-crossing device functions are verified on the CPU (tests/test_offeq_hostbuild.py); these two
+// kernels and their entry points are exercised by tests marked `gpu_unverified`, outside the `-m gpu` suite, until they have.
+// ---------------------------------------------------------------------------------------------------------------------
+KG_HD double nan_to_num(double x) {
+    if (x != x) return 0.0;
+    if (x > 1.7976931348623157e308) return 1.7976931348623157e308;
+    if (x < -1.7976931348623157e308) return -1.7976931348623157e308;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) jet_stokes_kernel(JetSpec J, double a, double th_o, size_t npix, size_t n,
+                                                         const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                         const double* __restrict__ r, const double* __restrict__ th,
+                                                         const double* __restrict__ kr, const double* __restrict__ kth, double nu,
+                                                         double sigma, double r0, double norm, double psitarget, double specind,
+                                                         double* I, double* Q, double* U, double* sinthb, double* dens) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t pix = e % npix;
+    const double rs = r[e], ths = th[e];
+    const double rho = jet_density(J, a, rs, ths, nu, sigma, r0, norm, psitarget);
+    if (dens) dens[e] = rho;
+    const StokesOut s = iobs_off_point(J, a, th_o, alpha[pix], beta[pix], rs, ths, kr[e], kth[e], nu, rho, specind);
+    const bool none = (rs == 0.0);                                       // iobs[rvals == 0] = 0: no field-line crossing
+    I[e] = none ? 0.0 : nan_to_num(s.I);
+    Q[e] = none ? 0.0 : nan_to_num(s.Q);
+    U[e] = none ? 0.0 : nan_to_num(s.U);
+    if (sinthb) sinthb[e] = nan_to_num(s.sinthb);
+}
+
+// geometry.sort_image (kgeo/geometry.py:38-62): planes 0..neqmax-1 = sum of the crossings of that order, plane neqmax = all
+__global__ void __launch_bounds__(256) jet_sort_kernel(size_t npix, int nguess, int neqmax, const double* __restrict__ I,
+                                                       const double* __restrict__ Q, const double* __restrict__ U,
+                                                       const double* __restrict__ neq, double* oI, double* oQ, double* oU) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    for (int plane = 0; plane <= neqmax; ++plane) {
+        double si = 0.0, sq_ = 0.0, su = 0.0;
+        for (int m = 0; m < nguess; ++m) {
+            const size_t e = (size_t)m * npix + pix;
+            if (plane == neqmax || neq[e] == (double)plane) {
+                si += I[e];
+                sq_ += Q[e];
+                su += U[e];
+            } else {
+                si += 0.0; sq_ += 0.0; su += 0.0;
+            }
+        }
+        oI[(size_t)plane * npix + pix] = si;
+        oQ[(size_t)plane * npix + pix] = sq_;
+        oU[(size_t)plane * npix + pix] = su;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // equatorial lensing / image
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef KG_IMG_THREADS
@@ -1168,6 +1225,36 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
                                                   signpth, neq);
     LAUNCHED("fieldline_finish_kernel");
     CU(cudaStreamSynchronize(st));    // the state buffers are freed on return
+    return 0;
+}
+
+int kgeo_jet_stokes(const kgeo_observer* obs, size_t npix, size_t nguess, const double* alpha, const double* beta, const double* r,
+                    const double* th, const double* signpr, const double* signpth, int field, double C, double pval, int usemono,
+                    const double* fr_table, int64_t fr_n, double nu_parallel, double sigma, double r0, double norm, double psitarget,
+                    double specind, double* I, double* Q, double* U, double* sinthb, double* density, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    const size_t n = npix * nguess;
+    if (n && (!alpha || !beta || !r || !th || !signpr || !signpth || !I || !Q || !U))
+        return fail_arg(KGEO_E_BADARG, "kgeo_jet_stokes: NULL pointer");
+    if (field != JET_MONO && field != JET_POWER) return fail_arg(KGEO_E_MODEL, "kgeo_jet_stokes: unknown jet field");
+    if (field == JET_MONO && (!fr_table || fr_n < 2)) return fail_arg(KGEO_E_MODEL, "kgeo_jet_stokes: the monopole needs its f(r) table");
+    if (n == 0) return 0;
+    JetSpec J{field, C, pval, usemono, fr_table, fr_table ? fr_table + fr_n : nullptr, (long long)fr_n};
+    jet_stokes_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(J, obs->a, obs->th_o, npix, n, alpha, beta, r, th, signpr,
+                                                                            signpth, nu_parallel, sigma, r0, norm, psitarget, specind,
+                                                                            I, Q, U, sinthb, density);
+    LAUNCHED("jet_stokes_kernel");
+    return 0;
+}
+
+int kgeo_jet_sort(size_t npix, size_t nguess, int neqmax, const double* I, const double* Q, const double* U, const double* neq,
+                  double* out_I, double* out_Q, double* out_U, void* stream) {
+    if (npix && nguess && (!I || !Q || !U || !neq || !out_I || !out_Q || !out_U)) return fail_arg(KGEO_E_BADARG, "kgeo_jet_sort: NULL pointer");
+    if (neqmax < 0 || nguess > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_jet_sort: bad neqmax / nguess");
+    if (npix == 0) return 0;
+    jet_sort_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(npix, (int)nguess, neqmax, I, Q, U, neq, out_I, out_Q, out_U);
+    LAUNCHED("jet_sort_kernel");
     return 0;
 }
 

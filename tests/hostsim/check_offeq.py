@@ -55,6 +55,14 @@ def run(so_path, verbose=True):
             err(uo[i::4], uref[i], k)
         err(outs[4], gref, 'g')
         err(outs[3], np.broadcast_to(sinthb, r.shape), 'sinthb')
+        # densities (jet_density: stagnation radius and normalisation from the product's host scalars)
+        from kgeo_b200 import off_eq
+        field, r0, norm = off_eq.jet_scalars(name, r, th, shape, psit, a, 2, pval)
+        rho = np.empty(n)
+        L.hs_jet_density(field, ctypes.c_double(1.0), ctypes.c_double(pval), 0, P(frx), P(frf), ctypes.c_longlong(frx.size),
+                         ctypes.c_double(a), n, P(r), P(th), ctypes.c_double(0.0), ctypes.c_double(2.0), ctypes.c_double(r0),
+                         ctypes.c_double(norm), ctypes.c_double(psit), P(rho))
+        err(rho, dens, 'density')
         for got, ref, k in ((outs[0], I, 'I'), (outs[1], Q, 'Q'), (outs[2], U, 'U')):
             err(np.nan_to_num(got), np.nan_to_num(ref), k)      # getstokes applies nan_to_num to the Stokes parameters
             err(np.where(hit, np.nan_to_num(got), 0.0), g[name + '_raw_' + k.lower()], k + ' vs ref')

@@ -17,4 +17,13 @@ void hs_offeq(int field, double C, double pval, int usemono, const double* fr_x,
         u[4 * i] = v.u0; u[4 * i + 1] = v.u1; u[4 * i + 2] = v.u2; u[4 * i + 3] = v.u3;
     }
 }
+void hs_jet_density(int field, double C, double pval, int usemono, const double* fr_x, const double* fr_f, long long fr_n, double a,
+                    int n, const double* r, const double* th, double nu, double sigma, double r0, double norm, double psitarget,
+                    double* rho) {
+    JetSpec J{field, C, pval, usemono, fr_x, fr_f, fr_n};
+    for (int i = 0; i < n; ++i) rho[i] = jet_density(J, a, r[i], th[i], nu, sigma, r0, norm, psitarget);
+}
+double hs_power_source_integral(double r, double r0, double a, double sigma, double psi, double pval) {
+    return power_source_integral(r, r0, a, sigma, psi, pval);
+}
 }

@@ -199,3 +199,32 @@ def test_solver_host_side():
     assert solver.psifunc(r, th, 0.7, model='nonsense') == 0
     assert [solver._model_id(m) for m in ('para', 'mono', 'power', 'nonsense')] == [0, 1, 2, 3]
     assert solver.MAXTAUFRAC == 1. - 1.e-10
+
+
+def test_jet_host_scalars(golden):
+    """kgeo_b200.off_eq: the one-per-call host scalars of getstokes -- field-line speed at the first crossing, stagnation radius
+    (quintic / nested secant solves restating SciPy's scalar `newton`), power-law normalisation by Gauss-Legendre -- against the
+    checker's SciPy versions on the crossings the unmodified reference found (tests/golden/jet_pipeline.npz)."""
+    import scipy.integrate as scint
+    from kgeo_b200 import off_eq
+    from oracle import kgeo_oracle as ko
+    g = golden('jet_pipeline')
+    for name in ('mono', 'power'):
+        a, r_o, th_o, psit, pval, neqmax, ngeo = [float(x) for x in g[name + '_par']]
+        shape = tuple(g[name + '_shape'])
+        r, th = g[name + '_root_r'], g[name + '_root_th']
+        field, r0, norm = off_eq.jet_scalars(name, r, th, shape, psit, a, 2, pval)
+        rn, thn = r.reshape(shape), np.arccos(np.abs(np.cos(th.reshape(shape))))
+        i0 = np.where(np.nan_to_num(rn)[0] != 0)[0][0]
+        with np.errstate(all='ignore'):
+            if name == 'mono':
+                om = ko.bfield_lab_omega(dict(type='bz_monopole'), a, rn[0][i0:i0 + 1], thn[0][i0])[3][0]
+                assert field == off_eq.JET_MONO and norm == 1.0 and abs(r0 - ko.r0min_mono(thn[0][i0], om, a)) <= 1e-13 * r0
+            else:
+                om = np.broadcast_to(ko.bfield_lab_omega(dict(type='power', p=pval), a, rn[0][i0:i0 + 1], thn[0][i0])[3], (1,))[0]
+                r0o, _ = ko.r0min_power(psit, om, a, pval)
+                want = scint.quad(lambda x: np.exp(-(x - r0o) ** 2 / 8) * (x ** 2 + a ** 2 * (1 - psit / x ** pval) ** 2), r0o, np.inf,
+                                  epsabs=1e-13, epsrel=1e-13)[0]
+                assert field == off_eq.JET_POWER and abs(r0 - r0o) <= 1e-13 * r0o and abs(norm - want) <= 1e-12 * want
+    with pytest.raises(NotImplementedError):
+        off_eq.getstokes(1.0, np.zeros((2, 2)), np.zeros((2, 2)), 1000., 0.3, 0.5, 50, model='para')

@@ -1,0 +1,40 @@
+"""Off-equatorial jet pipeline on the device (rest: kgeo_b200.off_eq.getstokes) vs off_eq.getstokes of the unmodified
+reference (tests/golden/jet_pipeline.npz).
+
+UNVERIFIED ON HARDWARE: written after the round's GPU budget was spent.  The per-crossing device functions, the densities and the host
+scalars are verified on the CPU (tests/test_offeq_hostbuild.py, tests/test_abi_and_host.py::test_jet_host_scalars); the two kernels
+(jet_stokes_kernel, jet_sort_kernel) and this test have not run yet.  Marked `gpu_unverified`: run with `-m gpu_unverified`; it is
+deliberately not part of `-m gpu` until it has passed on a B200."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+try:
+    import torch
+    _HAS_CUDA = torch.cuda.is_available()
+except Exception:
+    _HAS_CUDA = False
+
+pytestmark = [pytest.mark.gpu_unverified, pytest.mark.skipif(not _HAS_CUDA, reason="needs a CUDA device")]
+np.seterr(all='ignore')
+
+
+def test_getstokes_against_reference(golden):
+    from kgeo_b200 import off_eq
+    g = golden('jet_pipeline')
+    for name in json.loads(str(g['names'])):
+        a, r_o, th_o, psit, pval, neqmax, ngeo = [float(x) for x in g[name + '_par']]
+        A, B = g[name + '_alpha'], g[name + '_beta']
+        raw = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model=name, pval=pval, nu_parallel=0, sigma=2,
+                               sumsubring=False)
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            ref = g[name + '_raw_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
+        img = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model=name, pval=pval, nu_parallel=0, sigma=2,
+                               retvals=True, retsin=True)
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            ref = g[name + '_img_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
