@@ -255,8 +255,6 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
                          double* neq_dev, int32_t* iterations, int32_t* nfailed, void* stream);
 
 /* ---- off-equatorial jet emission (kgeo/off_eq.py:124-233 getstokes, kgeo/densityfuncs.py, kgeo/geometry.py:38-62) -------------
- * STATUS: the device functions behind these two entry points are verified on the CPU; the entry points themselves have not run
- * on a GPU yet (tests marked gpu_unverified).
  * kgeo_jet_stokes: for the nguess x npix crossings of kgeo_fieldline_solve (r, theta, sign p^r, sign p^theta; r = 0 = none) the
  *   density of the jet model (field 0 = BZ monopole with its f(r) table of 2 x fr_n doubles, 1 = power law r^pval; r0 =
  *   stagnation radius, norm = source integral from r0 to infinity for the power law) and Iobs_off's polarized Stokes parameters

@@ -2,9 +2,9 @@
 // metric, the BZ monopole / power-law fields with their field-line speed, the E x B drift frame, redshift, fluid-frame
 // tetrad, Penrose-Walker transport -- per-crossing device functions for the rest of SURVEY 8 f4.
 //
-// STATUS: verified on the CPU only (tests/hostsim/check_offeq.py compiles this header for the host and compares every output
-// with the reference-pinned CPU checker on the crossings of tests/golden/jet_pipeline.npz); no kernel uses it yet and nothing here has run on a
-// GPU.  The equatorial image kernel keeps its own plane-specialised versions (kg_image.cuh).
+// Used by jet_stokes_kernel (kgeo_b200.cu).  tests/hostsim/check_offeq.py also compiles this header for the host and compares every
+// output with the reference-pinned CPU checker on the crossings of tests/golden/jet_pipeline.npz.  The equatorial image kernel
+// keeps its own plane-specialised versions (kg_image.cuh).
 #pragma once
 #include "kg_image.cuh"
 

@@ -600,8 +600,8 @@ __global__ void __launch_bounds__(256) fieldline_finish_kernel(Observer o, size_
 
 // ---------------------------------------------------------------------------------------------------------------------
 // off-equatorial jet emission (kgeo/off_eq.py getstokes: density + Iobs_off per crossing, geometry.sort_image)
-// NOT YET RUN ON A GPU: the per-crossing device functions are verified on the CPU (tests/test_offeq_hostbuild.py); these two
-// kernels and their entry points are exercised by tests marked `gpu_unverified`, outside the `-m gpu` suite, until they have.
+// The per-crossing device functions are also checked on the CPU through a host build (tests/test_offeq_hostbuild.py); the
+// kernels against the unmodified reference's getstokes in tests/test_gpu_jet.py.
 // ---------------------------------------------------------------------------------------------------------------------
 KG_HD double nan_to_num(double x) {
     if (x != x) return 0.0;

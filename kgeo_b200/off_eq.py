@@ -5,10 +5,8 @@ subring sums) runs in libkgeo_b200.so kernels; what stays on the host is one sca
 field-line angular speed at the first crossing, the stagnation surface (kgeo/ff_boost.py: a quintic for the monopole, two nested
 secant solves for the power law) and the normalisation of the power law's mass loading.
 
-STATUS: the device functions are verified on the CPU against the reference-pinned checker (tests/test_offeq_hostbuild.py), the host
-scalars in tests/test_abi_and_host.py; the two jet kernels have not run on a GPU yet (tests/test_gpu_jet.py is marked
-`gpu_unverified` and is not part of the `-m gpu` suite).  The paraboloid model raises: in the reference itself
-densityfuncs.eta_para fails on the complex numbers SciPy's lambertw produces.
+Parity with the unmodified reference's getstokes (monopole and power-law models): tests/test_gpu_jet.py.  The paraboloid model
+raises: in the reference itself densityfuncs.eta_para fails on the complex numbers SciPy's lambertw produces.
 
 getstokes -- kgeo/off_eq.py:124-233        density_*_all -- kgeo/densityfuncs.py:44-79,186-219        r0min_* -- kgeo/ff_boost.py:8-45
 """

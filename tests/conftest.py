@@ -12,8 +12,6 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_unverified: needs a CUDA device, written without one: kernels whose device functions are "
-                            "CPU-verified but which have not run on a GPU yet (run with -m gpu_unverified; not part of -m gpu)")
 
 
 @pytest.fixture(scope="session")

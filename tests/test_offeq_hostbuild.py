@@ -1,8 +1,8 @@
 """CPU check of the off-equatorial jet physics written for the rest of SURVEY 8 f4 (kgeo_b200/csrc/kg_offeq.cuh: metric, BZ monopole /
 power-law field with its field-line speed, drift frame, redshift, tetrad, Penrose-Walker transport, per-crossing Stokes parameters).
 The header's functions are __host__ __device__: it is compiled for the host with g++ and compared with the pinned oracle on the
-crossings of tests/golden/jet_pipeline.npz (and with the unmodified reference's raw Stokes parameters stored there).  No kernel uses
-these functions yet; nothing here is a GPU result."""
+crossings of tests/golden/jet_pipeline.npz (and with the unmodified reference's raw Stokes parameters stored there).  The GPU side of
+the same comparison is tests/test_gpu_jet.py."""
 import os
 import shutil
 import subprocess
