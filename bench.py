@@ -219,7 +219,7 @@ def run_ours(args):
     obs = _engine.observer_struct(SPIN, R_O, th_o)
     d_alpha, d_beta = _engine.to_device(A, dev), _engine.to_device(B, dev)
     nw = L.kgeo_ray_workspace_slots()
-    d_w = torch.empty((nw, npix), dtype=torch.float64, device=dev)
+    d_w = torch.empty((int(L.kgeo_ray_workspace_doubles(npix)),), dtype=torch.float64, device=dev)
     d_flags = torch.empty((npix,), dtype=torch.int32, device=dev)
     outs = [torch.empty((NGEO, npix), dtype=torch.float64, device=dev) for _ in range(4)]    # t, r, th, ph
     null = ctypes.cast(None, _lib.c_double_p)

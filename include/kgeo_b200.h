@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KGEO_B200_ABI_VERSION 2
+#define KGEO_B200_ABI_VERSION 3
 
 #define KGEO_E_BADARG (-1)   /* NULL pointer, negative size, inconsistent shapes */
 #define KGEO_E_RANGE (-2)    /* |a| >= 1, r_o < 100, th_o outside (0,pi) or == pi/2 (the reference's own checks) */
@@ -109,8 +109,14 @@ int kgeo_abi_version(void);
 const char* kgeo_last_error(void);
 /* number of CUDA devices visible to the library, or a negative/positive error code */
 int kgeo_device_count(int* count);
-/* doubles per ray in the ray-constant workspace (slot-major SoA: slot s of ray i at w[s*npix + i]) */
+/* Ray-constant workspace.  kgeo_ray_workspace_slots(): doubles per ray.  Layout: rays in groups of four (four consecutive
+ * pixels = one 32-byte sector of every output row), group g = the contiguous block w[g*slots*4 ...) laid out [slot][ray in
+ * group], i.e. slot s of ray i at w[(i/4)*slots*4 + s*4 + i%4].  A buffer for npix rays holds kgeo_ray_workspace_doubles(npix)
+ * doubles (npix rounded up to a multiple of four rays) and must be 16-byte aligned (the track pass fetches a group's block
+ * with one cp.async.bulk).  kgeo_ray_slot copies one slot out as a plain [npix] array (slot 2 = total Mino time). */
 int kgeo_ray_workspace_slots(void);
+size_t kgeo_ray_workspace_doubles(size_t npix);
+int kgeo_ray_slot(size_t npix, const double* w_dev, int slot, double* out_dev, void* stream);
 /* cumulative number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 long long kgeo_launch_count(void);
 
@@ -134,7 +140,7 @@ int kgeo_special_ellipj(size_t n, const double* u_dev, const double* m_dev, doub
 /* ---- per-ray setup --------------------------------------------------------------------------------------------
  * Replaces radial_roots, mino_total, uplus_uminus, angular_turning (kgeo/kerr_raytracing_utils.py:242-548) and the
  * observer-side antiderivatives of th_integrate / r_integrate (kgeo/kerr_raytracing_ana.py:231-251,312-327,431-434,
- * 508-510,583-584).  w_dev: kgeo_ray_workspace_slots()*npix doubles; flags_dev: npix int32. */
+ * 508-510,583-584).  w_dev: kgeo_ray_workspace_doubles(npix) doubles; flags_dev: npix int32. */
 int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
                    double* w_dev, int32_t* flags_dev, void* stream);
 /* Unpacked per-ray summary for the host API: roots_dev[8*npix] = Re r1..r4, Im r1..r4 (plane-major), rclass_dev = the
@@ -243,7 +249,10 @@ int kgeo_trim_memory(int device);
  * kgeo_fieldline_solve: scipy.optimize.newton's vectorised secant iteration on psi(r(tau), theta(tau)) - psitarget for the
  *   nguess x npix guesses (all elements iterate until every one has converged, as in the reference), then r, theta at the
  *   roots, the signs of p^r and p^theta and the crossing count of getneq; elements whose guess is -1 come back as zeros.
- *   Blocks until done (the iteration count depends on device-side convergence flags).  iterations / nfailed: host ints. */
+ *   Blocks until done (the iteration count depends on device-side convergence flags).  iterations / nfailed: host ints.
+ *   nfailed (only when maxiter ran out): the number of elements scipy.optimize.newton reports as failed (|dp| >= tol at the
+ *   last step, or never updated), NEGATED when some of them had a zero secant derivative at the last step (SciPy then only
+ *   warns; with all elements failed and none of them zero-derivative it raises RuntimeError). */
 int kgeo_fieldline_guesses(const kgeo_observer* obs, size_t npix, size_t ngeo, const double* r_dev, const double* th_dev,
                            const double* tau_dev, size_t ld, const double* alpha_dev, const double* beta_dev, const double* w,
                            const int32_t* flags, int model, double pval, double psitarget, int neqmax, double maxtaufrac,

@@ -28,3 +28,12 @@ def pixel_arrays(alpha, beta, what="alpha, beta are different lengths!"):
     if len(alpha) != len(beta):
         raise Exception(what)
     return np.asarray(alpha, dtype=np.float64), np.asarray(beta, dtype=np.float64)
+
+
+def require_equatorial(th, what):
+    """The element-wise model kernels evaluate in the equatorial plane only; the reference accepts any polar angle."""
+    import numpy as np
+    th = np.asarray(th, dtype=np.float64)
+    if not np.all(th == np.pi / 2):
+        raise NotImplementedError("%s: only th = pi/2 (the equatorial plane) is built; off-equatorial evaluation "
+                                  "exists on the device for the jet pipeline (off_eq.getstokes) only" % what)

@@ -113,20 +113,32 @@ class RayBundle(object):
         else:
             self.clamped = False
         self.mode = mode
+        # host copies of the pixel coordinates (when they came from the host): callers that want to reuse this bundle for
+        # "the same rays" compare against them (solver._bundle_of)
+        self.alpha_host = np.array(alpha, dtype=np.float64) if not hasattr(alpha, "is_cuda") else None
+        self.beta_host = np.array(beta, dtype=np.float64) if not hasattr(beta, "is_cuda") else None
         self.alpha = to_device(alpha, self.dev)
         self.beta = to_device(beta, self.dev)
         self.npix = int(self.alpha.numel())
         t = torch()
         self.nw = L.kgeo_ray_workspace_slots()
         with t.cuda.device(self.dev):
-            self.w = empty((self.nw, self.npix), self.dev)
+            self.w = empty((int(L.kgeo_ray_workspace_doubles(self.npix)),), self.dev)   # grouped layout, see kgeo_b200.h
             self.flags = empty((self.npix,), self.dev, t.int32)
             _lib.check(L.kgeo_ray_setup(ctypes.byref(self.obs), self.npix, dptr(self.alpha), dptr(self.beta), self.mode,
                                         dptr(self.w), iptr(self.flags), stream_ptr()))
 
+    def slot(self, index):
+        """one slot of the ray-constant workspace as an [npix] device tensor"""
+        t = torch()
+        out = empty((self.npix,), self.dev)
+        with t.cuda.device(self.dev):
+            _lib.check(_lib.lib().kgeo_ray_slot(self.npix, dptr(self.w), int(index), dptr(out), stream_ptr()))
+        return out
+
     @property
     def tau_tot(self):
-        return self.w[2]          # slot S_TAUTOT
+        return self.slot(2)       # slot S_TAUTOT
 
     def tracks(self, ntau=None, maxtaufrac=1.0, tau=None, full=True, want=("t", "r", "th", "ph", "sig", "tau")):
         """Launch the track kernel.  tau: None (linspace samples) or a [ntau, npix] device tensor.

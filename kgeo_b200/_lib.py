@@ -47,6 +47,8 @@ SIGNATURES = {
     "kgeo_last_error": (ctypes.c_char_p, []),
     "kgeo_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
     "kgeo_ray_workspace_slots": (ctypes.c_int, []),
+    "kgeo_ray_workspace_doubles": (ctypes.c_size_t, [_S]),
+    "kgeo_ray_slot": (ctypes.c_int, [_S, _P, ctypes.c_int, _P, _V]),
     "kgeo_launch_count": (ctypes.c_longlong, []),
     "kgeo_special_rf": (ctypes.c_int, [_S, _P, _P, _P, _P, _V]),
     "kgeo_special_rd": (ctypes.c_int, [_S, _P, _P, _P, _P, _V]),
@@ -117,7 +119,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.kgeo_abi_version() != 2:
+        if L.kgeo_abi_version() != 3:
             raise ImportError("kgeo_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -7,7 +7,7 @@ import ctypes
 
 import numpy as np
 
-from . import _engine, _lib
+from . import _checks, _engine, _lib
 
 RMAXINTERP = 100       # kgeo/bfields.py:16-20: bz_fr_data.dat holds f(r) on linspace(1, RMAXINTERP, NINTERP)
 NINTERP = 100000
@@ -159,12 +159,14 @@ class Bfield(object):
 
     def bfield_lab(self, a, r, th=np.pi / 2):
         """lab frame b field starF^i0 = (B1, B2, B3)"""
+        _checks.require_equatorial(th, "Bfield.bfield_lab")
         return self._run(a, r, None, False)
 
     def omega_field(self, a, r, th=np.pi / 2):
         """fieldline angular speed (kgeo/bfields.py:175-197)"""
         if self.fieldtype not in ('bz_monopole', 'monopoleA', 'bz_guess', 'bz_para', 'power', 'gen_power'):
             raise Exception("self.omega_field not implemented for fieldtype %s'!" % self.fieldtype)
+        _checks.require_equatorial(th, "Bfield.omega_field")
         from .models import pack_models
         if not isinstance(r, np.ndarray):
             r = np.array([r]).flatten()
@@ -180,6 +182,7 @@ class Bfield(object):
     def efield_lab(self, a, r, th=np.pi / 2):
         """lab frame electric field F^{0i} of a stationary, axisymmetric field (kgeo/bfields.py:199-235), in the
         equatorial plane: assembled from the device's B^i and omega"""
+        _checks.require_equatorial(th, "Bfield.efield_lab")
         if not isinstance(r, np.ndarray):
             r = np.array([r]).flatten()
         if self.fieldtype == 'bz_monopole' and self.secondorder_only:   # Efield_BZmonopole, kgeo/bfields.py:595-606
@@ -198,4 +201,5 @@ class Bfield(object):
 
     def bsq(self, a, r, velocity, th=np.pi / 2.):
         """b^2 in the frame u^mu of `velocity`, ideal MHD"""
+        _checks.require_equatorial(th, "Bfield.bsq")
         return self._run(a, r, velocity, True)

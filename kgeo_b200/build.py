@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libkgeo_b200.so")
 SOURCES = [os.path.join(CSRC, "kgeo_b200.cu")]
-HEADERS = [os.path.join(CSRC, h) for h in ("kg_special.cuh", "kg_math.cuh", "kg_geodesic.cuh", "kg_image.cuh", "kg_fieldline.cuh", "kg_offeq.cuh", "kg_theta.cuh", "kg_theta_layout.cuh")] + [
+HEADERS = [os.path.join(CSRC, h) for h in ("kg_special.cuh", "kg_math.cuh", "kg_geodesic.cuh", "kg_image.cuh", "kg_fieldline.cuh", "kg_offeq.cuh", "kg_theta.cuh", "kg_theta_layout.cuh", "kg_hot.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "kgeo_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=true",

@@ -82,19 +82,31 @@ enum Slot {
     R_Q0, R_Q1, R_Q2, R_Q3, R_Q4, R_Q5, R_Q6, R_Q7, R_Q8, R_Q9, R_Q10,
     T_ISQ,                      // 1 / T_SQ
     T_I2K, R_I2K,               // 1/(2 K(m)), 1/(2 K(k)) (0 when K is infinite)
-    T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
-    R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
     // per-ray reciprocals / prefactors of the case-3 and case-4 algebra (see radial_eval): no per-sample division by a constant
     R_C0, R_C1, R_C2, R_C3, R_C4, R_C5, R_C6, R_C7, R_C8, R_C9, R_C10, R_C11, R_C12,
     // theta-function path (kg_theta.cuh): polar block = base + 1 Pi, radial block = base + 3 Pi
     T_TH_G, T_TH_IM, T_TH_SLOPE, T_TH_COEF,       // 1 + (E/K - 1)/m, 1/m, G_phi slope and coefficient
     T_TH, T_TH_END = T_TH + TB_SIZE + TP_SIZE - 1,
     R_TH, R_TH_END = R_TH + TB_SIZE + 3 * TP_SIZE - 1,
+    // AGM ladders (Carlson fallback only) LAST: the hot pass copies slots [0, T_LAD) of a ray group with one bulk copy
+    T_LAD, T_LAD_END = T_LAD + kLadderSize - 1,   // AGM ladder of the polar Jacobi parameter m
+    R_LAD, R_LAD_END = R_LAD + kLadderSize - 1,   // AGM ladder of the radial parameter k
     NW
 };
-// ray_setup<.., LADDER = false> (image / lensing kernels: register- or local-memory workspace) touches only the slots below
-// the ladders; those kernels size their per-thread workspace with NW_LITE instead of NW
-constexpr int NW_LITE = T_LAD;
+// ray_setup<PHI_T = false, LADDER = false> (image / lensing kernels: register- or local-memory workspace) touches only the
+// slots below R_C0; those kernels size their per-thread workspace with NW_LITE instead of NW
+constexpr int NW_LITE = R_C0;
+constexpr int NW_HOT = T_LAD;       // slots the theta-function-only hot pass reads
+
+// ---- layout of the ray-constant workspace in HBM ----------------------------------------------------------------------------
+// Rays are stored in GROUPS OF FOUR (the track kernels' unit of work: four consecutive pixels = one 32-byte sector of every
+// output row): group g owns the contiguous block w[g * NW * 4 ... ), laid out [slot][ray in group].  A track CTA therefore
+// stages a group's constants with one contiguous copy (the hot pass: ONE cp.async.bulk of NW_HOT * 32 bytes), and the setup
+// kernels write whole 32-byte sectors.  Buffers hold ws_doubles(npix) doubles (npix rounded up to a multiple of four rays).
+constexpr int kRaysPerGroup = 4;
+constexpr int kGroupDoubles = NW * kRaysPerGroup;
+KG_HD size_t ws_offset(size_t ray) { return (ray / kRaysPerGroup) * (size_t)kGroupDoubles + (ray % kRaysPerGroup); }
+KG_HD size_t ws_doubles(size_t npix) { return ((npix + kRaysPerGroup - 1) / kRaysPerGroup) * (size_t)kGroupDoubles; }
 // case-specific meaning of the R_Q* slots
 //  case 2: Q0..Q3 = r1..r4, Q4 = sqrt(r31 r42), Q5 = H_o
 //  case 3: Q0 = r1, Q1 = r2, Q2 = A, Q3 = B, Q4..Q6 = al0, alp, alm, Q7..Q9 = p1(al_i), Q10 = sqrt(AB)
@@ -1104,11 +1116,12 @@ struct ArrayW {
     const double* p;
     KG_HD double operator()(int i) const { return p[i]; }
 };
-// accessor over a strided SoA workspace: slot i of pixel `pix` lives at base[i*stride + pix]
+// accessor over the grouped workspace in HBM: slot i of ray `pix` lives at w[ws_offset(pix) + i * kRaysPerGroup]
 struct StridedW {
-    const double* base;
-    long long stride;
-    KG_HD double operator()(int i) const { return base[(long long)i * stride]; }
+    const double* base;      // w + ws_offset(pix)
+    KG_HD double operator()(int i) const { return base[i * kRaysPerGroup]; }
 };
+KG_HD StridedW ray_view(const double* w, size_t pix) { return StridedW{w + ws_offset(pix)}; }
+KG_HD WsPtr ray_ptr(double* w, size_t pix) { return WsPtr{w + ws_offset(pix), (size_t)kRaysPerGroup}; }
 
 }  // namespace kg

@@ -24,6 +24,7 @@
 
 #include "../../include/kgeo_b200.h"
 #include "kg_image.cuh"
+#include "kg_hot.cuh"
 #include "kg_fieldline.cuh"
 #include "kg_offeq.cuh"
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_k
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     int fl;
-    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, WsPtr{w_out + i, npix}, &fl);   // constants go straight to the [slot][ray] workspace
+    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
     flags_out[i] = fl;
 }
 
@@ -161,8 +162,14 @@ __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) theta_setup
     if (i >= npix) return;
     int fl = flags_io[i];
     if (!(fl & (F_TH_PENDING | F_R_PENDING))) return;
-    theta_setup(o, WsPtr{w_io + i, npix}, &fl);
+    theta_setup(o, ray_ptr(w_io, i), &fl);
     flags_io[i] = fl;
+}
+
+// one slot of the grouped workspace as a plain [npix] array
+__global__ void __launch_bounds__(SETUP_THREADS) ray_slot_kernel(size_t npix, const double* __restrict__ w, int slot, double* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) out[i] = ray_view(w, i)(slot);
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS) ray_summary_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
@@ -355,11 +362,9 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
         }
         if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
         staged = true;
-        for (int i = threadIdx.x; i < NW * TRK_RPW; i += THREADS) {
-            const int s = i / TRK_RPW, jj = i % TRK_RPW;
-            if (PASS == P_HOT && s >= T_LAD && s <= R_LAD_END) continue;       // AGM ladders: Carlson fallback only
-            sw[i] = (jj < nvalid) ? w_in[(size_t)s * npix + pix0 + jj] : 0.0;
-        }
+        // the group's block of the workspace is [slot][4] already: a contiguous copy (rays beyond npix are padding)
+        const double* const gsrc = w_in + (pix0 / TRK_RPW) * (size_t)kGroupDoubles;
+        for (int i = threadIdx.x; i < (PASS == P_HOT ? NW_HOT : NW) * TRK_RPW; i += THREADS) sw[i] = gsrc[i];
         if (PASS == P_ALL && threadIdx.x < TRK_RPW)
             sw[NW * TRK_RPW + threadIdx.x] = (threadIdx.x < nvalid) ? (double)flags_in[pix0 + threadIdx.x] : 0.0;
         __syncthreads();
@@ -414,6 +419,159 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
     }
 }
 
+// The hot pass of a full trace (rays with F_TH_THETA and F_R_THETA): the lane mapping of track_kernel (lane = 4 * sample + ray,
+// whole 32-byte sectors per store) with the theta-function-only code of kg_hot.cuh, and NO cooperative staging: the ray
+// constants of all HOT_GROUPS four-ray groups of the CTA are fetched by one elected thread with one 1-D TMA bulk copy
+// (cp.async.bulk, NW_HOT * 32 = 6 KB) per group, each signalling its own mbarrier; the warps wait on a group's barrier right
+// before they use it.  No __syncthreads in the sample loop, no staging instructions, no buffer reuse (8 groups x 6 KB = 48 KB
+// per CTA, four CTAs per SM); while group g is traced the copies of g+1.. are long complete.  (ncu of the staged version: 12 %
+// of all warp-stall samples sat on the staging loads, their stores and the two barriers per group.)
+#ifndef KG_HOT_NS
+#define KG_HOT_NS 1                     // Mino-time samples per thread (2 was measured: 21.7 against 19.3 ms, it halves the warps)
+#endif
+#ifndef KG_HOT_WARPS
+#define KG_HOT_WARPS 8
+#endif
+#ifndef KG_HOT_MINBLOCKS
+#define KG_HOT_MINBLOCKS 4
+#endif
+#ifndef KG_HOT_TMA
+#define KG_HOT_TMA 1                    // 0: cooperative staging with two barriers per group (the round-1 scheme), for A/B
+#endif
+constexpr int HOT_NS = KG_HOT_NS, HOT_WARPS = KG_HOT_WARPS;
+constexpr int HOT_GROUPS = TRK_GROUPS;
+constexpr unsigned HOT_GROUP_BYTES = NW_HOT * TRK_RPW * sizeof(double);
+static_assert(HOT_GROUP_BYTES % 16 == 0 && (kGroupDoubles * sizeof(double)) % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr size_t HOT_SMEM = KG_HOT_TMA ? (size_t)HOT_GROUPS * HOT_GROUP_BYTES + HOT_GROUPS * sizeof(unsigned long long)
+                                       : (size_t)HOT_GROUP_BYTES;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "KG_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra KG_MBAR_DONE;\n"
+        "bra KG_MBAR_WAIT;\n"
+        "KG_MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * HOT_WARPS, KG_HOT_MINBLOCKS)
+track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int32_t* __restrict__ flags_in, int ntau,
+                 double maxtaufrac, TrackOut out, size_t ld, int k_begin, int k_end, int chunk) {
+    constexpr int WARPS = HOT_WARPS, THREADS = 32 * WARPS;
+    constexpr int KSTEP = WARPS * (32 / TRK_RPW);                        // samples one CTA-wide pass covers (per sample slot)
+    extern __shared__ __align__(128) unsigned char hot_smem[];
+    double* const sw = reinterpret_cast<double*>(hot_smem);             // [HOT_GROUPS][NW_HOT][4] (TMA) or [NW_HOT][4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & (TRK_RPW - 1), ks = lane / TRK_RPW;
+    // byte offset of this thread's ray column, passed through a shuffle so that ptxas keeps it in a register (see track_kernel)
+    const unsigned joff = __shfl_sync(0xffffffffu, (unsigned)j * (unsigned)sizeof(double), lane);
+    const int k0 = k_begin + blockIdx.y * chunk;
+    const int k1 = min(k_end, k0 + chunk);
+    const int kfirst = k0 + warp * (32 / TRK_RPW) + ks;
+    const int klast = (ntau > 1) ? ntau - 1 : -1;                        // numpy.linspace: the last sample is `stop` exactly
+    static_assert(HOT_GROUPS * TRK_RPW <= 32, "one flag per lane");
+    const size_t p = (size_t)blockIdx.x * (HOT_GROUPS * TRK_RPW) + lane;
+    const bool inside = lane < HOT_GROUPS * TRK_RPW && p < npix;
+    const int tile_flag = inside ? __ldg(flags_in + p) : 0;
+    const unsigned mine_mask = __ballot_sync(0xffffffffu, inside && trk_hot(tile_flag));
+    if (mine_mask == 0) return;                                         // uniform over the CTA
+    const double* const tile_src = w_in + (size_t)blockIdx.x * HOT_GROUPS * (size_t)kGroupDoubles;
+#if KG_HOT_TMA
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(hot_smem + (size_t)HOT_GROUPS * HOT_GROUP_BYTES);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int g = 0; g < HOT_GROUPS; ++g) mbar_init(bar + g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // inits visible to the async proxy
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int g = 0; g < HOT_GROUPS; ++g) {
+            if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // no hot ray: never waited for
+            mbar_expect_tx(bar + g, HOT_GROUP_BYTES);
+            bulk_copy_g2s(hot_smem + (size_t)g * HOT_GROUP_BYTES, tile_src + (size_t)g * kGroupDoubles, HOT_GROUP_BYTES, bar + g);
+        }
+    }
+#else
+    bool staged = false;
+#endif
+    for (int g = 0; g < HOT_GROUPS; ++g) {
+        const size_t pix0 = ((size_t)blockIdx.x * HOT_GROUPS + g) * TRK_RPW;
+        if (pix0 >= npix) break;                                        // uniform over the CTA
+        const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
+        const int fl = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + j);
+        if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // uniform over the CTA
+#if KG_HOT_TMA
+        mbar_wait(bar + g, 0);
+        const double* const gsw = sw + (size_t)g * (NW_HOT * TRK_RPW);
+#else
+        if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
+        staged = true;
+        for (int i = threadIdx.x; i < NW_HOT * TRK_RPW; i += THREADS) sw[i] = tile_src[(size_t)g * kGroupDoubles + i];
+        __syncthreads();
+        const double* const gsw = sw;
+#endif
+        if (j >= nvalid || !trk_hot(fl)) continue;
+        const size_t pix = pix0 + j;
+        SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(gsw) + joff)};
+        // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
+        const double stop = maxtaufrac * W(S_TAUTOT);
+        const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+        const double lam = W(S_LAM);
+        size_t q = (size_t)(kfirst - k_begin) * ld + pix;              // output index of sample slot 0
+        const size_t qs = (size_t)KSTEP * ld, qstep = (size_t)NS * qs;
+        for (int k = kfirst; k < k1; k += NS * KSTEP, q += qstep) {
+            double tau[NS];
+            bool live[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int kk = k + s * KSTEP;
+                live[s] = (s == 0) || kk < k1;                          // a dead slot re-evaluates sample k and stores nothing
+                const int kc = live[s] ? kk : k;
+                tau[s] = (kc == klast) ? stop : (double)kc * step;
+            }
+            double th[NS], Gph[NS], Gt[NS], r[NS], Iph[NS], It[NS], Isig[NS];
+            polar_hot<SmemW, NS>(W, fl, tau, th, Gph, Gt);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if (out.th && live[s]) __stcs(out.th + q + s * qs, th[s]);
+                Gph[s] *= lam;
+                Gt[s] *= o.a2;
+            }
+            radial_hot<SmemW, NS>(W, o, fl, tau, r, Iph, It, Isig);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if (!live[s]) continue;
+                const size_t qq = q + s * qs;
+                if (out.r) __stcs(out.r + qq, r[s]);
+                if (out.t) __stcs(out.t + qq, It[s] + Gt[s]);
+                if (out.ph) __stcs(out.ph + qq, Iph[s] + Gph[s]);
+                if (out.sig) __stcs(out.sig + qq, Isig[s] + Gt[s]);
+                if (out.tau) __stcs(out.tau + qq, tau[s]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o, size_t npix, const double* __restrict__ beta,
                                                                       const double* __restrict__ w_in,
                                                                       const int32_t* __restrict__ flags_in, int ntau,
@@ -421,7 +579,7 @@ __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o
                                                                       double* npol) {
     size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
-    StridedW W{w_in + pix, (long long)npix};
+    const StridedW W = ray_view(w_in, pix);
     int fl = flags_in[pix];
     double b = beta[pix];
     for (int k = blockIdx.y; k < ntau; k += gridDim.y) {
@@ -452,7 +610,7 @@ __global__ void __launch_bounds__(256) fieldline_guess_kernel(Observer o, PsiSpe
                                                               int maxlen, double* guesses, double* taumax_out) {
     const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
-    StridedW W{w_in + pix, (long long)npix};
+    const StridedW W = ray_view(w_in, pix);
     const int fl = flags_in[pix];
     const double al = alpha[pix], be = beta[pix];
     const double taumax = maxtau_forwardjet(W, fl, be, neqmax, maxtaufrac);
@@ -528,7 +686,7 @@ __global__ void __launch_bounds__(256) fieldline_eval_kernel(Observer o, PsiSpec
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const size_t pix = e % npix;
-    StridedW W{w_in + pix, (long long)npix};
+    const StridedW W = ray_view(w_in, pix);
     double rr, tt;
     double v = psi_residual(W, o, flags_in[pix], ps.model, ps.pval, ps.psitarget, tau[e], &rr, &tt);
     if (guesses[e] == -1.0) v = 0.0;                                    // arrhere[guesses == -1] = 0
@@ -554,7 +712,7 @@ __global__ void __launch_bounds__(256) fieldline_secant_step_kernel(size_t n, do
     const double p = st.p[e], p1 = st.p1[e], q0 = st.q0[e], q1 = st.q1[e];
     const bool nz = (q1 != q0);
     double pn = p;
-    int act = st.active[e], fail = st.fail[e];
+    int act = st.active[e], fail = st.fail[e] & 1;
     if (nz) {
         const double dp = (q1 * (p1 - p)) / (q1 - q0);
         pn = p1 - dp;
@@ -567,7 +725,7 @@ __global__ void __launch_bounds__(256) fieldline_secant_step_kernel(size_t n, do
     act = act && nz;
     st.pnew[e] = pn;
     st.active[e] = act;
-    st.fail[e] = fail;
+    st.fail[e] = (fail & 1) | (nz ? 0 : 2);           // bit 0: scipy's `failures`, bit 1: zero derivative at this step
 }
 
 __global__ void __launch_bounds__(256) fieldline_average_kernel(size_t n, const double* p, const double* p1, double* out) {
@@ -584,7 +742,7 @@ __global__ void __launch_bounds__(256) fieldline_finish_kernel(Observer o, size_
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const size_t pix = e % npix;
-    StridedW W{w_in + pix, (long long)npix};
+    const StridedW W = ray_view(w_in, pix);
     const int fl = flags_in[pix];
     const double tau = root[e];
     const Point a = point_eval(W, o, fl, tau, false);
@@ -916,6 +1074,26 @@ static cudaError_t keep_pool_memory(int device) {
     if (e == cudaSuccess) done.fetch_or(1ULL << device);
     return e;
 }
+// cudaSetDevice for the duration of a host-buffer entry point; the caller's current device is restored on every return path
+// (a torch process would otherwise find torch.cuda.current_device() changed behind its back)
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t set(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { prev = -1; return e; }
+        return cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+// declared AFTER buffers a stream still reads from, so that it runs before their destructors on early (error) returns
+struct SyncOnExit {
+    cudaStream_t* s;
+    ~SyncOnExit() {
+        if (*s) cudaStreamSynchronize(*s);
+    }
+};
 struct StreamPair {
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
@@ -944,6 +1122,7 @@ int kgeo_device_count(int* count) {
     return 0;
 }
 int kgeo_ray_workspace_slots(void) { return NW; }
+size_t kgeo_ray_workspace_doubles(size_t npix) { return ws_doubles(npix); }
 long long kgeo_launch_count(void) { return g_launches.load(); }
 
 #define EW_ENTRY(kernel, ...)                                                             \
@@ -1014,6 +1193,15 @@ int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha, c
     return launch_setup(o, npix, alpha, beta, mode, w, flags, (cudaStream_t)stream);
 }
 
+int kgeo_ray_slot(size_t npix, const double* w, int slot, double* out, void* stream) {
+    if (npix && (!w || !out)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_slot: NULL pointer");
+    if (slot < 0 || slot >= NW) return fail_arg(KGEO_E_BADARG, "kgeo_ray_slot: slot out of range");
+    if (npix == 0) return 0;
+    ray_slot_kernel<<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, (cudaStream_t)stream>>>(npix, w, slot, out);
+    LAUNCHED("ray_slot_kernel");
+    return 0;
+}
+
 int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* roots,
                      int32_t* rclass, double* tau_tot, double* uplus, double* uminus, double* uratio, double* a2uminus,
                      double* outside, double* thplus, double* thminus, void* stream) {
@@ -1068,6 +1256,37 @@ static int launch_track_pass(const Observer& o, size_t npix, const double* w, co
 }
 }  // extern "C++"
 
+static int launch_hot_pass(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin, int k_end,
+                           double maxtaufrac, const double*, size_t, TrackOut out, size_t ld, cudaStream_t stream) {
+    const size_t tiles_ = (npix + TRK_RPW * TRK_GROUPS - 1) / (TRK_RPW * TRK_GROUPS);
+    if (tiles_ > 0x7fffffffu) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many rays in one launch");
+    const unsigned tiles = (unsigned)tiles_;
+    const int ns = k_end - k_begin;
+    const int want = 148 * 8;
+    int ychunks = (int)((want + tiles - 1) / tiles);
+    int per = (ns + ychunks - 1) / ychunks;
+    const int blk = HOT_NS * HOT_WARPS * (32 / TRK_RPW);    // samples one CTA-wide pass covers
+    per = ((per + blk - 1) / blk) * blk;
+    ychunks = (ns + per - 1) / per;
+    if (ychunks > 65535) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many Mino-time samples");
+    dim3 grid(tiles, (unsigned)ychunks);
+    const size_t smem = HOT_SMEM;
+    CU(cudaFuncSetAttribute(track_hot_kernel<HOT_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    track_hot_kernel<HOT_NS><<<grid, 32 * HOT_WARPS, smem, stream>>>(o, npix, w, flags, (int)ntau, maxtaufrac, out, ld, k_begin,
+                                                                      k_end, per);
+    LAUNCHED("track_hot_kernel");
+    return 0;
+}
+
+// KGEO_B200_TRK_PASSES=oldhot (developer A/B switch): the round-1 hot pass (one sample per thread) instead of track_hot_kernel
+static bool track_old_hot_pass() {
+    static const bool v = [] {
+        const char* e = getenv("KGEO_B200_TRK_PASSES");
+        return e && !strcmp(e, "oldhot");
+    }();
+    return v;
+}
+
 // KGEO_B200_TRK_PASSES=fused (developer A/B switch, read once): trace every ray with the complete code in a single pass
 static bool track_single_pass() {
     static const bool fused = [] {
@@ -1086,7 +1305,7 @@ static int launch_tracks(const Observer& o, size_t npix, const double* w, const 
     if (tau) return full ? launch_track_pass<true, P_ALL, true>(TRK_ARGS) : launch_track_pass<false, P_ALL, true>(TRK_ARGS);
     if (!full) return launch_track_pass<false, P_ALL, false>(TRK_ARGS);
     if (track_single_pass()) return launch_track_pass<true, P_ALL, false>(TRK_ARGS);
-    const int rc = launch_track_pass<true, P_HOT, false>(TRK_ARGS);
+    const int rc = track_old_hot_pass() ? launch_track_pass<true, P_HOT, false>(TRK_ARGS) : launch_hot_pass(TRK_ARGS);
     if (rc) return rc;
     return launch_track_pass<true, P_FIXUP, false>(TRK_ARGS);
 }
@@ -1217,9 +1436,21 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
         result = S.p;
     }
     if (iterations) *iterations = it;
-    if (!converged && nfailed) {      // count the elements scipy would report as not converged
-        // (failures & nz_der are not distinguished here: the caller only needs all / some / none)
-        *nfailed = 1;
+    if (!converged && nfailed) {      // the elements scipy.optimize.newton reports as not converged: |dp| >= tol at the last step
+        int32_t* h = (int32_t*)malloc(n * sizeof(int32_t));
+        if (!h) return fail_arg(KGEO_E_BADARG, "kgeo_fieldline_solve: out of host memory");
+        cudaError_t e = cudaMemcpyAsync(h, S.fail, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        long long bad = 0, zero_der = 0;
+        if (e == cudaSuccess)
+            for (size_t i = 0; i < n; ++i) {
+                bad += (h[i] & 1) != 0;
+                zero_der += h[i] == 3;                // ~nz_der & failures
+            }
+        free(h);
+        if (e != cudaSuccess) return fail_cuda(e, "kgeo_fieldline_solve: failure count");
+        const int32_t cnt = (int32_t)(bad > 0x7fffffffLL ? 0x7fffffffLL : bad);
+        *nfailed = zero_der ? -cnt : cnt;             // negated: some of them are zero-derivative elements (scipy only warns)
     }
     fieldline_finish_kernel<<<grid, 256, 0, st>>>(o, npix, n, w, flags, beta, guesses, result, tau_out, r_out, th_out, signpr,
                                                   signpth, neq);
@@ -1400,7 +1631,8 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_raytrace_host: NULL pointer");
     if (ngeo > 0x7fffffff) return fail_arg(KGEO_E_BADARG, "kgeo_raytrace_host: ngeo too large");
     if (npix == 0 || ngeo == 0) return 0;
-    CU(cudaSetDevice(device));
+    DeviceGuard dg;
+    CU(dg.set(device));
     // KGEO_B200_TRACE_HOST=1 (developer): wall-clock phases of this call on stderr
     static const bool trace = getenv("KGEO_B200_TRACE_HOST") != nullptr;
     const auto tc0 = std::chrono::steady_clock::now();
@@ -1424,7 +1656,7 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     PoolBuf d_alpha, d_beta, d_w, d_flags;            // freed (stream-ordered, on sp.compute) before sp goes out of scope
     CU(d_alpha.alloc(npix * sizeof(double), sp.compute));
     CU(d_beta.alloc(npix * sizeof(double), sp.compute));
-    CU(d_w.alloc((size_t)NW * npix * sizeof(double), sp.compute));
+    CU(d_w.alloc(ws_doubles(npix) * sizeof(double), sp.compute));
     CU(d_flags.alloc(npix * sizeof(int32_t), sp.compute));
     CU(cudaMemcpyAsync(d_alpha.p, alpha, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
     CU(cudaMemcpyAsync(d_beta.p, beta, npix * sizeof(double), cudaMemcpyHostToDevice, sp.compute));
@@ -1440,6 +1672,7 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     slab = (slab < 32) ? 32 : (slab / 32) * 32;
     if (slab > ngeo) slab = ngeo;
     PoolBuf d_out[2][6];
+    SyncOnExit drain{&sp.copy};                       // an error return must not free slabs the copy stream still reads
     for (int b = 0; b < 2; ++b)
         for (int i = 0; i < 6; ++i)
             if (host[i]) CU(d_out[b][i].alloc(slab * npix * sizeof(double), sp.compute));
@@ -1470,9 +1703,12 @@ int kgeo_raytrace_host(const kgeo_observer* obs, size_t npix, const double* alph
     return 0;
 }
 
+// The host-buffer entry points raise the release threshold of the device's DEFAULT memory pool (keep_pool_memory): a
+// process-wide setting, i.e. other cudaMallocAsync users of that device also keep their freed blocks cached until this call.
 int kgeo_trim_memory(int device) {
     cudaMemPool_t pool;
-    CU(cudaSetDevice(device));
+    DeviceGuard dg;
+    CU(dg.set(device));
     CU(cudaDeviceSynchronize());
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     CU(cudaMemPoolTrimTo(pool, 0));
@@ -1491,7 +1727,8 @@ int kgeo_equatorial_image_host(const kgeo_observer* obs, const kgeo_models* mode
     if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_host: bad mbar range");
     if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_host: NULL pointer");
     if (npix == 0) return 0;
-    CU(cudaSetDevice(device));
+    DeviceGuard dg;
+    CU(dg.set(device));
     cudaStream_t st;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct Guard {

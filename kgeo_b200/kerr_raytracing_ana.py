@@ -69,12 +69,14 @@ def raytrace_ana(a=SPIN,
     geos = Geodesics(a, observer_coords, [alpha, beta], out.get("tau"), out.get("sig"),
                      [out["t"], out["r"], out["th"], out["ph"]], _bundle=bundle, _recompute=recompute)
 
-    if savedata and do_phi_and_t:
+    if savedata and do_phi_and_t:      # the reference wraps this in try / except and carries on (:103-108)
         print('saving data...')
-        print("Error saving to file!")     # HDF5 output is outside the accelerated path
+        try:
+            geos.savegeos()
+        except ImportError as exc:
+            print("not saved: %s" % exc)
     if plotdata and do_phi_and_t:
-        print('plotting data...')
-        print("Error plotting data!")      # matplotlib output is outside the accelerated path
+        print("plotdata=True ignored: plotgeos is not built (matplotlib host-side code, SURVEY 2 out of scope)")
 
     _engine.torch().cuda.synchronize(bundle.dev)
     tstop = time.time()

@@ -1,7 +1,8 @@
 """Drop-in for kgeo/kerr_raytracing_utils.py on the hot path: the Geodesics result type and the per-ray helper
 functions, computed by libkgeo_b200.so kernels (no NumPy arithmetic on geodesic quantities here).
 
-Out of scope: plotgeos / savegeos / loadgeos (matplotlib / h5py host-side code) and n_angular_turnings.
+savegeos / loadgeos write / read the reference's HDF5 layout when h5py is installed (ImportError otherwise).
+Out of scope: plotgeos (matplotlib host-side code) and n_angular_turnings.
 """
 import numpy as np
 
@@ -45,9 +46,34 @@ class Geodesics(object):
             self._dev[name] = self._recompute(name)
         return self._dev[name]
 
+    def _materialise(self, names):
+        """Bring the named arrays to the host in ONE overlapped pass: page-locked NumPy arrays (torch's caching pinned
+        allocator: a block freed by an earlier result is reused without re-pinning), one asynchronous D2H copy per array
+        queued back to back, one synchronisation.  A script that reads `geo_coords` sees the PCIe link rate instead of four
+        serial pageable copies."""
+        todo = [n for n in names if n not in self._host]
+        if not todo:
+            return
+        t = _engine.torch()
+        pending = []
+        for name in todo:
+            src = self.device_array(name)
+            if not hasattr(src, "is_cuda"):               # NumPy input (loadgeos, user-constructed objects)
+                self._host[name] = src
+                continue
+            try:
+                dst = t.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            except RuntimeError:                          # page-locked memory exhausted: pageable destination
+                dst = t.empty(src.shape, dtype=src.dtype)
+            dst.copy_(src, non_blocking=True)
+            pending.append((name, dst, src.device))
+        for dev in set(d for _, _, d in pending):
+            t.cuda.current_stream(dev).synchronize()
+        for name, dst, _ in pending:
+            self._host[name] = dst.numpy()                # the array keeps the pinned block alive (arr.base)
+
     def _get(self, name):
-        if name not in self._host:
-            self._host[name] = _np(self.device_array(name))
+        self._materialise((name,))
         return self._host[name]
 
     @property
@@ -60,7 +86,8 @@ class Geodesics(object):
 
     @property
     def geo_coords(self):
-        return [self._get("t"), self._get("r"), self._get("th"), self._get("ph")]
+        self._materialise(("t", "r", "th", "ph"))
+        return [self._host["t"], self._host["r"], self._host["th"], self._host["ph"]]
 
     # observer
     @property
@@ -142,10 +169,52 @@ class Geodesics(object):
         return self.affine_times
 
     def plotgeos(self, *args, **kwargs):
-        raise NotImplementedError("plotgeos is host-side matplotlib code outside the accelerated path (SURVEY 8f)")
+        raise NotImplementedError("plotgeos is not built: host-side matplotlib code outside the accelerated path (SURVEY 2, out of scope)")
 
-    def savegeos(self, *args, **kwargs):
-        raise NotImplementedError("savegeos is host-side h5py code outside the accelerated path (SURVEY 8f)")
+    def savegeos(self, outfile=None, path='./'):
+        """HDF5 file with the reference's dataset names (kgeo/kerr_raytracing_utils.py:201-221).  Needs h5py."""
+        h5py = _require_h5py()
+        if outfile is None:
+            fname = path + 'a%0.2f_th%0.2f_geo.h5' % (self.a, self.th_o * 180 / np.pi)
+        else:
+            fname = outfile
+        self._materialise(("t", "r", "th", "ph", "sig", "tau"))
+        with h5py.File(fname, 'w') as hf:
+            hf.create_dataset('spin', data=self.a)
+            hf.create_dataset('inc', data=self.th_o)
+            hf.create_dataset('r_o', data=self.r_o)
+            hf.create_dataset('alpha', data=self.alpha)
+            hf.create_dataset('beta', data=self.beta)
+            hf.create_dataset('t', data=self.t_s)
+            hf.create_dataset('r', data=self.r_s)
+            hf.create_dataset('theta', data=self.th_s)
+            hf.create_dataset('phi', data=self.ph_s)
+            hf.create_dataset('affine', data=self.sig_s)
+            hf.create_dataset('mino', data=self.tausteps)
+        return fname
+
+
+def _require_h5py():
+    try:
+        import h5py
+    except ImportError as exc:
+        raise ImportError("savegeos / loadgeos need h5py, which is not installed (kgeo_b200 has no HDF5 writer of its own)") from exc
+    return h5py
+
+
+def loadgeos(infile):
+    """Geodesics object from a file written by savegeos (kgeo/kerr_raytracing_utils.py:223-240); host (NumPy) arrays."""
+    h5py = _require_h5py()
+    with h5py.File(infile, 'r') as hf:
+        a = hf['spin'][()]
+        r_o = hf['r_o'][()]
+        th_o = hf['inc'][()]
+        alpha = hf['alpha'][()]
+        beta = hf['beta'][()]
+        mino_times = hf['mino'][()]
+        affine_times = hf['affine'][()]
+        coords = [hf[k][()] for k in ('t', 'r', 'theta', 'phi')]
+    return Geodesics(a, [0, r_o, th_o, 0], [alpha, beta], mino_times, affine_times, coords)
 
 
 def _lam_eta_arrays(lam, eta):

@@ -52,8 +52,9 @@ def psifunc(r, theta, a, model='para', pval=1):
 def _bundle_of(outgeo, a, r_o, th_o, alpha, beta):
     """the device-resident rays of `outgeo` (made by raytrace_ana), or a fresh per-ray setup for the same pixels"""
     b = getattr(outgeo, '_bundle', None)
-    if b is not None and b.npix == len(alpha) and b.a == float(a) and b.r_o == float(r_o) and b.th_o == float(th_o):
-        return b
+    if (b is not None and b.npix == len(alpha) and b.a == float(a) and b.r_o == float(r_o) and b.th_o == float(th_o)
+            and b.alpha_host is not None and np.array_equal(b.alpha_host, alpha) and np.array_equal(b.beta_host, beta)):
+        return b                             # same observer AND the same pixels (the reference recomputes from alpha, beta)
     return _engine.RayBundle(a, r_o, th_o, np.asarray(alpha, dtype=np.float64), np.asarray(beta, dtype=np.float64),
                              clamp_lowspin=True)
 
@@ -66,12 +67,13 @@ def _guess_call(bundle, outgeo, psitarget, neqmax, model, pval, maxlen, count=No
     else:
         r, th, tau = [_engine.to_device(outgeo.device_array(k), bundle.dev) for k in ('r', 'th', 'tau')]
         ngeo = int(r.shape[0])
-    _lib.check(L.kgeo_fieldline_guesses(ctypes.byref(bundle.obs), bundle.npix, ngeo, _engine.dptr(r), _engine.dptr(th),
-                                        _engine.dptr(tau), bundle.npix, _engine.dptr(bundle.alpha), _engine.dptr(bundle.beta),
-                                        _engine.dptr(bundle.w), _engine.iptr(bundle.flags), _model_id(model), float(pval),
-                                        float(psitarget), -1 if neqmax is None else int(neqmax), MAXTAUFRAC, int(maxlen),
-                                        _engine.iptr(count), _engine.iptr(maxcount), _engine.dptr(guesses),
-                                        _engine.dptr(taumax), _engine.stream_ptr()))
+    with _engine.torch().cuda.device(bundle.dev):
+        _lib.check(L.kgeo_fieldline_guesses(ctypes.byref(bundle.obs), bundle.npix, ngeo, _engine.dptr(r), _engine.dptr(th),
+                                            _engine.dptr(tau), bundle.npix, _engine.dptr(bundle.alpha), _engine.dptr(bundle.beta),
+                                            _engine.dptr(bundle.w), _engine.iptr(bundle.flags), _model_id(model), float(pval),
+                                            float(psitarget), -1 if neqmax is None else int(neqmax), MAXTAUFRAC, int(maxlen),
+                                            _engine.iptr(count), _engine.iptr(maxcount), _engine.dptr(guesses),
+                                            _engine.dptr(taumax), _engine.stream_ptr()))
 
 
 def get_maxtau_forwardjet(a, r_o, th_o, alpha, beta, neqmax=1):
@@ -118,13 +120,21 @@ def findroot(outgeo, psitarget, alpha, beta, r_o, th_o, a, ngeo, model='para', n
     outs = [_engine.empty((n,), bundle.dev) for _ in range(6)]
     iters, nfailed = ctypes.c_int32(0), ctypes.c_int32(0)
     print('before solve')
-    _lib.check(L.kgeo_fieldline_solve(ctypes.byref(bundle.obs), bundle.npix, guesses_shape[0], _engine.dptr(bundle.beta),
-                                      _engine.dptr(bundle.w), _engine.iptr(bundle.flags), _model_id(model), float(pval),
-                                      float(psitarget), _engine.dptr(guesses), float(tol), 500,
-                                      *[_engine.dptr(o) for o in outs], ctypes.byref(iters), ctypes.byref(nfailed),
-                                      _engine.stream_ptr()))
+    with _engine.torch().cuda.device(bundle.dev):
+        _lib.check(L.kgeo_fieldline_solve(ctypes.byref(bundle.obs), bundle.npix, guesses_shape[0], _engine.dptr(bundle.beta),
+                                          _engine.dptr(bundle.w), _engine.iptr(bundle.flags), _model_id(model), float(pval),
+                                          float(psitarget), _engine.dptr(guesses), float(tol), 500,
+                                          *[_engine.dptr(o) for o in outs], ctypes.byref(iters), ctypes.byref(nfailed),
+                                          _engine.stream_ptr()))
     print('after solve')
-    if nfailed.value:
-        warnings.warn('some failed to converge after 500 iterations', RuntimeWarning, stacklevel=2)
+    # scipy.optimize.newton's array contract (_array_newton): every element failed -> RuntimeError, some -> RuntimeWarning
+    # (zero-derivative elements, e.g. the -1 padding whose objective is identically 0, only ever warn there)
+    if nfailed.value < 0:
+        warnings.warn('%d elements failed to converge after %d iterations (some with zero secant derivative)'
+                      % (-nfailed.value, iters.value), RuntimeWarning, stacklevel=2)
+    elif nfailed.value >= n:
+        raise RuntimeError('convergence failed after %d iterations' % iters.value)
+    elif nfailed.value:
+        warnings.warn('some failed to converge after %d iterations' % iters.value, RuntimeWarning, stacklevel=2)
     tau, r_s, th_s, signpr, signptheta, neqvals = [o.cpu().numpy() for o in outs]
     return tau, r_s, th_s, signpr, signptheta, neqvals, guesses_shape

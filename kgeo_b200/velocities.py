@@ -5,7 +5,7 @@ import ctypes
 
 import numpy as np
 
-from . import _engine, _lib
+from . import _checks, _engine, _lib
 
 # defaults of the reference (kgeo/velocities.py:14-21)
 BETA = 0.3
@@ -101,6 +101,10 @@ class Velocity(object):
     def u_lab(self, a, r, th=np.pi / 2., retqty=False):
         """Return lab frame contravariant velocity vector (u0, u1, u2, u3) at radii r (equatorial plane)"""
         from .models import pack_models
+        _checks.require_equatorial(th, "Velocity.u_lab")
+        if retqty:
+            raise NotImplementedError("Velocity.u_lab(retqty=True) is not built (the reference returns intermediate "
+                                      "quantities of the drift-frame construction there)")
         if not isinstance(r, np.ndarray):
             r = np.array([r]).flatten()
         L = _lib.lib()

@@ -164,6 +164,21 @@ def angular_consts(a, th_o, lam, eta):
     return up, um, ratio, a2um
 
 
+def angular_turning(a, th_o, lam, eta):
+    """u_plus, u_minus, theta_plus, theta_minus, thclass (kerr_raytracing_utils.py:242-274)."""
+    lam = _arr(lam)
+    eta = _arr(eta)
+    up, um, _, _ = angular_consts(a, th_o, lam, eta)
+    th_plus = np.arccos(-np.sqrt(up))                     # :257 (GL19a theta_4)
+    th_minus = np.arccos(np.sqrt(up))                     # :258 (GL19a theta_1)
+    th_plus = np.where(eta < 0, np.arccos(np.sqrt(np.where(eta < 0, um, 0.0))), th_plus)   # :262 vortical: theta_2
+    thclass = np.zeros(lam.shape, dtype=int)              # :265-272
+    thclass[eta > 0] = 1
+    thclass[eta < 0] = 2
+    thclass[eta == 0] = 3
+    return up, um, th_plus, th_minus, thclass
+
+
 def _cbrt_realmost(x):
     """Complex cube root with the largest real part (kerr_raytracing_utils.py:828-855)."""
     x = np.asarray(x, dtype=complex)

@@ -27,7 +27,7 @@ from kgeo.equatorial_images import make_image  # noqa: E402
 from kgeo.equatorial_lensing import (critical_curve, nmax_equatorial, nmax_poloidal, r_equatorial,  # noqa: E402
                                      rho_of_req, rho_of_req_single)
 from kgeo.kerr_raytracing_ana import coords_at_tau, raytrace_ana  # noqa: E402
-from kgeo.kerr_raytracing_utils import (is_outside_crit, mino_total, n_equatorial_crossings,  # noqa: E402
+from kgeo.kerr_raytracing_utils import (angular_turning, is_outside_crit, mino_total, n_equatorial_crossings,  # noqa: E402
                                          n_poloidal_orbits, radial_roots, uplus_uminus)
 from kgeo.scipy_ellip_binding import ellip_pi_arr  # noqa: E402
 from kgeo.velocities import Velocity  # noqa: E402
@@ -119,7 +119,9 @@ def setup():
         up, um, ratio, a2um = uplus_uminus(a, th_o, lam.copy(), eta.copy())
         r1, r2, r3, r4, rclass = radial_roots(a, lam, eta)
         tmax = mino_total(a, r_o, eta, r1, r2, r3, r4)
+        _, _, thp, thm, thclass = angular_turning(a, th_o, lam.copy(), eta.copy())      # theta_+-, kerr_raytracing_utils.py:242-274
         out.update({
+            'c%d_thp' % i: thp, 'c%d_thm' % i: thm, 'c%d_thclass' % i: thclass,
             'c%d_par' % i: np.array([a, th_o, r_o]), 'c%d_alpha' % i: A, 'c%d_beta' % i: B,
             'c%d_up' % i: up, 'c%d_um' % i: um, 'c%d_ratio' % i: ratio, 'c%d_a2um' % i: a2um,
             'c%d_roots' % i: np.array([r1, r2, r3, r4]), 'c%d_rclass' % i: rclass, 'c%d_tmax' % i: tmax,
@@ -421,7 +423,7 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()

@@ -35,80 +35,9 @@ def image_models(spec_json):
     return em, vel, bf, spec['kw']
 
 
-# ---- parity gates of the GPU tests (SURVEY 8d "Parity gates") ----------------------------------------------------
-TRACK_RTOL = 1.0e-10      # north_star: <= 1e-10 relative on r / theta / phi / t
-IMAGE_RTOL = 1.0e-8       # north_star: images <= 1e-8 relative
-HORIZON_TAIL = 0.999      # samples beyond this fraction of tau_tot on horizon-terminating rays are log-divergent
-
-
-def track_errors(got, ref, tau, r_ref, floor, rplus):
-    """Scaled error of one track array [ntau, npix] against the reference:  |got - ref| / (cond * max(|ref|, floor)).
-
-    floor: phi crosses zero and theta is O(1) -> 1;  t and sigma are differences of antiderivatives of size ~r_o that
-    cancel to 0 at tau = 0 (the reference itself returns t(0) ~ +-1e-9 instead of 0 at r_o = 1000) -> r_o;  r -> tiny.
-    cond = max(1, r/1000): the map tau -> r has condition number ~ r / (r4 - r3), so next to a distant observer
-    (r_o = 1e5 in the reference's default example) BOTH implementations are only good to ~1e-10 * r/1000 -- the exact value
-    r(0) = r_o shows it: the reference returns 1e5 * (1 +- 2e-10) there.
-    Returns (core, tail): max scaled error over well-conditioned samples, and over the log-divergent tail
-    (tau > HORIZON_TAIL * tau_tot on rays that end on the horizon; kgeo/kerr_raytracing_ana.py:26 stops at
-    (1 - 1e-10) tau_tot, where r - r_+ ~ 1e-10 and t, phi ~ log(r - r_+)).
-    """
-    got, ref = np.asarray(got), np.asarray(ref)
-    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs"
-    cond = np.maximum(1.0, np.abs(r_ref) / 1000.0)
-    err = np.abs(got - ref) / (cond * np.maximum(np.abs(ref), floor))
-    err = np.where(np.isfinite(err), err, 0.0)
-    ends_on_horizon = np.nanmin(r_ref, axis=0) < rplus * (1 + 1e-3)
-    tail = (tau > HORIZON_TAIL * tau[-1]) & ends_on_horizon[None, :]
-    core = np.max(np.where(tail, 0.0, err)) if err.size else 0.0
-    tl = np.max(np.where(tail, err, 0.0)) if err.size else 0.0
-    return float(core), float(tl)
-
-
-PV_WIDTH = 1.0e-3         # |1 - n sn^2| below which a sample sits on a removable singularity of the reference's formulas
-PV_RTOL = 1.0e-7          # gate for those samples (phi, t, sigma only)
-
-
-def removable_singularity_mask(a, r_o, th_o, alpha, beta, r_ref):
-    """Samples [ntau, npix] at which the REFERENCE's closed forms for I_phi / I_t are 0/0-type expressions.
-
-    Radial cases 3 and 4 write the third-kind integrals as R1 = (Pi(n; phi|j) - alpha f1)/(1 - alpha^2) resp.
-    S1 = (F + alpha^2 Pi(n; phi|j) - alpha f2)/(1 + alpha^2) with n > 1 (kgeo/kerr_raytracing_ana.py:648-683, GL19a B48-B65).
-    Pi (a Cauchy principal value, scipy_ellip_binding.py:207-230) and the logarithm f1/f2 BOTH diverge where 1 - n sin^2 phi
-    = 0.  One of the two amplitudes with that sine is the genuine singularity (r = r_+-, or r = inf); at the mirror amplitude
-    the divergences cancel analytically but not numerically: the reference loses eps / |1 - n sn^2| there (its own error
-    against 40-digit arithmetic reaches 1e-9 on isolated samples of a 128^2 x 50 trace).  No implementation can agree with
-    it to 1e-10 on those samples, so they get the looser, stated gate PV_RTOL (they are ~0.1 % of the samples).
-    """
-    from oracle import kgeo_oracle as ko
-    alpha, beta = np.asarray(alpha, dtype=float), np.asarray(beta, dtype=float)
-    r_ref = np.asarray(r_ref, dtype=float)
-    lam, eta = ko.conserved(a, th_o, alpha, beta)
-    if abs(a) < ko.MINSPIN and np.any(eta < 0):
-        eta = np.where(eta < 0, ko.EP, eta)
-    r1, r2, r3, r4, _ = ko.quartic_roots(a, lam, eta)
-    dist = np.full(r_ref.shape, np.inf)
-    with np.errstate(all='ignore'):
-        m4 = (r1.imag != 0)
-        if m4.any():
-            p = ko._case4_params(a, r_o, r2[m4], r4[m4])
-            g0 = p['g0']
-            gs = [g0, (g0 * p['x4rp'] - 1.0) / (g0 + p['x4rp']), (g0 * p['x4rm'] - 1.0) / (g0 + p['x4rm'])]
-            tn = np.tan(np.arctan((r_ref[:, m4] + p['b1']) / p['a2']) + np.arctan(g0))
-            # 1 - n sn^2 = (1 - g tan)(1 + g tan)/(1 + tan^2), n = 1 + g^2: genuine at g tan = -1, mirror at g tan = +1
-            dist[:, m4] = np.min([np.where(g * tn > 0, np.abs((1.0 - g * tn) * (1.0 + g * tn) / (1.0 + tn * tn)), np.inf)
-                                  for g in gs], axis=0)
-        m3 = (r3.imag != 0) & ~m4
-        if m3.any():
-            p = ko._case3_params(a, r_o, r1[m3], r2[m3], r4[m3])
-            AA, BB = p['AA'], p['BB']
-            u, v = AA * (r_ref[:, m3] - p['rr1']), BB * (r_ref[:, m3] - p['rr2'])
-            cn = (u - v) / (u + v)
-            als = [(BB + AA) / (BB - AA), -1.0 / p['x3rp'], -1.0 / p['x3rm']]
-            # 1 - n sn^2 = (al cn - 1)(al cn + 1)/(al^2 - 1), n = al^2/(al^2 - 1): genuine at al cn = -1, mirror at al cn = +1
-            dist[:, m3] = np.min([np.where(al * cn > 0, np.abs((al * cn - 1.0) * (al * cn + 1.0) / (al * al - 1.0)), np.inf)
-                                  for al in als], axis=0)
-    return np.nan_to_num(dist, nan=np.inf) < PV_WIDTH
+# ---- parity gates of the GPU tests (SURVEY 8d "Parity gates"): defined next to the oracle, oracle/gates.py ---------
+from oracle.gates import (AXIS_SIN, HORIZON_TAIL, IMAGE_RTOL, PV_RTOL, PV_WIDTH, TRACK_RTOL,  # noqa: E402,F401
+                          axis_weight, removable_singularity_mask, track_errors)
 
 
 def assert_tracks_close(got, ref, what="", pixels=None):
@@ -124,12 +53,14 @@ def assert_tracks_close(got, ref, what="", pixels=None):
     # tau = linspace(0, tau_tot): inherits the reference's own root noise (its tau_tot is good to ~5e-11 against
     # 40-digit quadrature at high spin / small r2), hence the same 1e-10 gate
     assert_close(got['tau'], tau, TRACK_RTOL, what=what + ' tau')
+    axw = axis_weight(ref['th'])          # phi within 0.01 rad of the rotation axis: gated on the arc length (oracle/gates.py)
     for key, floor in (('r', 1e-3), ('th', 1.0), ('ph', 1.0), ('t', r_o), ('sig', r_o)):
         g = np.asarray(got[key])
+        wgt = axw if key == 'ph' else None
         if pv is not None and key in ('ph', 't', 'sig') and pv.any():
-            core, _ = track_errors(np.where(pv, g, ref[key]), ref[key], tau, np.asarray(ref['r']), floor, rplus)
+            core, _ = track_errors(np.where(pv, g, ref[key]), ref[key], tau, np.asarray(ref['r']), floor, rplus, wgt)
             assert core <= PV_RTOL, "%s %s: scaled error %.3e > %.1e on removable-singularity samples" % (what, key, core, PV_RTOL)
             g = np.where(pv, ref[key], g)
-        core, tail = track_errors(g, ref[key], tau, np.asarray(ref['r']), floor, rplus)
+        core, tail = track_errors(g, ref[key], tau, np.asarray(ref['r']), floor, rplus, wgt)
         assert core <= TRACK_RTOL, "%s %s: scaled error %.3e > %.1e" % (what, key, core, TRACK_RTOL)
         assert tail <= 1e-2, "%s %s: horizon-tail error %.3e" % (what, key, tail)

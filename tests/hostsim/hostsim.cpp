@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include "kg_geodesic.cuh"
+#include "kg_hot.cuh"
 
 using namespace kg;
 
@@ -45,6 +46,24 @@ int hostsim_tracks(double a, double r_o, double th_o, size_t npix, const double*
         ArrayW W{w};
         const double stop = maxtaufrac * w[S_TAUTOT];
         const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
+        if (force == 4 && (fl & (F_TH_THETA | F_R_THETA)) == (F_TH_THETA | F_R_THETA)) {   // hot code, two samples at a time
+            for (int k = 0; k < ntau; k += 2) {
+                double tau[2];
+                for (int s = 0; s < 2; ++s) {
+                    int kk = (k + s < ntau) ? k + s : k;
+                    tau[s] = (kk == ntau - 1 && ntau > 1) ? stop : (double)kk * step;
+                }
+                double th_[2], Gph[2], Gt[2], r_[2], Iph[2], It[2], Isig[2];
+                polar_hot<ArrayW, 2>(W, fl, tau, th_, Gph, Gt);
+                radial_hot<ArrayW, 2>(W, o, fl, tau, r_, Iph, It, Isig);
+                for (int s = 0; s < 2 && k + s < ntau; ++s) {
+                    size_t q = (size_t)(k + s) * npix + i;
+                    t[q] = It[s] + o.a2 * Gt[s]; r[q] = r_[s]; th[q] = th_[s]; ph[q] = Iph[s] + w[S_LAM] * Gph[s];
+                    sig[q] = Isig[s] + o.a2 * Gt[s];
+                }
+            }
+            continue;
+        }
         for (int k = 0; k < ntau; ++k) {
             double tau = (k == ntau - 1 && ntau > 1) ? stop : (double)k * step;
             Point p = point_eval(W, o, fl, tau, true);

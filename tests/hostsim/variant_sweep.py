@@ -53,7 +53,7 @@ def main():
             os.environ.pop("KGEO_B200_TRK_PASSES", None)
         L = load(so)
         nw = L.kgeo_ray_workspace_slots()
-        d_w = torch.empty((nw, npix), dtype=torch.float64, device=dev)
+        d_w = torch.empty((int(L.kgeo_ray_workspace_doubles(npix)),), dtype=torch.float64, device=dev)
         d_flags = torch.empty((npix,), dtype=torch.int32, device=dev)
         for o in outs:
             o.fill_(float("nan"))

@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_and_struct_layout(lib):
     L = lib.lib()
-    assert L.kgeo_abi_version() == 2
+    assert L.kgeo_abi_version() == 3
     assert L.kgeo_ray_workspace_slots() > 30
     assert L.kgeo_launch_count() == 0
     assert ctypes.sizeof(lib.Observer) == 24

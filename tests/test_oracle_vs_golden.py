@@ -39,6 +39,10 @@ def test_setup_against_reference(golden):
         up, um, ratio, a2um = ko.angular_consts(a, th_o, lam, eta)
         for got, key in ((up, 'up'), (um, 'um'), (ratio, 'ratio'), (a2um, 'a2um')):
             assert_close(got, g['c%d_%s' % (i, key)], 0.0, what='case %d %s' % (i, key))
+        _, _, thp, thm, thclass = ko.angular_turning(a, th_o, lam, eta)
+        assert_close(thp, g['c%d_thp' % i], 0.0, what='case %d theta_plus' % i)
+        assert_close(thm, g['c%d_thm' % i], 0.0, what='case %d theta_minus' % i)
+        assert np.array_equal(thclass, g['c%d_thclass' % i])
         r1, r2, r3, r4, region = ko.quartic_roots(a, lam, eta)
         roots = g['c%d_roots' % i]
         for got, ref in zip((r1, r2, r3, r4), roots):
