@@ -1,28 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- fp64 geodesic points/s of the analytic Kerr ray tracer (BASELINE.json metric).
 
-One "step" = one pass of the hot path over the workload: per-ray setup kernel + fused track kernel producing
-r, theta, phi, t for every (pixel, Mino-time sample) of BASELINE config 3 (1024 x 1024 pixels x 500 samples, a=0.94,
-theta_o=17 deg, r_o=1000, +-10 M).  With N>1 ranks (one process per GPU under torchrun) every rank traces its own
-1024 interleaved rows (row % N == rank) of a (1024*N) x 1024 image plane -- weak scaling, no data-path collective.
-
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
+
+One "step" = one pass of the hot path over the workload.
+  N = 1   BASELINE cfg 3: per-ray setup + track pass producing r, theta, phi, t for 1024 x 1024 pixels x 500 Mino-time samples
+          (a = 0.94, theta_o = 17 deg, r_o = 1000, +-10 M).
+  N > 1   BASELINE cfg 4, the north_star's target run: 4096 x 4096 pixels x 500 samples, image rows INTERLEAVED over the N ranks
+          (row % N == rank), and per step on every rank: setup + track pass of its rows (r, theta, phi, t stay resident:
+          268 GB / N per GPU), the fused n = 0..2 equatorial image of its rows, and the gather of the image planes to rank 0
+          (one NCCL all_gather_into_tensor over NVLink + the row un-interleave on rank 0).  `value` counts the geodesic
+          points of all ranks; image_ms and collective_ms are reported separately.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      FP64-pipe roofline of the track pass (hot kernel + fix-up kernel, back to back on one stream): achieved =
-                FP64 flops the two kernels execute per point (608: the DFMA/DMUL/DADD mix of the committed ncu capture,
-                profiles/) x points per launch / CUDA-event duration of the pass;
-                peak = DFMA-chain rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry).  "canonical"
-                restates the same launch in SURVEY 8(d)'s work model (2400 flop/point for Carlson duplication): the kernel
-                evaluates the integrals by per-ray theta-function series instead, so that figure may exceed the peak.
-                Plus the HBM side (32 B/point written) against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the CPU oracle port of the reference (oracle/kgeo_oracle.py, SciPy path) timed on this box's host cores on
-                a bounded sample of the same workload.
-  e2e           same metric through the host-buffer C-ABI call kgeo_raytrace_host: host alpha/beta in, r/theta/phi/t
-                copied back into pinned host arrays inside the timed region.
+  roofline      FP64-pipe roofline of the track pass (hot kernel + fix-up kernel): achieved = executed FP64 flops per point (ncu
+                DFMA/DMUL/DADD thread-instruction counts of the capture recorded in profiles/r02_ncu_summary.json -- used only
+                while the kernel sources still hash to what that capture profiled, else null) x points / CUDA-event duration;
+                peak = DFMA-chain rate measured live (MEASURED_PEAKS.json has no FP64 entry).  "canonical" restates the launch
+                in SURVEY 8(d)'s work model of the reference's algorithm (2400 flop/point, Carlson duplication per sample).
+  parity        (N = 1) the GPU output of the benched launch against the CPU oracle at 4096 cfg-3 pixels x 500 samples: per
+                coordinate max / 99.9th percentile / fraction above a plain 1e-10, and the same with the stated gates
+                (oracle/gates.py); the run FAILS if a gate breaks.  (N > 1) shard_check: sharded == whole, bit for bit.
+  cpu_baseline  the CPU oracle port of the reference (oracle/kgeo_oracle.py, SciPy path) on this box's host cores.
+  e2e           same metric through the host-buffer C-ABI call kgeo_raytrace_host (host alpha/beta in, r/theta/phi/t into
+                pinned host arrays inside the timed region); e2e.python = the same through the Python drop-in
+                raytrace_ana(...).geo_coords; e2e.ceiling_gbs = bare pinned D2H copies of the same size on all ranks at once.
+  secondary     the fused n = 0..2 image kernel at 4096^2 with its own roofline / e2e / cpu_baseline; at N = 8 the cfg-5 sweep.
 """
 import argparse
+import contextlib
 import ctypes
+import hashlib
+import io
 import json
 import os
 import subprocess
@@ -36,51 +46,94 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SPIN, INC_DEG, R_O, HALF_FOV = 0.94, 17.0, 1000.0, 10.0
-NPIX_SIDE, NGEO = 1024, 500
+NGEO = 500
 MAXTAUFRAC = 1.0 - 1.0e-10
 CANONICAL_FLOP_PER_POINT = 2400.0   # SURVEY.md 8(d) work model: Carlson duplication, the reference's algorithm
-# FP64 flops the track pass executes per point on this workload (thread-level, predicated-on, ncu --set full of this
-# command, profiles/r01_final4_ncu_full_subset.csv): hot kernel 223.9 DFMA x 2 + 113.2 DMUL + 35.0 DADD = 596.1, fix-up
-# kernel (the 0.3 % Carlson-fallback rays, spread over all points) 12.3
-EXECUTED_FLOP_PER_POINT = 608.0
-FP64_PIPE_ACTIVE_NCU = 0.609        # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the hot kernel, same capture
-BYTES_PER_POINT = 32.0      # r, theta, phi, t written once
+CANONICAL_FLOP_PER_PIXEL = 3000.0   # n = 0..2 image
+BYTES_PER_POINT = 32.0              # r, theta, phi, t written once
+IMG_PLANES = 24                     # I,Q,U,r,Ir,g,sinthb x 3 orders + nmax, npol, imax: doubles per pixel of an n=0..2 image
+PARITY_PIXELS = 4096
 
 
-def workload_pixels(rank, world, side=NPIX_SIDE):
-    """Rows rank, rank+world, ... of the (side*world) x side plane spanning +-10 M (cfg 3 when world == 1).  Rows are
-    interleaved so that every rank sees the same mix of root classes: rays through the shadow cost more than
-    rays that escape, and contiguous row blocks would make the central ranks the stragglers."""
-    x = np.linspace(-HALF_FOV, HALF_FOV, side)
-    y_all = np.linspace(-HALF_FOV, HALF_FOV, side * world)
-    y = y_all[rank::world]
-    A, B = np.meshgrid(x, y)
+def grid_shape(world):
+    """(rows, cols) of the benched image plane: cfg 3 on one GPU, cfg 4 on several."""
+    return (1024, 1024) if world == 1 else (4096, 4096)
+
+
+def plane_pixels(world):
+    rows, cols = grid_shape(world)
+    x = np.linspace(-HALF_FOV, HALF_FOV, cols)
+    y = np.linspace(-HALF_FOV, HALF_FOV, rows)
+    return x, y
+
+
+def workload_pixels(rank, world):
+    """Rows rank, rank + world, ... of the plane spanning +-10 M.  Rows are interleaved so that every rank sees the
+    same mix of root classes: rays through the shadow cost more than rays that escape."""
+    x, y = plane_pixels(world)
+    A, B = np.meshgrid(x, y[rank::world])
     return np.ascontiguousarray(A.flatten()), np.ascontiguousarray(B.flatten())
+
+
+def workload_name(world):
+    rows, cols = grid_shape(world)
+    if world == 1:
+        return ("BASELINE cfg 3 geodesic tracks: a=0.94, theta_o=17deg, r_o=1000, +-10M, %dx%d px x %d Mino-time samples -> "
+                "r,theta,phi,t" % (rows, cols, NGEO))
+    return ("BASELINE cfg 4: a=0.94, theta_o=17deg, +-10M, %dx%d px x %d Mino-time samples -> r,theta,phi,t (r_o=1000) + fused "
+            "n=0..2 equatorial image (r_o=inf, bpl/zamo/rad) of the same pixels, rows interleaved over %d GPUs, image planes "
+            "gathered to rank 0" % (rows, cols, NGEO, world))
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources: ties the ncu-derived constants of profiles/r02_ncu_summary.json to the code they profiled."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "kgeo_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_summary():
+    """profiles/r02_ncu_summary.json if it describes the kernels as they are now, else None."""
+    try:
+        s = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+    except Exception:
+        return None
+    return s if s.get("csrc_sha256_16") == kernel_source_hash() else None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's SciPy path (test infrastructure, used here only as the thing compared to)
 # ---------------------------------------------------------------------------------------------------------------------
 def _cpu_chunk(args):
-    a, r_o, th_o, A, B, ngeo = args
+    a, r_o, th_o, A, B, ngeo, keep = args
     np.seterr(all="ignore")
     from oracle import kgeo_oracle as ko
     tau, sig, (t, r, th, ph) = ko.raytrace(a, [0, r_o, th_o, 0], [A, B], ngeo, MAXTAUFRAC)
+    if keep:
+        return dict(tau=tau, t=t, r=r, th=th, ph=ph)
     return float(np.nansum(r[1]))
 
 
-def cpu_sample(npix_per_worker, workers):
-    """A strided (class-representative) subset of the cfg-3 pixel grid, split into one chunk per worker."""
-    A, B = workload_pixels(0, 1)
-    n = npix_per_worker * workers
-    stride = max(1, A.size // n)
-    idx = np.arange(0, A.size, stride)[:n]
+def sample_indices(npix, n):
+    """n distinct pixels spread over the whole plane (257 is coprime to the power-of-two pixel counts: every column and
+    row of the image is visited, unlike a power-of-two stride, which would walk down four columns only)."""
+    return (np.arange(n, dtype=np.int64) * 257) % npix
+
+
+def cpu_sample(npix_per_worker, workers, world=1, keep=False):
+    x, y = plane_pixels(world)
+    A, B = [v.flatten() for v in np.meshgrid(x, y)]
+    idx = sample_indices(A.size, npix_per_worker * workers)
     th_o = INC_DEG * np.pi / 180
-    return [(SPIN, R_O, th_o, A[idx[w::workers]], B[idx[w::workers]], NGEO) for w in range(workers)]
+    return idx, A, B, [(SPIN, R_O, th_o, A[idx[w::workers]], B[idx[w::workers]], NGEO, keep) for w in range(workers)]
 
 
-def time_cpu(npix_per_worker, workers, steps, warmup):
-    chunks = cpu_sample(npix_per_worker, workers)
+def time_cpu(npix_per_worker, workers, steps, warmup, world=1, keep=False):
+    idx, A, B, chunks = cpu_sample(npix_per_worker, workers, world, keep)
     npts = sum(c[3].size for c in chunks) * NGEO
     if workers == 1:
         run = lambda: [_cpu_chunk(c) for c in chunks]
@@ -94,32 +147,35 @@ def time_cpu(npix_per_worker, workers, steps, warmup):
             run()
         t0 = time.perf_counter()
         for _ in range(steps):
-            run()
+            res = run()
         dt = (time.perf_counter() - t0) / steps
     finally:
         if pool is not None:
             pool.close()
             pool.join()
-    return npts / dt, dt, npts
+    return npts / dt, dt, npts, idx, res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     per_worker = 512           # 512 px x 500 samples = 2.6e5 points per worker per step (~2-3 s of SciPy)
-    value, dt, npts = time_cpu(per_worker, workers, args.steps, args.warmup)
-    sample = "%d pixels (strided subset of the 1024x1024 cfg-3 grid) x %d samples per step, %d processes" % (
-        per_worker * workers, NGEO, workers)
+    value, dt, npts, _, _ = time_cpu(per_worker, workers, args.steps, args.warmup, world)
+    rows, cols = grid_shape(world)
+    sample = "%d pixels (spread over the %dx%d grid) x %d samples per step, %d processes" % (
+        per_worker * workers, rows, cols, NGEO, workers)
     line = {
         "impl": "reference", "metric": "fp64 geodesic points/sec (raytrace_ana)", "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE cfg 3 geodesic tracks: a=0.94, theta_o=17deg, r_o=1000, 1024x1024 px x 500 samples",
+        "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(world),
                    "note": "reference algorithm (oracle port of kgeo's SciPy path; the Python reference itself cannot "
-                           "travel to the GPU box) on the host cores"},
+                           "travel to the GPU box) on the host cores, geodesic tracks of a bounded pixel sample"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -128,7 +184,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# clocks sampler
+# clocks sampler, affinity
 # ---------------------------------------------------------------------------------------------------------------------
 def local_cpu_affinity(gpu_index):
     """Bind this process to the CPUs nvidia-smi reports as local to the GPU, so that the pinned result buffers of the e2e
@@ -198,7 +254,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import kgeo_b200                                   # fails loudly if libkgeo_b200.so is missing
-    from kgeo_b200 import _engine, _lib
+    from kgeo_b200 import _engine, _lib, sharding
+    from kgeo_b200 import equatorial_images as ei
+    from kgeo_b200.models import pack_models
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,22 +269,45 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     th_o = INC_DEG * np.pi / 180
+    profile_only = bool(os.environ.get("KGEO_BENCH_PROFILE"))
+    rows, cols = grid_shape(world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        v = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
 
     A, B = workload_pixels(rank, world)
     npix = A.size
+    rows_local = npix // cols
     npts_rank = npix * NGEO
     mode, _ = _engine.setup_mode(SPIN, th_o, A, B, True)
     obs = _engine.observer_struct(SPIN, R_O, th_o)
     d_alpha, d_beta = _engine.to_device(A, dev), _engine.to_device(B, dev)
-    nw = L.kgeo_ray_workspace_slots()
     d_w = torch.empty((int(L.kgeo_ray_workspace_doubles(npix)),), dtype=torch.float64, device=dev)
     d_flags = torch.empty((npix,), dtype=torch.int32, device=dev)
     outs = [torch.empty((NGEO, npix), dtype=torch.float64, device=dev) for _ in range(4)]    # t, r, th, ph
     null = ctypes.cast(None, _lib.c_double_p)
     stream = _engine.stream_ptr()
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    setup_ms, track_ms = [], []
+    # image of the same pixels (N > 1: part of the step; N = 1: the secondary metric below uses its own 4096^2 plane)
+    with_image = world > 1
+    if with_image:
+        iobs = _engine.observer_struct(SPIN, float("inf"), th_o)
+        M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
+        iopts = _lib.ImageOpts(0, 2, 0, 0, float(ei.SPECIND), ei.DISKANGLE, ei.OBSFREQ)
+        img = torch.empty((IMG_PLANES, npix), dtype=torch.float64, device=dev)        # this rank's rows, plane-major
+        gathered = torch.empty((world, IMG_PLANES, npix), dtype=torch.float64, device=dev)
+        final = torch.empty((IMG_PLANES, rows * cols), dtype=torch.float64, device=dev) if rank == 0 else None
+        img_ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
     def step(timed=False):
         if timed:
@@ -240,20 +321,28 @@ def run_ours(args):
                                  _engine.dptr(outs[3]), null, null, npix, stream))
         if timed:
             ev[2].record()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        if with_image:
+            _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
+                                               _engine.dptr(d_alpha), _engine.dptr(d_beta), *img_ptrs, null, null, stream))
+            if timed:
+                ev[3].record()
+            sharding.gather_interleaved_rows(img, gathered, final, rows_local, cols)
+            if timed:
+                ev[4].record()
 
     for _ in range(args.warmup):
         step()
-    # per-kernel durations (CUDA events on the launching stream), measured outside the headline region
+    # per-phase durations (CUDA events on the launching stream), measured outside the headline region
+    setup_ms, track_ms, image_ms, coll_ms = [], [], [], []
     for _ in range(3):
+        barrier()
         step(timed=True)
         torch.cuda.synchronize()
         setup_ms.append(ev[0].elapsed_time(ev[1]))
         track_ms.append(ev[1].elapsed_time(ev[2]))
+        if with_image:
+            image_ms.append(ev[2].elapsed_time(ev[3]))
+            coll_ms.append(ev[3].elapsed_time(ev[4]))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -267,74 +356,69 @@ def run_ours(args):
     t_stop.record()
     barrier()
     launches = _lib.launch_count() - launches0
-    ms = t_start.elapsed_time(t_stop)
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tms.item()) / args.steps
-    clocks = sampler.stop() if (rank == 0 and not os.environ.get("KGEO_BENCH_PROFILE")) else None
+    ms_per_step = allmax(t_start.elapsed_time(t_stop)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
     value = world * npts_rank / (ms_per_step * 1e-3)
+    phases = {"setup_ms": allmax(np.median(setup_ms)), "track_ms": allmax(np.median(track_ms))}
+    if with_image:
+        phases["image_ms"] = allmax(np.median(image_ms))
+        phases["collective_ms"] = allmax(np.median(coll_ms))
 
-    # sanity of the produced data (finite radii on the first samples of every ray)
-    chk = outs[1][1, ::997]
-    if not bool(torch.isfinite(chk).all()):
-        raise RuntimeError("bench: non-finite radii in the output")
-
-    if os.environ.get("KGEO_BENCH_PROFILE"):      # under ncu: kernels only, no e2e / CPU legs, no JSON claim
+    if profile_only:                                  # under ncu: kernels only, no e2e / CPU legs, no JSON claim
         if rank == 0:
-            sampler.stop()
-            emit({"profile_only": True, "ms_per_step": ms_per_step, "track_kernel_ms": float(np.median(track_ms))})
+            emit({"profile_only": True, "ms_per_step": ms_per_step, "track_kernel_ms": float(np.median(track_ms)),
+                  "setup_kernel_ms": float(np.median(setup_ms))})
         return
 
-    # ---- e2e through the host-buffer C ABI ----
-    e2e = None
-    pin_cpus = local_cpu_affinity(local)     # pinned result buffers on the GPU's own NUMA node (first touch)
-    try:
-        import psutil
-        avail = psutil.virtual_memory().available
-    except Exception:
-        avail = 0
-    need = 4 * 8 * npts_rank
-    rows = NPIX_SIDE
-    while need * 1.5 > avail and rows > 32:
-        rows //= 2
-        need = 4 * 8 * rows * NPIX_SIDE * NGEO
-    e_npix = rows * NPIX_SIDE
-    hA, hB = np.ascontiguousarray(A[:e_npix]), np.ascontiguousarray(B[:e_npix])
-    host = [torch.empty((NGEO, e_npix), dtype=torch.float64, pin_memory=True) for _ in range(4)]
-    hp = [ctypes.cast(h.data_ptr(), _lib.c_double_p) for h in host]
+    # sanity of the produced data (finite radii on the first samples of every ray)
+    if not bool(torch.isfinite(outs[1][1, ::997]).all()):
+        raise RuntimeError("bench: non-finite radii in the output")
 
-    def e2e_step():
-        _lib.check(L.kgeo_raytrace_host(ctypes.byref(obs), e_npix, _engine.hptr(hA), _engine.hptr(hB), mode, NGEO,
-                                        MAXTAUFRAC, hp[0], hp[1], hp[2], hp[3], null, null, local))
+    # ---- parity of the benched launch ----
+    parity, cpu_baseline = None, None
+    if world == 1:
+        # the oracle on PARITY_PIXELS cfg-3 pixels x 500 samples, 1 core: the timing is the cpu_baseline, the values the checker
+        from oracle import gates
+        cpu_value, cpu_dt, cpu_pts, idx, res = time_cpu(PARITY_PIXELS, 1, 1, 0, keep=True)
+        ref = res[0]
+        cpu_baseline = {"value": cpu_value, "unit": "points/s", "cores": 1, "kind": "port",
+                        "sample": "%d pixels (spread over the cfg-3 grid) x %d samples = %d points, %.1f s, oracle port of "
+                                  "the reference's SciPy path; host has %d cores" % (PARITY_PIXELS, NGEO, cpu_pts, cpu_dt,
+                                                                                     os.cpu_count() or 1)}
+        ix = torch.as_tensor(idx, device=dev)
+        got = {k: outs[i][:, ix].cpu().numpy() for i, k in enumerate(("t", "r", "th", "ph"))}
+        budget = gates.parity_budget(got, ref, ref["tau"], SPIN, R_O, th_o, A[idx], B[idx])
+        parity = {"against": "oracle/kgeo_oracle.py (pinned to the unmodified reference by tests/golden), same pixels, ngeo=500",
+                  "pixels": PARITY_PIXELS, "samples": budget["n_samples"], "n_pv_masked": budget["n_pv_masked"],
+                  "n_tail": budget["n_tail"], "n_axis": budget["n_axis"], "passes_gates": gates.budget_passes(budget)}
+        for k, c in budget["coords"].items():
+            parity[k] = {"max_rel": c["plain"]["max"], "p99.9": c["plain"]["p999"], "frac_gt_1e-10": c["plain"]["frac_gt_1e10"],
+                         "gated_max": c["gated"]["max"], "gated_frac_gt_1e-10": c["gated"]["frac_gt_1e10"],
+                         "pv_max": c["pv_max"], "tail_max": c["tail_max"], "nan_pattern_equal": c["nan_pattern_equal"]}
+        if not parity["passes_gates"]:
+            emit({"error": "parity gate broken on the benched workload", "parity": parity})
+            raise RuntimeError("bench: parity gate broken on the benched workload: %r" % parity)
+    else:
+        parity = {"shard_check": shard_check(world, rank, dev)}
 
-    e_steps = max(1, min(args.steps, 3))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e_dt = (time.perf_counter() - t0) / e_steps
-    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * e_npix * NGEO / float(te.item()), "unit": "points/s", "h2d_bytes_per_step": 16 * e_npix,
-           "d2h_bytes_per_step": 32 * e_npix * NGEO, "steps": e_steps, "ms_per_step": float(te.item()) * 1e3,
-           "pixels_per_rank": e_npix, "host_cpu_affinity": pin_cpus,
-           "note": "kgeo_raytrace_host: host alpha/beta -> setup + track kernels in 256 MiB sample slabs overlapped with "
-                   "D2H into pinned host r/theta/phi/t arrays; wall clock around the blocking C call"}
-    if not np.isfinite(host[1][1, ::997].numpy()).all():
-        raise RuntimeError("bench: non-finite radii in the e2e output")
+    # ---- free the resident tracks before the host-buffer legs (N = 2 holds 134 GB of them) ----
+    del outs
+    if with_image:
+        del gathered, final, img
+    torch.cuda.empty_cache()
+
+    e2e = e2e_legs(L, obs, mode, A, B, npix, cols, world, rank, local, dev, barrier, allmax)
+
+    sweep = cfg5_sweep(world, rank, dev, barrier, allmax) if world == 8 else None
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (track_kernel) ----
-    flops = ctypes.c_double()
-    pms = ctypes.c_float()
+    # ---- roofline of the dominant kernel (the track pass) ----
+    flops, pms = ctypes.c_double(), ctypes.c_float()
     peak_tf = None
     try:
         best = 0.0
@@ -350,56 +434,237 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    summ = ncu_summary()
+    trk = (summ or {}).get("track_pass", {})
+    fpp = trk.get("flop_per_point")
     tk = float(np.median(track_ms)) * 1e-3
-    ach_tf = EXECUTED_FLOP_PER_POINT * npts_rank / tk / 1e12
+    ach_tf = fpp * npts_rank / tk / 1e12 if fpp else None
     canon_tf = CANONICAL_FLOP_PER_POINT * npts_rank / tk / 1e12
     nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12
     roofline = {
-        "bound": "fp64", "kernel": "track_kernel<full, hot> + track_kernel<full, fix-up> (one track pass)",
+        "bound": "fp64", "kernel": "track_hot_kernel + track_kernel<full, fix-up> (one track pass)",
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": (ach_tf / peak_tf) if peak_tf else None,
-        "flop_per_point": EXECUTED_FLOP_PER_POINT,
-        "flop_source": "FP64 flops executed per point (ncu: hot kernel 224 DFMA + 113 DMUL + 35 DADD thread instructions, "
-                       "fix-up kernel 12 flop)",
-        "fp64_pipe_active_ncu": FP64_PIPE_ACTIVE_NCU,
+        "frac": (ach_tf / peak_tf) if (peak_tf and ach_tf) else None,
+        "flop_per_point": fpp,
+        "flop_source": ("executed FP64 flops per point, ncu thread-instruction counts (2 DFMA + DMUL + DADD) of the capture in "
+                        "profiles/r02_ncu_summary.json (git %s)" % summ.get("git_sha", "?")) if summ else
+                       "null: the kernel sources changed since the capture in profiles/r02_ncu_summary.json",
+        "fp64_pipe_active_ncu": trk.get("fp64_pipe_active_hot"),
+        "warp_instructions_per_32_points_ncu": trk.get("warp_inst_per_32_points_hot"),
         "canonical": {"flop_per_point": CANONICAL_FLOP_PER_POINT, "achieved": canon_tf,
                       "frac": (canon_tf / peak_tf) if peak_tf else None,
                       "note": "SURVEY 8(d) work model of the reference's algorithm (Carlson duplication per sample); this "
                               "kernel computes the same values with per-ray theta-function series, ~4x fewer flops"},
-        # dram__bytes_read.sum + dram__bytes_write.sum of one track pass on this workload, from the committed ncu --set full
-        # capture (profiles/r01_final4_ncu_full_subset.csv): hot 2.19 + 16.92 GB, fix-up 0.39 + 0.45 GB; algorithmic 16.78 GB
-        # of results + 1.62 GB of ray constants (2.16 GB workspace less the AGM ladders the hot pass does not stage)
-        "traffic": 19.95e9 if npix == NPIX_SIDE * NPIX_SIDE else None, "traffic_unit": "B/pass",
+        "traffic": trk.get("dram_bytes_per_pass") if (world == 1 and summ) else None, "traffic_unit": "B/pass",
         "peak_source": "DFMA-chain probe (kgeo_fp64_peak_probe) measured live on this GPU; MEASURED_PEAKS.json has no "
                        "FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s" % nominal_tf,
-        "points_per_launch": npts_rank, "kernel_ms": tk * 1e3,
-        "setup_kernel_ms": float(np.median(setup_ms)),
+        "points_per_launch": npts_rank, "kernel_ms": tk * 1e3, "setup_kernel_ms": float(np.median(setup_ms)),
         "hbm": {"achieved": BYTES_PER_POINT * npts_rank / tk / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": BYTES_PER_POINT * npts_rank / tk / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
     }
+    if world > 1 and ach_tf and peak_tf:
+        # all ranks run the same kernels on interleaved rows: aggregate = N x this rank's rate against N x the measured peak
+        step_tf = fpp * world * npts_rank / (ms_per_step * 1e-3) / 1e12
+        roofline["aggregate"] = {"achieved_track_pass": ach_tf * world, "achieved_whole_step": step_tf, "peak": peak_tf * world,
+                                 "frac_track_pass": ach_tf / peak_tf, "frac_whole_step": step_tf / (peak_tf * world),
+                                 "note": "whole step = setup + tracks + image + gather; north_star target >= 0.30"}
 
-    # ---- secondary: fused n=0..2 equatorial image (BASELINE cfg 2 models at 4096 x 4096), kernel only ----
-    secondary = None
+    secondary = image_secondary(L, ei, pack_models, th_o, dev, stream, peak_tf, summ) if world == 1 else sweep
+    if cpu_baseline is None:   # N > 1: a short 1-core run of the port on cfg-4 pixels
+        cpu_value, cpu_dt, cpu_pts, _, _ = time_cpu(1024, 1, 1, 0, world)
+        cpu_baseline = {"value": cpu_value, "unit": "points/s", "cores": 1, "kind": "port",
+                        "sample": "1024 pixels (spread over the cfg-4 grid) x 500 samples = %d points, %.1f s, oracle port of the "
+                                  "reference's SciPy path; host has %d cores" % (cpu_pts, cpu_dt, os.cpu_count() or 1)}
+
+    bytes_tracks = 32 * npts_rank
+    line = {
+        "metric": "fp64 geodesic points/sec (raytrace_ana)", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(world), "points_per_gpu_per_step": npts_rank,
+                   "outputs": "r,theta,phi,t fp64 [500, %d] = %.1f GB per GPU per step" % (npix, bytes_tracks / 1e9),
+                   "l2": "each step writes %.1f GB per GPU (>> 126 MB L2) and re-reads no output; no flush needed" % (bytes_tracks / 1e9),
+                   "parallelism": ("1 GPU" if world == 1 else "rows interleaved over %d ranks; no data-path collective in the "
+                                   "trace; final all_gather_into_tensor of the image planes (%.2f GB) + un-interleave on rank 0"
+                                   % (world, IMG_PLANES * 8 * rows * cols / 1e9))},
+        "phases": phases, "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "secondary": secondary,
+    }
+    if world > 1:
+        line["image_ms"] = phases["image_ms"]
+        line["collective_ms"] = phases["collective_ms"]
+        line["shard_check"] = parity["shard_check"]
+        line["efficiency_limiter"] = ("step = setup %.1f + tracks %.1f + image %.1f + gather %.1f ms (max over ranks); the image, "
+                                      "its gather and the per-ray setup add time but no geodesic points" %
+                                      (phases["setup_ms"], phases["track_ms"], phases["image_ms"], phases["collective_ms"]))
+        dist.barrier()
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def shard_check(world, rank, dev):
+    """N > 1: a 120 x 120 x 50 trace and a 250 x 250 polarized n = 0..2 image, sharded over the ranks, against the same
+    computed whole on rank 0: bit for bit (tests/dist_check.py's check, run here because the driver's 1-GPU test tier skips it)."""
+    import torch
+    import torch.distributed as dist
+    import kgeo_b200 as kg
+    from kgeo_b200 import sharding
+    a, th_o = 0.94, 17 * np.pi / 180
+    with contextlib.redirect_stdout(io.StringIO()):
+        kw = dict(emissivity=kg.Emissivity('ring'), velocity=kg.Velocity('general', fac_subkep=0.7, beta_phi=0.7, beta_r=0.7),
+                  bfield=kg.Bfield('bz_guess', C=1.), polarization=True, specind=1.)
+        res = sharding.make_image_sharded(a, np.inf, th_o, 2, -10., 10., -10., 10., 20. / 250, dst=0, **kw)
+        x = np.linspace(-8, 8, 120)
+        A, B = [v.flatten() for v in np.meshgrid(x, x)]
+        geos, (r0, r1) = sharding.raytrace_sharded(a, [0, 1000., th_o, 0], [A, B], 120, ngeo=50)
+        whole = kg.raytrace_ana(a, [0, 1000., th_o, 0], [A, B], ngeo=50, plotdata=False)
+        ok = all(np.array_equal(w[:, r0 * 120:r1 * 120], p, equal_nan=True) for w, p in zip(whole.geo_coords, geos.geo_coords))
+        if rank == 0:
+            single = kg.make_image(a, np.inf, th_o, 2, -10., 10., -10., 10., 20. / 250, **kw)
+            ok = ok and all(g.shape == w.shape and np.array_equal(g, w, equal_nan=True) for g, w in zip(res, single))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise RuntimeError("bench: sharded results differ from the whole-plane results")
+    return "ok"
+
+
+def cfg5_sweep(world, rank, dev, barrier, allmax):
+    """N = 8: BASELINE cfg 5, 64 (spin, inclination) configurations of 512 x 512 n = 0..2 images dealt round-robin to the ranks
+    (one fused launch per image) and gathered to rank 0; wall time of the whole sweep including the gather and the copy of the
+    planes to host memory on rank 0."""
+    import torch
+    from kgeo_b200 import sharding
+    spins = np.linspace(0.0, 0.99, 8)
+    incs = np.linspace(5.0, 85.0, 8) * np.pi / 180
+    cfgs = [(float(a), float(t)) for a in spins for t in incs]
+
+    def run():
+        with contextlib.redirect_stdout(io.StringIO()):
+            return sharding.make_image_sweep_sharded(cfgs, np.inf, 2, -10., 10., -10., 10., 20. / 512, dst=0)
+    run()
+    barrier()
+    t0 = time.perf_counter()
+    res = run()
+    torch.cuda.synchronize()
+    dt = allmax(time.perf_counter() - t0)
+    if rank == 0 and not all(np.isfinite(r[0][::4099, 0]).all() for r in res):
+        raise RuntimeError("bench: non-finite intensities in the cfg-5 sweep")
+    return {"metric": "BASELINE cfg 5 wall time: 64 (a, theta_o) configs x 512x512 px n=0..2 images over %d GPUs, gathered to rank 0 "
+                      "and copied to host" % world, "value": dt, "unit": "s", "pixels_per_s": 64 * 512 * 512 / dt,
+            "configs": len(cfgs)}
+
+
+def e2e_legs(L, obs, mode, A, B, npix, cols, world, rank, local, dev, barrier, allmax):
+    """End-to-end legs with HOST buffers: C ABI (kgeo_raytrace_host), Python drop-in (raytrace_ana(...).geo_coords), and the
+    box's D2H ceiling for the same bytes on all ranks at once.  On several GPUs each rank runs a bounded block of its rows
+    (at most the cfg-3 volume, 16.8 GB of results): the legs are host-link-bound, more rows only repeat the measurement."""
+    import torch
+    import kgeo_b200
+    from kgeo_b200 import _engine, _lib
+    null = ctypes.cast(None, _lib.c_double_p)
+    pin_cpus = local_cpu_affinity(local)     # pinned result buffers on the GPU's own NUMA node (first touch)
     try:
-        from kgeo_b200 import equatorial_images as ei
-        from kgeo_b200.models import pack_models
+        import psutil
+        avail = psutil.virtual_memory().available / max(1, world)
+    except Exception:
+        avail = 0
+    e_rows = min(npix // cols, (1024 * 1024) // cols)
+    while 4 * 8 * e_rows * cols * NGEO * 1.3 > avail and e_rows > 8:
+        e_rows //= 2
+    e_npix = e_rows * cols
+    hA, hB = np.ascontiguousarray(A[:e_npix]), np.ascontiguousarray(B[:e_npix])
+    host = [torch.empty((NGEO, e_npix), dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    hp = [ctypes.cast(h.data_ptr(), _lib.c_double_p) for h in host]
+    nbytes = 32 * e_npix * NGEO
+
+    def c_step():
+        _lib.check(L.kgeo_raytrace_host(ctypes.byref(obs), e_npix, _engine.hptr(hA), _engine.hptr(hB), mode, NGEO,
+                                        MAXTAUFRAC, hp[0], hp[1], hp[2], hp[3], null, null, local))
+
+    def timed(fn, steps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return allmax((time.perf_counter() - t0) / steps)
+
+    e_steps = 3
+    c_dt = timed(c_step, e_steps)
+    if not np.isfinite(host[1][1, ::997].numpy()).all():
+        raise RuntimeError("bench: non-finite radii in the e2e output")
+
+    # ceiling: the same bytes as bare pinned D2H copies (device slab -> the same pinned arrays), all ranks at once
+    slab = torch.empty((min(NGEO, 64), e_npix), dtype=torch.float64, device=dev)
+
+    def copy_step():
+        for h in host:
+            for k0 in range(0, NGEO, slab.shape[0]):
+                k1 = min(NGEO, k0 + slab.shape[0])
+                h[k0:k1].copy_(slab[:k1 - k0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ceil_dt = timed(copy_step, 2)
+    del slab
+    _lib.check(L.kgeo_trim_memory(local))
+
+    # Python drop-in: raytrace_ana(...).geo_coords (device-resident tracks, then one overlapped pass into pinned NumPy arrays;
+    # the pinned blocks of `host` go back to torch's caching host allocator and are reused by the result arrays)
+    del host, hp
+    th_o = INC_DEG * np.pi / 180
+
+    def py_step():
+        with contextlib.redirect_stdout(io.StringIO()):
+            g = kgeo_b200.raytrace_ana(SPIN, [0, R_O, th_o, 0], [hA, hB], ngeo=NGEO, plotdata=False)
+            t, r, th, ph = g.geo_coords
+        if not np.isfinite(r[1, ::997]).all():
+            raise RuntimeError("bench: non-finite radii in the Python e2e output")
+        del g, t, r, th, ph
+
+    py_dt = timed(py_step, 2)
+    torch.cuda.empty_cache()
+    return {"value": world * e_npix * NGEO / c_dt, "unit": "points/s", "h2d_bytes_per_step": 16 * e_npix,
+            "d2h_bytes_per_step": nbytes, "steps": e_steps, "ms_per_step": c_dt * 1e3, "pixels_per_rank": e_npix,
+            "host_cpu_affinity": pin_cpus, "d2h_gbs": world * nbytes / c_dt / 1e9,
+            "ceiling_gbs": world * nbytes / ceil_dt / 1e9,
+            "frac_of_ceiling": ceil_dt / c_dt,
+            "ceiling_note": "the same bytes as bare cudaMemcpyAsync D2H into the same pinned arrays on all %d rank(s) at once "
+                            "(64-sample slabs): what this box's host links carry; e2e / ceiling says how much of it the call "
+                            "reaches" % world,
+            "python": {"value": world * e_npix * NGEO / py_dt, "unit": "points/s", "ms_per_step": py_dt * 1e3,
+                       "frac_of_c_abi": c_dt / py_dt,
+                       "call": "kgeo_b200.raytrace_ana(a, observer, [alpha, beta], ngeo=500).geo_coords (NumPy arrays)"},
+            "note": "kgeo_raytrace_host: host alpha/beta -> setup + track kernels in 256 MiB sample slabs overlapped with "
+                    "D2H into pinned host r/theta/phi/t arrays; wall clock around the blocking C call, max over ranks"}
+
+
+def image_secondary(L, ei, pack_models, th_o, dev, stream, peak_tf, summ):
+    """N = 1: the fused n = 0..2 equatorial image kernel (BASELINE cfg 2 models at cfg 4 size): kernel-only rate with its
+    roofline, e2e through kgeo_equatorial_image_host with host buffers, and the oracle port's make_image at 256^2 beside it."""
+    import torch
+    from kgeo_b200 import _engine, _lib
+    null = ctypes.cast(None, _lib.c_double_p)
+    try:
         side = 4096
         x = np.linspace(-HALF_FOV, HALF_FOV, side)
         IA, IB = [np.ascontiguousarray(v.flatten()) for v in np.meshgrid(x, x)]
         npx = side * side
         dIA, dIB = _engine.to_device(IA, dev), _engine.to_device(IB, dev)
-        planes = [torch.empty((3, npx), dtype=torch.float64, device=dev) for _ in range(7)]
-        scal = [torch.empty((npx,), dtype=torch.float64, device=dev) for _ in range(3)]
+        img = torch.empty((IMG_PLANES, npx), dtype=torch.float64, device=dev)
+        ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
         iobs = _engine.observer_struct(SPIN, float("inf"), th_o)
         M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
         opts = _lib.ImageOpts(0, 2, 0, 0, float(ei.SPECIND), ei.DISKANGLE, ei.OBSFREQ)
 
         def run_img():
             _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(opts), npx, _engine.dptr(dIA),
-                                               _engine.dptr(dIB), *[_engine.dptr(p) for p in planes],
-                                               *[_engine.dptr(v) for v in scal], null, null, stream))
-        run_img()
+                                               _engine.dptr(dIB), *ptrs, null, null, stream))
+        for _ in range(3):
+            run_img()
         torch.cuda.synchronize()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         i0.record()
@@ -408,38 +673,51 @@ def run_ours(args):
         i1.record()
         torch.cuda.synchronize()
         img_ms = i0.elapsed_time(i1) / 5
-        if not bool(torch.isfinite(planes[0][0, ::9973]).all()):
+        if not bool(torch.isfinite(img[0, ::9973]).all()):
             raise RuntimeError("non-finite image")
-        secondary = {"metric": "equatorial image pixels/s (n=0..2, all orders fused)", "value": npx / (img_ms * 1e-3),
-                     "unit": "pixels/s", "workload": "4096x4096 px, a=0.94, theta_o=17deg, r_o=inf, bpl/zamo/rad (BASELINE cfg 2 "
-                     "models at cfg 4 size)", "ms": img_ms, "includes": "image_kernel only (outputs preallocated, resident)",
-                     "fp64_frac": 3000.0 * npx / (img_ms * 1e-3) / 1e12 / peak_tf if peak_tf else None,
-                     "hbm_gbs": 184.0 * npx / (img_ms * 1e-3) / 1e9}
-        del planes, scal, dIA, dIB
+        # e2e: host alpha/beta in, all 24 planes back into pinned host memory, through the C ABI
+        himg = torch.empty((IMG_PLANES, npx), dtype=torch.float64, pin_memory=True)
+        hp = [ctypes.cast(himg[3 * i:3 * i + 3].data_ptr(), _lib.c_double_p) for i in range(7)] + \
+             [ctypes.cast(himg[21 + i].data_ptr(), _lib.c_double_p) for i in range(3)]
+
+        def e2e_img():
+            _lib.check(L.kgeo_equatorial_image_host(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(opts), npx, _engine.hptr(IA),
+                                                    _engine.hptr(IB), *hp, null, null, torch.cuda.current_device()))
+        e2e_img()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_img()
+        e_dt = (time.perf_counter() - t0) / 3
+        same = bool(torch.equal(himg[0], img[0].cpu()))
+        # CPU: the oracle port's make_image at 256 x 256 (BASELINE cfg 2), 1 core
+        from oracle import kgeo_oracle as ko
+        np.seterr(all="ignore")
+        c0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ko.make_image(SPIN, np.inf, th_o, 2, -10., 10., -10., 10., 20. / 256, dict(type='bpl'), dict(type='zamo'),
+                          dict(type='rad'))
+        c_dt = time.perf_counter() - c0
+        isum = (summ or {}).get("image_kernel", {})
+        fpx = isum.get("flop_per_pixel")
+        ach = fpx * npx / (img_ms * 1e-3) / 1e12 if fpx else None
+        return {"metric": "equatorial image pixels/s (n=0..2, all orders fused)", "value": npx / (img_ms * 1e-3),
+                "unit": "pixels/s", "workload": "4096x4096 px, a=0.94, theta_o=17deg, r_o=inf, bpl/zamo/rad (BASELINE cfg 2 "
+                "models at cfg 4 size)", "ms": img_ms, "includes": "image_kernel only (outputs preallocated, resident)",
+                "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": (ach / peak_tf) if (ach and peak_tf) else None, "flop_per_pixel": fpx,
+                             "flop_source": "executed FP64 flops per pixel (ncu, profiles/r02_ncu_summary.json)" if fpx else
+                                            "null: kernel sources changed since the capture",
+                             "fp64_pipe_active_ncu": isum.get("fp64_pipe_active"),
+                             "canonical_frac": CANONICAL_FLOP_PER_PIXEL * npx / (img_ms * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+                             "traffic": isum.get("dram_bytes_per_launch"), "algorithmic_bytes": (16 + 8 * IMG_PLANES) * npx,
+                             "hbm_gbs": (16 + 8 * IMG_PLANES) * npx / (img_ms * 1e-3) / 1e9},
+                "e2e": {"value": npx / e_dt, "unit": "pixels/s", "ms": e_dt * 1e3, "h2d_bytes_per_step": 16 * npx,
+                        "d2h_bytes_per_step": 8 * IMG_PLANES * npx, "matches_device_path": same,
+                        "call": "kgeo_equatorial_image_host (host alpha/beta in, 24 planes into pinned host memory)"},
+                "cpu_baseline": {"value": 65536 / c_dt, "unit": "pixels/s", "cores": 1, "kind": "port",
+                                 "sample": "oracle port of make_image, 256 x 256 px, n = 0..2 (BASELINE cfg 2), %.2f s" % c_dt}}
     except Exception as exc:                                       # the headline metric must still be reported
-        secondary = {"error": repr(exc)}
-
-    # ---- CPU baseline on this box's host cores (bounded sample, 1 core: the reference as shipped is single-threaded) ----
-    cpu_value, cpu_dt, cpu_pts = time_cpu(4096, 1, 1, 0)
-    cpu_baseline = {"value": cpu_value, "unit": "points/s", "cores": 1, "kind": "port",
-                    "sample": "4096 pixels (strided subset of the cfg-3 grid) x 500 samples = %d points, %.1f s, "
-                              "oracle port of the reference's SciPy path; host has %d cores" % (cpu_pts, cpu_dt, os.cpu_count() or 1)}
-
-    line = {
-        "metric": "fp64 geodesic points/sec (raytrace_ana)", "value": value, "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE cfg 3 geodesic tracks: a=0.94, theta_o=17deg, r_o=1000, +-10M, 1024x1024 px x 500 "
-                               "Mino-time samples -> r,theta,phi,t (per GPU; N GPUs trace a (1024N)x1024 plane by rows)",
-                   "points_per_gpu_per_step": npts_rank, "outputs": "r,theta,phi,t fp64 [500, 1048576] = 16.8 GB per step",
-                   "l2": "each step writes 16.8 GB (>> 126 MB L2) and re-reads no output; no flush needed",
-                   "parallelism": "rows interleaved over %d rank(s), no collective" % world},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "secondary": secondary,
-    }
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        return {"error": repr(exc)}
 
 
 _JSON_FD = None

@@ -161,7 +161,11 @@ int kgeo_mino_total(const kgeo_observer* obs, size_t n, const double* roots_dev,
  * reference's (ngeo, npix) arrays when ld == npix; any output pointer may be NULL (not materialised).
  *  tau_dev == NULL : samples are numpy.linspace(0, maxtaufrac*tau_tot, ntau) per ray (raytrace_ana :93-94);
  *  tau_dev != NULL : [ntau, tau_ld] user Mino times (coords_at_tau).
- *  full == 0       : only r and theta are computed (do_phi_and_t=False), t/phi/sigma outputs are zero-filled. */
+ *  full == 0       : only r and theta are computed (do_phi_and_t=False), t/phi/sigma outputs are zero-filled;
+ *  full == 1       : all coordinates; with tau_dev == NULL two launches (theta-function-only hot pass over the four-ray groups
+ *                    whose rays all qualify, complete code for the other groups);
+ *  full == 2       : all coordinates, every ray through the complete per-point code in one launch (A/B reference: r and theta
+ *                    are bit-identical to full == 1, phi / t / sigma agree to the last bits). */
 int kgeo_tracks(const kgeo_observer* obs, size_t npix, const double* w_dev, const int32_t* flags_dev, size_t ntau,
                 double maxtaufrac, const double* tau_dev, size_t tau_ld, int full, double* t_dev, double* r_dev,
                 double* th_dev, double* ph_dev, double* sig_dev, double* tau_out_dev, size_t ld, void* stream);

@@ -141,7 +141,8 @@ class RayBundle(object):
         return self.slot(2)       # slot S_TAUTOT
 
     def tracks(self, ntau=None, maxtaufrac=1.0, tau=None, full=True, want=("t", "r", "th", "ph", "sig", "tau")):
-        """Launch the track kernel.  tau: None (linspace samples) or a [ntau, npix] device tensor.
+        """Launch the track kernel.  tau: None (linspace samples) or a [ntau, npix] device tensor.  full: False = r, theta
+        only; True = all coordinates (hot + fix-up launches); 2 = all coordinates through the one-pass complete kernel.
         Returns a dict name -> [ntau, npix] float64 CUDA tensor for the names in `want`."""
         L = _lib.lib()
         t = torch()
@@ -153,7 +154,7 @@ class RayBundle(object):
             for name in ("t", "r", "th", "ph", "sig", "tau"):
                 out[name] = empty((ntau, self.npix), self.dev) if name in want else None
             _lib.check(L.kgeo_tracks(ctypes.byref(self.obs), self.npix, dptr(self.w), iptr(self.flags), ntau,
-                                     float(maxtaufrac), dptr(tau), self.npix, int(bool(full)),
+                                     float(maxtaufrac), dptr(tau), self.npix, (2 if full == 2 else int(bool(full))),
                                      dptr(out["t"]), dptr(out["r"]), dptr(out["th"]), dptr(out["ph"]), dptr(out["sig"]),
                                      dptr(out["tau"]), self.npix, stream_ptr()))
         return {k: v for k, v in out.items() if v is not None}

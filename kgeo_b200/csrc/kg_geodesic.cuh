@@ -434,12 +434,12 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 // ---- theta blocks of a motion (setup) -------------------------------------------------------------------------------------
 // Builds base + NP Pi blocks at w[slot...]; returns true when the theta path is usable for every integral of the motion.
 template <class P>
-KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double pmax, P blk) {
+KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double pmax, double edge, P blk) {
     ThetaRay r = theta_ray(m);
     int J = theta_make_base(r, blk);
     bool ok = r.ok != 0;
     for (int i = 0; i < NP; ++i) {
-        int Ji = theta_make_pi(r, n[i], nmm ? nmm[i] : n[i] - m, omn ? omn[i] : 1.0 - n[i], pmax, blk + TB_SIZE + i * TP_SIZE);
+        int Ji = theta_make_pi(r, n[i], nmm ? nmm[i] : n[i] - m, omn ? omn[i] : 1.0 - n[i], pmax, edge, blk + TB_SIZE + i * TP_SIZE);
         if (Ji < 0) ok = false;
         else if (Ji > J) J = Ji;
     }
@@ -456,7 +456,7 @@ template <class WP>
 KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double n, double D3, WP w, int* flags) {
     const double Km = ellip_K(m);
     const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
-    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, kThetaPMaxPolar, w + T_TH);
+    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, kThetaPMaxPolar, kThetaEdgePolar, w + T_TH);
     const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
     const double mn = m / npr;
     w[T_TH_SLOPE] = D3 * sq1m * fma(1.0 - mn, A, mn);
@@ -468,7 +468,7 @@ KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, dou
 
 template <class WP>
 KG_HD void radial_theta_setup(double k, const double* n, WP w, int* flags) {
-    if (!theta_make_motion(3, k, n, nullptr, nullptr, kThetaPMax, w + R_TH)) return;
+    if (!theta_make_motion(3, k, n, nullptr, nullptr, kThetaPMax, kThetaEdge, w + R_TH)) return;
     *flags |= F_R_THETA;
     const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
                  k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
@@ -485,7 +485,17 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
 // AGM descent inline instead.
-template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
+// SYNC (setup kernels only; every thread of the CTA must be inside): the warps of a CTA re-converge at the stage boundaries.
+// Every warp walks this code once, front to back, so what decides its speed is instruction fetch; warps that drift apart
+// (data-dependent duplication loops) spread over the code and miss the instruction caches, warps that walk it together share
+// the fetched lines.
+template <bool SYNC>
+KG_HD void stage_sync() {
+#if defined(__CUDA_ARCH__)
+    if constexpr (SYNC) __syncthreads();
+#endif
+}
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*, bool SYNC = false>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     // Two-kernel setup (DEFER): the AGM ladders are only read by the Carlson fallback, so they are built where the theta path
@@ -493,9 +503,16 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
     // ray, and neither they nor the theta blocks are zero-filled first: 190 of the 257 slots, which the first version
     // wrote twice (ncu: 3.1 GB of DRAM writes for a 2.15 GB workspace).  Slots a ray does not use stay undefined.
     const bool defer_ladders = DEFER && !(mode & M_CARLSON_ONLY);
-    for (int i = 0; i < (LADDER ? NW : NW_LITE); ++i) {
-        if (DEFER && ((i >= T_LAD && i <= R_LAD_END) || (i >= T_TH && i <= R_TH_END))) continue;
-        w[i] = 0.0;
+    if constexpr (!LADDER) {
+        // register-resident workspace of the image / lensing kernels: static indices only (a rolled loop would index the array
+        // dynamically and put all of it in local memory)
+#pragma unroll
+        for (int i = 0; i < NW_LITE; ++i) w[i] = 0.0;
+    } else {
+        for (int i = 0; i < NW; ++i) {
+            if (DEFER && ((i >= T_LAD && i <= R_LAD_END) || (i >= T_TH && i <= R_TH_END))) continue;
+            w[i] = 0.0;
+        }
     }
     int flags = 0;
     double lam = -alpha * o.sth;
@@ -510,6 +527,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
 
     double up, um, ratio, a2um;
     angular_consts(o, lam, eta, &up, &um, &ratio, &a2um);
+    stage_sync<SYNC>();
 
     // ---------------- polar motion (kgeo/kerr_raytracing_ana.py:216-363) ----------------
     if (any_eta_pos && eta >= 0.0) {
@@ -601,7 +619,9 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
     }
 
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
+    stage_sync<SYNC>();
     Roots R = quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0);
+    stage_sync<SYNC>();
     flags |= (R.region << F_REGION_SHIFT);
     if (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) flags |= F_OUTSIDE;   // utils :817-824
     const double rp = o.rplus, rm = o.rminus, r_o = o.r_o;
@@ -783,6 +803,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
             tau_tot = 2.0 * Iro;
         }
     }
+    stage_sync<SYNC>();
     w[S_TAUTOT] = tau_tot;
     if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0) {
         if (DEFER) flags |= F_R_PENDING;            // k and the characteristics are in w[R_K], w[R_N0..2]
@@ -837,14 +858,14 @@ KG_HD double reduce_half_periods(double u, double K, double i2K, double* ur, dou
     return j;
 }
 
-// THETA_ONLY: the caller guarantees F_TH_THETA / F_R_THETA (hot track kernels: the Carlson fallback is compiled out, which
-// takes 30-60 registers off the kernel; rays without the flag are traced by the fix-up launch with the complete code)
-template <class W, bool THETA_ONLY = false>
+// (The hot track kernel does not come through here: kg_hot.cuh restates the theta branches below without the Carlson
+// fallback, which takes 30-60 registers off that kernel.)
+template <class W>
 KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, double* Gph, double* Gt) {
     *th = 0.0; *Gph = 0.0; *Gt = 0.0;
     if (!(flags & (F_TH_ORD | F_TH_VORT))) return;
     double snarg = fma(-w(T_W), tau, w(T_X0));
-    if (THETA_ONLY || (flags & F_TH_THETA)) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
+    if (flags & F_TH_THETA) {   // theta-function path (kg_theta.cuh): no duplication, no period bookkeeping
         const double sq1m_ = w(T_SQ), ua = snarg * w(T_ISQ);
         double L = 0.0;
         const ThetaOut t = full ? theta_eval_motion<W, 1, 0x2>(w, T_TH, ua, &L) : theta_eval_motion<W, 0, 0>(w, T_TH, ua, &L);
@@ -864,7 +885,6 @@ KG_HD void theta_eval(const W& w, int flags, double tau, bool full, double* th, 
         *Gt = fma(w(T_C3), snarg, 3.0 * w(T_C1) * Dtot) - w(T_GT0);
         return;
     }
-    if (THETA_ONLY) return;
     double sq1m = w(T_SQ);
     const double uarg = snarg * w(T_ISQ);
     const SnCnDn jt = jacobi_from_ladder(SlotView<W>{w, T_LAD}, uarg);
@@ -925,7 +945,7 @@ KG_HD void radial_legendre(const W& w, double X, double Kc, double sn, double cn
     }
 }
 
-template <class W, bool LADDER = true, bool THETA_ONLY = false>
+template <class W, bool LADDER = true>
 KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, bool full, double* r_s, double* Iph,
                        double* It, double* Isig) {
     double X = fma(-w(R_SC), tau, w(R_X0));
@@ -936,7 +956,7 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
     double E = 0.0, Pi[3] = {0.0, 0.0, 0.0};
     bool th_case2 = false;           // theta path of case 2: r(tau) and 1/den come out of the merged reciprocal below
     double rs2 = 0.0, iden2 = 0.0;
-    if (LADDER && (THETA_ONLY || (flags & F_R_THETA))) {   // theta-function path (kg_theta.cuh)
+    if (LADDER && (flags & F_R_THETA)) {   // theta-function path (kg_theta.cuh)
         double L[3] = {0.0, 0.0, 0.0};
         ThetaOut t;
         if (!full) t = theta_eval_motion<W, 0, 0>(w, R_TH, X, L);
@@ -971,7 +991,7 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
             for (int i = 0; i < 3; ++i)
                 Pi[i] = fma(w(R_TH + TB_SIZE + i * TP_SIZE + TP_A), X, w(R_TH + TB_SIZE + i * TP_SIZE + TP_P) * L[i]);
         }
-    } else if (!THETA_ONLY) {
+    } else {
         if (LADDER) {
             jr = jacobi_from_ladder(SlotView<W>{w, R_LAD}, X);
         } else {
@@ -1082,12 +1102,12 @@ KG_HD void radial_eval(const W& w, const Observer& o, int flags, double tau, boo
 }
 
 // one full point (kgeo/kerr_raytracing_ana.py:172-188)
-template <class W, bool THETA_ONLY = false>
+template <class W>
 KG_HD Point point_eval(const W& w, const Observer& o, int flags, double tau, bool full) {
     Point p;
     double Gph, Gt, Iph, It, Isig;
-    theta_eval<W, THETA_ONLY>(w, flags, tau, full, &p.th, &Gph, &Gt);
-    radial_eval<W, true, THETA_ONLY>(w, o, flags, tau, full, &p.r, &Iph, &It, &Isig);
+    theta_eval<W>(w, flags, tau, full, &p.th, &Gph, &Gt);
+    radial_eval<W, true>(w, o, flags, tau, full, &p.r, &Iph, &It, &Isig);
     p.sig = Isig + o.a2 * Gt;
     p.t = It + o.a2 * Gt;
     p.ph = Iph + w(S_LAM) * Gph;

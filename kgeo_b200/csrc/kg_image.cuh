@@ -379,7 +379,7 @@ KG_HD void bfield_lab(const kgeo_models& M, double a, double r, double* B1, doub
 }
 
 // drift-frame velocity of the image's B-field model (kgeo/velocities.py:487-623 with a numeric nu_parallel and no gammamax)
-KG_HD U4 u_driftframe(const kgeo_models& M, double a, double r, double nu_parallel) {
+KG_HD U4 u_driftframe_B(double a, double r, double nu_parallel, double B1, double B2, double B3, double omegaf) {
     const double a2 = a * a, r2 = r * r;
     const double cth = kCosHalfPi, cth2 = cth * cth;
     const double Delta = r2 - 2.0 * r + a2;
@@ -390,8 +390,6 @@ KG_HD U4 u_driftframe(const kgeo_models& M, double a, double r, double nu_parall
     const double g11 = Sigma / Delta, g22 = Sigma, g33 = Xi / Sigma;
     const double alpha = sqrt(Delta * Sigma / Xi);
     const double eta3 = 2.0 * a * r / sqrt(Delta * Sigma * Xi);
-    double B1, B2, B3, omegaf;
-    bfield_lab_omega(M, a, r, &B1, &B2, &B3, &omegaf);
     const double E1 = (omegaf - omegaz) * Xi * B2 / Sigma;
     const double E2 = -(omegaf - omegaz) * Xi * B1 / (Sigma * Delta);
     const double E3 = 0.0;
@@ -411,6 +409,52 @@ KG_HD U4 u_driftframe(const kgeo_models& M, double a, double r, double nu_parall
     const double vsq = g11 * v1 * v1 + g22 * v2 * v2 + g33 * v3 * v3;
     const double gamma = 1.0 / sqrt(1.0 - vsq);
     return U4{gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)};
+}
+
+KG_HD U4 u_driftframe(const kgeo_models& M, double a, double r, double nu_parallel) {
+    double B1, B2, B3, omegaf;
+    bfield_lab_omega(M, a, r, &B1, &B2, &B3, &omegaf);
+    return u_driftframe_B(a, r, nu_parallel, B1, B2, B3, omegaf);
+}
+
+// the closed-form velocity models (everything but the drift frame, which needs the B-field model)
+KG_HD U4 velocity_closed_form(const kgeo_models& M, double a, double r) {
+    const double* p = M.velocity_p;
+    switch (M.velocity_type) {
+        case KGEO_VEL_ZAMO: return u_zamo(a, r);
+        case KGEO_VEL_INFALL: return u_infall(a, r);
+        case KGEO_VEL_KEP: return u_kep(a, r, p[0] != 0.0);
+        case KGEO_VEL_SUBKEP: return u_subkep(a, r, p[0] != 0.0, p[1]);
+        case KGEO_VEL_GENERAL: return u_general(a, r, p[0] != 0.0, p[1], p[2], p[3]);
+        case KGEO_VEL_GELLES: return u_gelles(a, r, p[0], p[1]);
+        case KGEO_VEL_FROMFILE: return u_fromfile(M, a, r);
+        default: return u_simfit(a, r, p[0], p[1], p[2], p[3], p[4]);
+    }
+}
+
+// Velocity and lab-frame field of the models at one equatorial radius.  The image kernel walks this ONE copy of the model code
+// (once per crossing, twice for the thermal emissivity's normalisation radius) instead of inlining the model switches at each
+// of their five call sites: the kernel was 34 k instructions, and instruction fetch its top stall.
+struct FluidAt {
+    U4 u;
+    double B1, B2, B3, omega;
+};
+KG_HD FluidAt fluid_at(const kgeo_models& M, double a, double r, bool need_B) {
+    FluidAt f;
+    f.B1 = f.B2 = f.B3 = 0.0;
+    f.omega = kg_nan();
+    const bool drift = (M.velocity_type == KGEO_VEL_DRIFTFRAME);
+    if (need_B || drift) bfield_lab_omega(M, a, r, &f.B1, &f.B2, &f.B3, &f.omega);
+    f.u = drift ? u_driftframe_B(a, r, M.velocity_p[0], f.B1, f.B2, f.B3, f.omega) : velocity_closed_form(M, a, r);
+    return f;
+}
+// b^2 in the fluid frame from B^i and u^mu at the same radius (kgeo/bfields.py:330-396)
+KG_HD double bsq_of(const EqMetric& g, const FluidAt& f) {
+    const U4& u = f.u;
+    double l1 = g.g11 * u.u1, l2 = g.g22 * u.u2, l3 = g.g33 * u.u3 + g.g03 * u.u0;
+    double b0 = f.B1 * l1 + f.B2 * l2 + f.B3 * l3;
+    double b1 = (f.B1 + b0 * u.u1) / u.u0, b2 = (f.B2 + b0 * u.u2) / u.u0, b3 = (f.B3 + b0 * u.u3) / u.u0;
+    return b0 * (g.g00 * b0 + g.g03 * b3) + b1 * (g.g11 * b1) + b2 * (g.g22 * b2) + b3 * (g.g33 * b3 + g.g03 * b0);
 }
 
 KG_HD U4 velocity_u_lab(const kgeo_models& M, double a, double r) {   // velocities.py:70-96
@@ -526,7 +570,19 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
     double kr = ((!(flags & F_OUTSIDE)) || (Ir <= 0.5 * w(S_TAUTOT))) ? 1.0 : -1.0;        // :266-288
     double par = (mbar & 1) ? -1.0 : 1.0;
     double kth = o.north ? -par : par;                                                      // :290-305
-    U4 u = velocity_u_lab(M, a, r);
+    // the models at the crossing radius and, for the thermal emissivity's field normalisation (:221-223), at its radius R_b
+    // first: one rolled loop over one copy of the model code
+    const bool thermal = (M.emissivity_type == KGEO_EM_THERMAL);
+    const bool need_B = opt.polarization || thermal;
+    FluidAt fl_at;
+    double B0 = 1.0;
+#pragma unroll 1
+    for (int pass = thermal ? 1 : 0; pass >= 0; --pass) {
+        const double rr = pass ? M.emissivity_p[0] : r;
+        fl_at = fluid_at(M, a, rr, need_B);
+        if (pass) B0 = sqrt(bsq_of(eq_metric(a, rr), fl_at));
+    }
+    const U4 u = fl_at.u;
     EqMetric gm = eq_metric(a, r);
     double Delta = gm.Delta;
     double Rpot = sq(r2 + a2 - a * lam) - Delta * (eta + sq(lam - a));
@@ -543,8 +599,7 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
         double ex[4] = {l1 * u.u0 / Nr, -(l0 * u.u0 + l3 * u.u3) / Nr, 0.0, l1 * u.u3 / Nr};
         double ey[4] = {l2 * u.u0 / Nth, l2 * u.u1 / Nth, (1.0 + l2 * u.u2) / Nth, l2 * u.u3 / Nth};
         double ez[4] = {l3 / Nph, 0.0, 0.0, -l0 / Nph};
-        double B1, B2, B3;
-        bfield_lab(M, a, r, &B1, &B2, &B3);
+        const double B1 = fl_at.B1, B2 = fl_at.B2, B3 = fl_at.B3;
         double b0 = B1 * l1 + B2 * l2 + B3 * l3;
         double b1 = (B1 + b0 * u.u1) / u.u0, b2 = (B2 + b0 * u.u2) / u.u0, b3 = (B3 + b0 * u.u3) / u.u0;
         double bl[4] = {gm.g00 * b0 + gm.g03 * b3, gm.g11 * b1, gm.g22 * b2, gm.g33 * b3 + gm.g03 * b0};
@@ -581,15 +636,11 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
         s2chi = (2.0 * p1 * p2) / den;
     } else {
         sinthb = kHalfPi * 0.5;   // SINTHB = pi/4, equatorial_images.py:20,206
-        bsq = bfield_bsq(M, a, r, u);
+        bsq = thermal ? bsq_of(gm, fl_at) : 0.0;   // only the thermal emissivity reads the field strength
     }
     out.sinthb = sinthb;
     double Bmag = sqrt(bsq);
-    if (M.emissivity_type == KGEO_EM_THERMAL) {   // :221-223
-        double Rb = M.emissivity_p[0];
-        double B0 = sqrt(bfield_bsq(M, a, Rb, velocity_u_lab(M, a, Rb)));
-        Bmag = (Bmag / B0) * M.emissivity_p[3];
-    }
+    if (thermal) Bmag = (Bmag / B0) * M.emissivity_p[3];   // :221-223
     double je = emissivity_jrest(M, a, r, true, g, true, sinthb, Bmag, opt.nu_obs, opt.specind);
     double I;
     if (opt.pathlength) {   // calc_pathlength_equatorial :489-522

@@ -54,9 +54,16 @@ constexpr double kPio4 = 0.78539816339744830962;
 KG_NOINLINE double kg_log_cold(double x) { return log(x); }
 KG_NOINLINE double kg_acos_cold(double x) { return acos(x); }
 KG_NOINLINE double kg_atan2_cold(double y, double x) { return atan2(y, x); }
-KG_NOINLINE void kg_sincos_cold(double v, double* s, double* c) {
-    *s = sin(v);
-    *c = cos(v);
+// (returned by value: with pointer out-parameters the CALLER's sine and cosine had to live on the stack on the hot path too --
+// two 16-byte local stores and loads per sincos, four per point)
+struct SinCos {
+    double s, c;
+};
+KG_NOINLINE SinCos kg_sincos_cold(double v) {
+    SinCos r;
+    r.s = sin(v);
+    r.c = cos(v);
+    return r;
 }
 
 KG_HD int kg_hiint(double x) {
@@ -147,7 +154,9 @@ KG_HD double atanh_ratio(double X, double Y) {
 KG_HD void fsincos(double v, double* sv, double* cv) {
     // |v| < 2^19 (and not NaN / inf): compared on the exponent field (integer pipe instead of an FP64-pipe DSETP)
     if ((unsigned)(kg_hiint(v) & 0x7fffffff) >= 0x41200000u) {
-        kg_sincos_cold(v, sv, cv);
+        const SinCos r = kg_sincos_cold(v);
+        *sv = r.s;
+        *cv = r.c;
         return;
     }
     const double fn = rint(v * kTwoOverPi);

@@ -34,9 +34,13 @@ KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D
 // Rays outside these bounds keep the Carlson path (decided once per ray in the setup):
 //   nome: the series need J = 7 harmonics at q = 0.4 (kThJM = 8 are stored); beyond that the ray is within ~1e-3 of the
 //   critical curve, where the reference itself loses digits (looser gate next to the critical curve);
-//   prefactor P = sn a/(cn a dn a) of Pi = A u + P L: A = 1 + P Z(a) is formed with an absolute error ~ P eps (radial bound);
+//   prefactor P = sn a/(cn a dn a) of Pi = A u + P L: A = 1 + P Z(a) is formed with an absolute error ~ P eps (radial bound
+//   3000, and n no closer than 1e-6 to m or 1);
 //   for the polar motion (kind 2, L = arg theta3(v - i beta)) a ray that passes next to the rotation axis drives theta3 to
-//   within ~1/P of its zero, so L carries eps P and Pi eps P^2 there (measured 9e-11 at P = 780): polar bound 300.
+//   within ~1/P of its zero, so L carries eps P and Pi eps P^2 there (measured 9e-11 at P = 780) -- but ONLY there, within
+//   ~1/P of the pole, where the azimuth is a coordinate singularity and phi is gated on the arc length sin(theta) dphi
+//   (oracle/gates.py "axis": the arc-length error stays ~eps P).  Polar bound 4000 / edge 1e-8: the two pixel columns next to
+//   alpha = 0 of a 1024-wide image (2/3 of all fallback rays of BASELINE cfg 3 under the earlier bound of 300) take the hot pass.
 #ifndef KG_THETA_QMAX
 #define KG_THETA_QMAX 0.4
 #endif
@@ -44,9 +48,16 @@ KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D
 #define KG_THETA_PMAX 3000.0
 #endif
 #ifndef KG_THETA_PMAX_POLAR
-#define KG_THETA_PMAX_POLAR 300.0
+#define KG_THETA_PMAX_POLAR 4000.0
+#endif
+#ifndef KG_THETA_EDGE
+#define KG_THETA_EDGE 1.0e-6          // n within this (relative) distance of m or 1: no theta form (radial motion)
+#endif
+#ifndef KG_THETA_EDGE_POLAR
+#define KG_THETA_EDGE_POLAR 1.0e-8
 #endif
 constexpr double kThetaQMax = KG_THETA_QMAX, kThetaPMax = KG_THETA_PMAX, kThetaPMaxPolar = KG_THETA_PMAX_POLAR;
+constexpr double kThetaEdge = KG_THETA_EDGE, kThetaEdgePolar = KG_THETA_EDGE_POLAR;
 
 struct ThetaRay {
     double m, K, Kp, q, eokm1, eokm1p;   // eokm1p = E(m')/K' - 1
@@ -119,12 +130,11 @@ KG_HD int theta_make_base(const ThetaRay& r, P out) {
 // nmm = n - m and omn = 1 - n are passed separately so that callers who know them without cancellation (the polar motion:
 // n' - m = n (1 - m), 1 - n' = (1 - n)(1 - m)) keep full accuracy next to the edges n -> m, n -> 1.
 template <class WP>
-KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, double pmax, WP out) {
+KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, double pmax, double edge, WP out) {
     for (int i = 0; i < TP_SIZE; ++i) out[i] = 0.0;
     out[TP_A] = 1.0;
     if (!r.ok || !(n == n)) return -1;
     const double m = r.m, mp = 1.0 - m, q = r.q;
-    const double edge = 1.0e-6;
     if (n == 0.0) return 1;                                    // Pi = F = u
     if (fabs(nmm) < edge * m || fabs(omn) < edge) return -1;
     double sh, P, Zs;

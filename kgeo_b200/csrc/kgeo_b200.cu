@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const d
 #define KG_SETUP_THREADS 256
 #endif
 constexpr int SETUP_THREADS = KG_SETUP_THREADS;
+#ifndef KG_SETUP_SYNC
+#define KG_SETUP_SYNC 0
+#endif
 #ifndef KG_SETUP_MINBLOCKS
 #define KG_SETUP_MINBLOCKS 2          // CTAs per SM the two setup kernels are compiled for (register cap = 65536/(threads*n))
 #endif
@@ -148,10 +151,12 @@ template <bool PHI_T>
 __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                   const double* __restrict__ beta, int mode,
                                                                   double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
+    // threads beyond the last ray redo the last ray (identical values to identical addresses) so that the whole CTA can meet
+    // at the stage barriers of ray_setup<.., SYNC>
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
+    if (i >= npix) i = npix - 1;
     int fl;
-    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
+    ray_setup<PHI_T, true, true, WsPtr, KG_SETUP_SYNC != 0>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
     flags_out[i] = fl;
 }
 
@@ -254,12 +259,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) mino_total_kernel(Observer o, s
 constexpr int TRK_WARPS = KG_TRK_WARPS;             // warps per CTA
 constexpr int TRK_THREADS = 32 * TRK_WARPS;
 constexpr int TRK_RPW = 4;                          // rays per warp = doubles per 32-byte sector
-constexpr int TRK_XS = 1;                           // extra per-ray slot staged behind the workspace: flags
-constexpr int TRK_WSLOTS = NW + TRK_XS;
 #ifndef KG_TRK_PAD_SMEM
 #define KG_TRK_PAD_SMEM 0               // experiments only: unused shared memory that limits the CTAs per SM
 #endif
-constexpr size_t TRK_SMEM = (size_t)TRK_WSLOTS * TRK_RPW * sizeof(double) + KG_TRK_PAD_SMEM;
+constexpr size_t TRK_SMEM = (size_t)NW * TRK_RPW * sizeof(double) + KG_TRK_PAD_SMEM;
 
 struct SmemW {
     const double* p;   // &sw[0][j]: slot i of ray j of this warp (a broadcast load)
@@ -280,109 +283,90 @@ struct TrackOut {
 #endif
 constexpr int TRK_GROUPS = KG_TRK_GROUPS;           // 4-ray groups a CTA works through one after the other
 
-// Passes of a full (r, theta, phi, t) trace.  The Carlson-duplication fallback (0.3 % of the rays of BASELINE cfg 3) costs
-// every thread 50-60 registers whether it runs or not (ptxas wants 154 for the complete per-point code, 64-80 without the
-// fallback), so a full trace is two launches:
-//   P_HOT      theta-function code only, for the rays that are `hot` (F_TH_THETA and F_R_THETA): 64 registers, 32 warps / SM
-//   P_FIXUP    the complete code (theta or Carlson per motion) for the other rays; CTAs whose rays are all hot exit
-//              after reading their flags
-//   P_ALL      every ray through the complete code in one pass: do_phi_and_t = False, caller-supplied Mino times
-//              (coords_at_tau) and KGEO_B200_TRK_PASSES=fused
-// (A third variant -- polar and radial motion as separate passes of 61 / 79 registers that hand lam*G_phi, a^2 G_t over
-// through the output arrays -- was measured and is slower: 9.2 + 18.8 ms against 22.1 ms, profiles/r01_pass_variants.txt.)
-enum TrkPass { P_ALL = 0, P_HOT = 1, P_FIXUP = 2 };
-#ifndef KG_TRK_HOT_MINBLOCKS
-#define KG_TRK_HOT_MINBLOCKS 4
-#endif
-template <int PASS> struct TrkCfg { static constexpr int warps = TRK_WARPS, minblocks = KG_TRK_MINBLOCKS; };
-template <> struct TrkCfg<P_HOT> { static constexpr int warps = TRK_WARPS, minblocks = KG_TRK_HOT_MINBLOCKS; };
+// Passes of a full (r, theta, phi, t) trace.  The Carlson-duplication fallback (0.1 % of the rays of BASELINE cfg 3) costs
+// every thread 50-60 registers whether it runs or not (ptxas wants 154 for the complete per-point code, 64 without the
+// fallback), so a full trace is two launches over the same tiles:
+//   hot pass (track_hot_kernel)   rays that are `hot` (F_TH_THETA and F_R_THETA): theta-function code only, 64 registers,
+//                                 32 warps / SM
+//   P_FIXUP                       the other rays through the complete code, ONE RAY PER WARP STEP (lanes = 32 consecutive
+//                                 samples): fix-up rays are isolated, with lane = 4 * sample + ray three lanes of four idle
+//   P_ALL                         every ray through the complete code in one pass: do_phi_and_t = False, caller-supplied
+//                                 Mino times (coords_at_tau), full = 2 (the A/B reference of the tests)
+// Measured and dropped: splitting by four-ray GROUP instead (fix-up = every ray of a group with a fallback ray, so that both
+// passes write whole 32-byte sectors): the fix-up pass then drags three theta-path rays through the Carlson code's divergent
+// warps at 8 of 32 lanes -- 1.19 ms against 0.76 ms (profiles/r02_hot_variants.txt); polar and radial motion as separate
+// passes of 61 / 79 registers -- 9.2 + 18.8 ms against 22.1 ms (profiles/r01_pass_variants.txt).
+enum TrkPass { P_ALL = 0, P_FIXUP = 2 };
 
 __device__ __forceinline__ bool trk_hot(int fl) { return (fl & (F_TH_THETA | F_R_THETA)) == (F_TH_THETA | F_R_THETA); }
-// does this pass trace the ray with these flags?
-template <int PASS>
-__device__ __forceinline__ bool trk_mine(int fl) {
-    return PASS == P_ALL ? true : (PASS == P_FIXUP ? !trk_hot(fl) : trk_hot(fl));
+
+// The flags of a tile's 32 rays, one per lane (every warp of the CTA loads them: one coalesced load), and the ballots of the
+// rays inside the image and of the hot ones.  Uniform over the CTA.
+struct TileRays {
+    int flag;               // this lane's ray flag (lane = ray within the tile)
+    unsigned in, hot;       // ray masks
+};
+__device__ __forceinline__ TileRays tile_rays(const int32_t* __restrict__ flags_in, size_t npix, int lane, int ngroups) {
+    const size_t p = (size_t)blockIdx.x * (ngroups * TRK_RPW) + lane;
+    const bool inside = lane < ngroups * TRK_RPW && p < npix;
+    TileRays t;
+    t.flag = inside ? __ldg(flags_in + p) : 0;
+    t.in = __ballot_sync(0xffffffffu, inside);
+    t.hot = __ballot_sync(0xffffffffu, inside && trk_hot(t.flag));
+    return t;
 }
 
 template <bool FULL, int PASS, bool HAS_TAU>
-__global__ void __launch_bounds__(32 * TrkCfg<PASS>::warps, TrkCfg<PASS>::minblocks)
+__global__ void __launch_bounds__(TRK_THREADS, KG_TRK_MINBLOCKS)
 track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int32_t* __restrict__ flags_in, int ntau,
              double maxtaufrac, const double* __restrict__ tau_in, size_t tau_ld, TrackOut out, size_t ld, int k_begin,
              int k_end, int chunk) {
-    constexpr int WARPS = TrkCfg<PASS>::warps, THREADS = 32 * WARPS;
-    constexpr bool THETA_ONLY = (PASS == P_HOT);
+    constexpr int WARPS = TRK_WARPS, THREADS = 32 * WARPS;
     constexpr int KSTEP = WARPS * (32 / TRK_RPW);                        // samples one CTA-wide pass covers
-    extern __shared__ double sw[];                                      // [TRK_WSLOTS][4] constants of the current ray group
+    extern __shared__ double sw[];                                      // [NW][4] constants of the current ray group
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // lane = 4 * (sample of the warp's 8-sample block) + ray.  A 64-bit shared-memory load with 4 distinct addresses per half
-    // warp costs two wavefronts, with <= 2 per half warp one (research/ubench/lds_wavefronts.cu: 2.01 against 1.03 cycles per
-    // warp-wide load); the mapping that exploits this (KG_TRK_LANES_HALFWARP: rays (0,1) in lanes 0-15, (2,3) in 16-31,
-    // same full-sector stores) halves the constant-load wavefronts but measured 20.44 against 20.29 ms: the LSU data pipe
-    // (72 % busy) is not what the kernel waits for.
-#ifdef KG_TRK_LANES_HALFWARP
-    const int j = ((lane >> 4) << 1) | (lane & 1), ks = (lane >> 1) & 7;
-#else
+    // lane = 4 * (sample of the warp's 8-sample block) + ray.  (A 64-bit shared-memory load with 4 distinct addresses per half
+    // warp costs two wavefronts, with <= 2 one -- research/ubench/lds_wavefronts.cu -- but the mapping that exploits this was
+    // measured and did not pay: the LSU data pipe is not what the kernel waits for.)
     const int j = lane & (TRK_RPW - 1), ks = lane / TRK_RPW;
-#endif
-#ifndef KG_TRK_NO_OPAQUE
     // byte offset of this thread's ray column, passed through a shuffle: ptxas otherwise re-derives it from %tid (S2R, LOP3,
     // LEA: ~50 instructions per point) in front of the constant loads instead of keeping one register alive
     const unsigned joff = __shfl_sync(0xffffffffu, (unsigned)j * (unsigned)sizeof(double), lane);
-#else
-    const unsigned joff = (unsigned)j * (unsigned)sizeof(double);
-#endif
     // this CTA covers samples [k0, k1) of the ntau-sample track; output row = k - k_begin
     const int k0 = k_begin + blockIdx.y * chunk;
     const int k1 = min(k_end, k0 + chunk);
     const int kfirst = k0 + warp * (32 / TRK_RPW) + ks;
     const int klast = (ntau > 1) ? ntau - 1 : -1;                        // numpy.linspace: the last sample is `stop` exactly
-    // flags of the CTA's 32 rays: one coalesced load per warp, and a ballot of the rays this pass traces (every warp gets the
-    // same mask).  A CTA without such rays exits after this single load -- the fix-up pass is thousands of those.
     static_assert(TRK_GROUPS * TRK_RPW <= 32, "one flag per lane");
-    int tile_flag = 0;
-    unsigned mine_mask = 0xffffffffu;
-    if (PASS != P_ALL) {
-        const size_t p = (size_t)blockIdx.x * (TRK_GROUPS * TRK_RPW) + lane;
-        const bool inside = lane < TRK_GROUPS * TRK_RPW && p < npix;
-        tile_flag = inside ? __ldg(flags_in + p) : 0;
-        mine_mask = __ballot_sync(0xffffffffu, inside && trk_mine<PASS>(tile_flag));
-        if (mine_mask == 0) return;                                     // uniform over the CTA
-    }
-    // (Staging the next group's constants with cp.async into a second buffer while the current group is traced was
-    // measured: 20.25 against 19.99 ms -- with four CTAs per SM the other CTAs already cover the staging latency.)
+    const TileRays tr = tile_rays(flags_in, npix, lane, TRK_GROUPS);
+    const unsigned todo = (PASS == P_ALL) ? tr.in : (tr.in & ~tr.hot);  // rays of this pass
+    if (todo == 0) return;                                              // uniform over the CTA: the fix-up pass is thousands of those
     bool staged = false;
     for (int g = 0; g < TRK_GROUPS; ++g) {
+        const unsigned gm = (todo >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u);
+        if (gm == 0) continue;                                          // uniform over the CTA
         const size_t pix0 = ((size_t)blockIdx.x * TRK_GROUPS + g) * TRK_RPW;
-        if (pix0 >= npix) break;                                        // uniform over the CTA
         const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
-        int fl = 0;
-        if (PASS != P_ALL) {
-            fl = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + j);
-            if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // uniform over the CTA
-        }
+        const int fl = __shfl_sync(0xffffffffu, tr.flag, g * TRK_RPW + j);
         if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
         staged = true;
         // the group's block of the workspace is [slot][4] already: a contiguous copy (rays beyond npix are padding)
         const double* const gsrc = w_in + (pix0 / TRK_RPW) * (size_t)kGroupDoubles;
-        for (int i = threadIdx.x; i < (PASS == P_HOT ? NW_HOT : NW) * TRK_RPW; i += THREADS) sw[i] = gsrc[i];
-        if (PASS == P_ALL && threadIdx.x < TRK_RPW)
-            sw[NW * TRK_RPW + threadIdx.x] = (threadIdx.x < nvalid) ? (double)flags_in[pix0 + threadIdx.x] : 0.0;
+        for (int i = threadIdx.x; i < NW * TRK_RPW; i += THREADS) sw[i] = gsrc[i];
         __syncthreads();
         if (PASS == P_FIXUP) {
-            // Fix-up rays are isolated (1-3 of a group's 4 are typical), so lane = 4 ks + ray would leave most lanes idle (17 of
-            // 32 active, measured): here a warp takes ONE ray at a time and its lanes 32 consecutive samples.  The stores are
-            // then 8-byte pieces of 32 different rows -- partial sectors, but only for the 0.3 % of the rays traced here.
-            const unsigned gm = (mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u);
+            // a warp takes ONE ray at a time and its lanes 32 consecutive samples: the stores are 8-byte pieces of 32 different
+            // rows -- partial sectors, but only for the 0.1 % of the rays traced here
             for (int jr = 0; jr < nvalid; ++jr) {
                 if (!((gm >> jr) & 1u)) continue;                       // uniform over the CTA
-                const int flr = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + jr);
+                const int flr = __shfl_sync(0xffffffffu, tr.flag, g * TRK_RPW + jr);
                 const size_t pixr = pix0 + jr;
                 SmemW Wr{sw + jr};
                 const double stop = maxtaufrac * Wr(S_TAUTOT);
                 const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
                 for (int k = k0 + warp * 32 + lane; k < k1; k += WARPS * 32) {
                     const double tau = (k == klast) ? stop : (double)k * step;
-                    const Point p = point_eval<SmemW, false>(Wr, o, flr, tau, FULL);
+                    const Point p = point_eval<SmemW>(Wr, o, flr, tau, FULL);
                     const size_t q = (size_t)(k - k_begin) * ld + pixr;
                     if (out.r) __stcs(out.r + q, p.r);
                     if (out.th) __stcs(out.th + q, p.th);
@@ -397,8 +381,6 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
         if (j >= nvalid) continue;
         const size_t pix = pix0 + j;
         SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(sw) + joff)};
-        if (PASS == P_ALL) fl = (int)W(NW);
-        else if (!trk_mine<PASS>(fl)) continue;
         // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
         const double stop = maxtaufrac * W(S_TAUTOT);
         const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
@@ -408,7 +390,7 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
             double tau;
             if (HAS_TAU) tau = tau_in[(size_t)(k - k_begin) * tau_ld + pix];
             else tau = (k == klast) ? stop : (double)k * step;
-            const Point p = point_eval<SmemW, THETA_ONLY>(W, o, fl, tau, FULL);
+            const Point p = point_eval<SmemW>(W, o, fl, tau, FULL);
             if (out.r) __stcs(out.r + q, p.r);
             if (out.th) __stcs(out.th + q, p.th);
             if (out.t) __stcs(out.t + q, FULL ? p.t : 0.0);
@@ -421,11 +403,14 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
 
 // The hot pass of a full trace (rays with F_TH_THETA and F_R_THETA): the lane mapping of track_kernel (lane = 4 * sample + ray,
 // whole 32-byte sectors per store) with the theta-function-only code of kg_hot.cuh, and NO cooperative staging: the ray
-// constants of all HOT_GROUPS four-ray groups of the CTA are fetched by one elected thread with one 1-D TMA bulk copy
-// (cp.async.bulk, NW_HOT * 32 = 6 KB) per group, each signalling its own mbarrier; the warps wait on a group's barrier right
-// before they use it.  No __syncthreads in the sample loop, no staging instructions, no buffer reuse (8 groups x 6 KB = 48 KB
-// per CTA, four CTAs per SM); while group g is traced the copies of g+1.. are long complete.  (ncu of the staged version: 12 %
-// of all warp-stall samples sat on the staging loads, their stores and the two barriers per group.)
+// constants of a four-ray group are one contiguous block of the grouped workspace, fetched by ONE elected thread with ONE 1-D
+// TMA bulk copy (cp.async.bulk, NW_HOT * 32 B = 6 KB) into a ring of HOT_NBUF shared-memory buffers.  A `full` mbarrier per
+// buffer counts the bytes in; the warps wait on it right before they use the group; an `empty` mbarrier per buffer (one
+// arrival per warp) tells the elected thread when the buffer may be refilled, which it does two groups ahead.  No
+// __syncthreads, no staging loads / stores in the sample loop.  (ncu of the staged version: 12 % of all warp-stall samples sat
+// on the staging loads, their stores and the two barriers per group.  Holding all 8 groups of a CTA in shared memory instead
+// of a ring was measured and is slower, 20.1 against 19.3 ms: 4 x 48 KB leave the L1 too small for the kernel's register
+// spills, whose reloads then come from L2.)
 #ifndef KG_HOT_NS
 #define KG_HOT_NS 1                     // Mino-time samples per thread (2 was measured: 21.7 against 19.3 ms, it halves the warps)
 #endif
@@ -436,13 +421,16 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
 #define KG_HOT_MINBLOCKS 4
 #endif
 #ifndef KG_HOT_TMA
-#define KG_HOT_TMA 1                    // 0: cooperative staging with two barriers per group (the round-1 scheme), for A/B
+#define KG_HOT_TMA 0                    // 0: cooperative staging with two barriers per group (the round-1 scheme), for A/B
+#endif
+#ifndef KG_HOT_NBUF
+#define KG_HOT_NBUF 2                   // ring of group buffers the bulk copies land in
 #endif
 constexpr int HOT_NS = KG_HOT_NS, HOT_WARPS = KG_HOT_WARPS;
-constexpr int HOT_GROUPS = TRK_GROUPS;
+constexpr int HOT_GROUPS = TRK_GROUPS, HOT_NBUF = KG_HOT_NBUF;
 constexpr unsigned HOT_GROUP_BYTES = NW_HOT * TRK_RPW * sizeof(double);
 static_assert(HOT_GROUP_BYTES % 16 == 0 && (kGroupDoubles * sizeof(double)) % 16 == 0, "bulk copies move multiples of 16 bytes");
-constexpr size_t HOT_SMEM = KG_HOT_TMA ? (size_t)HOT_GROUPS * HOT_GROUP_BYTES + HOT_GROUPS * sizeof(unsigned long long)
+constexpr size_t HOT_SMEM = KG_HOT_TMA ? (size_t)HOT_NBUF * HOT_GROUP_BYTES + 2 * HOT_NBUF * sizeof(unsigned long long)
                                        : (size_t)HOT_GROUP_BYTES;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -457,6 +445,9 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
@@ -489,40 +480,64 @@ track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const
     const int kfirst = k0 + warp * (32 / TRK_RPW) + ks;
     const int klast = (ntau > 1) ? ntau - 1 : -1;                        // numpy.linspace: the last sample is `stop` exactly
     static_assert(HOT_GROUPS * TRK_RPW <= 32, "one flag per lane");
-    const size_t p = (size_t)blockIdx.x * (HOT_GROUPS * TRK_RPW) + lane;
-    const bool inside = lane < HOT_GROUPS * TRK_RPW && p < npix;
-    const int tile_flag = inside ? __ldg(flags_in + p) : 0;
-    const unsigned mine_mask = __ballot_sync(0xffffffffu, inside && trk_hot(tile_flag));
-    if (mine_mask == 0) return;                                         // uniform over the CTA
+    const TileRays tr = tile_rays(flags_in, npix, lane, HOT_GROUPS);
+    if (tr.hot == 0) return;                                            // uniform over the CTA
+    unsigned gmask = 0;                                                 // groups of this tile with hot rays
+#pragma unroll
+    for (int g = 0; g < HOT_GROUPS; ++g)
+        if ((tr.hot >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) gmask |= 1u << g;
     const double* const tile_src = w_in + (size_t)blockIdx.x * HOT_GROUPS * (size_t)kGroupDoubles;
 #if KG_HOT_TMA
-    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(hot_smem + (size_t)HOT_GROUPS * HOT_GROUP_BYTES);
+    unsigned long long* const full = reinterpret_cast<unsigned long long*>(hot_smem + (size_t)HOT_NBUF * HOT_GROUP_BYTES);
+    unsigned long long* const empty = full + HOT_NBUF;
+    // the n-th hot group of the tile (bit order of gmask) uses ring buffer n % HOT_NBUF
+    auto issue = [&](int g, int buf) {
+        mbar_expect_tx(full + buf, HOT_GROUP_BYTES);
+        bulk_copy_g2s(hot_smem + (size_t)buf * HOT_GROUP_BYTES, tile_src + (size_t)g * kGroupDoubles, HOT_GROUP_BYTES, full + buf);
+    };
+    unsigned pending = gmask;                 // groups not yet requested (only thread 0 uses it)
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int g = 0; g < HOT_GROUPS; ++g) mbar_init(bar + g, 1);
+        for (int b = 0; b < HOT_NBUF; ++b) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // inits visible to the async proxy
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int g = 0; g < HOT_GROUPS; ++g) {
-            if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // no hot ray: never waited for
-            mbar_expect_tx(bar + g, HOT_GROUP_BYTES);
-            bulk_copy_g2s(hot_smem + (size_t)g * HOT_GROUP_BYTES, tile_src + (size_t)g * kGroupDoubles, HOT_GROUP_BYTES, bar + g);
+        for (int b = 0; b < HOT_NBUF && pending; ++b) {
+            const int g = __ffs(pending) - 1;
+            pending &= pending - 1;
+            issue(g, b);
         }
     }
+    int nth = 0;                              // index of the current group among the tile's hot groups
 #else
     bool staged = false;
 #endif
     for (int g = 0; g < HOT_GROUPS; ++g) {
+        if (!((gmask >> g) & 1u)) continue;                             // uniform over the CTA
         const size_t pix0 = ((size_t)blockIdx.x * HOT_GROUPS + g) * TRK_RPW;
-        if (pix0 >= npix) break;                                        // uniform over the CTA
         const int nvalid = (npix - pix0 < (size_t)TRK_RPW) ? (int)(npix - pix0) : TRK_RPW;
-        const int fl = __shfl_sync(0xffffffffu, tile_flag, g * TRK_RPW + j);
-        if (((mine_mask >> (g * TRK_RPW)) & ((1u << TRK_RPW) - 1u)) == 0) continue;   // uniform over the CTA
+        const int fl = __shfl_sync(0xffffffffu, tr.flag, g * TRK_RPW + j);
 #if KG_HOT_TMA
-        mbar_wait(bar + g, 0);
-        const double* const gsw = sw + (size_t)g * (NW_HOT * TRK_RPW);
+        const int buf = nth % HOT_NBUF;
+        const unsigned round = (unsigned)(nth / HOT_NBUF);
+        constexpr int LAG = HOT_NBUF - 1;
+        if (nth >= LAG && threadIdx.x == 0 && pending) {
+            // refill the buffer of the group traced LAG groups ago (every warp arrives on its `empty` barrier when it is done
+            // with a group) with the next group not yet requested, i.e. the one after the current: it lands while the current
+            // group is traced.  With two buffers this warp waits here for the slowest warp of the previous group.
+            const int pbuf = (nth - LAG) % HOT_NBUF;
+            mbar_wait(empty + pbuf, (unsigned)((nth - LAG) / HOT_NBUF) & 1u);
+            const int gn = __ffs(pending) - 1;
+            pending &= pending - 1;
+            issue(gn, pbuf);
+        }
+        ++nth;
+        mbar_wait(full + buf, round & 1u);
+        const double* const gsw = sw + (size_t)buf * (NW_HOT * TRK_RPW);
 #else
         if (staged) __syncthreads();                                    // everyone is done with the previous group's constants
         staged = true;
@@ -530,7 +545,7 @@ track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const
         __syncthreads();
         const double* const gsw = sw;
 #endif
-        if (j >= nvalid || !trk_hot(fl)) continue;
+        if (j < nvalid && trk_hot(fl)) {
         const size_t pix = pix0 + j;
         SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(gsw) + joff)};
         // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
@@ -569,6 +584,11 @@ track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const
                 if (out.tau) __stcs(out.tau + qq, tau[s]);
             }
         }
+        }
+#if KG_HOT_TMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + buf);                        // this warp is done with the group's constants
+#endif
     }
 }
 
@@ -1232,7 +1252,7 @@ template <bool FULL, int PASS, bool HAS_TAU>
 static int launch_track_pass(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
                              int k_end, double maxtaufrac, const double* tau, size_t tau_ld, TrackOut out, size_t ld,
                              cudaStream_t stream) {
-    constexpr int WARPS = TrkCfg<PASS>::warps;
+    constexpr int WARPS = TRK_WARPS;
     // samples [k_begin, k_end) of an ntau-sample track; output (and tau) rows are indexed by (k - k_begin)
     const size_t tiles_ = (npix + TRK_RPW * TRK_GROUPS - 1) / (TRK_RPW * TRK_GROUPS);
     if (tiles_ > 0x7fffffffu) return fail_arg(KGEO_E_BADARG, "kgeo_tracks: too many rays in one launch");
@@ -1278,34 +1298,22 @@ static int launch_hot_pass(const Observer& o, size_t npix, const double* w, cons
     return 0;
 }
 
-// KGEO_B200_TRK_PASSES=oldhot (developer A/B switch): the round-1 hot pass (one sample per thread) instead of track_hot_kernel
-static bool track_old_hot_pass() {
-    static const bool v = [] {
-        const char* e = getenv("KGEO_B200_TRK_PASSES");
-        return e && !strcmp(e, "oldhot");
-    }();
-    return v;
-}
-
-// KGEO_B200_TRK_PASSES=fused (developer A/B switch, read once): trace every ray with the complete code in a single pass
-static bool track_single_pass() {
-    static const bool fused = [] {
-        const char* e = getenv("KGEO_B200_TRK_PASSES");
-        return e && !strcmp(e, "fused");
-    }();
-    return fused;
-}
-
 // (Forking the fix-up pass onto a side stream so that its few long-running CTAs overlap the hot pass was measured: 20.02
 // against 20.08 ms -- not worth a second stream inside the library.)
 #define TRK_ARGS o, npix, w, flags, ntau, k_begin, k_end, maxtaufrac, tau, tau_ld, out, ld, stream
+// full: 0 = r, theta only; 1 = all coordinates, hot + fix-up launches; 2 = all coordinates, every ray through the complete
+// code in one launch (the A/B reference of the tests; also KGEO_B200_TRK_PASSES=fused)
 static int launch_tracks(const Observer& o, size_t npix, const double* w, const int32_t* flags, size_t ntau, int k_begin,
                          int k_end, double maxtaufrac, const double* tau, size_t tau_ld, int full, TrackOut out, size_t ld,
                          cudaStream_t stream) {
+    static const bool fused_env = [] {
+        const char* e = getenv("KGEO_B200_TRK_PASSES");
+        return e && !strcmp(e, "fused");
+    }();
     if (tau) return full ? launch_track_pass<true, P_ALL, true>(TRK_ARGS) : launch_track_pass<false, P_ALL, true>(TRK_ARGS);
     if (!full) return launch_track_pass<false, P_ALL, false>(TRK_ARGS);
-    if (track_single_pass()) return launch_track_pass<true, P_ALL, false>(TRK_ARGS);
-    const int rc = track_old_hot_pass() ? launch_track_pass<true, P_HOT, false>(TRK_ARGS) : launch_hot_pass(TRK_ARGS);
+    if (full == 2 || fused_env) return launch_track_pass<true, P_ALL, false>(TRK_ARGS);
+    const int rc = launch_hot_pass(TRK_ARGS);
     if (rc) return rc;
     return launch_track_pass<true, P_FIXUP, false>(TRK_ARGS);
 }

@@ -2,7 +2,7 @@
 
 The per-pixel computation has no cross-pixel dependence, so there is NO data-path collective: every rank traces its own
 contiguous block of image rows.  The only communication is the final gather of the (small) image planes to one rank
-(NCCL over NVLink on GPUs, gloo in the CPU tests); geodesic tracks stay sharded on the devices that produced them
+(one NCCL all_gather_into_tensor over NVLink on GPUs -- gather_interleaved_rows -- gloo in the CPU tests); geodesic tracks stay sharded on the devices that produced them
 (1024^2 x 500 samples x 4 coordinates is 16.8 GB, 4096^2 is 268 GB -- they are consumed where they are).
 """
 import numpy as np
@@ -52,6 +52,21 @@ def shard_pixels(alpha, beta, ncols, rank, world):
     return alpha[r0 * ncols:r1 * ncols], beta[r0 * ncols:r1 * ncols], (r0, r1)
 
 
+def gather_interleaved_rows(local, gathered, final, rows_local, ncols, group=None):
+    """The final gather of a row-interleaved image (row % world == rank), without padding, Python loops or temporaries:
+    ONE all_gather_into_tensor of every rank's plane-major shard `local` [nplane, rows_local * ncols] into the preallocated
+    `gathered` [world, nplane, rows_local * ncols] (NCCL over NVLink), then -- on ranks that pass `final`
+    [nplane, rows_local * world * ncols] -- one strided device copy that puts local row lr of rank r at image row
+    lr * world + r.  Needs equal shards (nrows % world == 0); gather_rows handles the ragged case."""
+    import torch.distributed as dist
+    world = gathered.shape[0]
+    nplane = local.shape[0]
+    dist.all_gather_into_tensor(gathered.view(-1), local.reshape(-1), group=group)
+    if final is not None:
+        final.view(nplane, rows_local, world, ncols).copy_(gathered.view(world, nplane, rows_local, ncols).permute(1, 2, 0, 3))
+    return final
+
+
 def gather_rows(local, nrows, ncols, dst=0, group=None, interleave=False):
     """Gather row-sharded planes to rank `dst` (rows distributed as by row_indices).
 
@@ -65,6 +80,13 @@ def gather_rows(local, nrows, ncols, dst=0, group=None, interleave=False):
     rank = dist.get_rank(group)
     rows = [row_indices(nrows, r, world, interleave) for r in range(world)]
     lead = tuple(local.shape[:-1])
+    if interleave and nrows % world == 0 and local.is_contiguous():     # equal shards: one collective, one strided copy
+        rl = nrows // world
+        flat = local.reshape(-1, rl * ncols)
+        gathered = torch.empty((world,) + tuple(flat.shape), dtype=local.dtype, device=local.device)
+        final = torch.empty((flat.shape[0], nrows * ncols), dtype=local.dtype, device=local.device) if rank == dst else None
+        gather_interleaved_rows(flat, gathered, final, rl, ncols, group)
+        return final.reshape(lead + (nrows * ncols,)) if rank == dst else None
     maxrows = max(len(ix) for ix in rows)
     buf = torch.zeros(lead + (maxrows * ncols,), dtype=local.dtype, device=local.device)
     buf[..., :local.shape[-1]] = local

@@ -156,7 +156,7 @@ def test_theta_path_agrees_with_duplication_path_on_a_dense_grid(kg, monkeypatch
     with KGEO_B200_CARLSON_ONLY) over 512 x 512 rays x 40 samples of the BASELINE cfg 3 view and of an edge-on view: the
     two must agree to the parity gate on every sample that is not a removable singularity of the reference's formulas
     (see helpers.removable_singularity_mask), for all four coordinates."""
-    from helpers import removable_singularity_mask, track_errors, TRACK_RTOL, PV_RTOL
+    from helpers import axis_weight, removable_singularity_mask, track_errors, TRACK_RTOL, PV_RTOL
     for a, inc, half in ((0.94, 17.0, 10.0), (0.7, 80.0, 8.0)):
         th_o, r_o = inc * np.pi / 180, 1000.
         x = np.linspace(-half, half, 512)
@@ -170,45 +170,42 @@ def test_theta_path_agrees_with_duplication_path_on_a_dense_grid(kg, monkeypatch
         rplus = 1 + np.sqrt(1 - a * a)
         pv = removable_singularity_mask(a, r_o, th_o, A, B, g0.geo_coords[1])
         assert pv.mean() < 0.01
+        axw = axis_weight(g0.geo_coords[2])      # phi within 0.01 rad of the rotation axis: arc length (oracle/gates.py)
         for key, got, ref, floor in (('r', g1.geo_coords[1], g0.geo_coords[1], 1e-3), ('th', g1.geo_coords[2], g0.geo_coords[2], 1.0),
                                      ('ph', g1.geo_coords[3], g0.geo_coords[3], 1.0), ('t', g1.geo_coords[0], g0.geo_coords[0], r_o)):
+            wgt = axw if key == 'ph' else None
             if key in ('ph', 't'):
-                core, _ = track_errors(np.where(pv, got, ref), ref, g0.tausteps, g0.geo_coords[1], floor, rplus)
+                core, _ = track_errors(np.where(pv, got, ref), ref, g0.tausteps, g0.geo_coords[1], floor, rplus, wgt)
                 assert core <= PV_RTOL, "a=%g inc=%g %s on removable singularities: %.3e" % (a, inc, key, core)
                 got = np.where(pv, ref, got)
-            core, tail = track_errors(got, ref, g0.tausteps, g0.geo_coords[1], floor, rplus)
+            core, tail = track_errors(got, ref, g0.tausteps, g0.geo_coords[1], floor, rplus, wgt)
             assert core <= TRACK_RTOL, "a=%g inc=%g %s: theta vs duplication path %.3e" % (a, inc, key, core)
             assert tail <= 1e-2
 
 
-def test_two_launch_pass_equals_the_single_pass_kernel(kg, tmp_path):
-    """A full trace is a hot launch (theta-function code only) plus a fix-up launch (Carlson-fallback rays).  Against the one-pass
-    kernel with the complete per-point code (KGEO_B200_TRK_PASSES=fused, read once per process, hence the subprocess): every ray
-    is written exactly once (no NaN holes, no ray traced twice differently), r and theta are bit-identical, phi and t agree to the
-    last bits away from the horizon (ptxas contracts the final sums differently under the hot kernel's register cap)."""
-    import os
-    import subprocess
-    import sys
-    from helpers import track_errors
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    a, r_o, th_o, n, ngeo = 0.94, 1000., 17 * np.pi / 180, 203, 57      # 203^2 rays: not a multiple of the 32-ray tile
-    script = ("import sys, numpy as np; sys.path.insert(0, %r); import kgeo_b200 as kg; x = np.linspace(-9, 9, %d); "
-              "A, B = [v.flatten() for v in np.meshgrid(x, x)]; g = kg.raytrace_ana(%r, [0, %r, %r, 0], [A, B], ngeo=%d, plotdata=False); "
-              "np.savez(%r, t=g.geo_coords[0], r=g.geo_coords[1], th=g.geo_coords[2], ph=g.geo_coords[3], sig=g.affine_times, tau=g.mino_times)"
-              % (root, n, a, r_o, th_o, ngeo, str(tmp_path / "fused.npz")))
-    env = dict(os.environ, KGEO_B200_TRK_PASSES="fused")
-    subprocess.run([sys.executable, "-c", script], env=env, check=True, capture_output=True, timeout=300)
-    ref = np.load(str(tmp_path / "fused.npz"))
-    x = np.linspace(-9, 9, n)
+@pytest.mark.parametrize('n,ngeo,half', [(203, 57, 9.0), (512, 41, 10.0)])
+def test_two_launch_pass_equals_the_single_pass_kernel(kg, n, ngeo, half):
+    """A full trace is a hot launch (theta-function code only, groups of four rays that are all hot) plus a fix-up launch (the
+    other groups, complete code).  Against the one-pass kernel with the complete per-point code (full = 2): every ray is
+    written exactly once (no NaN holes, no ray traced twice differently), r and theta are bit-identical, phi and t agree to the
+    last bits away from the horizon (ptxas contracts the final sums differently under the hot kernel's register cap).
+    203^2 rays x 57 samples: not a multiple of the 32-ray tile / the 64-sample pass; 512^2 x 41: the dense BASELINE cfg 3 view."""
+    from kgeo_b200 import _engine
+    from helpers import axis_weight, track_errors
+    a, r_o, th_o = 0.94, 1000., 17 * np.pi / 180
+    x = np.linspace(-half, half, n)
     A, B = [v.flatten() for v in np.meshgrid(x, x)]
-    g = kg.raytrace_ana(a, [0, r_o, th_o, 0], [A, B], ngeo=ngeo, plotdata=False)
-    t, r, th, ph = g.geo_coords
-    assert np.array_equal(g.mino_times, ref['tau'])
-    assert np.array_equal(r, ref['r'], equal_nan=True) and np.array_equal(th, ref['th'], equal_nan=True)
+    bundle = _engine.RayBundle(a, r_o, th_o, A, B)
+    got = {k: v.cpu().numpy() for k, v in bundle.tracks(ntau=ngeo, maxtaufrac=1. - 1e-10, full=True).items()}
+    ref = {k: v.cpu().numpy() for k, v in bundle.tracks(ntau=ngeo, maxtaufrac=1. - 1e-10, full=2).items()}
+    assert np.array_equal(got['tau'], ref['tau'])
+    assert np.array_equal(got['r'], ref['r'], equal_nan=True) and np.array_equal(got['th'], ref['th'], equal_nan=True)
     rplus = 1 + np.sqrt(1 - a * a)
-    for key, got, floor in (('ph', ph, 1.0), ('t', t, r_o), ('sig', g.affine_times, r_o)):
-        assert np.array_equal(np.isnan(got), np.isnan(ref[key])), key
-        core, tail = track_errors(got, ref[key], g.mino_times, r, floor, rplus)
+    for key, floor in (('ph', 1.0), ('t', r_o), ('sig', r_o)):
+        assert np.array_equal(np.isnan(got[key]), np.isnan(ref[key])), key
+        # phi next to the rotation axis: last-bit differences of the two instantiations are amplified by 1 / sin(theta) there
+        # (a coordinate singularity; gated on the arc length like everywhere else, oracle/gates.py)
+        core, tail = track_errors(got[key], ref[key], ref['tau'], ref['r'], floor, rplus, axis_weight(ref['th']) if key == 'ph' else None)
         assert core <= 1e-11 and tail <= 1e-5, (key, core, tail)
 
 
