@@ -272,12 +272,19 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
  *   density of the jet model (field 0 = BZ monopole with its f(r) table of 2 x fr_n doubles, 1 = power law r^pval; r0 =
  *   stagnation radius, norm = source integral from r0 to infinity for the power law) and Iobs_off's polarized Stokes parameters
  *   with Emissivity('constant') in the drift frame of the field; NaN -> 0 as in getstokes.
+ *   Parallel boost of the drift frame (kgeo/velocities.py:474-516): nu_ff == 0: the number nu_parallel; nu_ff != 0:
+ *   nu_parallel = 'FF', the energy-conserving boost of getnu_cons, with the field-line constants (r0, omega, E - Omega_F L =
+ *   ff_boost.getEco) of Iobs_off's velocity in ff_global[3] (host) and those of the density's velocity, one triple per crossing
+ *   order, in ff_rows_dev[3 * nguess] (device).  gammamax > 0: Lorentz factor capped as in :593-611 (gamma_eff rescaled at the
+ *   crossing of smallest gamma_eff: a device-side argmin pre-pass).  *nu_out_of_range (host int, optional) is set when a boost
+ *   left [-1, 1], where the reference raises.  Blocks until done.
  * kgeo_jet_sort: geometry.sort_image: (neqmax + 1) x npix planes, plane k < neqmax = crossings of order k, last plane = all. */
 int kgeo_jet_stokes(const kgeo_observer* obs, size_t npix, size_t nguess, const double* alpha_dev, const double* beta_dev,
                     const double* r_dev, const double* th_dev, const double* signpr_dev, const double* signpth_dev, int field, double C,
-                    double pval, int usemono, const double* fr_table_dev, int64_t fr_n, double nu_parallel, double sigma, double r0,
-                    double norm, double psitarget, double specind, double* I_dev, double* Q_dev, double* U_dev, double* sinthb_dev,
-                    double* density_dev, void* stream);
+                    double pval, int usemono, const double* fr_table_dev, int64_t fr_n, double nu_parallel, int nu_ff,
+                    const double* ff_global, const double* ff_rows_dev, double gammamax, double sigma, double r0, double norm,
+                    double psitarget, double specind, double* I_dev, double* Q_dev, double* U_dev, double* sinthb_dev,
+                    double* density_dev, int32_t* nu_out_of_range, void* stream);
 int kgeo_jet_sort(size_t npix, size_t nguess, int neqmax, const double* I_dev, const double* Q_dev, const double* U_dev,
                   const double* neq_dev, double* out_I_dev, double* out_Q_dev, double* out_U_dev, void* stream);
 

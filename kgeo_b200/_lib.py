@@ -87,8 +87,9 @@ SIGNATURES = {
     "kgeo_fieldline_solve": (ctypes.c_int, [_OBS, _S, _S, _P, _P, c_int32_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, _P,
                                             ctypes.c_double, ctypes.c_int, _P, _P, _P, _P, _P, _P, c_int32_p, c_int32_p, _V]),
     "kgeo_jet_stokes": (ctypes.c_int, [_OBS, _S, _S, _P, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
-                                       _P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                       ctypes.c_double, ctypes.c_double, _P, _P, _P, _P, _P, _V]),
+                                       _P, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _P, _P, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P, _P, _P, _P, _P,
+                                       c_int32_p, _V]),
     "kgeo_jet_sort": (ctypes.c_int, [_S, _S, ctypes.c_int, _P, _P, _P, _P, _P, _P, _P, _V]),
     "kgeo_trim_memory": (ctypes.c_int, [ctypes.c_int]),
     "kgeo_fp64_peak_probe": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_float), _V]),

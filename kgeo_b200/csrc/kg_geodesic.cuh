@@ -485,17 +485,7 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
 // AGM descent inline instead.
-// SYNC (setup kernels only; every thread of the CTA must be inside): the warps of a CTA re-converge at the stage boundaries.
-// Every warp walks this code once, front to back, so what decides its speed is instruction fetch; warps that drift apart
-// (data-dependent duplication loops) spread over the code and miss the instruction caches, warps that walk it together share
-// the fetched lines.
-template <bool SYNC>
-KG_HD void stage_sync() {
-#if defined(__CUDA_ARCH__)
-    if constexpr (SYNC) __syncthreads();
-#endif
-}
-template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*, bool SYNC = false>
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     // Two-kernel setup (DEFER): the AGM ladders are only read by the Carlson fallback, so they are built where the theta path
@@ -527,7 +517,6 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
 
     double up, um, ratio, a2um;
     angular_consts(o, lam, eta, &up, &um, &ratio, &a2um);
-    stage_sync<SYNC>();
 
     // ---------------- polar motion (kgeo/kerr_raytracing_ana.py:216-363) ----------------
     if (any_eta_pos && eta >= 0.0) {
@@ -619,9 +608,7 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
     }
 
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
-    stage_sync<SYNC>();
     Roots R = quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0);
-    stage_sync<SYNC>();
     flags |= (R.region << F_REGION_SHIFT);
     if (!R.c34 && R.re[3] > o.rplus && !(eta < 0.0)) flags |= F_OUTSIDE;   // utils :817-824
     const double rp = o.rplus, rm = o.rminus, r_o = o.r_o;
@@ -803,7 +790,6 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
             tau_tot = 2.0 * Iro;
         }
     }
-    stage_sync<SYNC>();
     w[S_TAUTOT] = tau_tot;
     if (PHI_T && LADDER && !(mode & M_CARLSON_ONLY) && th_k > 0.0) {
         if (DEFER) flags |= F_R_PENDING;            // k and the characteristics are in w[R_K], w[R_N0..2]

@@ -86,8 +86,22 @@ KG_HD void jet_field(const JetSpec& J, double a, double r, double th, double* B1
     *omega = Om;
 }
 
-// drift-frame four-velocity at (r, theta) (kgeo/velocities.py:487-623, numeric nu_parallel, no gammamax)
-KG_HD U4 jet_driftframe(const JetSpec& J, double a, double r, double th, double nu_parallel) {
+// How u_driftframe picks its parallel boost and caps the Lorentz factor (kgeo/velocities.py:491-516,593-611)
+struct JetBoost {
+    int ff;                     // 1: nu_parallel = 'FF', the energy-conserving boost of getnu_cons (:474-486)
+    double nu;                  // numeric nu_parallel (ff == 0)
+    double r0, omega, Aconst;   // FF: stagnation radius, angular speed and E - Omega_F L (ff_boost.getEco) of the field line
+    double gammamax, gscale;    // gammamax > 0: gamma_eff = (gammamax^-2 + gamma^-2)^(-1/2) * gscale (gscale = gamma / gamma_eff at
+                                // the element of smallest gamma_eff: "ensure gamma > 1 always")
+};
+KG_HD JetBoost jet_boost_numeric(double nu) { return JetBoost{0, nu, 0.0, 0.0, 0.0, 0.0, 1.0}; }
+struct DriftOut {
+    U4 u;
+    double nu, gamma, gammaeff;   // the boost used, the force-free Lorentz factor and (gammamax > 0) the capped one before scaling
+};
+
+// drift-frame four-velocity at (r, theta) (kgeo/velocities.py:487-623)
+KG_HD DriftOut jet_driftframe_boost(const JetSpec& J, double a, double r, double th, const JetBoost& b) {
     const double a2 = a * a, r2 = r * r;
     const double sth = sin(th), cth = cos(th), sth2 = sth * sth, cth2 = cth * cth;
     const double Delta = r2 - 2.0 * r + a2, Sigma = r2 + a2 * cth2;
@@ -109,31 +123,61 @@ KG_HD U4 jet_driftframe(const JetSpec& J, double a, double r, double th, double 
     const double vperp2 = pre * (-B3c * E1c);
     const double vperp3 = pre * (E1c * B2c - B1c * E2c);
     const double vpar_max = sqrt(1.0 - Esq / Bsq), sB = sqrt(Bsq);
-    const double v1 = vperp1 + nu_parallel * vpar_max * B1 / sB;
-    const double v2 = vperp2 + nu_parallel * vpar_max * B2 / sB;
-    const double v3 = vperp3 + nu_parallel * vpar_max * B3 / sB;
+    DriftOut out;
+    double nu = b.nu;
+    if (b.ff) {   // getnu_cons: the boost that conserves E - Omega_F L along the field line, from the nu = 0 frame's quantities
+        const KerrMetric gm = kerr_metric(a, r, th);
+        const double gfac = gm.g03 + gm.g33 * b.omega;
+        const double gammap = 1.0 / vpar_max, Bhatphi = B3 / sB;
+        const double ffunc = gammap * (alpha - gfac * vperp3);
+        const double bred = Bhatphi * gfac;
+        const double A = b.Aconst;
+        const double nunum = ffunc * bred + sgn0(cos(th)) * sgn0(r - b.r0) * A * sqrt(A * A - ffunc * ffunc + bred * bred);
+        nu = nunum / (A * A + bred * bred);
+    }
+    out.nu = nu;
+    double v1 = vperp1 + nu * vpar_max * B1 / sB;
+    double v2 = vperp2 + nu * vpar_max * B2 / sB;
+    double v3 = vperp3 + nu * vpar_max * B3 / sB;
     const double vsq = g11 * v1 * v1 + g22 * v2 * v2 + g33 * v3 * v3;
-    const double gamma = 1.0 / sqrt(1.0 - vsq);
-    return U4{gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)};
+    double gamma = 1.0 / sqrt(1.0 - vsq);
+    out.gamma = gamma;
+    out.gammaeff = gamma;
+    if (b.gammamax > 0.0) {   // approximate MHD gamma: gamma_FF and gamma_max summed "in series" (:593-611, eps < 0 branch)
+        const double gammaeff = pow(1.0 / (b.gammamax * b.gammamax) + 1.0 / (gamma * gamma), -0.5);
+        out.gammaeff = gammaeff;
+        const double gammaeff0 = gammaeff * b.gscale;
+        const double vsqeff = 1.0 - 1.0 / (gammaeff0 * gammaeff0);
+        const double sc = sqrt(vsqeff / vsq);
+        v1 *= sc; v2 *= sc; v3 *= sc;
+        gamma = gammaeff0;
+    }
+    out.u = U4{gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)};
+    return out;
+}
+KG_HD U4 jet_driftframe(const JetSpec& J, double a, double r, double th, double nu_parallel) {
+    return jet_driftframe_boost(J, a, r, th, jet_boost_numeric(nu_parallel)).u;
 }
 
 struct StokesOut {
-    double I, Q, U, sinthb, g;
+    double I, Q, U, sinthb, g, nu;
 };
 
 // One crossing of Iobs_off as getstokes calls it (kgeo/off_eq.py:15-121: Emissivity('constant'), polarization=True):
 // redshift (equatorial_images.py:307-334), tetrad + fluid-frame field + path length + Penrose-Walker kappa (:336-487), EVPA
 // (:524-544), I = g^(3+specind) l_p density b^(1+specind) sin^(1+specind) theta_b, zero inside the horizon
 KG_HD StokesOut iobs_off_point(const JetSpec& J, double a, double th_o, double alpha, double beta, double r, double th,
-                               double kr_sign, double kth_sign, double nu_parallel, double density, double specind) {
-    StokesOut out{0.0, 0.0, 0.0, 0.0, 0.0};
+                               double kr_sign, double kth_sign, const JetBoost& boost, double density, double specind) {
+    StokesOut out{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const double a2 = a * a, r2 = r * r;
     const double sth_o = sin(th_o), cth_o = cos(th_o);
     const double lam = -alpha * sth_o;
     const double eta = (alpha * alpha - a2) * cth_o * cth_o + beta * beta;
     const KerrMetric gm = kerr_metric(a, r, th);
     const double Delta = gm.Delta, Sigma = gm.Sigma, sth2 = gm.sth2, cth2 = gm.cth2;
-    const U4 u = jet_driftframe(J, a, r, th, nu_parallel);
+    const DriftOut dr = jet_driftframe_boost(J, a, r, th, boost);
+    const U4 u = dr.u;
+    out.nu = dr.nu;
     const double Rpot = sq(r2 + a2 - a * lam) - Delta * (eta + sq(lam - a));
     const double TH = eta + a2 * cth2 - lam * lam * cth2 / sth2;
     const double sqR = sqrt(Rpot), sqTH = sqrt(TH);
@@ -240,12 +284,14 @@ KG_HD double power_source_integral(double r, double r0, double a, double sigma, 
 
 // rho = eta B^r / u^r at a crossing reflected into the northern hemisphere (density_mono_all / density_power_all,
 // kgeo/densityfuncs.py:44-79,186-219); r0 = stagnation radius, norm = source integral from r0 to infinity (power law)
-KG_HD double jet_density(const JetSpec& J, double a, double r, double th, double nu_parallel, double sigma, double r0, double norm,
-                         double psitarget) {
+KG_HD double jet_density(const JetSpec& J, double a, double r, double th, const JetBoost& boost, double sigma, double r0, double norm,
+                         double psitarget, double* nu_used = nullptr) {
     const double thn = acos(fabs(cos(th)));
     double B1, B2, B3, om;
     jet_field(J, a, r, thn, &B1, &B2, &B3, &om);
-    const U4 u = jet_driftframe(J, a, r, thn, nu_parallel);
+    const DriftOut dr = jet_driftframe_boost(J, a, r, thn, boost);   // the density's velocity never caps gamma (gammamax = None there)
+    const U4 u = dr.u;
+    if (nu_used) *nu_used = dr.nu;
     double eta;
     if (J.field == JET_MONO) eta = eta_mono(r, thn, r0, a, sigma);
     else if (sigma == 0.0) eta = sgn0(r - r0);

@@ -39,7 +39,7 @@ KG_NOINLINE void legendre_F_D(double s, double c, double m, double* F, double* D
 //   for the polar motion (kind 2, L = arg theta3(v - i beta)) a ray that passes next to the rotation axis drives theta3 to
 //   within ~1/P of its zero, so L carries eps P and Pi eps P^2 there (measured 9e-11 at P = 780) -- but ONLY there, within
 //   ~1/P of the pole, where the azimuth is a coordinate singularity and phi is gated on the arc length sin(theta) dphi
-//   (oracle/gates.py "axis": the arc-length error stays ~eps P).  Polar bound 4000 / edge 1e-8: the two pixel columns next to
+//   (the "axis" gate of the parity tests: the arc-length error stays ~eps P).  Polar bound 4000 / edge 1e-8: the two pixel columns next to
 //   alpha = 0 of a 1024-wide image (2/3 of all fallback rays of BASELINE cfg 3 under the earlier bound of 300) take the hot pass.
 #ifndef KG_THETA_QMAX
 #define KG_THETA_QMAX 0.4

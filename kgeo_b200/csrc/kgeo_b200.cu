@@ -140,9 +140,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const d
 #define KG_SETUP_THREADS 256
 #endif
 constexpr int SETUP_THREADS = KG_SETUP_THREADS;
-#ifndef KG_SETUP_SYNC
-#define KG_SETUP_SYNC 0
-#endif
+
 #ifndef KG_SETUP_MINBLOCKS
 #define KG_SETUP_MINBLOCKS 2          // CTAs per SM the two setup kernels are compiled for (register cap = 65536/(threads*n))
 #endif
@@ -151,12 +149,12 @@ template <bool PHI_T>
 __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                   const double* __restrict__ beta, int mode,
                                                                   double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
-    // threads beyond the last ray redo the last ray (identical values to identical addresses) so that the whole CTA can meet
-    // at the stage barriers of ray_setup<.., SYNC>
+    // (Re-converging the CTA's warps with barriers at the stage boundaries of ray_setup, so that they share fetched instruction
+    // lines, was measured: no change, 1.75 ms either way.)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) i = npix - 1;
+    if (i >= npix) return;
     int fl;
-    ray_setup<PHI_T, true, true, WsPtr, KG_SETUP_SYNC != 0>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
+    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
     flags_out[i] = fl;
 }
 
@@ -402,15 +400,21 @@ track_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const int
 }
 
 // The hot pass of a full trace (rays with F_TH_THETA and F_R_THETA): the lane mapping of track_kernel (lane = 4 * sample + ray,
-// whole 32-byte sectors per store) with the theta-function-only code of kg_hot.cuh, and NO cooperative staging: the ray
-// constants of a four-ray group are one contiguous block of the grouped workspace, fetched by ONE elected thread with ONE 1-D
-// TMA bulk copy (cp.async.bulk, NW_HOT * 32 B = 6 KB) into a ring of HOT_NBUF shared-memory buffers.  A `full` mbarrier per
-// buffer counts the bytes in; the warps wait on it right before they use the group; an `empty` mbarrier per buffer (one
-// arrival per warp) tells the elected thread when the buffer may be refilled, which it does two groups ahead.  No
-// __syncthreads, no staging loads / stores in the sample loop.  (ncu of the staged version: 12 % of all warp-stall samples sat
-// on the staging loads, their stores and the two barriers per group.  Holding all 8 groups of a CTA in shared memory instead
-// of a ring was measured and is slower, 20.1 against 19.3 ms: 4 x 48 KB leave the L1 too small for the kernel's register
-// spills, whose reloads then come from L2.)
+// whole 32-byte sectors per store) with the theta-function-only code of kg_hot.cuh.  The constants of a four-ray group are one
+// contiguous block of the grouped workspace; they are staged into shared memory by a cooperative contiguous copy (two
+// __syncthreads per group).  Every alternative to that staging was built and measured on cfg 3 (profiles/r02_hot_variants.txt;
+// kept behind KG_HOT_TMA for A/B):
+//   * 1-D TMA bulk copies (cp.async.bulk + mbarrier) of all 8 groups of the CTA up front: 20.1 against 19.3 ms -- 4 x 48 KB of
+//     shared memory leave the L1 too small for the kernel's ~100 B/thread of register spills (local-load hit rate 23 %);
+//   * the same through a ring of 2 / 3 buffers with full / empty mbarriers and an elected producer thread: 20.4 / 19.8 ms;
+//   * no staging at all, the constants read with ld.global.nc from the L1-resident block: 21.9 ms (a 64-bit base instead of a
+//     32-bit shared address: more spills, and the L1 tag stage per load);
+//   * two / three Mino-time samples per thread (KG_HOT_NS: constants and ray-property branches paid once per NS samples, NS
+//     independent dependency chains): 21.7 / 31.0 ms -- 128 / 168 registers halve / third the resident warps;
+//   * 56 / 48 registers (36 / 40 warps per SM): 20.7 / 21.9 ms; 72 registers with 7-warp CTAs (28 warps): 19.8 ms.
+// ncu of the shipped configuration: FP64 pipe 62 %, issue slots 66 %, LSU data pipe 76 % busy -- per 32 points ~200 cycles of
+// FP64 pipe, ~215 of issue and ~230 of shared-memory wavefronts against 320 elapsed: three co-limiters within 15 % of each
+// other, which is why removing instructions of one kind (8 DFMA per point, 8 local-memory round trips per point) moved nothing.
 #ifndef KG_HOT_NS
 #define KG_HOT_NS 1                     // Mino-time samples per thread (2 was measured: 21.7 against 19.3 ms, it halves the warps)
 #endif
@@ -547,7 +551,8 @@ track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const
 #endif
         if (j < nvalid && trk_hot(fl)) {
         const size_t pix = pix0 + j;
-        SmemW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(gsw) + joff)};
+        using HotW = SmemW;
+        HotW W{reinterpret_cast<const double*>(reinterpret_cast<const char*>(gsw) + joff)};
         // numpy.linspace(0, stop, ntau): k * (stop / (ntau-1)), last sample = stop exactly
         const double stop = maxtaufrac * W(S_TAUTOT);
         const double step = (ntau > 1) ? stop / (double)(ntau - 1) : 0.0;
@@ -565,14 +570,14 @@ track_hot_kernel(Observer o, size_t npix, const double* __restrict__ w_in, const
                 tau[s] = (kc == klast) ? stop : (double)kc * step;
             }
             double th[NS], Gph[NS], Gt[NS], r[NS], Iph[NS], It[NS], Isig[NS];
-            polar_hot<SmemW, NS>(W, fl, tau, th, Gph, Gt);
+            polar_hot<HotW, NS>(W, fl, tau, th, Gph, Gt);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 if (out.th && live[s]) __stcs(out.th + q + s * qs, th[s]);
                 Gph[s] *= lam;
                 Gt[s] *= o.a2;
             }
-            radial_hot<SmemW, NS>(W, o, fl, tau, r, Iph, It, Isig);
+            radial_hot<HotW, NS>(W, o, fl, tau, r, Iph, It, Isig);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 if (!live[s]) continue;
@@ -788,19 +793,77 @@ KG_HD double nan_to_num(double x) {
     return x;
 }
 
+// Boost of one crossing: the velocity of Iobs_off takes ONE field line's (r0, omega, E - Omega_F L) for all crossings (`glob`,
+// from the first crossing of the flattened arrays, kgeo/velocities.py:495-516), the velocity inside the density takes one per
+// crossing ORDER (row m of the (nguess, npix) arrays: density_*_all loop over the rows, kgeo/densityfuncs.py:60-72).
+struct JetBoostRows {
+    const double* rows;     // [nguess][3] = r0, omega, Aconst per crossing order (FF only), or NULL
+};
+__device__ __forceinline__ JetBoost density_boost(const JetBoost& glob, const JetBoostRows& R, size_t m) {
+    JetBoost b = glob;
+    b.gammamax = 0.0;       // gammamax = None in density_*_all
+    b.gscale = 1.0;
+    if (glob.ff && R.rows) {
+        b.r0 = R.rows[3 * m];
+        b.omega = R.rows[3 * m + 1];
+        b.Aconst = R.rows[3 * m + 2];
+    }
+    return b;
+}
+
+// |nan_to_num(x, nan = inf)| as NumPy computes it (+-inf become +-DBL_MAX), as the bits of a non-negative double (ordered like
+// unsigned integers)
+__device__ __forceinline__ unsigned long long argmin_key(double x) {
+    double v;
+    if (x != x) v = KG_INF;
+    else if (isinf(x)) v = 1.7976931348623157e308;
+    else v = fabs(x);
+    return (unsigned long long)__double_as_longlong(v);
+}
+
+// gammamax pre-pass (kgeo/velocities.py:593-603): gamma_FF and gamma_eff of every crossing, and the smallest |gamma_eff|
+__global__ void __launch_bounds__(256) jet_gamma_kernel(JetSpec J, double a, size_t n, const double* __restrict__ r,
+                                                        const double* __restrict__ th, JetBoost boost, double* gam, double* geff,
+                                                        unsigned long long* minkey) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    boost.gscale = 1.0;
+    const DriftOut d = jet_driftframe_boost(J, a, r[e], th[e], boost);
+    gam[e] = d.gamma;
+    geff[e] = d.gammaeff;
+    atomicMin(minkey, argmin_key(d.gammaeff));
+}
+// np.argmin: the FIRST element that attains the minimum
+__global__ void __launch_bounds__(256) jet_argmin_kernel(size_t n, const double* __restrict__ geff, const unsigned long long* minkey,
+                                                         unsigned long long* argidx) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (argmin_key(geff[e]) == *minkey) atomicMin(argidx, (unsigned long long)e);
+}
+__global__ void jet_gscale_kernel(const double* gam, const double* geff, const unsigned long long* argidx, double* gscale) {
+    const unsigned long long i = *argidx;
+    gscale[0] = gam[i] / geff[i];
+}
+
 __global__ void __launch_bounds__(256) jet_stokes_kernel(JetSpec J, double a, double th_o, size_t npix, size_t n,
                                                          const double* __restrict__ alpha, const double* __restrict__ beta,
                                                          const double* __restrict__ r, const double* __restrict__ th,
-                                                         const double* __restrict__ kr, const double* __restrict__ kth, double nu,
+                                                         const double* __restrict__ kr, const double* __restrict__ kth,
+                                                         JetBoost boost, JetBoostRows rows, const double* __restrict__ gscale,
                                                          double sigma, double r0, double norm, double psitarget, double specind,
-                                                         double* I, double* Q, double* U, double* sinthb, double* dens) {
+                                                         double* I, double* Q, double* U, double* sinthb, double* dens,
+                                                         int32_t* nu_out_of_range) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const size_t pix = e % npix;
     const double rs = r[e], ths = th[e];
-    const double rho = jet_density(J, a, rs, ths, nu, sigma, r0, norm, psitarget);
+    if (gscale) boost.gscale = gscale[0];
+    double nu_d = 0.0;
+    const double rho = jet_density(J, a, rs, ths, density_boost(boost, rows, e / npix), sigma, r0, norm, psitarget, &nu_d);
     if (dens) dens[e] = rho;
-    const StokesOut s = iobs_off_point(J, a, th_o, alpha[pix], beta[pix], rs, ths, kr[e], kth[e], nu, rho, specind);
+    const StokesOut s = iobs_off_point(J, a, th_o, alpha[pix], beta[pix], rs, ths, kr[e], kth[e], boost, rho, specind);
+    // u_driftframe raises when any boost leaves [-1, 1] (NaN compares false, as in NumPy): reported to the host wrapper
+    if (nu_out_of_range && (s.nu > 1.0 || s.nu < -1.0 || nu_d > 1.0 || nu_d < -1.0)) atomicOr(nu_out_of_range, 1);
     const bool none = (rs == 0.0);                                       // iobs[rvals == 0] = 0: no field-line crossing
     I[e] = none ? 0.0 : nan_to_num(s.I);
     Q[e] = none ? 0.0 : nan_to_num(s.Q);
@@ -1469,8 +1532,10 @@ int kgeo_fieldline_solve(const kgeo_observer* obs, size_t npix, size_t nguess, c
 
 int kgeo_jet_stokes(const kgeo_observer* obs, size_t npix, size_t nguess, const double* alpha, const double* beta, const double* r,
                     const double* th, const double* signpr, const double* signpth, int field, double C, double pval, int usemono,
-                    const double* fr_table, int64_t fr_n, double nu_parallel, double sigma, double r0, double norm, double psitarget,
-                    double specind, double* I, double* Q, double* U, double* sinthb, double* density, void* stream) {
+                    const double* fr_table, int64_t fr_n, double nu_parallel, int nu_ff, const double* ff_global,
+                    const double* ff_rows_dev, double gammamax, double sigma, double r0, double norm, double psitarget,
+                    double specind, double* I, double* Q, double* U, double* sinthb, double* density, int32_t* nu_out_of_range,
+                    void* stream) {
     int rc = check_observer(obs, true);
     if (rc) return rc;
     const size_t n = npix * nguess;
@@ -1478,12 +1543,46 @@ int kgeo_jet_stokes(const kgeo_observer* obs, size_t npix, size_t nguess, const 
         return fail_arg(KGEO_E_BADARG, "kgeo_jet_stokes: NULL pointer");
     if (field != JET_MONO && field != JET_POWER) return fail_arg(KGEO_E_MODEL, "kgeo_jet_stokes: unknown jet field");
     if (field == JET_MONO && (!fr_table || fr_n < 2)) return fail_arg(KGEO_E_MODEL, "kgeo_jet_stokes: the monopole needs its f(r) table");
+    if (nu_ff && (!ff_global || !ff_rows_dev)) return fail_arg(KGEO_E_BADARG, "kgeo_jet_stokes: nu_parallel = 'FF' needs the field-line constants");
+    if (nu_out_of_range) *nu_out_of_range = 0;
     if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
     JetSpec J{field, C, pval, usemono, fr_table, fr_table ? fr_table + fr_n : nullptr, (long long)fr_n};
-    jet_stokes_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(J, obs->a, obs->th_o, npix, n, alpha, beta, r, th, signpr,
-                                                                            signpth, nu_parallel, sigma, r0, norm, psitarget, specind,
-                                                                            I, Q, U, sinthb, density);
+    JetBoost boost = jet_boost_numeric(nu_parallel);
+    if (nu_ff) {
+        boost.ff = 1;
+        boost.r0 = ff_global[0];
+        boost.omega = ff_global[1];
+        boost.Aconst = ff_global[2];
+    }
+    boost.gammamax = (gammamax > 0.0) ? gammamax : 0.0;
+    JetBoostRows rows{nu_ff ? ff_rows_dev : nullptr};
+    DevBuf scratch;
+    double* gscale = nullptr;
+    int32_t* flag = nullptr;
+    // scratch: [gamma n][gamma_eff n][gscale 1][minkey 1][argidx 1][flag 1]
+    CU(scratch.alloc((2 * n + 4) * sizeof(double)));
+    double* gam = scratch.as<double>();
+    double* geff = gam + n;
+    unsigned long long* minkey = reinterpret_cast<unsigned long long*>(geff + n + 1);
+    unsigned long long* argidx = minkey + 1;
+    flag = reinterpret_cast<int32_t*>(argidx + 1);
+    CU(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    if (boost.gammamax > 0.0) {
+        gscale = geff + n;
+        CU(cudaMemsetAsync(minkey, 0xff, 2 * sizeof(unsigned long long), st));    // both start at the largest key / index
+        jet_gamma_kernel<<<grid_for(n, 256), 256, 0, st>>>(J, obs->a, n, r, th, boost, gam, geff, minkey);
+        LAUNCHED("jet_gamma_kernel");
+        jet_argmin_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, geff, minkey, argidx);
+        LAUNCHED("jet_argmin_kernel");
+        jet_gscale_kernel<<<1, 1, 0, st>>>(gam, geff, argidx, gscale);
+        LAUNCHED("jet_gscale_kernel");
+    }
+    jet_stokes_kernel<<<grid_for(n, 256), 256, 0, st>>>(J, obs->a, obs->th_o, npix, n, alpha, beta, r, th, signpr, signpth, boost, rows,
+                                                         gscale, sigma, r0, norm, psitarget, specind, I, Q, U, sinthb, density, flag);
     LAUNCHED("jet_stokes_kernel");
+    if (nu_out_of_range) CU(cudaMemcpyAsync(nu_out_of_range, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));          // the scratch is freed on return
     return 0;
 }
 

@@ -3,7 +3,8 @@
 Per-crossing work (field-line crossings, densities, drift-frame velocity, redshift, Penrose-Walker transport, Stokes parameters,
 subring sums) runs in libkgeo_b200.so kernels; what stays on the host is one scalar chain per call, as in the reference: the
 field-line angular speed at the first crossing, the stagnation surface (kgeo/ff_boost.py: a quintic for the monopole, two nested
-secant solves for the power law) and the normalisation of the power law's mass loading.
+secant solves for the power law), the normalisation of the power law's mass loading and, for nu_parallel='FF', the conserved
+E - Omega_F L of the field line (ff_boost.getEco).
 
 Parity with the unmodified reference's getstokes (monopole and power-law models): tests/test_gpu_jet.py.  The paraboloid model
 raises: in the reference itself densityfuncs.eta_para fails on the complex numbers SciPy's lambertw produces.
@@ -74,6 +75,32 @@ def r0min_mono(theta, Omegaf, spin, M=1.0):
     coefs = [-spin ** 2 / 2 * M * np.cos(theta) ** 2 * fac, -2 * spin ** 4 * Omegaf ** 2 * np.cos(theta) ** 4 * np.sin(theta) ** 2,
              M / 2 * fac, -spin ** 2 * Omegaf ** 2 * np.sin(2 * theta) ** 2, 0.0, -2 * Omegaf ** 2 * np.sin(theta) ** 2]
     return float(np.real(np.polynomial.polynomial.Polynomial(coefs).roots()[4]))
+
+
+def getEco(r0, theta, Omegaf, spin, M=1.0):
+    """E - Omega_F L of the cold flow launched at rest from (r0, theta) (kgeo/ff_boost.py:102-119, metric of :122-146)"""
+    Sig = r0 ** 2 + spin ** 2 * np.cos(theta) ** 2
+    Del = r0 ** 2 - 2 * M * r0 + spin ** 2
+    s2 = np.sin(theta) ** 2
+    gtt = -(1 - 2 * M * r0 / Sig)
+    gtphi = -2 * spin * M * r0 / Sig * s2
+    gphiphi = (r0 ** 2 + spin ** 2 + 2 * M * r0 * spin ** 2 / Sig * s2) * s2
+    ginvtt = -(r0 ** 2 + spin ** 2 + 2 * M * r0 * spin ** 2 / Sig * s2) / Del
+    ginvtphi = -2 * M * r0 * spin / Sig / Del
+    ginvphiphi = (Del - spin ** 2 * s2) / (Sig * Del * s2)
+    gtphifac = gtphi + gphiphi * Omegaf
+    gttfac = gtt + gtphi * Omegaf
+    coef0 = (gtt + Omegaf * (2 * gtphi + gphiphi * Omegaf)) ** 2
+    coef1 = ginvphiphi * gtphifac ** 2 + 2 * ginvtphi * gtphifac * gttfac + ginvtt * gttfac ** 2
+    return float(np.sqrt(-coef0 / coef1))
+
+
+def ff_constants_mono(r_first, th_first, spin):
+    """(r0, omega, E - Omega_F L) of the monopole field line through (r_first, th_first): what u_driftframe(nu_parallel='FF')
+    derives from the first crossing it is given (kgeo/velocities.py:495-516)"""
+    omega = _omega_mono(th_first, spin)
+    r0 = r0min_mono(th_first, omega, spin, 1.0)
+    return r0, float(omega), getEco(r0, th_first, omega, spin, 1.0)
 
 
 def _power_field_r_th(a, r, th, pval, usemono):
@@ -159,8 +186,12 @@ def getstokes(psitarget, alphavals, betavals, r_o, th_o, a, ngeo, do_phi_and_t=T
                                   "(densityfuncs.eta_para on SciPy's complex lambertw values)")
     if model not in ('mono', 'power'):
         raise Exception("model %s not recognized in getstokes!" % model)
-    if isinstance(nu_parallel, str) or gammamax:
-        raise NotImplementedError("getstokes with nu_parallel='FF' or a gammamax needs ff_boost.getnu_cons (not built)")
+    nu_ff = isinstance(nu_parallel, str)
+    if nu_ff and nu_parallel != 'FF':
+        raise Exception("nu_parallel should be a number in [-1,1] or 'FF'")
+    if nu_ff and not (model == 'mono' or (model == 'power' and pval == 0)):
+        raise NotImplementedError("getstokes(nu_parallel='FF') is built for the monopole field only (the reference's own "
+                                  "power-law path raises inside u_driftframe)")
     alphavals, betavals = np.asarray(alphavals, dtype=np.float64), np.asarray(betavals, dtype=np.float64)
     ashape = alphavals.shape
     alpha, beta = alphavals.flatten(), betavals.flatten()
@@ -183,11 +214,30 @@ def getstokes(psitarget, alphavals, betavals, r_o, th_o, a, ngeo, do_phi_and_t=T
         table = _engine.to_device(np.ascontiguousarray(np.vstack((rs, fs))), dev)
     I, Q, U, sinthb = [_engine.empty((n,), dev) for _ in range(4)]
     obs = _engine.observer_struct(a, r_o, th_o)
+    # nu_parallel = 'FF': the field-line constants of the two places the reference evaluates u_driftframe (host scalars, as the
+    # reference derives them from the first crossing it is handed: kgeo/velocities.py:495-516)
+    ff_global, ff_rows = None, None
+    if nu_ff:
+        rflat, thflat = np.nan_to_num(np.asarray(rvals, dtype=np.float64)), np.asarray(thvals, dtype=np.float64)
+        i0 = np.where(rflat != 0)[0][0]                      # Iobs_off: flattened crossings, angles as they are
+        ff_global = np.array(ff_constants_mono(rflat[i0], thflat[i0], a), dtype=np.float64)
+        rnew = rflat.reshape(shape)
+        thnew = np.arccos(np.abs(np.cos(thflat.reshape(shape))))
+        rows = []
+        for m in range(nguess):                              # density_mono_all: one u_driftframe call per crossing order
+            im = np.where(rnew[m] != 0)[0][0]                # (IndexError when an order has no crossing at all, as there)
+            rows.append(ff_constants_mono(rnew[m][im], thnew[m][im], a))
+        ff_rows = _engine.to_device(np.ascontiguousarray(np.array(rows, dtype=np.float64).ravel()), dev)
+    bad_nu = ctypes.c_int32(0)
     _lib.check(L.kgeo_jet_stokes(ctypes.byref(obs), npix, nguess, _engine.dptr(d['alpha']), _engine.dptr(d['beta']), _engine.dptr(d['r']),
                                  _engine.dptr(d['th']), _engine.dptr(d['kr']), _engine.dptr(d['kth']), field, 1.0, float(pval),
                                  int(bool(usemono)), _engine.dptr(table), 0 if table is None else int(table.shape[1]),
-                                 float(nu_parallel), float(sigma), float(r0), float(norm), float(psitarget), float(SPECIND),
-                                 _engine.dptr(I), _engine.dptr(Q), _engine.dptr(U), _engine.dptr(sinthb), None, _engine.stream_ptr()))
+                                 0.0 if nu_ff else float(nu_parallel), int(nu_ff), _engine.hptr(ff_global), _engine.dptr(ff_rows),
+                                 float(gammamax) if gammamax else 0.0, float(sigma), float(r0), float(norm), float(psitarget),
+                                 float(SPECIND), _engine.dptr(I), _engine.dptr(Q), _engine.dptr(U), _engine.dptr(sinthb), None,
+                                 ctypes.byref(bad_nu), _engine.stream_ptr()))
+    if bad_nu.value:
+        raise Exception("nu_parallel should be in the range (-1,1)")
     if not sumsubring:
         return (I.cpu().numpy(), Q.cpu().numpy(), U.cpu().numpy(), neqvals, np.nan_to_num(rvals), np.nan_to_num(thvals), shape)
     outs = [_engine.empty((neqmax + 1, npix), dev) for _ in range(3)]

@@ -901,7 +901,7 @@ def velocity_u_lab(vel, a, r, th=np.pi / 2):
     if t == 'fromfile':
         return u_from_table(a, r, load_table(vel['file'], ('U1', 'U2', 'U3')))
     if t == 'driftframe':
-        return u_driftframe(a, r, vel['bfield'], vel.get('nu_parallel', 0), th)
+        return u_driftframe(a, r, vel['bfield'], vel.get('nu_parallel', 0), th, vel.get('gammamax'))
     raise Exception("veltype %s not in oracle" % t)
 
 
@@ -1143,9 +1143,53 @@ def bfield_lab_omega(bf, a, r, th=np.pi / 2):
     raise Exception("self.omega_field not implemented for fieldtype %s'!" % t)
 
 
-def u_driftframe(a, r, bf, nu_parallel=0, th=np.pi / 2):
-    """kgeo/velocities.py:487-623 with a numeric nu_parallel and gammamax=None (theta = pi/2 unless given)."""
+def get_eco(r0, theta, Omegaf, spin, M=1.0):
+    """E - Omega_F L as a function of the launch point (kgeo/ff_boost.py:102-119 with metric / invmetric of :122-146)."""
+    Sig = r0 ** 2 + spin ** 2 * np.cos(theta) ** 2
+    Del = r0 ** 2 - 2 * M * r0 + spin ** 2
+    s2 = np.sin(theta) ** 2
+    gtt = -(1 - 2 * M * r0 / Sig)
+    gtphi = -2 * spin * M * r0 / Sig * s2
+    gphiphi = (r0 ** 2 + spin ** 2 + 2 * M * r0 * spin ** 2 / Sig * s2) * s2
+    ginvtt = -1 / Del * (r0 ** 2 + spin ** 2 + 2 * M * r0 * spin ** 2 / Sig * s2)
+    ginvtphi = -2 * M * r0 * spin / (Sig * Del)
+    ginvphiphi = (Del - spin ** 2 * s2) / (Sig * Del * s2)
+    gtphifac = gtphi + gphiphi * Omegaf
+    gttfac = gtt + gtphi * Omegaf
+    coef0 = (gtt + Omegaf * (2 * gtphi + gphiphi * Omegaf)) ** 2
+    coef1 = ginvphiphi * gtphifac ** 2 + 2 * ginvtphi * gtphifac * gttfac + ginvtt * gttfac ** 2
+    return np.sqrt(-coef0 / coef1)
+
+
+def getnu_cons(bf, r, theta, r0, theta0, Omegaf, spin, M=1.0):
+    """parallel boost that conserves E - Omega_F L along the field line (kgeo/velocities.py:474-486)."""
+    Aconst = get_eco(r0, theta0, Omegaf, spin, M)
     r = _arr(r)
+    Sig = r ** 2 + spin ** 2 * np.cos(theta) ** 2
+    g03 = -2 * spin * M * r / Sig * np.sin(theta) ** 2
+    g33 = (r ** 2 + spin ** 2 + 2 * M * r * spin ** 2 / Sig * np.sin(theta) ** 2) * np.sin(theta) ** 2
+    alpha, vphiupper, gammap, Bhatphi = u_driftframe(spin, r, bf, 0, theta, retbunit=True)
+    ffunc = gammap * (alpha - (g03 + g33 * Omegaf) * vphiupper)
+    bred = Bhatphi * (g03 + g33 * Omegaf)
+    nunum = ffunc * bred + np.sign(np.cos(theta)) * np.sign(r - r0) * Aconst * np.sqrt(Aconst ** 2 - ffunc ** 2 + bred ** 2)
+    return np.real(nunum / (Aconst ** 2 + bred ** 2))
+
+
+def u_driftframe(a, r, bf, nu_parallel=0, th=np.pi / 2, gammamax=None, retbunit=False):
+    """kgeo/velocities.py:487-623 (theta = pi/2 unless given).  nu_parallel='FF' (monopole field): the energy-conserving boost
+    of getnu_cons on the field line of the first crossing handed in; gammamax: the Lorentz-factor cap of :593-611 (eps < 0)."""
+    r = _arr(r)
+    if isinstance(nu_parallel, str):                      # :494-516
+        tha = np.broadcast_to(np.asarray(th, dtype=float), r.shape)
+        ind = np.where(np.nan_to_num(r) != 0)[0][0]
+        omega = bfield_lab_omega(bf, a, r[ind:ind + 1], tha[ind])[3]
+        omega = float(np.broadcast_to(omega, (1,))[0])
+        theta0 = tha[ind]
+        r0 = r0min_mono(theta0, omega, a, 1.0)
+        nu_parallel = getnu_cons(bf, r, th, r0, theta0, omega, a, 1.0)
+    nu_parallel = nu_parallel * np.ones_like(r)
+    if np.any(np.logical_or(nu_parallel > 1, nu_parallel < -1)):
+        raise Exception("nu_parallel should be in the range (-1,1)")
     a2, r2 = a ** 2, r ** 2
     cth2, sth2 = np.cos(th) ** 2, np.sin(th) ** 2
     Delta = r2 - 2 * r + a2
@@ -1171,8 +1215,20 @@ def u_driftframe(a, r, bf, nu_parallel=0, th=np.pi / 2):
     v1 = vperp1 + nu_parallel * vpar_max * B1 / np.sqrt(Bsq)
     v2 = vperp2 + nu_parallel * vpar_max * B2 / np.sqrt(Bsq)
     v3 = vperp3 + nu_parallel * vpar_max * B3 / np.sqrt(Bsq)
+    if retbunit:                                          # :588-589
+        return alpha, v3, 1 / vpar_max, B3 / np.sqrt(Bsq)
     vsq = g11 * v1 * v1 + g22 * v2 * v2 + g33 * v3 * v3
     gamma = 1. / np.sqrt(1 - vsq)
+    if gammamax:                                          # :593-611
+        pval0 = 2.0
+        gmax = gammamax * np.ones_like(gamma)
+        gammaeff = (1 / gmax ** pval0 + 1 / gamma ** pval0) ** (-1 / pval0)
+        argdiv = np.argmin(np.abs(np.nan_to_num(gammaeff, nan=np.inf)))
+        gammaeff0 = gammaeff * gamma[argdiv] / gammaeff[argdiv]
+        vsqeff = 1 - 1 / gammaeff0 ** 2
+        sc = np.sqrt(vsqeff / vsq)
+        v1, v2, v3 = v1 * sc, v2 * sc, v3 * sc
+        gamma = np.real(gammaeff0)
     return gamma / alpha, gamma * v1, gamma * v2, gamma * (v3 + eta3)
 
 
@@ -1672,8 +1728,8 @@ def sort_image(iobs, qobs, uobs, neqvals, shape, ashape, neqmax):
 
 
 def getstokes(psitarget, alphavals, betavals, r_o, th_o, a, ngeo, neqmax=1, tol=1e-8, model='mono', pval=1, nu_parallel=0, sigma=2,
-              sumsubring=True):
-    """off_eq.getstokes for the monopole and power-law jets (kgeo/off_eq.py:124-233; nu_parallel numeric, gammamax None)"""
+              sumsubring=True, gammamax=None):
+    """off_eq.getstokes for the monopole and power-law jets (kgeo/off_eq.py:124-233); nu_parallel numeric or (monopole) 'FF'"""
     ashape = alphavals.shape
     A, B = alphavals.flatten(), betavals.flatten()
     tau_s, _, (_, r_t, th_t, _) = raytrace(a, [0, r_o, th_o, 0], [A, B], ngeo)
@@ -1686,7 +1742,7 @@ def getstokes(psitarget, alphavals, betavals, r_o, th_o, a, ngeo, neqmax=1, tol=
     else:
         bf = dict(type='power', p=pval)
         dvals = density_power_all(rvals, thvals, shape, psitarget, a, nu_parallel, sigma, pval)
-    vel = dict(type='driftframe', bfield=bf, nu_parallel=nu_parallel)
+    vel = dict(type='driftframe', bfield=bf, nu_parallel=nu_parallel, gammamax=gammamax)
     I, Q, U, sinthb = iobs_off(a, r_o, rvals, th_o, At, Bt, signpr, signpth, vel, bf, thvals, dvals, 1)
     none = (rvals == 0)
     I, Q, U = [np.real(np.nan_to_num(np.where(none, 0, x))) for x in (I, Q, U)]

@@ -400,6 +400,36 @@ def jet_pipeline():
     save('jet_pipeline', **out)
 
 
+def jet_boost():
+    """off_eq.getstokes of the unmodified reference for the monopole jet with the energy-conserving parallel boost
+    (nu_parallel='FF': velocities.getnu_cons, ff_boost.getEco) and with a Lorentz-factor cap (gammamax): raw per-crossing Stokes
+    parameters and the sorted images, on the grid of jet_pipeline's monopole case (same crossings)."""
+    import contextlib
+    import io
+    from kgeo.off_eq import getstokes
+    out = {}
+    a, r_o, th_o, psit, neqmax, ngeo = 0.5, 1000., 20 * DEG, 0.3, 1, 100
+    x = np.linspace(-8, 8, 11)
+    A2, B2 = np.meshgrid(x, x)
+    with np.errstate(all='ignore'), contextlib.redirect_stdout(io.StringIO()):
+        geo = raytrace_ana(a, [0, r_o, th_o, 0], [A2.flatten(), B2.flatten()], ngeo, plotdata=False)
+    cases = [('ff', dict(nu_parallel='FF')), ('ff_gmax', dict(nu_parallel='FF', gammamax=5.0)), ('gmax', dict(nu_parallel=0.3, gammamax=3.0))]
+    out['par'] = np.array([a, r_o, th_o, psit, neqmax, ngeo])
+    out['alpha'], out['beta'] = A2, B2
+    out['names'] = np.array(json.dumps([c[0] for c in cases]))
+    out['kwargs'] = np.array(json.dumps([c[1] for c in cases]))
+    for name, kw in cases:
+        with np.errstate(all='ignore'), contextlib.redirect_stdout(io.StringIO()):
+            raw = getstokes(psit, A2, B2, r_o, th_o, a, ngeo, neqmax=neqmax, outgeo=geo, model='mono', sigma=2, sumsubring=False, **kw)
+            img = getstokes(psit, A2, B2, r_o, th_o, a, ngeo, neqmax=neqmax, outgeo=geo, model='mono', sigma=2, retvals=True,
+                            retsin=True, **kw)
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            out[name + '_raw_' + k] = np.real(np.asarray(v)).astype(float)
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            out[name + '_img_' + k] = np.real(np.asarray(v)).astype(float)
+    save('jet_boost', **out)
+
+
 def inverse_lensing():
     """rho_of_req / rho_of_req_single / critical_curve (equatorial_lensing.py:226-298)."""
     out = {}
@@ -423,7 +453,7 @@ def inverse_lensing():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -438,5 +468,6 @@ if __name__ == '__main__':
     bz_models()
     fieldline_crossings()
     jet_pipeline()
+    jet_boost()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

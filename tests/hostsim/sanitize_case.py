@@ -24,4 +24,12 @@ for bf in (bm, kg.Bfield('bz_para'), kg.Bfield('power', p=0.75)):
 from kgeo_b200 import solver
 gg = kg.raytrace_ana(0.5, [0, 1000., 20 * np.pi / 180, 0], [A[:333], B[:333]], ngeo=60, plotdata=False)
 fr = solver.findroot(gg, 2.0, A[:333], B[:333], 1000., 20 * np.pi / 180, 0.5, 60, model='para', neqmax=2)
+# jet pipeline (fieldline_* / jet_stokes / jet_sort kernels): odd sizes (7 x 9 rays, 47 samples), both jet models
+from kgeo_b200 import off_eq
+xa, xb = np.linspace(-7, 7, 7), np.linspace(-7, 7, 9)
+A2, B2 = np.meshgrid(xa, xb)
+for model, aa, inc, psit, pval, neqmax in (('mono', 0.5, 20., 0.3, 1, 1), ('power', 0.7, 30., 1.5, 0.75, 2)):
+    st = off_eq.getstokes(psit, A2, B2, 1000., inc * np.pi / 180, aa, 47, neqmax=neqmax, model=model, pval=pval, nu_parallel=0, sigma=2,
+                          retvals=True, retsin=True)
+    assert np.isfinite(st[0]).all()
 print("sanitize_case ok", g.geo_coords[1].shape, img[0].shape)

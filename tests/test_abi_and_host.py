@@ -228,3 +228,28 @@ def test_jet_host_scalars(golden):
                 assert field == off_eq.JET_POWER and abs(r0 - r0o) <= 1e-13 * r0o and abs(norm - want) <= 1e-12 * want
     with pytest.raises(NotImplementedError):
         off_eq.getstokes(1.0, np.zeros((2, 2)), np.zeros((2, 2)), 1000., 0.3, 0.5, 50, model='para')
+
+
+def test_savegeos_loadgeos_roundtrip(tmp_path):
+    """Geodesics.savegeos / loadgeos with the reference's HDF5 dataset names (kgeo/kerr_raytracing_utils.py:201-240), on a
+    host-constructed Geodesics object (no GPU).  Skipped when h5py is not installed; without it both raise ImportError."""
+    import numpy as np
+    from kgeo_b200 import kerr_raytracing_utils as ku
+    rng = np.random.default_rng(3)
+    arrs = [rng.normal(size=(5, 7)) for _ in range(6)]
+    g = ku.Geodesics(0.5, [0, 1000., 0.3, 0], [rng.normal(size=7), rng.normal(size=7)], arrs[0], arrs[1], arrs[2:])
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            g.savegeos(str(tmp_path / "x.h5"))
+        with pytest.raises(ImportError):
+            ku.loadgeos(str(tmp_path / "x.h5"))
+        pytest.skip("h5py is not installed")
+    fname = g.savegeos(str(tmp_path / "x.h5"))
+    with h5py.File(fname, 'r') as hf:
+        assert sorted(hf.keys()) == sorted(['spin', 'inc', 'r_o', 'alpha', 'beta', 't', 'r', 'theta', 'phi', 'affine', 'mino'])
+    g2 = ku.loadgeos(fname)
+    assert g2.a == g.a and g2.r_o == g.r_o and g2.th_o == g.th_o
+    for x, y in zip(g.geo_coords + [g.mino_times, g.affine_times], g2.geo_coords + [g2.mino_times, g2.affine_times]):
+        assert np.array_equal(x, y)

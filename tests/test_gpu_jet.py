@@ -36,3 +36,23 @@ def test_getstokes_against_reference(golden):
         for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
             ref = g[name + '_img_' + k]
             assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
+
+
+def test_getstokes_ff_boost_and_gammamax_against_reference(golden):
+    """nu_parallel='FF' (the energy-conserving boost of velocities.getnu_cons, field-line constants from ff_boost) and gammamax
+    (the Lorentz-factor cap with its global argmin) on the device vs the unmodified reference's getstokes for the monopole jet."""
+    from kgeo_b200 import off_eq
+    g = golden('jet_boost')
+    a, r_o, th_o, psit, neqmax, ngeo = [float(x) for x in g['par']]
+    A, B = g['alpha'], g['beta']
+    for name, kw in zip(json.loads(str(g['names'])), json.loads(str(g['kwargs']))):
+        raw = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model='mono', sigma=2, sumsubring=False, **kw)
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            ref = g[name + '_raw_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
+        img = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model='mono', sigma=2, retvals=True, retsin=True, **kw)
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            ref = g[name + '_img_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
+    with pytest.raises(NotImplementedError):
+        off_eq.getstokes(1.5, A, B, r_o, th_o, 0.7, int(ngeo), model='power', pval=0.75, nu_parallel='FF')

@@ -348,3 +348,25 @@ def test_jet_pipeline_oracle_against_reference(golden):
         for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
             ref = g[name + '_img_' + k]
             assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
+
+
+def test_jet_boost_oracle_against_reference(golden):
+    """nu_parallel='FF' (velocities.getnu_cons with ff_boost.getEco) and the gammamax cap of u_driftframe in the oracle's getstokes
+    vs the unmodified reference's (monopole jet; tests/golden/jet_boost.npz)."""
+    import warnings
+    g = golden('jet_boost')
+    a, r_o, th_o, psit, neqmax, ngeo = [float(x) for x in g['par']]
+    A, B = g['alpha'], g['beta']
+    for name, kw in zip(json.loads(str(g['names'])), json.loads(str(g['kwargs']))):
+        with np.errstate(all='ignore'), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            raw = ko.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), int(neqmax), 1e-8, 'mono', 1, kw['nu_parallel'], 2, sumsubring=False,
+                               gammamax=kw.get('gammamax'))
+            img = ko.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), int(neqmax), 1e-8, 'mono', 1, kw['nu_parallel'], 2,
+                               gammamax=kw.get('gammamax'))
+        for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
+            ref = g[name + '_raw_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
+        for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
+            ref = g[name + '_img_' + k]
+            assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
