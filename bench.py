@@ -409,7 +409,7 @@ def run_ours(args):
 
     e2e = e2e_legs(L, obs, mode, A, B, npix, cols, world, rank, local, dev, barrier, allmax)
 
-    sweep = cfg5_sweep(world, rank, dev, barrier, allmax) if world == 8 else None
+    sweep = cfg5_sweep(world, rank, dev, barrier, allmax) if (world == 8 or (world > 1 and os.environ.get("KGEO_BENCH_SWEEP"))) else None
 
     if rank != 0:
         if world > 1:

@@ -84,6 +84,7 @@ enum Slot {
     T_I2K, R_I2K,               // 1/(2 K(m)), 1/(2 K(k)) (0 when K is infinite)
     // per-ray reciprocals / prefactors of the case-3 and case-4 algebra (see radial_eval): no per-sample division by a constant
     R_C0, R_C1, R_C2, R_C3, R_C4, R_C5, R_C6, R_C7, R_C8, R_C9, R_C10, R_C11, R_C12,
+    R_RDC,                      // RD(0, 1-k, 1) of the radial parameter (kept for the theta-block setup)
     // theta-function path (kg_theta.cuh): polar block = base + 1 Pi, radial block = base + 3 Pi
     T_TH_G, T_TH_IM, T_TH_SLOPE, T_TH_COEF,       // 1 + (E/K - 1)/m, 1/m, G_phi slope and coefficient
     T_TH, T_TH_END = T_TH + TB_SIZE + TP_SIZE - 1,
@@ -434,8 +435,8 @@ KG_HD double S2_of(double al, double j, double sn, double cn, double dn, double 
 // ---- theta blocks of a motion (setup) -------------------------------------------------------------------------------------
 // Builds base + NP Pi blocks at w[slot...]; returns true when the theta path is usable for every integral of the motion.
 template <class P>
-KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const double* nmm, const double* omn, double pmax, double edge, P blk) {
-    ThetaRay r = theta_ray(m);
+KG_NOINLINE bool theta_make_motion(int NP, const ThetaRay& r, const double* n, const double* nmm, const double* omn, double pmax, double edge, P blk) {
+    const double m = r.m;
     int J = theta_make_base(r, blk);
     bool ok = r.ok != 0;
     for (int i = 0; i < NP; ++i) {
@@ -454,21 +455,23 @@ KG_NOINLINE bool theta_make_motion(int NP, double m, const double* n, const doub
 //   (F - E)(phi | k) / k = sqrt(1-m) [ (1 + (E/K - 1)/m) w + Z(w)/m - sn w cn w / dn w ]
 template <class WP>
 KG_NOINLINE void polar_theta_setup(const Observer& o, double m, double sq1m, double n, double D3, WP w, int* flags) {
-    const double Km = ellip_K(m);
+    const double Km = w[T_K];                      // K(m) of the first setup kernel
+    const ThetaRay tr = theta_ray(m, Km);
     const double npr = fma(n, 1.0 - m, m), nmm = n * (1.0 - m), omn = (1.0 - n) * (1.0 - m);
-    bool ok = theta_make_motion(1, m, &npr, &nmm, &omn, kThetaPMaxPolar, kThetaEdgePolar, w + T_TH);
+    bool ok = theta_make_motion(1, tr, &npr, &nmm, &omn, kThetaPMaxPolar, kThetaEdgePolar, w + T_TH);
     const double A = w[T_TH + TB_SIZE + TP_A], P = w[T_TH + TB_SIZE + TP_P];
     const double mn = m / npr;
     w[T_TH_SLOPE] = D3 * sq1m * fma(1.0 - mn, A, mn);
     w[T_TH_COEF] = D3 * sq1m * (1.0 - mn) * P;
-    w[T_TH_G] = 1.0 - ellip_RDc(m) / (3.0 * Km);
+    w[T_TH_G] = tr.ok ? 1.0 - tr.RDc / (3.0 * Km) : 0.0;      // only read on the theta path
     w[T_TH_IM] = 1.0 / m;
     if (ok && !o.lowspin && m > 1.0e-6 && w[T_TH + TB_SIZE + TP_KIND] == 2.0) *flags |= F_TH_THETA;
 }
 
 template <class WP>
 KG_HD void radial_theta_setup(double k, const double* n, WP w, int* flags) {
-    if (!theta_make_motion(3, k, n, nullptr, nullptr, kThetaPMax, kThetaEdge, w + R_TH)) return;
+    const ThetaRay tr = theta_ray(k, w[R_KC], w[R_RDC]);      // K(k), RD(0, 1-k, 1) of the first setup kernel
+    if (!theta_make_motion(3, tr, n, nullptr, nullptr, kThetaPMax, kThetaEdge, w + R_TH)) return;
     *flags |= F_R_THETA;
     const double k0 = w[R_TH + TB_SIZE + TP_KIND], k1 = w[R_TH + TB_SIZE + TP_SIZE + TP_KIND],
                  k2 = w[R_TH + TB_SIZE + 2 * TP_SIZE + TP_KIND];
@@ -530,10 +533,10 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         else F0 = legendre_F_sc(so, co, k);
         double m = k / (k - 1.0);
         double sq1m = sqrt(1.0 - m);
-        double Km = ellip_K(m);
+        double Km, RDc = 0.0, PicT = 0.0;
+        ellip_complete<0, true, false>(m, nullptr, &Km, nullptr, nullptr);
         double Kk = sq1m * Km;                   // K(k) for the negative parameter
-        double RDc = PHI_T ? ellip_RDc(k) : 0.0;
-        double PicT = PHI_T ? ellip_PicTail(up, k) : 0.0;      // Pi(u+|k) - K(k); +inf when u+ == 1
+        if (PHI_T) ellip_complete<1, false, true>(k, &up, nullptr, &RDc, &PicT);   // RD(0, 1-k, 1); Pi(u+|k) - K(k), +inf when u+ == 1
         w[T_W] = sqrt(-a2um);
         w[T_X0] = w[T_W] * s_o * (-pref * F0);
         w[T_M] = m;
@@ -578,10 +581,14 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         else F0 = legendre_F_sc(so, co, k);
         double m = k / (k - 1.0);
         double sq1m = sqrt(1.0 - m);
-        double Km = ellip_K(m);
+        double Km, Ek = 0.0, PicT = 0.0;
+        ellip_complete<0, true, false>(m, nullptr, &Km, nullptr, nullptr);
         double Kk = sq1m * Km;
-        double Ek = PHI_T ? ellip_Ec(k) : 0.0;
-        double PicT = PHI_T ? ellip_PicTail(nch, k) : 0.0;
+        if (PHI_T) {
+            double Kk_, RDk;
+            ellip_complete<1, true, true>(k, &nch, &Kk_, &RDk, &PicT);
+            Ek = Kk_ - (k * (1.0 / 3.0)) * RDk;  // E(k)
+        }
         w[T_W] = sqrt(a2um);
         w[T_X0] = w[T_W] * s_o * (-h * prefA * F0);
         w[T_M] = m;
@@ -650,13 +657,16 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[R_X0] = Fo;                          // X4 = (1/pref)(-tau + pref*Fo) = Fo - tau/pref
         if (PHI_T) {
             double dno = sqrt(fma(-k4 * sa, sa, 1.0));
-            w[R_KC] = ellip_K(k4);
-            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
-            w[R_EC] = ellip_Ec(k4);
+            double Kc_, RDc_, PicT_[3];
+            ellip_complete<3>(k4, nn, &Kc_, &RDc_, PicT_);      // K, RD(0, 1-k, 1) and the three Pi(n_i|k) - K(k): one track
+            w[R_KC] = Kc_;
+            w[R_I2K] = (Kc_ < kInf) ? 0.5 / Kc_ : 0.0;
+            w[R_RDC] = RDc_;
+            w[R_EC] = Kc_ - (k4 * (1.0 / 3.0)) * RDc_;            // E(k)
             for (int i = 0; i < 3; ++i) {
                 double p2 = sqrt((1.0 + al[i] * al[i]) / (1.0 - k4 + al[i] * al[i]));
                 w[R_N0 + i] = nn[i];
-                w[R_PC0 + i] = ellip_PicTail(nn[i], k4);
+                w[R_PC0 + i] = PicT_[i];
                 w[R_Q5 + i] = p2;
                 w[R_PO0 + i] = S1_of(al[i], p2, dno, Fo, Pio[i]);
             }
@@ -712,12 +722,15 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[R_X0] = Fo;                          // X3 = sqrt(AB)(-tau + Fo/sqrt(AB))
         if (PHI_T) {
             double dno = sqrt(fma(-k3 * sa, sa, 1.0));
-            w[R_KC] = ellip_K(k3);
-            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
-            w[R_EC] = ellip_Ec(k3);
+            double Kc_, RDc_, PicT_[3];
+            ellip_complete<3>(k3, nn, &Kc_, &RDc_, PicT_);      // K, RD(0, 1-k, 1) and the three Pi(n_i|k) - K(k): one track
+            w[R_KC] = Kc_;
+            w[R_I2K] = (Kc_ < kInf) ? 0.5 / Kc_ : 0.0;
+            w[R_RDC] = RDc_;
+            w[R_EC] = Kc_ - (k3 * (1.0 / 3.0)) * RDc_;            // E(k)
             for (int i = 0; i < 3; ++i) {
                 w[R_N0 + i] = nn[i];
-                w[R_PC0 + i] = ellip_PicTail(nn[i], k3);
+                w[R_PC0 + i] = PicT_[i];
                 w[R_Q4 + i] = al[i];
                 w[R_Q7 + i] = p1[i];
                 w[R_PO0 + i] = R1_of(al[i], p1[i], nn[i], sa, dno, Pio[i]);
@@ -759,12 +772,15 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         w[R_SC] = 0.5 * root;
         w[R_X0] = Fo;                          // X2 = 0.5 root (-tau + 2 Fo/root)
         if (PHI_T) {
-            w[R_KC] = ellip_K(k2);
-            w[R_I2K] = (w[R_KC] < kInf) ? 0.5 / w[R_KC] : 0.0;
-            w[R_EC] = ellip_Ec(k2);
+            double Kc_, RDc_, PicT_[3];
+            ellip_complete<3>(k2, nn, &Kc_, &RDc_, PicT_);      // K, RD(0, 1-k, 1) and the three Pi(n_i|k) - K(k): one track
+            w[R_KC] = Kc_;
+            w[R_I2K] = (Kc_ < kInf) ? 0.5 / Kc_ : 0.0;
+            w[R_RDC] = RDc_;
+            w[R_EC] = Kc_ - (k2 * (1.0 / 3.0)) * RDc_;            // E(k)
             for (int i = 0; i < 3; ++i) {
                 w[R_N0 + i] = nn[i];
-                w[R_PC0 + i] = ellip_PicTail(nn[i], k2);
+                w[R_PC0 + i] = PicT_[i];
                 w[R_PO0 + i] = Pio[i];
             }
             w[R_EO] = Eo;

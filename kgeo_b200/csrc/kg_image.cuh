@@ -484,6 +484,15 @@ KG_HD double bfield_bsq(const kgeo_models& M, double a, double r, const U4& u) {
     return b0 * (g.g00 * b0 + g.g03 * b3) + b1 * (g.g11 * b1) + b2 * (g.g22 * b2) + b3 * (g.g33 * b3 + g.g03 * b0);
 }
 
+// x ** p as NumPy evaluates it for the exponents an image actually uses: NumPy's power loop squares for p == 2 and libm's pow is
+// exact for p == 1, 2 (the default spectral index 1 gives g ** 1 and sin(theta_b) ** 2); everything else goes to pow.  Two pow
+// calls per order were ~13 % of the unpolarized image kernel's instructions.
+KG_HD double pow_small_int(double x, double p) {
+    if (p == 1.0) return x;
+    if (p == 2.0) return x * x;
+    return pow(x, p);
+}
+
 // rest-frame emissivity (kgeo/emissivities.py:83-157); has_g / has_s mirror the `is not None` tests
 KG_HD double emissivity_jrest(const kgeo_models& M, double a, double r, bool has_g, double g, bool has_s, double sinthb,
                               double Bmag, double nu_obs, double specind) {
@@ -525,8 +534,8 @@ KG_HD double emissivity_jrest(const kgeo_models& M, double a, double r, bool has
             break;
         }
     }
-    if (has_g) j *= pow(g, specind);
-    if (has_s) j *= pow(sinthb, 1.0 + specind);
+    if (has_g) j *= pow_small_int(g, specind);
+    if (has_s) j *= pow_small_int(sinthb, 1.0 + specind);
     return j;
 }
 
@@ -548,32 +557,48 @@ KG_HD void crossing_time(const W& w, const Observer& o, double beta, int mbar, d
     *Ir = (2.0 * m * K - sF * F0) / ww;
 }
 
+// Geometry of one order at one pixel: crossing Mino time, Nmax and crossing radius (r_equatorial, kgeo/equatorial_lensing.py:85-196).
+// This is all of an order that needs the ray constants; the emission physics below needs only (r_s, Ir, Nmax) and five per-ray
+// scalars, so the image kernel runs the geometry of ALL orders first and the ray constants are dead during the physics.
+struct OrderGeom {
+    double r, Ir, Nmax;
+};
 template <class W>
-KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_models& M, const kgeo_image_opts& opt,
-                           double alpha, double beta, int mbar) {
-    OrderOut out{0.0, 0.0, 0.0, 0.0, -1.0, 0.0, -1.0, -2.0, 0.0, 0.0};
-    double eta = w(S_ETA), lam = w(S_LAM);
-    if (!(eta > 0.0)) return out;   // vortical / eta == 0: r_s = Ir = -1, Nmax = -2 (equatorial_lensing.py:119-123)
+KG_HD OrderGeom image_geometry(const W& w, const Observer& o, int flags, double beta, int mbar) {
+    OrderGeom gq{-1.0, -1.0, -2.0};
+    if (!(w(S_ETA) > 0.0)) return gq;   // vortical / eta == 0: r_s = Ir = -1, Nmax = -2 (equatorial_lensing.py:119-123)
     double Ir, Nmax;
     crossing_time(w, o, beta, mbar, &Ir, &Nmax);
     double rs, d0, d1, d2;
     radial_eval<W, false>(w, o, flags, Ir, false, &rs, &d0, &d1, &d2);
     if (Nmax < (double)mbar) rs = 0.0;   // :188
-    out.r = rs;
-    out.Ir = Ir;
-    out.Nmax = Nmax;
+    gq.r = rs;
+    gq.Ir = Ir;
+    gq.Nmax = Nmax;
+    return gq;
+}
+
+// Emission of one order at one pixel from its crossing (equatorial_images.py:124-264 Iobs and helpers)
+// POL = opt.polarization as a compile-time constant: the unpolarized kernel does not carry the tetrad / Penrose-Walker code's
+// registers (two instantiations of the image kernel)
+template <bool POL>
+KG_HD OrderOut image_physics(const Observer& o, int flags, const kgeo_models& M, const kgeo_image_opts& opt, double alpha, double beta,
+                             double lam, double eta, double tau_tot, int mbar, const OrderGeom& gq) {
+    OrderOut out{0.0, 0.0, 0.0, 0.0, gq.r, 0.0, gq.Ir, gq.Nmax, 0.0, 0.0};
+    if (!(eta > 0.0)) return out;
+    const double rs = gq.r, Ir = gq.Ir, Nmax = gq.Nmax;
     bool dead = (Nmax < (double)mbar) || (Nmax == -1.0) || (rs <= o.rplus);   // equatorial_images.py:175
     if (M.emiscut_in > 0.0) dead = dead || (rs < M.emiscut_in);
     if (M.emiscut_out > 0.0) dead = dead || (rs > M.emiscut_out);
     if (dead) return out;   // a NaN radius is not masked (comparisons with NaN are False) and propagates, as in the reference
     const double a = o.a, a2 = o.a2, r = rs, r2 = rs * rs;
-    double kr = ((!(flags & F_OUTSIDE)) || (Ir <= 0.5 * w(S_TAUTOT))) ? 1.0 : -1.0;        // :266-288
+    double kr = ((!(flags & F_OUTSIDE)) || (Ir <= 0.5 * tau_tot)) ? 1.0 : -1.0;        // :266-288
     double par = (mbar & 1) ? -1.0 : 1.0;
     double kth = o.north ? -par : par;                                                      // :290-305
     // the models at the crossing radius and, for the thermal emissivity's field normalisation (:221-223), at its radius R_b
     // first: one rolled loop over one copy of the model code
     const bool thermal = (M.emissivity_type == KGEO_EM_THERMAL);
-    const bool need_B = opt.polarization || thermal;
+    const bool need_B = POL || thermal;
     FluidAt fl_at;
     double B0 = 1.0;
 #pragma unroll 1
@@ -591,7 +616,7 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
     double g = 1.0 / (u.u0 - lam * u.u3 - kth * u.u2 * sqTH - kr * u.u1 * sqR / Delta);   // :332
     out.g = g;
     double sinthb, bsq, c2chi = 0.0, s2chi = 0.0;
-    if (opt.polarization) {   // calc_polquantities :336-487 + calc_evpa :524-544
+    if (POL) {   // calc_polquantities :336-487 + calc_evpa :524-544
         double l0 = gm.g00 * u.u0 + gm.g03 * u.u3, l1 = gm.g11 * u.u1, l2 = gm.g22 * u.u2, l3 = gm.g33 * u.u3 + gm.g03 * u.u0;
         double Nr = sqrt(-gm.g11 * (l0 * u.u0 + l3 * u.u3) * (1.0 + l2 * u.u2));
         double Nth = sqrt(gm.g22 * (1.0 + l2 * u.u2));
@@ -654,11 +679,20 @@ KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_
         I = (g * g) * je;
     }
     out.I = I;
-    if (opt.polarization) {
+    if (POL) {
         out.Q = c2chi * I;
         out.U = s2chi * I;
     }
     return out;
+}
+
+// one order, geometry and emission together (host-side checks; the image kernel calls the two halves separately)
+template <class W>
+KG_HD OrderOut image_order(const W& w, const Observer& o, int flags, const kgeo_models& M, const kgeo_image_opts& opt,
+                           double alpha, double beta, int mbar) {
+    const OrderGeom gq = image_geometry(w, o, flags, beta, mbar);
+    return opt.polarization ? image_physics<true>(o, flags, M, opt, alpha, beta, w(S_LAM), w(S_ETA), w(S_TAUTOT), mbar, gq)
+                            : image_physics<false>(o, flags, M, opt, alpha, beta, w(S_LAM), w(S_ETA), w(S_TAUTOT), mbar, gq);
 }
 
 }  // namespace kg

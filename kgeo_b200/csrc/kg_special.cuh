@@ -388,6 +388,38 @@ KG_NOINLINE double ellip_PicTail(double n, double m) {
     return (n * (1.0 / 3.0)) * ((pp.p - 1.0) * rj - 3.0 * ellip_K(m)) / (q + 1.0);
 }
 
+// K(m), RD(0, 1-m, 1) and NP tails Pi(n_i|m) - K(m) of ONE parameter m on ONE shared duplication track (x = 0, y = 1 - m, z = 1)
+// with the 1-ulp seeded square roots / divisions of the per-sample code.  The per-ray setup needs 2 + NP complete integrals of
+// each motion's parameter; evaluated one by one through ellip_K / ellip_RDc / ellip_PicTail (stand-alone Carlson routines, IEEE
+// square roots and divisions, one duplication track EACH) they were three quarters of ray_setup_kernel's instructions.
+// Same mathematics, results within an ulp or two of the stand-alone routines.  n_i == 1 gives +inf as ellip_PicTail does.
+template <int NP, bool WANT_K = true, bool WANT_RD = true>
+KG_NOINLINE void ellip_complete(double m, const double* n, double* K, double* RDc, double* PicT) {
+    const double y = 1.0 - m;
+    PiPrep pp[NP > 0 ? NP : 1];
+    double pa[NP > 0 ? NP : 1], rj[NP > 0 ? NP : 1];
+    bool need_K = WANT_K;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        pp[i] = pi_prepare(n[i], 1.0, 0.0, y);
+        pa[i] = (n[i] == 1.0) ? 1.0 : pp[i].p;             // placeholder: the result is overwritten with +inf
+    }
+    double rf = 0.0, rd = 0.0;
+    // the principal-value branch of a tail (rho < 0) needs K(m) as well: always taken along when there are tails
+    carlson_bundle<NP, (WANT_K || NP > 0), WANT_RD>(0.0, y, pa, &rf, &rd, rj);
+    (void)need_K;
+    if (K) *K = rf;
+    if (RDc) *RDc = rd;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        double v;
+        if (n[i] == 1.0) v = kInf;
+        else if (pp[i].rho > 0.0) v = (n[i] * (1.0 / 3.0)) * rj[i];
+        else v = (n[i] * (1.0 / 3.0)) * ((pp[i].p - 1.0) * rj[i] - 3.0 * rf) / (-pp[i].rho + 1.0);
+        PicT[i] = v;
+    }
+}
+
 // ---- incomplete Legendre integrals of a general amplitude (setup + element-wise API) ---------------------------
 // Period reduction: phi = j*pi + phi_r, |phi_r| <= pi/2 (same mathematics as scipy_ellip_binding.py:164-192 and
 // cephes ellik/ellie).  Returns F, E and up to NP Pi's for one (phi, m).

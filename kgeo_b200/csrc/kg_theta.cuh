@@ -61,23 +61,35 @@ constexpr double kThetaEdge = KG_THETA_EDGE, kThetaEdgePolar = KG_THETA_EDGE_POL
 
 struct ThetaRay {
     double m, K, Kp, q, eokm1, eokm1p;   // eokm1p = E(m')/K' - 1
+    double RDc;                          // RD(0, 1 - m, 1) = 3 (K - E) / m
     int ok;
 };
 
-KG_HD ThetaRay theta_ray(double m) {
+// K_known / RDc_known: K(m) and RD(0, 1-m, 1) when the caller already has them (the first setup kernel stores both: every
+// complete integral is evaluated once per ray), NaN to have them computed here
+KG_HD ThetaRay theta_ray(double m, double K_known = kInf - kInf, double RDc_known = kInf - kInf) {
     ThetaRay r;
     r.m = m;
     r.ok = (m > 1.0e-12 && m < 1.0) ? 1 : 0;
     if (!r.ok) {
-        r.K = r.Kp = r.q = r.eokm1 = r.eokm1p = 0.0;
+        r.K = r.Kp = r.q = r.eokm1 = r.eokm1p = r.RDc = 0.0;
         return r;
     }
     double mp = 1.0 - m;
-    r.K = ellip_K(m);
-    r.Kp = ellip_K(mp);
+    const bool haveK = (K_known == K_known), haveRD = (RDc_known == RDc_known);
+    r.K = K_known;
+    r.RDc = RDc_known;
+    if (!haveK || !haveRD) {
+        double Kc, RDm;
+        ellip_complete<0>(m, nullptr, &Kc, &RDm, nullptr);
+        if (!haveK) r.K = Kc;
+        if (!haveRD) r.RDc = RDm;
+    }
+    double RDp;
+    ellip_complete<0>(mp, nullptr, &r.Kp, &RDp, nullptr);               // complementary parameter: K', RD(0, m, 1)
     r.q = exp(-kPi * r.Kp / r.K);
-    r.eokm1 = -m * ellip_RDc(m) / (3.0 * r.K);
-    r.eokm1p = -mp * ellip_RDc(mp) / (3.0 * r.Kp);
+    r.eokm1 = -m * r.RDc / (3.0 * r.K);
+    r.eokm1p = -mp * RDp / (3.0 * r.Kp);
     if (!(r.q <= kThetaQMax)) r.ok = 0;
     return r;
 }

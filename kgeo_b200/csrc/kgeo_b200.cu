@@ -1043,32 +1043,57 @@ struct ImageOut {
     double *I, *Q, *U, *r, *Ir, *g, *sinthb, *nmax, *npol, *imax, *lp, *Ie;
 };
 
+// Fused equatorial image.  Per pixel: setup once, then the GEOMETRY of every order (crossing time, Nmax, crossing radius: all
+// that needs the ray constants), parked in this thread's own shared-memory column, then the EMISSION of every order from the parked
+// crossings.  With geometry and emission interleaved per order (round 1) the ~14 ray constants the later orders need stayed live
+// across the emission code and the 80-register kernel spilled 690 B per thread (ncu: 9.2 GB written to DRAM for a 3.2 GB image).
+#ifndef KG_IMG_CHUNK
+#define KG_IMG_CHUNK 4                  // orders whose crossings are parked at a time (more orders: several rounds)
+#endif
+template <bool POL>
 __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
                                                             const double* __restrict__ alpha, const double* __restrict__ beta,
                                                             ImageOut out) {
+    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];             // [r, Ir, Nmax of order c][thread]
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     double w[NW_LITE];
     int fl;
-    double al = alpha[i], be = beta[i];
+    const double al = alpha[i], be = beta[i];
     ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
+    // (Building the AGM ladder of the radial parameter once per ray and ascending it per order, as the track kernels' Carlson path
+    // does, was measured: the ladder is a dynamically indexed local array -- r_equatorial 4.25 against 3.50 ms.)
     ArrayW W{w};
     if (out.npol) out.npol[i] = n_poloidal_at(W, w[S_TAUTOT]);
     if (out.imax) out.imax[i] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
+    const double lam = w[S_LAM], eta = w[S_ETA], tau_tot = w[S_TAUTOT];
     double lastN = -2.0;
-    for (int mbar = opt.mbar_min; mbar <= opt.mbar_max; ++mbar) {
-        OrderOut v = image_order(W, o, fl, M, opt, al, be, mbar);
-        size_t q = (size_t)(mbar - opt.mbar_min) * npix + i;
-        if (out.I) out.I[q] = v.I;
-        if (out.Q) out.Q[q] = v.Q;
-        if (out.U) out.U[q] = v.U;
-        if (out.r) out.r[q] = v.r;
-        if (out.Ir) out.Ir[q] = v.Ir;
-        if (out.g) out.g[q] = v.g;
-        if (out.sinthb) out.sinthb[q] = v.sinthb;
-        if (out.lp) out.lp[q] = v.lp;
-        if (out.Ie) out.Ie[q] = v.Ie;
-        lastN = v.Nmax;
+    for (int m0 = opt.mbar_min; m0 <= opt.mbar_max; m0 += KG_IMG_CHUNK) {
+        const int m1 = min(opt.mbar_max, m0 + KG_IMG_CHUNK - 1);
+        for (int mbar = m0; mbar <= m1; ++mbar) {
+            const OrderGeom gq = image_geometry(W, o, fl, be, mbar);
+            const int c = 3 * (mbar - m0);
+            park[c][threadIdx.x] = gq.r;
+            park[c + 1][threadIdx.x] = gq.Ir;
+            park[c + 2][threadIdx.x] = gq.Nmax;
+        }
+#pragma unroll 1
+        for (int mbar = m0; mbar <= m1; ++mbar) {
+            const int c = 3 * (mbar - m0);
+            const OrderGeom gq{park[c][threadIdx.x], park[c + 1][threadIdx.x], park[c + 2][threadIdx.x]};
+            const OrderOut v = image_physics<POL>(o, fl, M, opt, al, be, lam, eta, tau_tot, mbar, gq);
+            const size_t q = (size_t)(mbar - opt.mbar_min) * npix + i;
+            if (out.I) out.I[q] = v.I;
+            if (out.Q) out.Q[q] = v.Q;
+            if (out.U) out.U[q] = v.U;
+            if (out.r) out.r[q] = v.r;
+            if (out.Ir) out.Ir[q] = v.Ir;
+            if (out.g) out.g[q] = v.g;
+            if (out.sinthb) out.sinthb[q] = v.sinthb;
+            if (out.lp) out.lp[q] = v.lp;
+            if (out.Ie) out.Ie[q] = v.Ie;
+            lastN = v.Nmax;
+        }
     }
     if (out.nmax) out.nmax[i] = lastN;
 }
@@ -1665,7 +1690,8 @@ int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, c
     if (npix == 0) return 0;
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
     ImageOut out{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr};
-    image_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
+    if (opts->polarization) image_kernel<true><<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
+    else image_kernel<false><<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
     LAUNCHED("image_kernel");
     return 0;
 }

@@ -45,14 +45,20 @@ def test_getstokes_ff_boost_and_gammamax_against_reference(golden):
     g = golden('jet_boost')
     a, r_o, th_o, psit, neqmax, ngeo = [float(x) for x in g['par']]
     A, B = g['alpha'], g['beta']
+    # Gate 1e-7 on the Stokes parameters: the crossings come out of the secant solve at the reference's own tolerance (|d tau| <
+    # 1e-8, and a different but equally converged last iterate), and the energy-conserving boost amplifies a crossing's position
+    # error (with the REFERENCE's crossings the same device code reproduces its Stokes parameters to 1e-15:
+    # tests/test_offeq_hostbuild.py::test_ff_boost_and_gammamax_on_the_host).  Crossings themselves: 1e-8.
     for name, kw in zip(json.loads(str(g['names'])), json.loads(str(g['kwargs']))):
         raw = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model='mono', sigma=2, sumsubring=False, **kw)
         for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
             ref = g[name + '_raw_' + k]
-            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
+            tol = 1e-7 if k in ('i', 'q', 'u') else 1e-8
+            assert_close(np.asarray(v, dtype=float), ref, tol, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s raw %s' % (name, k))
         img = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model='mono', sigma=2, retvals=True, retsin=True, **kw)
         for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
             ref = g[name + '_img_' + k]
-            assert_close(np.asarray(v, dtype=float), ref, 1e-8, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
+            tol = 1e-7 if k in ('I', 'Q', 'U', 'evpa') else 1e-8
+            assert_close(np.asarray(v, dtype=float), ref, tol, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
     with pytest.raises(NotImplementedError):
         off_eq.getstokes(1.5, A, B, r_o, th_o, 0.7, int(ngeo), model='power', pval=0.75, nu_parallel='FF')

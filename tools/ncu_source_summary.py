@@ -2,10 +2,18 @@
 stall samples by opcode class, and the hottest instructions.  usage: ncu_source_summary.py file.csv [points]"""
 import csv, sys, collections, re
 rows = list(csv.reader(open(sys.argv[1])))
+# a report with several launches holds one section per launch ("Kernel Name" line + header + instructions): -k N picks the N-th
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if "-k" in sys.argv and starts:
+    k = int(sys.argv[sys.argv.index("-k") + 1])
+    rows = rows[starts[k]:(starts[k + 1] if k + 1 < len(starts) else len(rows))]
+    print("launch", k, ":", rows[0][1][:100])
+elif len(starts) > 1:
+    rows = rows[starts[0]:starts[1]]
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
-npts = float(sys.argv[2]) if len(sys.argv) > 2 else None
+npts = float(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("-") else None
 tot_inst = 0; tot_samp = 0
 by_op = collections.Counter(); samp_op = collections.Counter(); stall_tot = collections.Counter()
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
