@@ -57,8 +57,8 @@ def to_bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
 
 
-git = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-dirty = bool(subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "kgeo_b200/csrc"], capture_output=True, text=True).stdout.strip())
+git = os.environ.get("KGEO_GIT_SHA") or subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+dirty = (not os.environ.get("KGEO_GIT_SHA")) and bool(subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "kgeo_b200/csrc"], capture_output=True, text=True).stdout.strip())
 summ = {"what": "ncu --set full --clock-control none captures of `bench.py` (KGEO_BENCH_PROFILE=1) and tools/profile_image.py on one B200",
         "git_sha": git + ("+uncommitted kernel changes" if dirty else ""), "csrc_sha256_16": bench.kernel_source_hash()}
 if os.path.exists(args.out):
