@@ -159,6 +159,25 @@ class RayBundle(object):
                                      dptr(out["tau"]), self.npix, stream_ptr()))
         return {k: v for k, v in out.items() if v is not None}
 
+    def tracks_host(self, ntau, maxtaufrac=1.0, want=("t", "r", "th", "ph")):
+        """The host pipeline of the C ABI (kgeo_raytrace_host) for the rays of this bundle: setup + track kernels in sample
+        slabs overlapped with D2H copies into page-locked NumPy arrays (torch's caching pinned allocator).  Returns a dict
+        name -> (ntau, npix) float64 NumPy array for the names in `want`.  Bit-identical to `tracks` (same kernels)."""
+        L = _lib.lib()
+        t = torch()
+        host = {}
+        for name in ("t", "r", "th", "ph", "sig", "tau"):
+            if name in want:
+                try:
+                    host[name] = t.empty((ntau, self.npix), dtype=t.float64, pin_memory=True)
+                except RuntimeError:                      # page-locked memory exhausted: pageable destination
+                    host[name] = t.empty((ntau, self.npix), dtype=t.float64)
+        hp = lambda n: ctypes.cast(host[n].data_ptr(), c_double_p) if n in host else ctypes.cast(None, c_double_p)
+        _lib.check(L.kgeo_raytrace_host(ctypes.byref(self.obs), self.npix, hptr(self.alpha_host), hptr(self.beta_host), self.mode,
+                                        int(ntau), float(maxtaufrac), hp("t"), hp("r"), hp("th"), hp("ph"), hp("sig"), hp("tau"),
+                                        self.dev.index if self.dev.index is not None else t.cuda.current_device()))
+        return {k: v.numpy() for k, v in host.items()}        # the arrays keep the pinned blocks alive (arr.base)
+
     def crossing_counts(self, tau, want_eq=True, want_pol=True):
         L = _lib.lib()
         t = torch()

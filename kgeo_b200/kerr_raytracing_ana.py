@@ -59,15 +59,23 @@ def raytrace_ana(a=SPIN,
     if bundle.clamped:
         print("WARNING: there were eta<0 points for spin %f<MINSPIN!" % a)
 
-    names = _track_names(bundle.npix, ngeo, bundle.dev)
-    # as in the reference (:97) phi and t are always computed here, whatever do_phi_and_t says
-    out = bundle.tracks(ntau=ngeo, maxtaufrac=maxtaufrac, full=True, want=names)
+    # The (ngeo, npix) arrays are produced on first use, in the form the caller asks for:
+    #  * NumPy fields (geo_coords, r_s, mino_times, ...) -> the host pipeline of the C ABI (kgeo_raytrace_host): the track kernels
+    #    run in sample slabs while the previous slab drains into page-locked NumPy arrays, so a script that only reads the host
+    #    arrays gets them at the PCIe rate and the 16.8 GB of a 1024^2 x 500 trace never sit in HBM at once;
+    #  * device_array(name) (the solver, sharding, anything that stays on the GPU) -> one launch into device-resident tensors.
+    # As in the reference (:97) phi and t are always computed, whatever do_phi_and_t says.
+    def device_tracks(want):
+        names = set(want)
+        if names & {"t", "r", "th", "ph"}:            # one launch gives everything: take sigma and tau along when they fit
+            names |= set(_track_names(bundle.npix, ngeo, bundle.dev))
+        return bundle.tracks(ntau=ngeo, maxtaufrac=maxtaufrac, full=True, want=tuple(names))
 
-    def recompute(name):
-        return bundle.tracks(ntau=ngeo, maxtaufrac=maxtaufrac, full=True, want=(name,))[name]
+    def host_tracks(want):
+        return bundle.tracks_host(ntau=ngeo, maxtaufrac=maxtaufrac, want=tuple(want))
 
-    geos = Geodesics(a, observer_coords, [alpha, beta], out.get("tau"), out.get("sig"),
-                     [out["t"], out["r"], out["th"], out["ph"]], _bundle=bundle, _recompute=recompute)
+    geos = Geodesics(a, observer_coords, [alpha, beta], None, None, [None, None, None, None], _bundle=bundle,
+                     _device_tracks=device_tracks, _host_tracks=host_tracks if bundle.alpha_host is not None else None)
 
     if savedata and do_phi_and_t:      # the reference wraps this in try / except and carries on (:103-108)
         print('saving data...')

@@ -19,14 +19,14 @@ def _np(x):
 class Geodesics(object):
     """Result of raytrace_ana (kgeo/kerr_raytracing_utils.py:15-93): same fields and properties.
 
-    The track arrays live on the GPU (`*_device` attributes, [ngeo, npix] float64 torch tensors); the reference's
-    NumPy-valued fields (`mino_times`, `affine_times`, `geo_coords`) are materialised on first access and cached.
-    Arrays that were not produced by the launch (e.g. sigma / tau when memory is tight) are recomputed on demand by
-    the same kernel through `_recompute`.
+    The (ngeo, npix) arrays are produced on first use: the reference's NumPy-valued fields (`mino_times`, `affine_times`,
+    `geo_coords`, `r_s`, ...) through the host pipeline of the C ABI (slabs of samples computed while the previous slab drains
+    into page-locked memory), `device_array(name)` as device-resident [ngeo, npix] float64 torch tensors from one launch.  Both
+    are cached; objects built from NumPy arrays (loadgeos, user code) just hold them.
     """
 
     def __init__(self, a, observer_coords, image_coords, mino_times, affine_times, geo_coords, _bundle=None,
-                 _recompute=None):
+                 _device_tracks=None, _host_tracks=None):
         self.a = a
         self.observer_coords = observer_coords
         self.image_coords = image_coords
@@ -35,15 +35,20 @@ class Geodesics(object):
             self._dev[name] = arr
         self._host = {}
         self._bundle = _bundle
-        self._recompute = _recompute
+        self._device_tracks = _device_tracks      # names -> dict of [ngeo, npix] CUDA tensors (one kernel launch)
+        self._host_tracks = _host_tracks          # names -> dict of (ngeo, npix) NumPy arrays (slab pipeline of the C ABI)
 
     # ---- lazy host views ----
     def device_array(self, name):
         """[ngeo, npix] CUDA tensor of 't','r','th','ph','sig','tau' (NumPy inputs are returned unchanged)."""
         if self._dev.get(name) is None:
-            if self._recompute is None:
+            if self._device_tracks is None:
                 raise RuntimeError("Geodesics: array %r was not computed" % name)
-            self._dev[name] = self._recompute(name)
+            # the four coordinates come out of one launch: ask for all that are still missing
+            want = tuple(n for n in ("t", "r", "th", "ph") if self._dev.get(n) is None) if name in ("t", "r", "th", "ph") else (name,)
+            for k, v in self._device_tracks(want).items():
+                if self._dev.get(k) is None:
+                    self._dev[k] = v
         return self._dev[name]
 
     def _materialise(self, names):
@@ -53,6 +58,9 @@ class Geodesics(object):
         serial pageable copies."""
         todo = [n for n in names if n not in self._host]
         if not todo:
+            return
+        if self._host_tracks is not None and all(self._dev.get(n) is None for n in todo):
+            self._host.update(self._host_tracks(todo))    # nothing on the device yet: straight through the host pipeline
             return
         t = _engine.torch()
         pending = []
