@@ -52,6 +52,7 @@ CANONICAL_FLOP_PER_POINT = 2400.0   # SURVEY.md 8(d) work model: Carlson duplica
 CANONICAL_FLOP_PER_PIXEL = 3000.0   # n = 0..2 image
 BYTES_PER_POINT = 32.0              # r, theta, phi, t written once
 IMG_PLANES = 24                     # I,Q,U,r,Ir,g,sinthb x 3 orders + nmax, npol, imax: doubles per pixel of an n=0..2 image
+IMG_BLOCKS_DEFAULT = 0              # N > 1: cap on the thread blocks of the image kernel on its side stream (0 = full grid: measured best)
 PARITY_PIXELS = 4096
 
 
@@ -298,18 +299,46 @@ def run_ours(args):
 
     # image of the same pixels (N > 1: part of the step; N = 1: the secondary metric below uses its own 4096^2 plane)
     with_image = world > 1
+    peer = None
     if with_image:
         iobs = _engine.observer_struct(SPIN, float("inf"), th_o)
         M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
         iopts = _lib.ImageOpts(0, 2, 0, 0, float(ei.SPECIND), ei.DISKANGLE, ei.OBSFREQ)
-        img = torch.empty((IMG_PLANES, npix), dtype=torch.float64, device=dev)        # this rank's rows, plane-major
-        gathered = torch.empty((world, IMG_PLANES, npix), dtype=torch.float64, device=dev)
-        final = torch.empty((IMG_PLANES, rows * cols), dtype=torch.float64, device=dev) if rank == 0 else None
-        img_ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
+        npix_all = rows * cols
+        # gather fused into the image kernel: rank 0's planes are a peer buffer every rank stores to over NVLink; the kernel runs
+        # on a side stream next to the track pass.  None: the GPUs cannot map each other (or KGEO_B200_GATHER=nccl) -> all_gather.
+        peer = sharding.peer_buffer(IMG_PLANES * npix_all, 0)
+        gather_mode = "peer_stores" if peer is not None else "nccl_all_gather"
+        if peer is not None:
+            smap = _lib.ShardMap(cols, world, rank, npix_all, int(os.environ.get("KGEO_BENCH_IMG_BLOCKS", IMG_BLOCKS_DEFAULT)), 0)
+            vp = lambda plane: ctypes.cast(ctypes.c_void_p(peer.ptr + 8 * plane * npix_all), _lib.c_double_p)
+            img_ptrs = [vp(3 * i) for i in range(7)] + [vp(21 + i) for i in range(3)]
+            side = torch.cuda.Stream(device=dev, priority=-1)
+            side_ptr = ctypes.c_void_p(side.cuda_stream)
+            token = torch.zeros((1,), dtype=torch.float32, device=dev)
+            final = peer.tensor((IMG_PLANES, npix_all))
+            img = gathered = None
+            evi = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        else:
+            img = torch.empty((IMG_PLANES, npix), dtype=torch.float64, device=dev)        # this rank's rows, plane-major
+            gathered = torch.empty((world, IMG_PLANES, npix), dtype=torch.float64, device=dev)
+            final = torch.empty((IMG_PLANES, npix_all), dtype=torch.float64, device=dev) if rank == 0 else None
+            img_ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    main = torch.cuda.current_stream(dev)
 
     def step(timed=False):
+        fused = with_image and peer is not None
+        if fused:                                    # image + peer-store gather on the side stream, beside setup and tracks
+            side.wait_stream(main)
+            if timed:
+                evi[0].record(side)
+            _lib.check(L.kgeo_equatorial_image_sharded(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
+                                                       _engine.dptr(d_alpha), _engine.dptr(d_beta), ctypes.byref(smap),
+                                                       *img_ptrs, null, null, side_ptr))
+            if timed:
+                evi[1].record(side)
         if timed:
             ev[0].record()
         _lib.check(L.kgeo_ray_setup(ctypes.byref(obs), npix, _engine.dptr(d_alpha), _engine.dptr(d_beta), mode,
@@ -321,7 +350,12 @@ def run_ours(args):
                                  _engine.dptr(outs[3]), null, null, npix, stream))
         if timed:
             ev[2].record()
-        if with_image:
+        if fused:
+            main.wait_stream(side)
+            dist.all_reduce(token)                   # completion signal: behind every rank's image kernel in stream order
+            if timed:
+                ev[4].record()
+        elif with_image:
             _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
                                                _engine.dptr(d_alpha), _engine.dptr(d_beta), *img_ptrs, null, null, stream))
             if timed:
@@ -340,7 +374,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         setup_ms.append(ev[0].elapsed_time(ev[1]))
         track_ms.append(ev[1].elapsed_time(ev[2]))
-        if with_image:
+        if with_image and peer is not None:
+            image_ms.append(evi[0].elapsed_time(evi[1]))      # span of the image kernel on its own stream (beside the tracks)
+            coll_ms.append(ev[2].elapsed_time(ev[4]))         # exposed: end of the tracks -> planes complete on rank 0
+        elif with_image:
             image_ms.append(ev[2].elapsed_time(ev[3]))
             coll_ms.append(ev[3].elapsed_time(ev[4]))
 
@@ -367,8 +404,35 @@ def run_ours(args):
     if profile_only:                                  # under ncu: kernels only, no e2e / CPU legs, no JSON claim
         if rank == 0:
             emit({"profile_only": True, "ms_per_step": ms_per_step, "track_kernel_ms": float(np.median(track_ms)),
-                  "setup_kernel_ms": float(np.median(setup_ms))})
+                  "setup_kernel_ms": float(np.median(setup_ms)), "phases": phases,
+                  "gather": gather_mode if with_image else None})
+        if world > 1:
+            sharding.release_peer_buffers()
+            dist.destroy_process_group()
         return
+
+    # ---- the gathered planes on rank 0 against the same rows computed locally (bit for bit) ----
+    gather_check = None
+    if with_image:
+        ok = 1
+        if rank == 0:
+            probe = sorted(set([1, rows // 2 + 1, rows - 1]))                 # rows owned by other ranks
+            xs, ys = plane_pixels(world)
+            sel = np.concatenate([np.arange(r * cols, (r + 1) * cols) for r in probe])
+            pa = _engine.to_device(np.tile(xs, len(probe)), dev)
+            pb = _engine.to_device(np.repeat(ys[probe], cols), dev)
+            chk = torch.empty((IMG_PLANES, sel.size), dtype=torch.float64, device=dev)
+            cp = [_engine.dptr(chk[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(chk[21 + i]) for i in range(3)]
+            _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), sel.size,
+                                               _engine.dptr(pa), _engine.dptr(pb), *cp, null, null, stream))
+            got = final[:, torch.as_tensor(sel, device=dev)]
+            same = (got == chk) | (torch.isnan(got) & torch.isnan(chk))
+            ok = int(bool(same.all()))
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            raise RuntimeError("bench: the gathered image planes differ from the rows computed on rank 0")
+        gather_check = "ok"
 
     # sanity of the produced data (finite radii on the first samples of every ray)
     if not bool(torch.isfinite(outs[1][1, ::997]).all()):
@@ -405,6 +469,7 @@ def run_ours(args):
     del outs
     if with_image:
         del gathered, final, img
+        sharding.release_peer_buffers()
     torch.cuda.empty_cache()
 
     e2e = e2e_legs(L, obs, mode, A, B, npix, cols, world, rank, local, dev, barrier, allmax)
@@ -486,8 +551,11 @@ def run_ours(args):
                    "outputs": "r,theta,phi,t fp64 [500, %d] = %.1f GB per GPU per step" % (npix, bytes_tracks / 1e9),
                    "l2": "each step writes %.1f GB per GPU (>> 126 MB L2) and re-reads no output; no flush needed" % (bytes_tracks / 1e9),
                    "parallelism": ("1 GPU" if world == 1 else "rows interleaved over %d ranks; no data-path collective in the "
-                                   "trace; final all_gather_into_tensor of the image planes (%.2f GB) + un-interleave on rank 0"
-                                   % (world, IMG_PLANES * 8 * rows * cols / 1e9))},
+                                   "trace; image planes (%.2f GB) to rank 0: %s"
+                                   % (world, IMG_PLANES * 8 * rows * cols / 1e9,
+                                      "stored in place by every rank's image kernel over NVLink peer memory, on a side stream beside "
+                                      "the track pass; one 4-byte all_reduce as the completion signal" if gather_mode == "peer_stores"
+                                      else "all_gather_into_tensor + un-interleave on rank 0"))},
         "phases": phases, "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "secondary": secondary,
     }
@@ -495,9 +563,17 @@ def run_ours(args):
         line["image_ms"] = phases["image_ms"]
         line["collective_ms"] = phases["collective_ms"]
         line["shard_check"] = parity["shard_check"]
-        line["efficiency_limiter"] = ("step = setup %.1f + tracks %.1f + image %.1f + gather %.1f ms (max over ranks); the image, "
-                                      "its gather and the per-ray setup add time but no geodesic points" %
-                                      (phases["setup_ms"], phases["track_ms"], phases["image_ms"], phases["collective_ms"]))
+        line["gather"] = gather_mode
+        line["gather_check"] = gather_check
+        if gather_mode == "peer_stores":
+            line["efficiency_limiter"] = ("step = setup %.1f + tracks %.1f (with the image kernel, %.1f ms on its own stream, sharing "
+                                          "the SMs and storing to rank 0 over NVLink) + %.2f ms exposed wait for the planes (max over "
+                                          "ranks); the image and the per-ray setup add time but no geodesic points" %
+                                          (phases["setup_ms"], phases["track_ms"], phases["image_ms"], phases["collective_ms"]))
+        else:
+            line["efficiency_limiter"] = ("step = setup %.1f + tracks %.1f + image %.1f + gather %.1f ms (max over ranks); the image, "
+                                          "its gather and the per-ray setup add time but no geodesic points" %
+                                          (phases["setup_ms"], phases["track_ms"], phases["image_ms"], phases["collective_ms"]))
         dist.barrier()
     emit(line)
     if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KGEO_B200_ABI_VERSION 3
+#define KGEO_B200_ABI_VERSION 4
 
 #define KGEO_E_BADARG (-1)   /* NULL pointer, negative size, inconsistent shapes */
 #define KGEO_E_RANGE (-2)    /* |a| >= 1, r_o < 100, th_o outside (0,pi) or == pi/2 (the reference's own checks) */
@@ -104,6 +104,26 @@ typedef struct kgeo_image_opts {
     double diskangle;
     double nu_obs;
 } kgeo_image_opts;
+
+/* Where the pixels of a row shard go (kgeo_equatorial_image_sharded).  The shard is npix / cols whole image rows; local row lr is
+ * written to row lr * row_step + row_offset of every destination plane (rows interleaved over N ranks: row_step = N,
+ * row_offset = rank; a contiguous block of rows: row_step = 1, row_offset = first row; a whole image: cols = npix, 1, 0).
+ * Consecutive order planes of one output are plane_stride elements apart in the destination (>= the destination plane). */
+typedef struct kgeo_shard_map {
+    uint64_t cols;
+    uint64_t row_step;
+    uint64_t row_offset;
+    uint64_t plane_stride;
+    int32_t max_blocks;    /* > 0: at most this many 256-thread blocks walk the pixels (grid-stride), leaving the other SMs to
+                              concurrent work on another stream; 0: one block per 256 pixels */
+    int32_t reserved;
+} kgeo_shard_map;
+
+/* Exported CUDA IPC handle of a peer buffer (cudaIpcMemHandle_t, 64 bytes): plain data, sent to the other processes of the
+ * box by whatever transport the host program has. */
+typedef struct kgeo_peer_handle {
+    unsigned char bytes[64];
+} kgeo_peer_handle;
 
 int kgeo_abi_version(void);
 const char* kgeo_last_error(void);
@@ -218,6 +238,25 @@ int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, c
                           const double* alpha_dev, const double* beta_dev, double* I_dev, double* Q_dev, double* U_dev,
                           double* r_dev, double* Ir_dev, double* g_dev, double* sinthb_dev, double* nmax_dev,
                           double* npol_dev, double* imax_dev, double* lp_dev, double* Ie_dev, void* stream);
+/* Row-sharded image with the gather fused into the kernel (BASELINE cfg 4 / 5 over the GPUs of a box; the reference computes
+ * the whole plane in one process, kgeo/equatorial_images.py:23-122): as kgeo_equatorial_image for the npix pixels of this
+ * shard, but every output element is stored at its place in destination planes described by `map` -- which may be memory of
+ * ANOTHER GPU of the box mapped with kgeo_peer_open (coalesced stores over NVLink; no staging copy, no separate collective,
+ * no un-interleave pass).  The [npix] outputs (nmax, npol, imax) use the same row map.  The stores are complete when the
+ * kernel is; the owner of the destination must still order its reads after the writers' streams (any cross-rank barrier). */
+int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                                  const double* alpha_dev, const double* beta_dev, const kgeo_shard_map* map, double* I_dst,
+                                  double* Q_dst, double* U_dst, double* r_dst, double* Ir_dst, double* g_dst,
+                                  double* sinthb_dst, double* nmax_dst, double* npol_dst, double* imax_dst, double* lp_dst,
+                                  double* Ie_dst, void* stream);
+/* Peer buffers.  kgeo_peer_alloc: `bytes` of device memory on the current device plus the handle under which the other
+ * processes of the box open it; kgeo_peer_open (in another process, on ITS current device): the address at which that
+ * device reads and writes the exporter's memory (peer access over NVLink is enabled on first use); kgeo_peer_close unmaps,
+ * kgeo_peer_free releases the allocation in the exporting process (after every importer has closed it). */
+int kgeo_peer_alloc(size_t bytes, void** dev_ptr, kgeo_peer_handle* handle);
+int kgeo_peer_open(const kgeo_peer_handle* handle, void** dev_ptr);
+int kgeo_peer_close(void* dev_ptr);
+int kgeo_peer_free(void* dev_ptr);
 /* Host-buffer variant (end-to-end path).  Same layouts, HOST pointers. */
 int kgeo_equatorial_image_host(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts,
                                size_t npix, const double* alpha, const double* beta, double* I, double* Q, double* U,

@@ -34,6 +34,15 @@ class ImageOpts(ctypes.Structure):
                 ("nu_obs", ctypes.c_double)]
 
 
+class ShardMap(ctypes.Structure):
+    _fields_ = [("cols", ctypes.c_uint64), ("row_step", ctypes.c_uint64), ("row_offset", ctypes.c_uint64),
+                ("plane_stride", ctypes.c_uint64), ("max_blocks", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class PeerHandle(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.c_ubyte * 64)]
+
+
 VEL = dict(zamo=0, infall=1, kep=2, subkep=3, general=4, gelles=5, simfit=6, fromfile=7, driftframe=8)
 BF = dict(simple=0, simple_rm1=1, bz_guess=2, gen_power=3, monopoleA=4, fromfile=5, bz_monopole=6, bz_para=7, power=8)
 EM = dict(constant=0, bpl=1, glm=2, ring=3, thermal=4)
@@ -75,6 +84,11 @@ SIGNATURES = {
                                        ctypes.c_double, ctypes.c_double, ctypes.c_int, _P, _P, _P, c_int32_p, _V]),
     "kgeo_critical_curve": (ctypes.c_int, [ctypes.c_double] * 6 + [_S, _P, _P, _V]),
     "kgeo_equatorial_image": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [_V]),
+    "kgeo_equatorial_image_sharded": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P, ctypes.POINTER(ShardMap)] + [_P] * 12 + [_V]),
+    "kgeo_peer_alloc": (ctypes.c_int, [_S, ctypes.POINTER(_V), ctypes.POINTER(PeerHandle)]),
+    "kgeo_peer_open": (ctypes.c_int, [ctypes.POINTER(PeerHandle), ctypes.POINTER(_V)]),
+    "kgeo_peer_close": (ctypes.c_int, [_V]),
+    "kgeo_peer_free": (ctypes.c_int, [_V]),
     "kgeo_equatorial_image_host": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [ctypes.c_int]),
     "kgeo_velocity_u_lab": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, _P, _V]),
     "kgeo_bfield_lab": (ctypes.c_int, [_MOD, ctypes.c_double, _S, _P, _P, _P, _P, _P, _V]),
@@ -120,7 +134,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.kgeo_abi_version() != 3:
+        if L.kgeo_abi_version() != 4:
             raise ImportError("kgeo_b200: ABI version mismatch")
         _lib = L
     return _lib

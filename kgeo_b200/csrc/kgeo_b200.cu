@@ -1050,13 +1050,12 @@ struct ImageOut {
 #ifndef KG_IMG_CHUNK
 #define KG_IMG_CHUNK 4                  // orders whose crossings are parked at a time (more orders: several rounds)
 #endif
+// One pixel of the fused image: i = pixel of this launch, d = its place in the destination planes, pstride = elements between
+// the order planes of one output.
 template <bool POL>
-__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
-                                                            const double* __restrict__ alpha, const double* __restrict__ beta,
-                                                            ImageOut out) {
-    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];             // [r, Ir, Nmax of order c][thread]
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
+__device__ __forceinline__ void image_pixel(const Observer& o, const kgeo_models& M, const kgeo_image_opts& opt,
+                                            const double* __restrict__ alpha, const double* __restrict__ beta, const ImageOut& out,
+                                            size_t i, size_t d, size_t pstride, double (*park)[IMG_THREADS]) {
     double w[NW_LITE];
     int fl;
     const double al = alpha[i], be = beta[i];
@@ -1064,8 +1063,8 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Ob
     // (Building the AGM ladder of the radial parameter once per ray and ascending it per order, as the track kernels' Carlson path
     // does, was measured: the ladder is a dynamically indexed local array -- r_equatorial 4.25 against 3.50 ms.)
     ArrayW W{w};
-    if (out.npol) out.npol[i] = n_poloidal_at(W, w[S_TAUTOT]);
-    if (out.imax) out.imax[i] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
+    if (out.npol) out.npol[d] = n_poloidal_at(W, w[S_TAUTOT]);
+    if (out.imax) out.imax[d] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
     const double lam = w[S_LAM], eta = w[S_ETA], tau_tot = w[S_TAUTOT];
     double lastN = -2.0;
     for (int m0 = opt.mbar_min; m0 <= opt.mbar_max; m0 += KG_IMG_CHUNK) {
@@ -1082,7 +1081,7 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Ob
             const int c = 3 * (mbar - m0);
             const OrderGeom gq{park[c][threadIdx.x], park[c + 1][threadIdx.x], park[c + 2][threadIdx.x]};
             const OrderOut v = image_physics<POL>(o, fl, M, opt, al, be, lam, eta, tau_tot, mbar, gq);
-            const size_t q = (size_t)(mbar - opt.mbar_min) * npix + i;
+            const size_t q = (size_t)(mbar - opt.mbar_min) * pstride + d;
             if (out.I) out.I[q] = v.I;
             if (out.Q) out.Q[q] = v.Q;
             if (out.U) out.U[q] = v.U;
@@ -1095,7 +1094,40 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Ob
             lastN = v.Nmax;
         }
     }
-    if (out.nmax) out.nmax[i] = lastN;
+    if (out.nmax) out.nmax[d] = lastN;
+}
+
+template <bool POL>
+__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
+                                                            const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                            ImageOut out) {
+    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];             // [r, Ir, Nmax of order c][thread]
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    image_pixel<POL>(o, M, opt, alpha, beta, out, i, i, npix, park);
+}
+
+// The pixels are a block of image rows whose results go to rows lr * row_step + row_offset of destination planes that may live
+// on ANOTHER GPU (peer memory over NVLink: plain coalesced stores -- the gather of a row-sharded image is fused into the kernel
+// that computes it); the grid may be capped (grid-stride walk) to leave SMs to concurrent work on another stream.
+template <bool POL, bool WALK>
+__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_sharded_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
+                                                            const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                            ImageOut out, kgeo_shard_map map) {
+    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (WALK) {
+        const size_t walk = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+        for (size_t i = i0; i < npix; i += walk) {
+            const size_t d = ((i / map.cols) * map.row_step + map.row_offset) * map.cols + i % map.cols;
+            image_pixel<POL>(o, M, opt, alpha, beta, out, i, d, (size_t)map.plane_stride, park);
+        }
+    } else {
+        if (i0 >= npix) return;
+        const size_t d = ((i0 / map.cols) * map.row_step + map.row_offset) * map.cols + i0 % map.cols;
+        image_pixel<POL>(o, M, opt, alpha, beta, out, i0, d, (size_t)map.plane_stride, park);
+    }
 }
 
 // element-wise physics
@@ -1676,6 +1708,28 @@ int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0,
     return 0;
 }
 
+static int launch_image(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                        const double* alpha, const double* beta, const kgeo_shard_map* map, const ImageOut& out, cudaStream_t st) {
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    unsigned grid = grid_for(npix, IMG_THREADS);
+    if (map) {
+        const bool capped = map->max_blocks > 0 && (unsigned)map->max_blocks < grid;
+        if (capped) {
+            grid = (unsigned)map->max_blocks;
+            if (opts->polarization) image_sharded_kernel<true, true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
+            else image_sharded_kernel<false, true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
+        } else {
+            if (opts->polarization) image_sharded_kernel<true, false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
+            else image_sharded_kernel<false, false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
+        }
+    } else {
+        if (opts->polarization) image_kernel<true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out);
+        else image_kernel<false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out);
+    }
+    LAUNCHED("image_kernel");
+    return 0;
+}
+
 int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
                           const double* alpha, const double* beta, double* I, double* Q, double* U, double* r, double* Ir,
                           double* g, double* sinthb, double* nmax, double* npol, double* imax, double* lp, double* Ie,
@@ -1688,11 +1742,66 @@ int kgeo_equatorial_image(const kgeo_observer* obs, const kgeo_models* models, c
     if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image: bad mbar range");
     if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image: NULL pointer");
     if (npix == 0) return 0;
-    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
-    ImageOut out{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr};
-    if (opts->polarization) image_kernel<true><<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
-    else image_kernel<false><<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, *models, *opts, npix, alpha, beta, out);
-    LAUNCHED("image_kernel");
+    return launch_image(obs, models, opts, npix, alpha, beta, nullptr,
+                        ImageOut{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr},
+                        (cudaStream_t)stream);
+}
+
+int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
+                                  const double* alpha, const double* beta, const kgeo_shard_map* map, double* I, double* Q,
+                                  double* U, double* r, double* Ir, double* g, double* sinthb, double* nmax, double* npol,
+                                  double* imax, double* lp, double* Ie, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    rc = check_models(models);
+    if (rc) return rc;
+    if (!opts || !map) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: opts / map is NULL");
+    if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: bad mbar range");
+    if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: NULL pointer");
+    if (npix == 0) return 0;
+    if (map->cols == 0 || map->row_step == 0 || npix % map->cols != 0 || map->max_blocks < 0)
+        return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: the shard must be whole rows of cols > 0 pixels, row_step > 0");
+    const uint64_t last_row = (npix / map->cols - 1) * map->row_step + map->row_offset;
+    if (opts->mbar_max > opts->mbar_min && map->plane_stride < (last_row + 1) * map->cols)
+        return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: plane_stride is smaller than the destination plane");
+    return launch_image(obs, models, opts, npix, alpha, beta, map,
+                        ImageOut{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr},
+                        (cudaStream_t)stream);
+}
+
+// ---- peer buffers: device memory that other processes of the box map and write with plain stores ----
+int kgeo_peer_alloc(size_t bytes, void** dev_ptr, kgeo_peer_handle* handle) {
+    if (!dev_ptr || !handle || bytes == 0) return fail_arg(KGEO_E_BADARG, "kgeo_peer_alloc: bad argument");
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));                       // cudaMalloc, not a pool: legacy IPC handles export whole cudaMalloc allocations
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CU(e);
+    }
+    static_assert(sizeof(h) == sizeof(handle->bytes), "kgeo_peer_handle must hold a cudaIpcMemHandle_t");
+    memcpy(handle->bytes, &h, sizeof(h));
+    *dev_ptr = p;
+    return 0;
+}
+int kgeo_peer_open(const kgeo_peer_handle* handle, void** dev_ptr) {
+    if (!dev_ptr || !handle) return fail_arg(KGEO_E_BADARG, "kgeo_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // maps the exporter's memory into the CURRENT device's address space
+    *dev_ptr = p;
+    return 0;
+}
+int kgeo_peer_close(void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+int kgeo_peer_free(void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CU(cudaFree(dev_ptr));
     return 0;
 }
 

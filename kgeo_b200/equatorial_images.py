@@ -61,6 +61,35 @@ def image_device(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, velo
     return out
 
 
+_DST_ORDER = _PLANES + ("nmax", "npol", "imax", "lp", "Ie")
+
+
+def image_into(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, velocity, bfield, polarization, pathlength,
+               specind, diskangle, nu_obs, dst, cols, row_step, row_offset, plane_stride, max_blocks=0, dev=None):
+    """The fused image kernel for a shard of whole pixel rows (alpha/beta: NumPy arrays or CUDA tensors, `cols` pixels per row),
+    every result stored at its place in DESTINATION planes (kgeo_equatorial_image_sharded): `dst` maps an output name
+    ('I','Q','U','r','Ir','g','sinthb','nmax','npol','imax','lp','Ie') to the device address (int) of its first plane --
+    memory of this GPU or of another GPU of the box mapped by sharding.PeerBuffer; local row lr lands in row
+    lr * row_step + row_offset, order planes are plane_stride elements apart.  Runs on the current stream; returns nothing."""
+    L = _lib.lib()
+    _engine.require_cuda()
+    dev = dev or _engine.device()
+    obs = _engine.observer_struct(a, r_o, th_o)
+    M = pack_models(emissivity=emissivity, velocity=velocity, bfield=bfield)
+    opts = _lib.ImageOpts(int(mbar_min), int(mbar_max), int(bool(polarization)), int(bool(pathlength)), float(specind),
+                          float(diskangle), float(nu_obs))
+    al, be = _engine.to_device(alpha, dev), _engine.to_device(beta, dev)
+    smap = _lib.ShardMap(int(cols), int(row_step), int(row_offset), int(plane_stride), int(max_blocks), 0)
+    ptr = lambda k: ctypes.cast(ctypes.c_void_p(dst.get(k) or None), _lib.c_double_p)
+    t = _engine.torch()
+    with t.cuda.device(dev):
+        _lib.check(L.kgeo_equatorial_image_sharded(ctypes.byref(obs), ctypes.byref(M), ctypes.byref(opts), int(al.numel()),
+                                                   dptr(al), dptr(be), ctypes.byref(smap), *[ptr(k) for k in _DST_ORDER],
+                                                   _engine.stream_ptr()))
+        al.record_stream(t.cuda.current_stream(dev))
+        be.record_stream(t.cuda.current_stream(dev))
+
+
 def make_image(a, r_o, th_o, mbar_max, alpha_min, alpha_max, beta_min, beta_max, psize,
                nmax_only=False,
                emissivity=emis_default,

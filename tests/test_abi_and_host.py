@@ -38,12 +38,13 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_and_struct_layout(lib):
     L = lib.lib()
-    assert L.kgeo_abi_version() == 3
+    assert L.kgeo_abi_version() == 4
     assert L.kgeo_ray_workspace_slots() > 30
     assert L.kgeo_launch_count() == 0
     assert ctypes.sizeof(lib.Observer) == 24
     assert ctypes.sizeof(lib.Models) == 16 + 3 * 64 + 16 + 32
     assert ctypes.sizeof(lib.ImageOpts) == 16 + 24
+    assert ctypes.sizeof(lib.ShardMap) == 40 and ctypes.sizeof(lib.PeerHandle) == 64
     text = open(HEADER).read()
     for enum, table in (("kgeo_velocity_type", lib.VEL), ("kgeo_bfield_type", lib.BF), ("kgeo_emissivity_type", lib.EM)):
         body = re.search(r"enum %s \{(.*?)\}" % enum, text, re.S).group(1)

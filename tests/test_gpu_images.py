@@ -253,6 +253,65 @@ def test_image_argument_checks(kg):
         kg.Bfield('simple')
 
 
+@pytest.mark.parametrize("interleave,max_blocks,pol", [(True, 0, False), (True, 5, True), (False, 3, False)])
+def test_sharded_image_kernel_stores_rows_in_place(kg, interleave, max_blocks, pol):
+    """kgeo_equatorial_image_sharded: three ragged row shards (interleaved or blocks of rows; full or capped grid) written by
+    three launches into ONE destination buffer (a PeerBuffer: kgeo_peer_alloc memory, here on the same GPU) == the whole image."""
+    from kgeo_b200 import sharding, equatorial_images as ei
+    a, r_o, th_o, world = 0.94, np.inf, 17 * np.pi / 180, 3
+    kw = dict(polarization=pol, pathlength=pol)
+    if pol:
+        kw.update(emissivity=kg.Emissivity('ring'), velocity=kg.Velocity('general', fac_subkep=0.7, beta_phi=0.7, beta_r=0.7),
+                  bfield=kg.Bfield('bz_guess', C=1.), specind=1.)
+    whole = kg.make_image(a, r_o, th_o, 2, -10., 10., -10., 10., 20. / 50, **kw)
+    A, B = ei.pixel_grid(-10., 10., -10., 10., 20. / 50)
+    ncols = 50
+    nrows = A.size // ncols
+    off, total = sharding.plane_layout(3, A.size, pathlength=pol)
+    buf = sharding.PeerBuffer(total + 7)
+    try:
+        view = buf.tensor()
+        view.fill_(-7.0)
+        model = sharding._image_kwargs(kw)
+        for rank in range(world):
+            if interleave:
+                al, be, rows = sharding.shard_pixels_interleaved(A, B, ncols, rank, world)
+                step, offset = world, rank
+            else:
+                al, be, rows = sharding.shard_pixels(A, B, ncols, rank, world)
+                step, offset = 1, rows[0]
+            ei.image_into(a, r_o, th_o, 0, 2, al, be, *model, dst={k: buf.ptr + 8 * o for k, o in off.items()}, cols=ncols,
+                          row_step=step, row_offset=offset, plane_stride=A.size, max_blocks=max_blocks)
+        flat = sharding.to_host_pinned(view)
+        assert np.all(flat[total:] == -7.0)                      # nothing stored past the planes
+        got = sharding._image_tuple(flat[:total], off, 3, A.size, pol)
+        assert len(got) == len(whole)
+        for g_, w_ in zip(got, whole):
+            assert g_.shape == w_.shape and np.array_equal(g_, w_, equal_nan=True)
+        del view
+    finally:
+        buf.close()
+    assert nrows % world != 0                                    # the shards were ragged
+
+
+def test_sharded_image_argument_checks(kg):
+    import ctypes
+    from kgeo_b200 import _lib, _engine, equatorial_images as ei
+    from kgeo_b200.models import pack_models
+    L = _lib.lib()
+    obs = _engine.observer_struct(0.5, np.inf, 0.3)
+    M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
+    opts = _lib.ImageOpts(0, 2, 0, 0, 1.0, 0.1, 230e9)
+    x = _engine.to_device(np.zeros(12))
+    null = ctypes.cast(None, _lib.c_double_p)
+    for smap in (_lib.ShardMap(5, 1, 0, 12, 0, 0),       # 12 pixels are not whole rows of 5
+                 _lib.ShardMap(4, 0, 0, 12, 0, 0),       # row_step 0
+                 _lib.ShardMap(4, 2, 1, 12, 0, 0)):      # destination plane (rows 1, 3, 5 -> 24 pixels) larger than plane_stride
+        rc = L.kgeo_equatorial_image_sharded(ctypes.byref(obs), ctypes.byref(M), ctypes.byref(opts), 12, _engine.dptr(x),
+                                             _engine.dptr(x), ctypes.byref(smap), *([null] * 12), None)
+        assert rc == _lib.KGEO_E_BADARG, L.kgeo_last_error()
+
+
 def test_multi_gpu_sharded_image_and_tracks():
     """N-GPU path under torchrun + NCCL (skipped on a single-GPU box): tests/dist_check.py."""
     import os

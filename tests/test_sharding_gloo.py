@@ -108,3 +108,35 @@ def test_gather_configs_gloo(world, nconf):
         assert p.exitcode == 0
     want = np.array([[[10.0 * c + p + 0.25 * k for k in range(3)] for p in range(2)] for c in range(nconf)])
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("pathlength", [False, True])
+def test_plane_layout_and_row_map_on_the_host(pathlength):
+    """The destination layout of the fused image + gather (sharding.plane_layout / kgeo_shard_map): writing every shard's
+    pixels at (lr * row_step + row_offset) * cols + c with NumPy assembles exactly the whole planes, for interleaved rows and
+    for ragged blocks of rows; _image_tuple returns make_image's shapes."""
+    sys.path.insert(0, ROOT)
+    from kgeo_b200 import sharding
+    nrows, ncols, norder, world = 11, 7, 3, 4
+    npix = nrows * ncols
+    off, total = sharding.plane_layout(norder, npix, pathlength)
+    names = [k for k in off]
+    assert total == (len(names) - 2) * norder * npix + 2 * npix
+    rng = np.random.default_rng(5)
+    whole = rng.standard_normal(total)
+    for interleave in (True, False):
+        dst = np.full(total, np.nan)
+        for rank in range(world):
+            rows = sharding.row_indices(nrows, rank, world, interleave)
+            step, offset = (world, rank) if interleave else (1, rows[0] if len(rows) else 0)
+            i = np.arange(len(rows) * ncols)
+            d = (i // ncols * step + offset) * ncols + i % ncols          # the kernel's row map
+            assert np.array_equal(d, (rows[:, None] * ncols + np.arange(ncols)).ravel())
+            for k in names:
+                for m in range(1 if k in ("nmax", "npol") else norder):
+                    dst[off[k] + m * npix + d] = whole[off[k] + m * npix + d]
+        assert np.array_equal(dst, whole)
+    tup = sharding._image_tuple(whole, off, norder, npix, pathlength)
+    assert len(tup) == (11 if pathlength else 9)
+    assert tup[0].shape == (npix, norder) and tup[7].shape == (npix,)
+    assert np.array_equal(tup[3][:, 2], whole[off["r"] + 2 * npix:off["r"] + 3 * npix])
