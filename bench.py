@@ -52,6 +52,7 @@ CANONICAL_FLOP_PER_POINT = 2400.0   # SURVEY.md 8(d) work model: Carlson duplica
 CANONICAL_FLOP_PER_PIXEL = 3000.0   # n = 0..2 image
 BYTES_PER_POINT = 32.0              # r, theta, phi, t written once
 IMG_PLANES = 24                     # I,Q,U,r,Ir,g,sinthb x 3 orders + nmax, npol, imax: doubles per pixel of an n=0..2 image
+GATHER_DEFAULT = "copy_engine"     # N > 1: how the image planes reach rank 0 (see run_ours)
 IMG_BLOCKS_DEFAULT = 0              # N > 1: cap on the thread blocks of the image kernel on its side stream (0 = full grid: measured best)
 PARITY_PIXELS = 4096
 
@@ -305,40 +306,62 @@ def run_ours(args):
         M = pack_models(ei.emis_default, ei.vel_default, ei.bfield_default)
         iopts = _lib.ImageOpts(0, 2, 0, 0, float(ei.SPECIND), ei.DISKANGLE, ei.OBSFREQ)
         npix_all = rows * cols
-        # gather fused into the image kernel: rank 0's planes are a peer buffer every rank stores to over NVLink; the kernel runs
-        # on a side stream next to the track pass.  None: the GPUs cannot map each other (or KGEO_B200_GATHER=nccl) -> all_gather.
+        # rank 0's planes are a peer buffer every rank writes over NVLink, one of two ways (KGEO_BENCH_GATHER):
+        #   copy_engine  the image kernel writes local planes, then ONE strided 3-D copy by the copy engines on a side stream puts
+        #                them at their rows of rank 0's planes while setup and the track pass run (no SM is taken from them);
+        #   peer_stores  the image kernel stores every result straight to rank 0's planes (kgeo_equatorial_image_sharded) on a
+        #                side stream beside setup and tracks.
+        # None: the GPUs cannot map each other (or KGEO_B200_GATHER=nccl) -> all_gather_into_tensor + un-interleave on rank 0.
         peer = sharding.peer_buffer(IMG_PLANES * npix_all, 0)
-        gather_mode = "peer_stores" if peer is not None else "nccl_all_gather"
+        gather_mode = os.environ.get("KGEO_BENCH_GATHER", GATHER_DEFAULT) if peer is not None else "nccl_all_gather"
+        if gather_mode not in ("copy_engine", "peer_stores", "nccl_all_gather"):
+            raise ValueError("KGEO_BENCH_GATHER must be copy_engine or peer_stores")
+        side = torch.cuda.Stream(device=dev, priority=-1)
+        side_ptr = ctypes.c_void_p(side.cuda_stream)
+        evi = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev_img = torch.cuda.Event()
+        token = torch.zeros((1,), dtype=torch.float32, device=dev)
+        img = gathered = None
         if peer is not None:
             smap = _lib.ShardMap(cols, world, rank, npix_all, int(os.environ.get("KGEO_BENCH_IMG_BLOCKS", IMG_BLOCKS_DEFAULT)), 0)
             vp = lambda plane: ctypes.cast(ctypes.c_void_p(peer.ptr + 8 * plane * npix_all), _lib.c_double_p)
-            img_ptrs = [vp(3 * i) for i in range(7)] + [vp(21 + i) for i in range(3)]
-            side = torch.cuda.Stream(device=dev, priority=-1)
-            side_ptr = ctypes.c_void_p(side.cuda_stream)
-            token = torch.zeros((1,), dtype=torch.float32, device=dev)
+            peer_ptrs = [vp(3 * i) for i in range(7)] + [vp(21 + i) for i in range(3)]
             final = peer.tensor((IMG_PLANES, npix_all))
-            img = gathered = None
-            evi = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        else:
+        if gather_mode != "peer_stores":
             img = torch.empty((IMG_PLANES, npix), dtype=torch.float64, device=dev)        # this rank's rows, plane-major
+            img_ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
+        if gather_mode == "nccl_all_gather":
             gathered = torch.empty((world, IMG_PLANES, npix), dtype=torch.float64, device=dev)
             final = torch.empty((IMG_PLANES, npix_all), dtype=torch.float64, device=dev) if rank == 0 else None
-            img_ptrs = [_engine.dptr(img[3 * i:3 * i + 3]) for i in range(7)] + [_engine.dptr(img[21 + i]) for i in range(3)]
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     main = torch.cuda.current_stream(dev)
 
+    def image_local():
+        _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
+                                           _engine.dptr(d_alpha), _engine.dptr(d_beta), *img_ptrs, null, null, stream))
+
     def step(timed=False):
-        fused = with_image and peer is not None
-        if fused:                                    # image + peer-store gather on the side stream, beside setup and tracks
+        mode_g = gather_mode if with_image else None
+        if mode_g == "peer_stores":                  # image + peer-store gather on the side stream, beside setup and tracks
             side.wait_stream(main)
             if timed:
                 evi[0].record(side)
             _lib.check(L.kgeo_equatorial_image_sharded(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
                                                        _engine.dptr(d_alpha), _engine.dptr(d_beta), ctypes.byref(smap),
-                                                       *img_ptrs, null, null, side_ptr))
+                                                       *peer_ptrs, null, null, side_ptr))
             if timed:
                 evi[1].record(side)
+        elif mode_g == "copy_engine":                # image first, its planes travel while setup and tracks compute
+            if timed:
+                evi[0].record()
+            image_local()
+            if timed:
+                evi[1].record()
+            ev_img.record()
+            side.wait_event(ev_img)
+            _lib.check(L.kgeo_shard_scatter(_engine.dptr(img), IMG_PLANES, npix, ctypes.byref(smap),
+                                            ctypes.cast(ctypes.c_void_p(peer.ptr), _lib.c_double_p), side_ptr))
         if timed:
             ev[0].record()
         _lib.check(L.kgeo_ray_setup(ctypes.byref(obs), npix, _engine.dptr(d_alpha), _engine.dptr(d_beta), mode,
@@ -350,14 +373,13 @@ def run_ours(args):
                                  _engine.dptr(outs[3]), null, null, npix, stream))
         if timed:
             ev[2].record()
-        if fused:
+        if mode_g in ("peer_stores", "copy_engine"):
             main.wait_stream(side)
-            dist.all_reduce(token)                   # completion signal: behind every rank's image kernel in stream order
+            dist.all_reduce(token)                   # completion signal: behind every rank's writes in stream order
             if timed:
                 ev[4].record()
         elif with_image:
-            _lib.check(L.kgeo_equatorial_image(ctypes.byref(iobs), ctypes.byref(M), ctypes.byref(iopts), npix,
-                                               _engine.dptr(d_alpha), _engine.dptr(d_beta), *img_ptrs, null, null, stream))
+            image_local()
             if timed:
                 ev[3].record()
             sharding.gather_interleaved_rows(img, gathered, final, rows_local, cols)
@@ -374,8 +396,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         setup_ms.append(ev[0].elapsed_time(ev[1]))
         track_ms.append(ev[1].elapsed_time(ev[2]))
-        if with_image and peer is not None:
-            image_ms.append(evi[0].elapsed_time(evi[1]))      # span of the image kernel on its own stream (beside the tracks)
+        if with_image and gather_mode != "nccl_all_gather":
+            image_ms.append(evi[0].elapsed_time(evi[1]))      # the image kernel (peer_stores: on its own stream beside the tracks)
             coll_ms.append(ev[2].elapsed_time(ev[4]))         # exposed: end of the tracks -> planes complete on rank 0
         elif with_image:
             image_ms.append(ev[2].elapsed_time(ev[3]))
@@ -553,8 +575,12 @@ def run_ours(args):
                    "parallelism": ("1 GPU" if world == 1 else "rows interleaved over %d ranks; no data-path collective in the "
                                    "trace; image planes (%.2f GB) to rank 0: %s"
                                    % (world, IMG_PLANES * 8 * rows * cols / 1e9,
-                                      "stored in place by every rank's image kernel over NVLink peer memory, on a side stream beside "
-                                      "the track pass; one 4-byte all_reduce as the completion signal" if gather_mode == "peer_stores"
+                                      {"peer_stores": "stored in place by every rank's image kernel over NVLink peer memory, on a side "
+                                                      "stream beside the track pass; one 4-byte all_reduce as the completion signal",
+                                       "copy_engine": "computed into local planes, then put at their rows of rank 0's planes (peer memory "
+                                                      "over NVLink) by the copy engines on a side stream while setup and the track pass "
+                                                      "run; one 4-byte all_reduce as the completion signal"}.get(gather_mode)
+                                      if gather_mode != "nccl_all_gather"
                                       else "all_gather_into_tensor + un-interleave on rank 0"))},
         "phases": phases, "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "secondary": secondary,
@@ -570,6 +596,12 @@ def run_ours(args):
                                           "the SMs and storing to rank 0 over NVLink) + %.2f ms exposed wait for the planes (max over "
                                           "ranks); the image and the per-ray setup add time but no geodesic points" %
                                           (phases["setup_ms"], phases["track_ms"], phases["image_ms"], phases["collective_ms"]))
+        elif gather_mode == "copy_engine":
+            line["efficiency_limiter"] = ("step = image %.1f + setup %.1f + tracks %.1f ms, the planes travelling to rank 0 through the "
+                                          "copy engines meanwhile, + %.2f ms from the end of the tracks to the completion signal (max "
+                                          "over ranks: includes the skew between ranks); the image and the per-ray setup add time but "
+                                          "no geodesic points" %
+                                          (phases["image_ms"], phases["setup_ms"], phases["track_ms"], phases["collective_ms"]))
         else:
             line["efficiency_limiter"] = ("step = setup %.1f + tracks %.1f + image %.1f + gather %.1f ms (max over ranks); the image, "
                                           "its gather and the per-ray setup add time but no geodesic points" %

@@ -163,6 +163,17 @@ int kgeo_special_ellipj(size_t n, const double* u_dev, const double* m_dev, doub
  * 508-510,583-584).  w_dev: kgeo_ray_workspace_doubles(npix) doubles; flags_dev: npix int32. */
 int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
                    double* w_dev, int32_t* flags_dev, void* stream);
+/* The same setup from the conserved quantities themselves: lam, eta and s_o = the sign of the observer's polar momentum
+ * (NULL: +1 everywhere), as th_integrate / r_integrate receive them (kgeo/kerr_raytracing_ana.py:195-196,368-369).
+ * phi_and_t = 0 skips the constants only G_phi, G_t, I_phi, I_t, I_sigma need (do_phi_and_t=False; required for r_o = inf). */
+int kgeo_ray_setup_conserved(const kgeo_observer* obs, size_t npix, const double* lam_dev, const double* eta_dev,
+                             const double* s_o_dev, int mode, int phi_and_t, double* w_dev, int32_t* flags_dev, void* stream);
+/* th_integrate (:195-365) and r_integrate (:368-633) as separate results at user Mino times tau_dev [ntau, tau_ld]:
+ * (th, G_phi, G_t) and (r, I_phi, I_t, I_sigma), each [ntau, ld]; any output may be NULL, a whole side (polar / radial) whose
+ * outputs are all NULL is not evaluated.  phi_and_t = 0: only th and r are computed; the others are zero except I_t = -4 tau (as the reference's). */
+int kgeo_track_integrals(const kgeo_observer* obs, size_t npix, const double* w_dev, const int32_t* flags_dev, size_t ntau,
+                         const double* tau_dev, size_t tau_ld, int phi_and_t, double* th_dev, double* Gph_dev, double* Gt_dev,
+                         double* r_dev, double* Iph_dev, double* It_dev, double* Isig_dev, size_t ld, void* stream);
 /* Unpacked per-ray summary for the host API: roots_dev[8*npix] = Re r1..r4, Im r1..r4 (plane-major), rclass_dev = the
  * reference's region label 1..4 (0 on a boundary), tau_tot_dev, u_plus/u_minus/uratio/a2u_minus, outside_dev =
  * is_outside_crit, thplus/thminus = angular_turning's turning points.  Any output may be NULL.
@@ -223,6 +234,16 @@ int kgeo_rho_of_req(const kgeo_observer* obs, size_t n, const double* varphi_dev
                     double rho_max, double xtol, double rtol, int maxiter, double* rho_dev, double* alpha_dev,
                     double* beta_dev, int32_t* status_dev, void* stream);
 
+/* A library of such curves in one launch: generate_library / make_curves2 (:351-417; the reference's only multi-process job:
+ * a pool over 99 x 89 (spin, inclination) configurations, each running rho_of_req for mbar = 0..5 at 360 angles).  Configuration
+ * c has spin spin_dev[c], inclination th0_dev[c] (radians) and ring radius req_dev[c]; orders mbar_lo..mbar_hi with the bracket
+ * rho_of_req picks for each (:232-241).  rho_dev / status_dev: [nconf, norder, nphi]; status as kgeo_rho_of_req (the caller
+ * decides what a failed root find means: the reference drops the configuration's file).  The spins must satisfy |a| < 1 and
+ * the inclinations 0 < th0 < pi, th0 != pi/2 (checked by the caller: the arrays are device memory). */
+int kgeo_rho_library(size_t nconf, const double* spin_dev, const double* th0_dev, const double* req_dev, int mbar_lo, int mbar_hi,
+                     size_t nphi, const double* varphi_dev, double xtol, double rtol, int maxiter, double* rho_dev,
+                     int32_t* status_dev, void* stream);
+
 /* critical_curve (:268-298, GL19 eqs 38-40): (alpha, beta) of the n photon-orbit radii r = linspace(r_minus, r_plus, n);
  * the caller passes the scalars the reference computes with NumPy (r_minus, r_plus, sin/cos/tan th_0) so that the NaN mask
  * next to the end points is the reference's.  Outputs [n]; NaN entries are dropped and the curve mirrored by the caller. */
@@ -249,6 +270,10 @@ int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* m
                                   double* Q_dst, double* U_dst, double* r_dst, double* Ir_dst, double* g_dst,
                                   double* sinthb_dst, double* nmax_dst, double* npol_dst, double* imax_dst, double* lp_dst,
                                   double* Ie_dst, void* stream);
+/* The same placement for planes that were computed locally first: src_dev [nplanes, npix] (plane-major, this shard's rows) is
+ * copied to its rows of the destination planes by the COPY ENGINES (one strided 3-D cudaMemcpy; destination may be peer memory),
+ * so the transfer runs beside kernels of another stream without taking SMs from them.  map->max_blocks is ignored. */
+int kgeo_shard_scatter(const double* src_dev, size_t nplanes, size_t npix, const kgeo_shard_map* map, double* dst, void* stream);
 /* Peer buffers.  kgeo_peer_alloc: `bytes` of device memory on the current device plus the handle under which the other
  * processes of the box open it; kgeo_peer_open (in another process, on ITS current device): the address at which that
  * device reads and writes the exporter's memory (peer access over NVLink is enabled on first use); kgeo_peer_close unmaps,

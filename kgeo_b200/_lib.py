@@ -69,6 +69,8 @@ SIGNATURES = {
     "kgeo_special_ellippi": (ctypes.c_int, [_S, _P, _P, _P, _P, _V]),
     "kgeo_special_ellipj": (ctypes.c_int, [_S, _P, _P, _P, _P, _P, _P, _V]),
     "kgeo_ray_setup": (ctypes.c_int, [_OBS, _S, _P, _P, ctypes.c_int, _P, c_int32_p, _V]),
+    "kgeo_ray_setup_conserved": (ctypes.c_int, [_OBS, _S, _P, _P, _P, ctypes.c_int, ctypes.c_int, _P, c_int32_p, _V]),
+    "kgeo_track_integrals": (ctypes.c_int, [_OBS, _S, _P, c_int32_p, _S, _P, _S, ctypes.c_int] + [_P] * 7 + [_S, _V]),
     "kgeo_ray_summary": (ctypes.c_int, [_OBS, _S, _P, _P, ctypes.c_int, _P, c_int32_p, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _V]),
     "kgeo_mino_total": (ctypes.c_int, [_OBS, _S, _P, _P, _V]),
@@ -82,9 +84,12 @@ SIGNATURES = {
     "kgeo_r_equatorial": (ctypes.c_int, [_OBS, _S, _P, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P, _V]),
     "kgeo_rho_of_req": (ctypes.c_int, [_OBS, _S, _P, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_double, ctypes.c_int, _P, _P, _P, c_int32_p, _V]),
+    "kgeo_rho_library": (ctypes.c_int, [_S, _P, _P, _P, ctypes.c_int, ctypes.c_int, _S, _P, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_int, _P, c_int32_p, _V]),
     "kgeo_critical_curve": (ctypes.c_int, [ctypes.c_double] * 6 + [_S, _P, _P, _V]),
     "kgeo_equatorial_image": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P] + [_P] * 12 + [_V]),
     "kgeo_equatorial_image_sharded": (ctypes.c_int, [_OBS, _MOD, _OPT, _S, _P, _P, ctypes.POINTER(ShardMap)] + [_P] * 12 + [_V]),
+    "kgeo_shard_scatter": (ctypes.c_int, [_P, _S, _S, ctypes.POINTER(ShardMap), _P, _V]),
     "kgeo_peer_alloc": (ctypes.c_int, [_S, ctypes.POINTER(_V), ctypes.POINTER(PeerHandle)]),
     "kgeo_peer_open": (ctypes.c_int, [ctypes.POINTER(PeerHandle), ctypes.POINTER(_V)]),
     "kgeo_peer_close": (ctypes.c_int, [_V]),

@@ -488,8 +488,11 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 // LADDER = false skips the stored AGM ladders (their slots are indexed dynamically, which would push a register-resident
 // workspace into local memory): the image / lensing kernels evaluate only a few Jacobi functions per ray and run the
 // AGM descent inline instead.
+// ray_setup_conserved takes the conserved quantities themselves (lam, eta, and the sign s_o of the observer's polar momentum =
+// sign(beta)): what th_integrate / r_integrate receive from their callers (kgeo/kerr_raytracing_ana.py:195,368); ray_setup derives
+// them from the image coordinates (:76-79).
 template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
-KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
+KG_HD void ray_setup_conserved(const Observer& o, double lam, double eta, bool s_pos, int mode, P w, int* flags_out) {
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     // Two-kernel setup (DEFER): the AGM ladders are only read by the Carlson fallback, so they are built where the theta path
     // is turned down (theta_setup, or at the end of this function for motions that never were candidates) instead of for every
@@ -508,14 +511,12 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         }
     }
     int flags = 0;
-    double lam = -alpha * o.sth;
-    double eta = conserved_eta(o, alpha, beta);
     if (o.lowspin && (mode & M_CLAMP_LOWSPIN_ETA) && eta < 0.0) eta = kEP;   // kgeo/kerr_raytracing_ana.py:80-82 (tracks only)
     if (o.lowspin) flags |= F_LOWSPIN;
     w[S_LAM] = lam;
     w[S_ETA] = eta;
-    double s_o = (beta >= 0.0) ? 1.0 : -1.0;
-    if (beta >= 0.0) flags |= F_SPOS;
+    double s_o = s_pos ? 1.0 : -1.0;
+    if (s_pos) flags |= F_SPOS;
     if (o.th_o <= kHalfPi) flags |= F_HPOS;
 
     double up, um, ratio, a2um;
@@ -817,6 +818,11 @@ KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w
         if (!(flags & F_R_PENDING)) jacobi_make_ladder(w[R_K], w + R_LAD);
     }
     *flags_out = flags;
+}
+
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
+KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
+    ray_setup_conserved<PHI_T, LADDER, DEFER, P>(o, -alpha * o.sth, conserved_eta(o, alpha, beta), beta >= 0.0, mode, w, flags_out);
 }
 
 // Second half of the two-kernel setup: builds the theta blocks ray_setup<.., DEFER = true> left pending.  Splitting the

@@ -615,6 +615,54 @@ __global__ void __launch_bounds__(TRK_THREADS) crossing_counts_kernel(Observer o
     }
 }
 
+// th_integrate / r_integrate as separate calls (kgeo/kerr_raytracing_ana.py:195-365, 368-633): rays set up from the conserved
+// quantities, then the angular antiderivatives (theta, G_phi, G_t) and / or the radial ones (r, I_phi, I_t, I_sigma) at the user's
+// Mino times through the complete per-point code.  One thread per ray, grid.y over the samples.
+template <bool PHI_T>
+__global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_conserved_kernel(Observer o, size_t npix, const double* __restrict__ lam,
+                                                                            const double* __restrict__ eta, const double* __restrict__ s_o,
+                                                                            int mode, double* __restrict__ w_out,
+                                                                            int32_t* __restrict__ flags_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    int fl;
+    ray_setup_conserved<PHI_T, true, true>(o, lam[i], eta[i], s_o ? (s_o[i] >= 0.0) : true, mode, ray_ptr(w_out, i), &fl);
+    flags_out[i] = fl;
+}
+
+struct IntegralsOut {
+    double *th, *Gph, *Gt, *r, *Iph, *It, *Isig;
+};
+__global__ void __launch_bounds__(TRK_THREADS) track_integrals_kernel(Observer o, size_t npix, const double* __restrict__ w_in,
+                                                                      const int32_t* __restrict__ flags_in, int ntau,
+                                                                      const double* __restrict__ tau_in, size_t tau_ld, bool full,
+                                                                      IntegralsOut out, size_t ld) {
+    size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const StridedW W = ray_view(w_in, pix);
+    const int fl = flags_in[pix];
+    const bool polar = out.th || out.Gph || out.Gt, radial = out.r || out.Iph || out.It || out.Isig;
+    for (int k = blockIdx.y; k < ntau; k += gridDim.y) {
+        const double tau = tau_in[(size_t)k * tau_ld + pix];
+        const size_t q = (size_t)k * ld + pix;
+        if (polar) {
+            double th, Gph, Gt;
+            theta_eval<StridedW>(W, fl, tau, full, &th, &Gph, &Gt);
+            if (out.th) out.th[q] = th;
+            if (out.Gph) out.Gph[q] = full ? Gph : 0.0;
+            if (out.Gt) out.Gt[q] = full ? Gt : 0.0;
+        }
+        if (radial) {
+            double r, Iph, It, Isig;
+            radial_eval<StridedW, true>(W, o, fl, tau, full, &r, &Iph, &It, &Isig);
+            if (out.r) out.r[q] = r;
+            if (out.Iph) out.Iph[q] = full ? Iph : 0.0;
+            if (out.It) out.It[q] = full ? It : -4.0 * tau;      // the reference's I_t = I_tA + 4 I_0 + 2 I_1 + I_2 keeps I_0 = -tau (:627-631)
+            if (out.Isig) out.Isig[q] = full ? Isig : 0.0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // field-line crossings (kgeo/solver.py: getguesses / findroot)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -954,14 +1002,10 @@ __device__ __noinline__ double req_objective(const Observer& o, double rho, doub
     return rs - req;
 }
 
-// SciPy's brentq (scipy/optimize/Zeros/brentq.c), statement for statement, one thread per angle
-__global__ void __launch_bounds__(32) rho_of_req_kernel(Observer o, size_t n, const double* __restrict__ varphi, double req, int mbar,
-                                                        double xa, double xb, double xtol, double rtol, int maxiter,
-                                                        double* rho_out, double* alpha_out, double* beta_out,
-                                                        int32_t* status_out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double cv = cos(varphi[i]), sv = sin(varphi[i]);
+// SciPy's brentq (scipy/optimize/Zeros/brentq.c), statement for statement, on rho -> r_equatorial2(rho) - req along the image-plane
+// direction (cv, sv).  status: 0 converged, -1 no sign change over [xa, xb], -2 not converged after maxiter iterations.
+__device__ double brent_rho(const Observer& o, double cv, double sv, int mbar, double req, double xa, double xb, double xtol,
+                            double rtol, int maxiter, int* status_out) {
     double xpre = xa, xcur = xb, xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
     double fpre = req_objective(o, xpre, cv, sv, mbar, req);
     double fcur = req_objective(o, xcur, cv, sv, mbar, req);
@@ -1014,10 +1058,46 @@ __global__ void __launch_bounds__(32) rho_of_req_kernel(Observer o, size_t n, co
         fcur = req_objective(o, xcur, cv, sv, mbar, req);
     }
     if (!done) root = xcur;
+    *status_out = status;
+    return root;
+}
+
+// one thread per angle
+__global__ void __launch_bounds__(32) rho_of_req_kernel(Observer o, size_t n, const double* __restrict__ varphi, double req, int mbar,
+                                                        double xa, double xb, double xtol, double rtol, int maxiter,
+                                                        double* rho_out, double* alpha_out, double* beta_out,
+                                                        int32_t* status_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cv = cos(varphi[i]), sv = sin(varphi[i]);
+    int status;
+    const double root = brent_rho(o, cv, sv, mbar, req, xa, xb, xtol, rtol, maxiter, &status);
     if (rho_out) rho_out[i] = root;
     if (alpha_out) alpha_out[i] = cv * root;
     if (beta_out) beta_out[i] = sv * root;
     if (status_out) status_out[i] = status;
+}
+
+// A whole library of curves in one launch (the reference's generate_library / make_curves2, kgeo/equatorial_lensing.py:351-417:
+// a multiprocessing pool over (spin, inclination) configurations, each running rho_of_req for mbar = 0..mmax): one thread per
+// (configuration, order, angle), the bracket of each order as rho_of_req picks it (:232-241).
+__global__ void __launch_bounds__(32) rho_library_kernel(size_t nconf, const double* __restrict__ spin, const double* __restrict__ th0,
+                                                         const double* __restrict__ req, int mbar_lo, int norder, size_t nphi,
+                                                         const double* __restrict__ varphi, double xtol, double rtol, int maxiter,
+                                                         double* __restrict__ rho_out, int32_t* __restrict__ status_out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nconf * norder * nphi) return;
+    const size_t c = e / ((size_t)norder * nphi);
+    const int mbar = mbar_lo + (int)((e / nphi) % norder);
+    const size_t i = e % nphi;
+    const Observer o = make_observer(spin[c], kInf, th0[c]);
+    const double rq = req[c];
+    const double xa = (mbar <= 1) ? 0.0 : 1.0;
+    const double xb = (mbar == 0) ? rq + 5.0 : (mbar == 1 ? 100.0 : 10.0);
+    int status;
+    const double root = brent_rho(o, cos(varphi[i]), sin(varphi[i]), mbar, rq, xa, xb, xtol, rtol, maxiter, &status);
+    rho_out[e] = root;
+    if (status_out) status_out[e] = status;
 }
 
 // critical curve (kgeo/equatorial_lensing.py:268-290): NumPy's operation order with individually rounded operations (the
@@ -1331,6 +1411,41 @@ int kgeo_ray_setup(const kgeo_observer* obs, size_t npix, const double* alpha, c
     if (npix == 0) return 0;
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
     return launch_setup(o, npix, alpha, beta, mode, w, flags, (cudaStream_t)stream);
+}
+
+int kgeo_ray_setup_conserved(const kgeo_observer* obs, size_t npix, const double* lam, const double* eta, const double* s_o,
+                             int mode, int phi_and_t, double* w, int32_t* flags, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && (!lam || !eta || !w || !flags)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_setup_conserved: NULL pointer");
+    if (phi_and_t && isinf(obs->r_o)) return fail_arg(KGEO_E_RANGE, "kgeo_ray_setup_conserved: r_o must be finite for the phi, t, sigma integrals");
+    if (npix == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phi_and_t) ray_setup_conserved_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, st>>>(o, npix, lam, eta, s_o, mode, w, flags);
+    else ray_setup_conserved_kernel<false><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, st>>>(o, npix, lam, eta, s_o, mode, w, flags);
+    LAUNCHED("ray_setup_conserved_kernel");
+    if (!(mode & M_CARLSON_ONLY)) {
+        theta_setup_kernel<<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, st>>>(o, npix, w, flags);
+        LAUNCHED("theta_setup_kernel");
+    }
+    return 0;
+}
+
+int kgeo_track_integrals(const kgeo_observer* obs, size_t npix, const double* w, const int32_t* flags, size_t ntau,
+                         const double* tau, size_t tau_ld, int phi_and_t, double* th, double* Gph, double* Gt, double* r,
+                         double* Iph, double* It, double* Isig, size_t ld, void* stream) {
+    int rc = check_observer(obs, true);
+    if (rc) return rc;
+    if (npix && ntau && (!w || !flags || !tau)) return fail_arg(KGEO_E_BADARG, "kgeo_track_integrals: NULL pointer");
+    if (ld < npix || tau_ld < npix) return fail_arg(KGEO_E_BADARG, "kgeo_track_integrals: leading dimension smaller than npix");
+    if (npix == 0 || ntau == 0) return 0;
+    Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
+    dim3 grid(grid_for(npix, TRK_THREADS), (unsigned)(ntau < 1024 ? ntau : 1024));
+    track_integrals_kernel<<<grid, TRK_THREADS, 0, (cudaStream_t)stream>>>(o, npix, w, flags, (int)ntau, tau, tau_ld, phi_and_t != 0,
+                                                                          IntegralsOut{th, Gph, Gt, r, Iph, It, Isig}, ld);
+    LAUNCHED("track_integrals_kernel");
+    return 0;
 }
 
 int kgeo_ray_slot(size_t npix, const double* w, int slot, double* out, void* stream) {
@@ -1698,6 +1813,18 @@ int kgeo_rho_of_req(const kgeo_observer* obs, size_t n, const double* varphi, do
     return 0;
 }
 
+int kgeo_rho_library(size_t nconf, const double* spin, const double* th0, const double* req, int mbar_lo, int mbar_hi, size_t nphi,
+                     const double* varphi, double xtol, double rtol, int maxiter, double* rho, int32_t* status, void* stream) {
+    if (nconf && nphi && (!spin || !th0 || !req || !varphi || !rho)) return fail_arg(KGEO_E_BADARG, "kgeo_rho_library: NULL pointer");
+    if (mbar_lo < 0 || mbar_hi < mbar_lo || maxiter < 0 || !(xtol > 0.0)) return fail_arg(KGEO_E_BADARG, "kgeo_rho_library: bad mbar range / tolerance");
+    if (nconf == 0 || nphi == 0) return 0;
+    const int norder = mbar_hi - mbar_lo + 1;
+    rho_library_kernel<<<grid_for(nconf * norder * nphi, 32), 32, 0, (cudaStream_t)stream>>>(nconf, spin, th0, req, mbar_lo, norder, nphi,
+                                                                                            varphi, xtol, rtol, maxiter, rho, status);
+    LAUNCHED("rho_library_kernel");
+    return 0;
+}
+
 int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0, double cos_th0, double tan_th0, size_t n,
                         double* alpha, double* beta, void* stream) {
     if (n && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_critical_curve: NULL pointer");
@@ -1767,6 +1894,31 @@ int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* m
     return launch_image(obs, models, opts, npix, alpha, beta, map,
                         ImageOut{I, Q, U, r, Ir, g, sinthb, nmax, npol, imax, opts->pathlength ? lp : nullptr, opts->pathlength ? Ie : nullptr},
                         (cudaStream_t)stream);
+}
+
+// The same placement by the copy engines: one strided 3-D copy (rows x planes), no SM involved.
+int kgeo_shard_scatter(const double* src, size_t nplanes, size_t npix, const kgeo_shard_map* map, double* dst, void* stream) {
+    if (!map || (nplanes && npix && (!src || !dst))) return fail_arg(KGEO_E_BADARG, "kgeo_shard_scatter: NULL pointer");
+    if (nplanes == 0 || npix == 0) return 0;
+    if (map->cols == 0 || map->row_step == 0 || npix % map->cols != 0)
+        return fail_arg(KGEO_E_BADARG, "kgeo_shard_scatter: the shard must be whole rows of cols > 0 pixels, row_step > 0");
+    const size_t rows = npix / map->cols, row_bytes = map->cols * sizeof(double);
+    const size_t dpitch = map->row_step * row_bytes;
+    if (nplanes > 1 && (map->plane_stride * sizeof(double)) % dpitch != 0) {
+        // planes that are not a whole number of destination pitches apart: one 2-D copy per plane
+        for (size_t p = 0; p < nplanes; ++p)
+            CU(cudaMemcpy2DAsync(dst + p * map->plane_stride + map->row_offset * map->cols, dpitch, src + p * npix, row_bytes,
+                                 row_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
+        return 0;
+    }
+    cudaMemcpy3DParms c = {};
+    c.srcPtr = make_cudaPitchedPtr((void*)src, row_bytes, row_bytes, rows);
+    c.dstPtr = make_cudaPitchedPtr((void*)(dst + map->row_offset * map->cols), dpitch, dpitch,
+                                   nplanes > 1 ? map->plane_stride * sizeof(double) / dpitch : rows);
+    c.extent = make_cudaExtent(row_bytes, rows, nplanes);
+    c.kind = cudaMemcpyDefault;
+    CU(cudaMemcpy3DAsync(&c, (cudaStream_t)stream));
+    return 0;
 }
 
 // ---- peer buffers: device memory that other processes of the box map and write with plain stores ----

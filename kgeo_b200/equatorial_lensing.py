@@ -2,8 +2,12 @@
 inverse lensing of SURVEY 8(f2) -- rho_of_req (:226-247), rho_of_req_single (:249-266), critical_curve (:268-298) --
 computed by libkgeo_b200.so (the root find runs on the GPU, one thread per image-plane angle).
 
-Out of scope: plot_curves, generate_library (matplotlib / file output around rho_of_req).
+generate_library / make_curves2 (:351-417, the reference's multiprocessing job over 99 x 89 configurations) run as ONE kernel
+launch over (configuration, order, angle) -- rho_library -- and write the reference's text files.  Out of scope: plot_curves
+(matplotlib).
 """
+import os
+
 import ctypes
 
 import numpy as np
@@ -122,6 +126,100 @@ def rho_of_req_single(a, th0, req, varphi, mbar=0):
     """rho of one image-plane angle (kgeo/equatorial_lensing.py:249-266)"""
     rhos, _, _ = _rho_of_req_device(a, th0, req, mbar, [varphi])
     return float(rhos[0])
+
+
+def r_equatorial2(rho, varphi, a, th0, mbar=0):
+    """Emission radius of the mbar-th image at image-plane polar coordinates (rho, varphi), observer at infinity, made
+    sign-definite for the root find: 1e50 where the ray misses the plane outside the critical curve, 1 inside
+    (kgeo/equatorial_lensing.py:198-217).  Scalar in, scalar out, as the reference's."""
+    from .kerr_raytracing_utils import is_outside_crit
+    alpha = np.atleast_1d(np.cos(varphi) * rho).astype(float)
+    beta = np.atleast_1d(np.sin(varphi) * rho).astype(float)
+    r = r_equatorial(a, R0, th0, mbar, alpha, beta)[0][0]
+    if r <= 0:
+        r = INF if is_outside_crit(a, th0, alpha, beta)[0] == 1 else 1
+    return r
+
+
+def objfunc(rho, varphi, a, th0, r_target, mbar=0):
+    """r_equatorial2 - r_target: the objective of the reference's Brent solve (:219-224)"""
+    return r_equatorial2(rho, varphi, a, th0, mbar=mbar) - r_target
+
+
+def rho_library(spins, th0s, reqs, mmax=5, varphis=None):
+    """rho_of_req for MANY configurations in one kernel launch: spins[c], th0s[c] (radians), reqs[c] for c < nconf, orders
+    mbar = 0..mmax, angles `varphis` (default: rho_of_req's 360).  Returns (varphis, rhos[nconf, mmax+1, nphi],
+    status[nconf, mmax+1, nphi]) with status 0 = converged, -1 = no sign change over the bracket (SciPy's ValueError),
+    -2 = not converged (SciPy's RuntimeError)."""
+    L = _lib.lib()
+    _engine.require_cuda()
+    t = _engine.torch()
+    dev = _engine.device()
+    spins, th0s, reqs = [np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in (spins, th0s, reqs)]
+    if not (len(spins) == len(th0s) == len(reqs)):
+        raise Exception("spins, th0s, reqs are different lengths!")
+    for a, th0 in zip(spins, th0s):
+        _checks.check_observer(float(a), np.inf, float(th0))
+    if varphis is None:
+        varphis = np.linspace(-180, 179, 360) * np.pi / 180.
+    varphis = np.atleast_1d(np.asarray(varphis, dtype=np.float64))
+    nconf, nphi, norder = len(spins), len(varphis), int(mmax) + 1
+    d = [_engine.to_device(x, dev) for x in (spins, th0s, reqs, varphis)]
+    rho = _engine.empty((nconf, norder, nphi), dev)
+    status = _engine.empty((nconf, norder, nphi), dev, dtype=t.int32)
+    _lib.check(L.kgeo_rho_library(nconf, dptr(d[0]), dptr(d[1]), dptr(d[2]), 0, int(mmax), nphi, dptr(d[3]), BRENTQ_XTOL,
+                                  BRENTQ_RTOL, BRENTQ_MAXITER, dptr(rho), _engine.iptr(status), _engine.stream_ptr()))
+    return varphis, rho.cpu().numpy(), status.cpu().numpy()
+
+
+_LIBRARY_RADII = {'r10': 10., 'r100': 100., 'r1000': 1000., 'r10000': 10000.}
+
+
+def _library_radius(which, spin):
+    if which == 'rh':
+        return 1 + np.sqrt(1 - spin ** 2)
+    if which not in _LIBRARY_RADII:
+        raise Exception()
+    return _LIBRARY_RADII[which]
+
+
+def _write_curves(outpath, which, spins, incs, varphis, rhos, status):
+    written = 0
+    for c, (spin, inc) in enumerate(zip(spins, incs)):
+        name = '%s/a%02.0f_i%02.0f_%s.txt' % (outpath, 100 * spin, inc, which)
+        if os.path.isfile(name) or (status[c] != 0).any():   # the reference skips existing files and drops failed configurations
+            continue
+        np.savetxt(name, np.vstack((varphis, rhos[c])).T)
+        written += 1
+    return written
+
+
+def make_curves2(i, which, n, spin, inc, mmax, outpath):
+    """One configuration of the library (kgeo/equatorial_lensing.py:379-417): the file '<outpath>/aXX_iYY_<which>.txt' with
+    columns varphi, rho(mbar = 0), ..., rho(mbar = mmax); nothing is written when a root find fails or the file exists."""
+    rs = _library_radius(which, spin)
+    varphis, rhos, status = rho_library([spin], [inc * np.pi / 180.], [rs], mmax)
+    _write_curves(outpath, which, [spin], [inc], varphis, rhos, status)
+
+
+def make_curves(args):
+    return make_curves2(*args)
+
+
+def generate_library(which='rh', outpath=None, spins=None, incs=None, mmax=5):
+    """The reference's curve library (:351-374): spins linspace(0.01, 0.99, 99) x inclinations 1..89 deg, orders 0..5, 360 angles,
+    one text file per configuration under './curve_library_<which>'.  The 8811 x 6 x 360 root finds run as one kernel launch
+    (the reference: a multiprocessing pool); returns the number of files written."""
+    outpath = outpath or './curve_library_' + which
+    print(outpath)
+    spins = np.linspace(0.01, 0.99, 99) if spins is None else np.asarray(spins, dtype=float)
+    incs = np.linspace(1, 89, 89) if incs is None else np.asarray(incs, dtype=float)
+    allincs, allspins = np.meshgrid(incs, spins)
+    allincs, allspins = allincs.flatten(), allspins.flatten()
+    reqs = np.array([_library_radius(which, s) for s in allspins])
+    os.makedirs(outpath, exist_ok=True)
+    varphis, rhos, status = rho_library(allspins, allincs * np.pi / 180., reqs, mmax)
+    return _write_curves(outpath, which, allspins, allincs, varphis, rhos, status)
 
 
 def critical_curve(a, th0, n=100000):

@@ -451,9 +451,66 @@ def inverse_lensing():
     save('inverse_lensing', **out)
 
 
+def integrals():
+    """th_integrate / r_integrate called directly with the conserved quantities, as solver.py:168-195 and r_equatorial do
+    (kerr_raytracing_ana.py:195-365, 368-633), their auxiliaries S1_S2 / R1_R2 (:638-683) and the Brent objective
+    r_equatorial2 / objfunc (equatorial_lensing.py:198-224)."""
+    from kgeo.kerr_raytracing_ana import R1_R2, S1_S2, r_integrate, th_integrate
+    from kgeo.kerr_raytracing_utils import my_sign
+    from kgeo.equatorial_lensing import objfunc, r_equatorial2
+    out = {}
+    cases = [(0.94, 17 * DEG, 1000., 8., 14), (0.998, 10 * DEG, 1000., 3., 12), (0.5, 120 * DEG, 500., 10., 12)]
+    rng = np.random.default_rng(7)
+    for i, (a, th_o, r_o, half, n) in enumerate(cases):
+        A, B = grid(n, half)
+        lam = -A * np.sin(th_o)
+        eta = (A ** 2 - a ** 2) * np.cos(th_o) ** 2 + B ** 2
+        s_o = my_sign(B)
+        up, um, _, _ = uplus_uminus(a, th_o, lam.copy(), eta.copy())
+        r1, r2, r3, r4, _ = radial_roots(a, lam, eta)
+        tmax = mino_total(a, r_o, eta, r1, r2, r3, r4)
+        tau = (np.linspace(0., 0.97, 9)[:, None] ** 1.5) * tmax[None, :] + 0 * rng.random((9, len(A)))
+        th = th_integrate(a, th_o, s_o, lam, eta, up, um, tau)
+        rr = r_integrate(a, r_o, lam, eta, r1, r2, r3, r4, tau)
+        th0 = th_integrate(a, th_o, s_o, lam, eta, up, um, tau, do_phi_and_t=False)
+        rr0 = r_integrate(a, r_o, lam, eta, r1, r2, r3, r4, tau, do_phi_and_t=False)
+        out.update({'c%d_par' % i: np.array([a, th_o, r_o]), 'c%d_lam' % i: lam, 'c%d_eta' % i: eta, 'c%d_so' % i: s_o,
+                    'c%d_up' % i: up, 'c%d_um' % i: um, 'c%d_roots' % i: np.array([r1, r2, r3, r4]), 'c%d_tau' % i: tau,
+                    'c%d_th' % i: np.array(th), 'c%d_r' % i: np.array(rr), 'c%d_th_only' % i: np.array(th0[0]),
+                    'c%d_r_only' % i: np.array(rr0[0]), 'c%d_It_only' % i: np.array(rr0[2]),      # I_t = 4 I_0 = -4 tau remains (:627-631)
+                    'c%d_zero' % i: np.array([np.abs(th0[1]).max(), np.abs(th0[2]).max(), np.abs(rr0[1]).max(),
+                                              np.abs(rr0[3]).max()])})
+    # the observer at infinity, r only: what r_equatorial asks of r_integrate
+    a, th_o = 0.94, 17 * DEG
+    A, B = grid(12, 8.)
+    lam = -A * np.sin(th_o)
+    eta = (A ** 2 - a ** 2) * np.cos(th_o) ** 2 + B ** 2
+    r1, r2, r3, r4, _ = radial_roots(a, lam, eta)
+    tmax = mino_total(a, np.inf, eta, r1, r2, r3, r4)
+    tau = np.linspace(0.05, 0.9, 6)[:, None] * tmax[None, :]
+    out.update(inf_lam=lam, inf_eta=eta, inf_roots=np.array([r1, r2, r3, r4]), inf_tau=tau,
+               inf_r=r_integrate(a, np.inf, lam, eta, r1, r2, r3, r4, tau, do_phi_and_t=False)[0])
+    # auxiliaries at arguments of the ranges the radial cases produce (SURVEY 8d)
+    al = rng.uniform(0.05, 3.0, 400)
+    ph = rng.uniform(0.05, np.pi - 0.05, 400)
+    j = rng.uniform(0.02, 0.98, 400)
+    S1, S2 = S1_S2(al, ph, j)
+    alR = rng.uniform(1.05, 6.0, 400)
+    R1, R2 = R1_R2(alR, ph, j)
+    out.update(aux_al=al, aux_phi=ph, aux_j=j, aux_S1=S1, aux_S2=S2, aux_alR=alR, aux_R1=R1, aux_R2=R2)
+    # the Brent objective at a few image-plane points
+    pts = [(5.5, 0.3, 0.94, 17 * DEG, 0), (5.2, -2.0, 0.94, 17 * DEG, 1), (2.0, 1.0, 0.94, 17 * DEG, 0), (30., 2.5, 0.5, 60 * DEG, 2),
+           (4.0, 0.1, 0.5, 60 * DEG, 1)]
+    out['obj_pts'] = np.array(pts)
+    out['obj_r'] = np.array([quiet(r_equatorial2, rho, vp, a_, t_, mbar=int(m)) for rho, vp, a_, t_, m in pts])
+    out['obj_f'] = np.array([quiet(objfunc, rho, vp, a_, t_, 4.0, mbar=int(m)) for rho, vp, a_, t_, m in pts])
+    out['ncases'] = np.array(len(cases))
+    save('integrals', **out)
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('integrals', 'setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -469,5 +526,6 @@ if __name__ == '__main__':
     fieldline_crossings()
     jet_pipeline()
     jet_boost()
+    integrals()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

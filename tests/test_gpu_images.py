@@ -294,6 +294,27 @@ def test_sharded_image_kernel_stores_rows_in_place(kg, interleave, max_blocks, p
     assert nrows % world != 0                                    # the shards were ragged
 
 
+def test_shard_scatter_places_rows_with_the_copy_engines(kg):
+    """kgeo_shard_scatter: local planes [nplanes, npix] -> their rows of larger destination planes (interleaved rows: one 3-D copy;
+    planes that are not whole pitches apart: per-plane 2-D copies) == the NumPy placement."""
+    import ctypes
+    import torch
+    from kgeo_b200 import _lib, _engine
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    ncols, nplanes = 12, 5
+    for rows_local, step, offset, nrows in ((4, 3, 1, 12), (4, 1, 5, 11), (4, 3, 1, 11)):
+        src = rng.standard_normal((nplanes, rows_local * ncols))
+        d_src = _engine.to_device(src)
+        d_dst = torch.full((nplanes, nrows * ncols), -7.0, dtype=torch.float64, device=d_src.device)
+        smap = _lib.ShardMap(ncols, step, offset, nrows * ncols, 0, 0)
+        _lib.check(L.kgeo_shard_scatter(_engine.dptr(d_src), nplanes, rows_local * ncols, ctypes.byref(smap), _engine.dptr(d_dst),
+                                        _engine.stream_ptr()))
+        want = np.full((nplanes, nrows, ncols), -7.0)
+        want[:, offset + step * np.arange(rows_local), :] = src.reshape(nplanes, rows_local, ncols)
+        assert np.array_equal(d_dst.cpu().numpy().reshape(nplanes, nrows, ncols), want)
+
+
 def test_sharded_image_argument_checks(kg):
     import ctypes
     from kgeo_b200 import _lib, _engine, equatorial_images as ei

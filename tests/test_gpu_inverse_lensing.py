@@ -74,3 +74,43 @@ def test_critical_curve_against_reference(golden, kg):
         assert np.max(np.abs(al - ra)) <= 1e-12 * np.max(np.abs(ra))
         # beta = sqrt(difference that vanishes at both ends): absolute gate
         assert np.max(np.abs(be - rb)) <= 1e-9
+
+
+def test_brent_objective_against_reference(golden, kg):
+    """r_equatorial2 / objfunc (equatorial_lensing.py:198-224) at the fixture's image-plane points."""
+    from kgeo_b200 import equatorial_lensing as el
+    g = golden('integrals')
+    for (rho, vp, a, th0, m), r_ref, f_ref in zip(g['obj_pts'], g['obj_r'], g['obj_f']):
+        r = el.r_equatorial2(rho, vp, float(a), float(th0), mbar=int(m))
+        assert r == pytest.approx(r_ref, rel=1e-10)
+        assert el.objfunc(rho, vp, float(a), float(th0), 4.0, mbar=int(m)) == pytest.approx(f_ref, rel=1e-9, abs=1e-9)
+
+
+def test_rho_library_equals_rho_of_req(kg, tmp_path):
+    """generate_library's single launch over (configuration, order, angle) == rho_of_req per configuration and order, bit for bit;
+    the files have the reference's name and column layout (equatorial_lensing.py:351-417)."""
+    from kgeo_b200 import equatorial_lensing as el
+    spins, incs = np.array([0.3, 0.94]), np.array([17., 60., 80.])
+    varphis = np.linspace(-180, 165, 24) * np.pi / 180.
+    allincs, allspins = [x.flatten() for x in np.meshgrid(incs, spins)]
+    reqs = 1 + np.sqrt(1 - allspins ** 2)
+    vp, rhos, status = el.rho_library(allspins, allincs * np.pi / 180., reqs, mmax=3, varphis=varphis)
+    assert rhos.shape == (6, 4, 24) and status.shape == rhos.shape
+    for c, (a, inc) in enumerate(zip(allspins, allincs)):
+        for mbar in range(4):
+            if (status[c, mbar] != 0).any():
+                with pytest.raises((ValueError, RuntimeError)):
+                    el.rho_of_req(float(a), float(inc * np.pi / 180.), float(reqs[c]), mbar=mbar, varphis=varphis)
+            else:
+                single = el.rho_of_req(float(a), float(inc * np.pi / 180.), float(reqs[c]), mbar=mbar, varphis=varphis)[1]
+                assert np.array_equal(single, rhos[c, mbar])
+    assert (status == 0).all(axis=(1, 2)).any()
+    n = el.generate_library('rh', outpath=str(tmp_path), spins=spins, incs=incs, mmax=3)
+    full = el.rho_library(allspins, allincs * np.pi / 180., reqs, mmax=3)          # the library's own 360 angles
+    ok360 = (full[2] == 0).all(axis=(1, 2))
+    assert n == int(ok360.sum())
+    c = int(np.argmax(ok360))
+    tab = np.loadtxt(str(tmp_path / ('a%02.0f_i%02.0f_rh.txt' % (100 * allspins[c], allincs[c]))))
+    assert tab.shape == (360, 5)
+    assert np.allclose(tab[:, 0], full[0], rtol=0, atol=1e-15) and np.allclose(tab[:, 1:], full[1][c].T, rtol=1e-15)
+    assert el.generate_library('rh', outpath=str(tmp_path), spins=spins, incs=incs, mmax=3) == 0   # existing files are kept

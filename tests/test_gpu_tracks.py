@@ -320,3 +320,39 @@ def test_more_than_2_pow_32_points_in_one_launch(kg):
     tail_small = small.tracks(ntau=ngeo, maxtaufrac=1. - 1.e-10, want=("r",))["r"].cpu().numpy()
     assert np.array_equal(tail_big, tail_small, equal_nan=True)
     assert np.isfinite(tail_big[:-1]).all()
+
+
+def test_th_integrate_r_integrate_against_reference(golden):
+    """th_integrate / r_integrate called with the conserved quantities, as the reference's solver and r_equatorial call them
+    (kerr_raytracing_ana.py:195-365, 368-633), and S1_S2 / R1_R2 (:638-683) vs the unmodified reference."""
+    from kgeo_b200 import kerr_raytracing_ana as ka
+    g = golden('integrals')
+    for i in range(int(g['ncases'])):
+        a, th_o, r_o = [float(x) for x in g['c%d_par' % i]]
+        lam, eta, tau = g['c%d_lam' % i], g['c%d_eta' % i], g['c%d_tau' % i]
+        r1, r2, r3, r4 = g['c%d_roots' % i]
+        th = ka.th_integrate(a, th_o, g['c%d_so' % i], lam, eta, g['c%d_up' % i], g['c%d_um' % i], tau)
+        rr = ka.r_integrate(a, r_o, lam, eta, r1, r2, r3, r4, tau)
+        ref_r = g['c%d_r' % i][0]
+        cond = np.maximum(1.0, ref_r / 1000.)                     # the reference's own conditioning in r (oracle/gates.py)
+        for got, ref, k, tol in zip(th, g['c%d_th' % i], ('th', 'Gph', 'Gt'), (1e-10, 1e-9, 1e-9)):
+            assert got.shape == ref.shape
+            assert_close(got, ref, tol, floor=1e-2, what='case %d %s' % (i, k))
+        for got, ref, k, tol in zip(rr, g['c%d_r' % i], ('r', 'Iph', 'It', 'Isig'), (1e-10, 1e-8, 1e-8, 1e-8)):
+            assert_close(got / cond, ref / cond, tol, floor=1e-2 * (r_o if k in ('It', 'Isig') else 1.0), what='case %d %s' % (i, k))
+        th0 = ka.th_integrate(a, th_o, g['c%d_so' % i], lam, eta, g['c%d_up' % i], g['c%d_um' % i], tau, do_phi_and_t=False)
+        rr0 = ka.r_integrate(a, r_o, lam, eta, r1, r2, r3, r4, tau, do_phi_and_t=False)
+        assert np.array_equal(th0[0], th[0]) and np.array_equal(rr0[0], rr[0])
+        assert not th0[1].any() and not th0[2].any() and not rr0[1].any() and not rr0[3].any()
+        assert np.array_equal(rr0[2], -4 * tau)
+    r1, r2, r3, r4 = g['inf_roots']
+    r_inf = ka.r_integrate(0.94, np.inf, g['inf_lam'], g['inf_eta'], r1, r2, r3, r4, g['inf_tau'], do_phi_and_t=False)[0]
+    assert_close(r_inf, g['inf_r'], 1e-10, floor=1e-3, what='r at r_o = inf')
+    S1, S2 = ka.S1_S2(g['aux_al'], g['aux_phi'], g['aux_j'])
+    R1, R2 = ka.R1_R2(g['aux_alR'], g['aux_phi'], g['aux_j'])
+    for got, k in ((S1, 'aux_S1'), (S2, 'aux_S2'), (R1, 'aux_R1'), (R2, 'aux_R2')):
+        assert_close(got, g[k], 1e-10, floor=1e-6, what=k)
+    with pytest.raises(Exception, match="not the same length"):
+        ka.th_integrate(0.5, 0.3, np.ones(3), np.ones(2), np.ones(3), np.ones(3), np.ones(3), np.ones((2, 3)))
+    with pytest.raises(Exception, match="incompatible shape in r_integrate"):
+        ka.r_integrate(0.5, 1000., np.ones(3), np.ones(3), *([np.ones(3)] * 4), np.ones((2, 4)))

@@ -370,3 +370,33 @@ def test_jet_boost_oracle_against_reference(golden):
         for k, v in zip(['I', 'Q', 'U', 'evpa', 'r', 'th', 'sinthb'], img):
             ref = g[name + '_img_' + k]
             assert_close(np.asarray(v, dtype=float), ref, 1e-11, floor=1e-6 * max(np.max(np.abs(ref)), 1e-300), what='%s image %s' % (name, k))
+
+
+def test_integrals_oracle_against_reference(golden):
+    """theta_motion / radial_motion / _S1_S2 / _R1_R2 / r_equatorial2 of the oracle at the interface of the reference's th_integrate,
+    r_integrate, S1_S2, R1_R2, r_equatorial2 (called with the conserved quantities, incl. r_o = inf with r only)."""
+    g = golden('integrals')
+    for i in range(int(g['ncases'])):
+        a, th_o, r_o = [float(x) for x in g['c%d_par' % i]]
+        lam, eta, tau = g['c%d_lam' % i], g['c%d_eta' % i], g['c%d_tau' % i]
+        r1, r2, r3, r4 = g['c%d_roots' % i]
+        th = ko.theta_motion(a, th_o, g['c%d_so' % i], lam, eta, g['c%d_up' % i], g['c%d_um' % i], tau)
+        rr = ko.radial_motion(a, r_o, lam, eta, r1, r2, r3, r4, tau)
+        for got, ref, k in zip(th, g['c%d_th' % i], ('th', 'Gph', 'Gt')):
+            assert_close(got, ref, 1e-12, floor=1e-3, what='case %d %s' % (i, k))
+        for got, ref, k in zip(rr, g['c%d_r' % i], ('r', 'Iph', 'It', 'Isig')):
+            assert_close(got, ref, 1e-12, floor=1e-3, what='case %d %s' % (i, k))
+        assert np.all(g['c%d_zero' % i] == 0.0)          # do_phi_and_t=False leaves the other integrals zero ...
+        assert np.array_equal(g['c%d_It_only' % i], -4 * tau)   # ... except I_t = 4 I_0 = -4 tau (:627-631)
+        r_only = ko.radial_motion(a, r_o, lam, eta, r1, r2, r3, r4, tau, full=False)
+        assert_close(r_only[0], g['c%d_r_only' % i], 1e-12, floor=1e-3, what='case %d r only' % i)
+        assert np.array_equal(r_only[2], -4 * tau)
+    r1, r2, r3, r4 = g['inf_roots']
+    r_inf = ko.radial_motion(0.94, np.inf, g['inf_lam'], g['inf_eta'], r1, r2, r3, r4, g['inf_tau'], full=False)[0]
+    assert_close(r_inf, g['inf_r'], 1e-12, floor=1e-3, what='r at r_o = inf')
+    S1, S2 = ko._S1_S2(g['aux_al'], g['aux_phi'], g['aux_j'])
+    R1, R2 = ko._R1_R2(g['aux_alR'], g['aux_phi'], g['aux_j'])
+    for got, k in ((S1, 'aux_S1'), (S2, 'aux_S2'), (R1, 'aux_R1'), (R2, 'aux_R2')):
+        assert_close(got, g[k], 1e-12, floor=1e-6, what=k)
+    for (rho, vp, a_, t_, m), want in zip(g['obj_pts'], g['obj_r']):
+        assert ko.r_equatorial2(rho, vp, a_, t_, mbar=int(m)) == pytest.approx(want, rel=1e-12)
