@@ -32,4 +32,25 @@ for model, aa, inc, psit, pval, neqmax in (('mono', 0.5, 20., 0.3, 1, 1), ('powe
     st = off_eq.getstokes(psit, A2, B2, 1000., inc * np.pi / 180, aa, 47, neqmax=neqmax, model=model, pval=pval, nu_parallel=0, sigma=2,
                           retvals=True, retsin=True)
     assert np.isfinite(st[0]).all()
+# round-2 additions: the integrals entry points, the curve library, the row-sharded image into a destination buffer (odd sizes) and
+# the copy-engine placement
+from kgeo_b200 import kerr_raytracing_ana as ka, kerr_raytracing_utils as ku, equatorial_lensing as el, sharding, equatorial_images as ei
+lam, eta = -A * np.sin(th_o), (A ** 2 - a ** 2) * np.cos(th_o) ** 2 + B ** 2
+up, um, _, _ = ku.uplus_uminus(a, th_o, lam, eta)
+r1, r2, r3, r4, _ = ku.radial_roots(a, lam, eta)
+tau5 = np.asarray(g.tausteps[:5])
+ka.th_integrate(a, th_o, np.where(B >= 0, 1., -1.), lam, eta, up, um, tau5)
+ka.r_integrate(a, 1000., lam, eta, r1, r2, r3, r4, tau5)
+ka.r_integrate(a, np.inf, lam, eta, r1, r2, r3, r4, tau5, do_phi_and_t=False)
+el.rho_library([0.3, 0.94, 0.7], [0.3, 1.0, 1.4], [3., 4., 5.], mmax=2, varphis=np.linspace(-3, 3, 13))
+Ai, Bi = ei.pixel_grid(-10., 10., -10., 10., 20. / 37)
+off, total = sharding.plane_layout(3, Ai.size)
+buf = sharding.PeerBuffer(total)
+for rank in range(3):
+    al, be, rows = sharding.shard_pixels_interleaved(Ai, Bi, 37, rank, 3)
+    ei.image_into(a, np.inf, th_o, 0, 2, al, be, *sharding._image_kwargs({}), dst={k: buf.ptr + 8 * o for k, o in off.items()},
+                  cols=37, row_step=3, row_offset=rank, plane_stride=Ai.size, max_blocks=(2 if rank == 1 else 0))
+flat = sharding.to_host_pinned(buf.tensor())
+assert np.isfinite(flat[off["r"]:off["r"] + Ai.size]).all()
+buf.close()
 print("sanitize_case ok", g.geo_coords[1].shape, img[0].shape)
