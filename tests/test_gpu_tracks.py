@@ -4,7 +4,7 @@ at the BASELINE sizes, (4) the reference's own ipole known-answer rays."""
 import numpy as np
 import pytest
 
-from helpers import assert_close, assert_tracks_close
+from helpers import PV_RTOL, assert_close, assert_tracks_close, removable_singularity_mask
 
 pytestmark = pytest.mark.gpu
 np.seterr(all='ignore')
@@ -338,8 +338,19 @@ def test_th_integrate_r_integrate_against_reference(golden):
         for got, ref, k, tol in zip(th, g['c%d_th' % i], ('th', 'Gph', 'Gt'), (1e-10, 1e-9, 1e-9)):
             assert got.shape == ref.shape
             assert_close(got, ref, tol, floor=1e-2, what='case %d %s' % (i, k))
+        # the samples where the reference's own closed forms for the third-kind integrals are 0/0 expressions (oracle/gates.py):
+        # gated at PV_RTOL there, as in the track tests
+        alpha = -lam / np.sin(th_o)
+        beta = g['c%d_so' % i] * np.sqrt(np.maximum(eta - (alpha ** 2 - a ** 2) * np.cos(th_o) ** 2, 0.0))
+        pv = removable_singularity_mask(a, r_o, th_o, alpha, beta, ref_r)
+        assert pv.mean() < 0.05                      # 2.8 % for the a = 0.998 case (12 x 12 rays within 3 M), 0.2-0.3 % otherwise
         for got, ref, k, tol in zip(rr, g['c%d_r' % i], ('r', 'Iph', 'It', 'Isig'), (1e-10, 1e-8, 1e-8, 1e-8)):
-            assert_close(got / cond, ref / cond, tol, floor=1e-2 * (r_o if k in ('It', 'Isig') else 1.0), what='case %d %s' % (i, k))
+            floor = 1e-2 * (r_o if k in ('It', 'Isig') else 1.0)
+            if k == 'r':
+                assert_close(got / cond, ref / cond, tol, floor=floor, what='case %d %s' % (i, k))
+                continue
+            assert_close(np.where(pv, 0.0, got / cond), np.where(pv, 0.0, ref / cond), tol, floor=floor, what='case %d %s' % (i, k))
+            assert_close(np.where(pv, got / cond, 0.0), np.where(pv, ref / cond, 0.0), PV_RTOL, floor=floor, what='case %d %s (pv)' % (i, k))
         th0 = ka.th_integrate(a, th_o, g['c%d_so' % i], lam, eta, g['c%d_up' % i], g['c%d_um' % i], tau, do_phi_and_t=False)
         rr0 = ka.r_integrate(a, r_o, lam, eta, r1, r2, r3, r4, tau, do_phi_and_t=False)
         assert_close(th0[0], g['c%d_th_only' % i], 1e-10, floor=1e-2, what='case %d th (r, theta only)' % i)
