@@ -53,7 +53,6 @@ CANONICAL_FLOP_PER_PIXEL = 3000.0   # n = 0..2 image
 BYTES_PER_POINT = 32.0              # r, theta, phi, t written once
 IMG_PLANES = 24                     # I,Q,U,r,Ir,g,sinthb x 3 orders + nmax, npol, imax: doubles per pixel of an n=0..2 image
 GATHER_DEFAULT = "copy_engine"     # N > 1: how the image planes reach rank 0 (see run_ours)
-IMG_BLOCKS_DEFAULT = 0              # N > 1: cap on the thread blocks of the image kernel on its side stream (0 = full grid: measured best)
 PARITY_PIXELS = 4096
 
 
@@ -323,7 +322,7 @@ def run_ours(args):
         token = torch.zeros((1,), dtype=torch.float32, device=dev)
         img = gathered = None
         if peer is not None:
-            smap = _lib.ShardMap(cols, world, rank, npix_all, int(os.environ.get("KGEO_BENCH_IMG_BLOCKS", IMG_BLOCKS_DEFAULT)), 0)
+            smap = _lib.ShardMap(cols, world, rank, npix_all, 0)
             vp = lambda plane: ctypes.cast(ctypes.c_void_p(peer.ptr + 8 * plane * npix_all), _lib.c_double_p)
             peer_ptrs = [vp(3 * i) for i in range(7)] + [vp(21 + i) for i in range(3)]
             final = peer.tensor((IMG_PLANES, npix_all))
@@ -808,9 +807,10 @@ def image_secondary(L, ei, pack_models, th_o, dev, stream, peak_tf, summ):
         isum = (summ or {}).get("image_kernel", {})
         fpx = isum.get("flop_per_pixel")
         ach = fpx * npx / (img_ms * 1e-3) / 1e12 if fpx else None
-        return {"metric": "equatorial image pixels/s (n=0..2, all orders fused)", "value": npx / (img_ms * 1e-3),
+        return {"metric": "equatorial image pixels/s (n=0..2, all orders in one call: geometry kernel + emission kernel)", "value": npx / (img_ms * 1e-3),
                 "unit": "pixels/s", "workload": "4096x4096 px, a=0.94, theta_o=17deg, r_o=inf, bpl/zamo/rad (BASELINE cfg 2 "
-                "models at cfg 4 size)", "ms": img_ms, "includes": "image_kernel only (outputs preallocated, resident)",
+                "models at cfg 4 size)", "ms": img_ms, "includes": "kgeo_equatorial_image with device pointers: r_equatorial_kernel + "
+                "image_emission_kernel (outputs preallocated, resident)",
                 "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": (ach / peak_tf) if (ach and peak_tf) else None, "flop_per_pixel": fpx,
                              "flop_source": "executed FP64 flops per pixel (ncu, profiles/r02_ncu_summary.json)" if fpx else

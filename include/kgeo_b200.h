@@ -114,9 +114,7 @@ typedef struct kgeo_shard_map {
     uint64_t row_step;
     uint64_t row_offset;
     uint64_t plane_stride;
-    int32_t max_blocks;    /* > 0: at most this many 256-thread blocks walk the pixels (grid-stride), leaving the other SMs to
-                              concurrent work on another stream; 0: one block per 256 pixels */
-    int32_t reserved;
+    uint64_t reserved;     /* 0 */
 } kgeo_shard_map;
 
 /* Exported CUDA IPC handle of a peer buffer (cudaIpcMemHandle_t, 64 bytes): plain data, sent to the other processes of the
@@ -272,7 +270,7 @@ int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* m
                                   double* Ie_dst, void* stream);
 /* The same placement for planes that were computed locally first: src_dev [nplanes, npix] (plane-major, this shard's rows) is
  * copied to its rows of the destination planes by the COPY ENGINES (one strided 3-D cudaMemcpy; destination may be peer memory),
- * so the transfer runs beside kernels of another stream without taking SMs from them.  map->max_blocks is ignored. */
+ * so the transfer runs beside kernels of another stream without taking SMs from them. */
 int kgeo_shard_scatter(const double* src_dev, size_t nplanes, size_t npix, const kgeo_shard_map* map, double* dst, void* stream);
 /* Peer buffers.  kgeo_peer_alloc: `bytes` of device memory on the current device plus the handle under which the other
  * processes of the box open it; kgeo_peer_open (in another process, on ITS current device): the address at which that

@@ -36,7 +36,7 @@ class ImageOpts(ctypes.Structure):
 
 class ShardMap(ctypes.Structure):
     _fields_ = [("cols", ctypes.c_uint64), ("row_step", ctypes.c_uint64), ("row_offset", ctypes.c_uint64),
-                ("plane_stride", ctypes.c_uint64), ("max_blocks", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("plane_stride", ctypes.c_uint64), ("reserved", ctypes.c_uint64)]
 
 
 class PeerHandle(ctypes.Structure):

@@ -117,7 +117,7 @@ KG_HD int theta_make_base(const ThetaRay& r, P out) {
     NomePowers np(r.q);
     for (int j = 0; j < kThJM; ++j) {
         const double qe = np.qe, qo = np.qo;
-        if (qe < 1.0e-19 && qo < 1.0e-19) {     // harmonics 1..j (even) / 0..j-1 (odd) suffice
+        if (qe < 1.0e-17 && qo < 1.0e-17) {     // harmonics 1..j (even) / 0..j-1 (odd) suffice
             J = j;
             break;
         }
@@ -230,7 +230,7 @@ KG_HD int theta_make_pi(const ThetaRay& r, double n, double nmm, double omn, dou
             sy = qe * (0.5 * (ep - em));
             mag = fabs(cx);
         }
-        if (mag < 1.0e-19) {
+        if (mag < 1.0e-17) {
             J = j;
             break;
         }

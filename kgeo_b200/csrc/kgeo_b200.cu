@@ -8,8 +8,9 @@
 //                      the group's samples together (lane = 4 * sample + ray: every store instruction writes 8 full
 //                      32-byte sectors of the reference's (ngeo, npix) arrays).  A full trace is two launches: a hot
 //                      pass without the Carlson fallback (64 registers) and a fix-up pass for the fallback rays.
-//   image_kernel       fused equatorial image: per pixel one setup in registers/local memory, then all orders
-//                      mbar_min..mbar_max (crossing time, crossing radius, redshift, polarization, emissivity); no
+//   r_equatorial_kernel + image_emission_kernel
+//                      equatorial image in two launches: per pixel one setup in registers and the crossing time / radius of
+//                      every order mbar_min..mbar_max (planes), then redshift, polarization, emissivity per order; no
 //                      geodesic array ever goes through HBM.
 //   plus element-wise kernels for the special functions and the physics closed forms.
 //
@@ -947,17 +948,17 @@ __global__ void __launch_bounds__(256) jet_sort_kernel(size_t npix, int nguess, 
 // equatorial lensing / image
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef KG_IMG_THREADS
-#define KG_IMG_THREADS 256
+#define KG_IMG_THREADS 384
 #endif
 #ifndef KG_IMG_MINBLOCKS
-#define KG_IMG_MINBLOCKS 3
+#define KG_IMG_MINBLOCKS 2
 #endif
 constexpr int IMG_THREADS = KG_IMG_THREADS;
 
 __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                    const double* __restrict__ beta, int mbar_lo, int mbar_hi,
                                                                    double* rs_out, double* Ir_out, double* Nmax_out,
-                                                                   double* Imax_out, double* npol_out) {
+                                                                   double* Imax_out, double* npol_out, unsigned char* outside_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     double w[NW_LITE];
@@ -966,6 +967,7 @@ __global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) r_equatorial_ke
     ray_setup<false, false>(o, alpha[i], be, M_ANY_ETA_POS, w, &fl);
     ArrayW W{w};
     const bool reg = w[S_ETA] > 0.0;
+    if (outside_out) outside_out[i] = (fl & F_OUTSIDE) ? 1 : 0;      // is_outside_crit: the emission kernel's radial momentum sign
     if (Imax_out) Imax_out[i] = reg ? w[S_TAUTOT] : -1.0;
     if (npol_out) npol_out[i] = n_poloidal_at(W, w[S_TAUTOT]);
     for (int mbar = mbar_lo; mbar <= mbar_hi; ++mbar) {
@@ -1123,91 +1125,62 @@ struct ImageOut {
     double *I, *Q, *U, *r, *Ir, *g, *sinthb, *nmax, *npol, *imax, *lp, *Ie;
 };
 
-// Fused equatorial image.  Per pixel: setup once, then the GEOMETRY of every order (crossing time, Nmax, crossing radius: all
-// that needs the ray constants), parked in this thread's own shared-memory column, then the EMISSION of every order from the parked
-// crossings.  With geometry and emission interleaved per order (round 1) the ~14 ray constants the later orders need stayed live
-// across the emission code and the 80-register kernel spilled 690 B per thread (ncu: 9.2 GB written to DRAM for a 3.2 GB image).
-#ifndef KG_IMG_CHUNK
-#define KG_IMG_CHUNK 4                  // orders whose crossings are parked at a time (more orders: several rounds)
+// Equatorial image = TWO kernels.  r_equatorial_kernel (above) is the GEOMETRY: per pixel one setup, then per order the crossing
+// time, Nmax and the crossing radius, written as planes.  image_emission_kernel is the EMISSION: per pixel and order the masks,
+// momentum signs, fluid velocity, redshift, (polarization,) emissivity and Stokes parameters from the crossing planes.
+// One fused kernel (rounds 1 and 2a: geometry of all orders parked in shared memory, then emission) executed only 35 % more
+// instructions than the geometry alone but took 80 % longer (6.06 against 3.38 ms at 4096^2): ~17 k SASS instructions walked
+// once per warp stalled on instruction fetch (no-instruction 3.8 per issue against 1.3) and on spill reloads around the
+// 80-register cap.  Split, each kernel's code fits the instruction caches; the crossing planes r, Ir are outputs anyway and
+// only Nmax (per order) and a byte per pixel travel through scratch.
+struct GeomPlanes {
+    const double *r, *Ir, *N;          // [norder, npix]
+    const double *tau, *npol;          // [npix]: total Mino time (-1: vortical), nmax_poloidal (may be NULL)
+    const unsigned char* outside;      // [npix]
+};
+#ifndef KG_EMIS_THREADS
+#define KG_EMIS_THREADS 256
 #endif
-// One pixel of the fused image: i = pixel of this launch, d = its place in the destination planes, pstride = elements between
-// the order planes of one output.
-template <bool POL>
-__device__ __forceinline__ void image_pixel(const Observer& o, const kgeo_models& M, const kgeo_image_opts& opt,
-                                            const double* __restrict__ alpha, const double* __restrict__ beta, const ImageOut& out,
-                                            size_t i, size_t d, size_t pstride, double (*park)[IMG_THREADS]) {
-    double w[NW_LITE];
-    int fl;
-    const double al = alpha[i], be = beta[i];
-    ray_setup<false, false>(o, al, be, M_ANY_ETA_POS, w, &fl);
-    // (Building the AGM ladder of the radial parameter once per ray and ascending it per order, as the track kernels' Carlson path
-    // does, was measured: the ladder is a dynamically indexed local array -- r_equatorial 4.25 against 3.50 ms.)
-    ArrayW W{w};
-    if (out.npol) out.npol[d] = n_poloidal_at(W, w[S_TAUTOT]);
-    if (out.imax) out.imax[d] = (w[S_ETA] > 0.0) ? w[S_TAUTOT] : -1.0;
-    const double lam = w[S_LAM], eta = w[S_ETA], tau_tot = w[S_TAUTOT];
-    double lastN = -2.0;
-    for (int m0 = opt.mbar_min; m0 <= opt.mbar_max; m0 += KG_IMG_CHUNK) {
-        const int m1 = min(opt.mbar_max, m0 + KG_IMG_CHUNK - 1);
-        for (int mbar = m0; mbar <= m1; ++mbar) {
-            const OrderGeom gq = image_geometry(W, o, fl, be, mbar);
-            const int c = 3 * (mbar - m0);
-            park[c][threadIdx.x] = gq.r;
-            park[c + 1][threadIdx.x] = gq.Ir;
-            park[c + 2][threadIdx.x] = gq.Nmax;
-        }
-#pragma unroll 1
-        for (int mbar = m0; mbar <= m1; ++mbar) {
-            const int c = 3 * (mbar - m0);
-            const OrderGeom gq{park[c][threadIdx.x], park[c + 1][threadIdx.x], park[c + 2][threadIdx.x]};
-            const OrderOut v = image_physics<POL>(o, fl, M, opt, al, be, lam, eta, tau_tot, mbar, gq);
-            const size_t q = (size_t)(mbar - opt.mbar_min) * pstride + d;
-            if (out.I) out.I[q] = v.I;
-            if (out.Q) out.Q[q] = v.Q;
-            if (out.U) out.U[q] = v.U;
-            if (out.r) out.r[q] = v.r;
-            if (out.Ir) out.Ir[q] = v.Ir;
-            if (out.g) out.g[q] = v.g;
-            if (out.sinthb) out.sinthb[q] = v.sinthb;
-            if (out.lp) out.lp[q] = v.lp;
-            if (out.Ie) out.Ie[q] = v.Ie;
-            lastN = v.Nmax;
-        }
-    }
-    if (out.nmax) out.nmax[d] = lastN;
-}
-
-template <bool POL>
-__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
+#ifndef KG_EMIS_MINBLOCKS
+#define KG_EMIS_MINBLOCKS 4
+#endif
+constexpr int EMIS_THREADS = KG_EMIS_THREADS;
+// SHARDED: the pixels are a block of image rows whose results go to rows lr * row_step + row_offset of destination planes that
+// may live on ANOTHER GPU (peer memory over NVLink: plain coalesced stores -- the gather of a row-sharded image is fused into
+// the kernel that computes it); the crossing planes are then copied along.
+template <bool POL, bool SHARDED>
+__global__ void __launch_bounds__(EMIS_THREADS, KG_EMIS_MINBLOCKS) image_emission_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
                                                             const double* __restrict__ alpha, const double* __restrict__ beta,
-                                                            ImageOut out) {
-    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];             // [r, Ir, Nmax of order c][thread]
+                                                            GeomPlanes g, ImageOut out, kgeo_shard_map map) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    image_pixel<POL>(o, M, opt, alpha, beta, out, i, i, npix, park);
-}
-
-// The pixels are a block of image rows whose results go to rows lr * row_step + row_offset of destination planes that may live
-// on ANOTHER GPU (peer memory over NVLink: plain coalesced stores -- the gather of a row-sharded image is fused into the kernel
-// that computes it); the grid may be capped (grid-stride walk) to leave SMs to concurrent work on another stream.
-template <bool POL, bool WALK>
-__global__ void __launch_bounds__(IMG_THREADS, KG_IMG_MINBLOCKS) image_sharded_kernel(Observer o, kgeo_models M, kgeo_image_opts opt, size_t npix,
-                                                            const double* __restrict__ alpha, const double* __restrict__ beta,
-                                                            ImageOut out, kgeo_shard_map map) {
-    __shared__ double park[3 * KG_IMG_CHUNK][IMG_THREADS];
-    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if constexpr (WALK) {
-        const size_t walk = (size_t)gridDim.x * blockDim.x;
+    const size_t d = SHARDED ? ((i / map.cols) * map.row_step + map.row_offset) * map.cols + i % map.cols : i;
+    const size_t pstride = SHARDED ? (size_t)map.plane_stride : npix;
+    const double al = alpha[i], be = beta[i];
+    const double lam = -al * o.sth, eta = conserved_eta(o, al, be);    // as ray_setup forms them
+    const double tau_tot = g.tau[i];
+    const int fl = g.outside[i] ? F_OUTSIDE : 0;
+    if (out.npol && out.npol != g.npol) out.npol[d] = g.npol[i];
+    if (out.imax && out.imax != g.tau) out.imax[d] = tau_tot;
+    double lastN = -2.0;
 #pragma unroll 1
-        for (size_t i = i0; i < npix; i += walk) {
-            const size_t d = ((i / map.cols) * map.row_step + map.row_offset) * map.cols + i % map.cols;
-            image_pixel<POL>(o, M, opt, alpha, beta, out, i, d, (size_t)map.plane_stride, park);
-        }
-    } else {
-        if (i0 >= npix) return;
-        const size_t d = ((i0 / map.cols) * map.row_step + map.row_offset) * map.cols + i0 % map.cols;
-        image_pixel<POL>(o, M, opt, alpha, beta, out, i0, d, (size_t)map.plane_stride, park);
+    for (int mbar = opt.mbar_min; mbar <= opt.mbar_max; ++mbar) {
+        const size_t qi = (size_t)(mbar - opt.mbar_min) * npix + i;
+        const OrderGeom gq{g.r[qi], g.Ir[qi], g.N[qi]};
+        const OrderOut v = image_physics<POL>(o, fl, M, opt, al, be, lam, eta, tau_tot, mbar, gq);
+        const size_t q = (size_t)(mbar - opt.mbar_min) * pstride + d;
+        if (out.I) out.I[q] = v.I;
+        if (out.Q) out.Q[q] = v.Q;
+        if (out.U) out.U[q] = v.U;
+        if (out.r && out.r != g.r) out.r[q] = v.r;
+        if (out.Ir && out.Ir != g.Ir) out.Ir[q] = v.Ir;
+        if (out.g) out.g[q] = v.g;
+        if (out.sinthb) out.sinthb[q] = v.sinthb;
+        if (out.lp) out.lp[q] = v.lp;
+        if (out.Ie) out.Ie[q] = v.Ie;
+        lastN = v.Nmax;
     }
+    if (out.nmax) out.nmax[d] = lastN;
 }
 
 // element-wise physics
@@ -1790,7 +1763,7 @@ int kgeo_r_equatorial(const kgeo_observer* obs, size_t npix, const double* alpha
     if (npix == 0) return 0;
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
     r_equatorial_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, (cudaStream_t)stream>>>(o, npix, alpha, beta, mbar_lo,
-                                                                                              mbar_hi, rs, Ir, Nmax, Imax, npol);
+                                                                                              mbar_hi, rs, Ir, Nmax, Imax, npol, nullptr);
     LAUNCHED("r_equatorial_kernel");
     return 0;
 }
@@ -1835,25 +1808,39 @@ int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0,
     return 0;
 }
 
+// geometry into the caller's r / Ir / imax / npol planes where they are plain local planes, into pool scratch otherwise
+// (sharded: the destination may be peer memory, which the emission kernel must not read back), then the emission
 static int launch_image(const kgeo_observer* obs, const kgeo_models* models, const kgeo_image_opts* opts, size_t npix,
                         const double* alpha, const double* beta, const kgeo_shard_map* map, const ImageOut& out, cudaStream_t st) {
     Observer o = make_observer(obs->a, obs->r_o, obs->th_o);
-    unsigned grid = grid_for(npix, IMG_THREADS);
+    const size_t norder = (size_t)(opts->mbar_max - opts->mbar_min + 1), plane = norder * npix * sizeof(double);
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(keep_pool_memory(dev));
+    PoolBuf s_r, s_Ir, s_N, s_tau, s_npol, s_out;
+    const bool local = (map == nullptr);
+    double *g_r = local ? out.r : nullptr, *g_Ir = local ? out.Ir : nullptr, *g_tau = local ? out.imax : nullptr,
+           *g_npol = local ? out.npol : nullptr;
+    if (!g_r) { CU(s_r.alloc(plane, st)); g_r = s_r.as<double>(); }
+    if (!g_Ir) { CU(s_Ir.alloc(plane, st)); g_Ir = s_Ir.as<double>(); }
+    if (!g_tau) { CU(s_tau.alloc(npix * sizeof(double), st)); g_tau = s_tau.as<double>(); }
+    if (!g_npol && out.npol) { CU(s_npol.alloc(npix * sizeof(double), st)); g_npol = s_npol.as<double>(); }
+    CU(s_N.alloc(plane, st));
+    CU(s_out.alloc(npix, st));
+    const unsigned grid = grid_for(npix, EMIS_THREADS);
+    r_equatorial_kernel<<<grid_for(npix, IMG_THREADS), IMG_THREADS, 0, st>>>(o, npix, alpha, beta, opts->mbar_min, opts->mbar_max, g_r, g_Ir,
+                                                                             s_N.as<double>(), g_tau, g_npol, s_out.as<unsigned char>());
+    LAUNCHED("r_equatorial_kernel");
+    const GeomPlanes g{g_r, g_Ir, s_N.as<double>(), g_tau, g_npol, s_out.as<unsigned char>()};
     if (map) {
-        const bool capped = map->max_blocks > 0 && (unsigned)map->max_blocks < grid;
-        if (capped) {
-            grid = (unsigned)map->max_blocks;
-            if (opts->polarization) image_sharded_kernel<true, true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
-            else image_sharded_kernel<false, true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
-        } else {
-            if (opts->polarization) image_sharded_kernel<true, false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
-            else image_sharded_kernel<false, false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out, *map);
-        }
+        if (opts->polarization) image_emission_kernel<true, true><<<grid, EMIS_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, g, out, *map);
+        else image_emission_kernel<false, true><<<grid, EMIS_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, g, out, *map);
     } else {
-        if (opts->polarization) image_kernel<true><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out);
-        else image_kernel<false><<<grid, IMG_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, out);
+        const kgeo_shard_map id{};
+        if (opts->polarization) image_emission_kernel<true, false><<<grid, EMIS_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, g, out, id);
+        else image_emission_kernel<false, false><<<grid, EMIS_THREADS, 0, st>>>(o, *models, *opts, npix, alpha, beta, g, out, id);
     }
-    LAUNCHED("image_kernel");
+    LAUNCHED("image_emission_kernel");
     return 0;
 }
 
@@ -1886,7 +1873,7 @@ int kgeo_equatorial_image_sharded(const kgeo_observer* obs, const kgeo_models* m
     if (opts->mbar_min < 0 || opts->mbar_max < opts->mbar_min) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: bad mbar range");
     if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: NULL pointer");
     if (npix == 0) return 0;
-    if (map->cols == 0 || map->row_step == 0 || npix % map->cols != 0 || map->max_blocks < 0)
+    if (map->cols == 0 || map->row_step == 0 || npix % map->cols != 0)
         return fail_arg(KGEO_E_BADARG, "kgeo_equatorial_image_sharded: the shard must be whole rows of cols > 0 pixels, row_step > 0");
     const uint64_t last_row = (npix / map->cols - 1) * map->row_step + map->row_offset;
     if (opts->mbar_max > opts->mbar_min && map->plane_stride < (last_row + 1) * map->cols)

@@ -65,7 +65,7 @@ _DST_ORDER = _PLANES + ("nmax", "npol", "imax", "lp", "Ie")
 
 
 def image_into(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, velocity, bfield, polarization, pathlength,
-               specind, diskangle, nu_obs, dst, cols, row_step, row_offset, plane_stride, max_blocks=0, dev=None):
+               specind, diskangle, nu_obs, dst, cols, row_step, row_offset, plane_stride, dev=None):
     """The fused image kernel for a shard of whole pixel rows (alpha/beta: NumPy arrays or CUDA tensors, `cols` pixels per row),
     every result stored at its place in DESTINATION planes (kgeo_equatorial_image_sharded): `dst` maps an output name
     ('I','Q','U','r','Ir','g','sinthb','nmax','npol','imax','lp','Ie') to the device address (int) of its first plane --
@@ -79,7 +79,7 @@ def image_into(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, veloci
     opts = _lib.ImageOpts(int(mbar_min), int(mbar_max), int(bool(polarization)), int(bool(pathlength)), float(specind),
                           float(diskangle), float(nu_obs))
     al, be = _engine.to_device(alpha, dev), _engine.to_device(beta, dev)
-    smap = _lib.ShardMap(int(cols), int(row_step), int(row_offset), int(plane_stride), int(max_blocks), 0)
+    smap = _lib.ShardMap(int(cols), int(row_step), int(row_offset), int(plane_stride), 0)
     ptr = lambda k: ctypes.cast(ctypes.c_void_p(dst.get(k) or None), _lib.c_double_p)
     t = _engine.torch()
     with t.cuda.device(dev):

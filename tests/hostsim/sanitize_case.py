@@ -49,7 +49,7 @@ buf = sharding.PeerBuffer(total)
 for rank in range(3):
     al, be, rows = sharding.shard_pixels_interleaved(Ai, Bi, 37, rank, 3)
     ei.image_into(a, np.inf, th_o, 0, 2, al, be, *sharding._image_kwargs({}), dst={k: buf.ptr + 8 * o for k, o in off.items()},
-                  cols=37, row_step=3, row_offset=rank, plane_stride=Ai.size, max_blocks=(2 if rank == 1 else 0))
+                  cols=37, row_step=3, row_offset=rank, plane_stride=Ai.size)
 flat = sharding.to_host_pinned(buf.tensor())
 assert np.isfinite(flat[off["r"]:off["r"] + Ai.size]).all()
 buf.close()

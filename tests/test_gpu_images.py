@@ -253,10 +253,10 @@ def test_image_argument_checks(kg):
         kg.Bfield('simple')
 
 
-@pytest.mark.parametrize("interleave,max_blocks,pol", [(True, 0, False), (True, 5, True), (False, 3, False)])
-def test_sharded_image_kernel_stores_rows_in_place(kg, interleave, max_blocks, pol):
-    """kgeo_equatorial_image_sharded: three ragged row shards (interleaved or blocks of rows; full or capped grid) written by
-    three launches into ONE destination buffer (a PeerBuffer: kgeo_peer_alloc memory, here on the same GPU) == the whole image."""
+@pytest.mark.parametrize("interleave,pol", [(True, False), (True, True), (False, False)])
+def test_sharded_image_kernel_stores_rows_in_place(kg, interleave, pol):
+    """kgeo_equatorial_image_sharded: three ragged row shards (interleaved or blocks of rows) written by
+    three calls into ONE destination buffer (a PeerBuffer: kgeo_peer_alloc memory, here on the same GPU) == the whole image."""
     from kgeo_b200 import sharding, equatorial_images as ei
     a, r_o, th_o, world = 0.94, np.inf, 17 * np.pi / 180, 3
     kw = dict(polarization=pol, pathlength=pol)
@@ -281,7 +281,7 @@ def test_sharded_image_kernel_stores_rows_in_place(kg, interleave, max_blocks, p
                 al, be, rows = sharding.shard_pixels(A, B, ncols, rank, world)
                 step, offset = 1, rows[0]
             ei.image_into(a, r_o, th_o, 0, 2, al, be, *model, dst={k: buf.ptr + 8 * o for k, o in off.items()}, cols=ncols,
-                          row_step=step, row_offset=offset, plane_stride=A.size, max_blocks=max_blocks)
+                          row_step=step, row_offset=offset, plane_stride=A.size)
         flat = sharding.to_host_pinned(view)
         assert np.all(flat[total:] == -7.0)                      # nothing stored past the planes
         got = sharding._image_tuple(flat[:total], off, 3, A.size, pol)
@@ -307,7 +307,7 @@ def test_shard_scatter_places_rows_with_the_copy_engines(kg):
         src = rng.standard_normal((nplanes, rows_local * ncols))
         d_src = _engine.to_device(src)
         d_dst = torch.full((nplanes, nrows * ncols), -7.0, dtype=torch.float64, device=d_src.device)
-        smap = _lib.ShardMap(ncols, step, offset, nrows * ncols, 0, 0)
+        smap = _lib.ShardMap(ncols, step, offset, nrows * ncols, 0)
         _lib.check(L.kgeo_shard_scatter(_engine.dptr(d_src), nplanes, rows_local * ncols, ctypes.byref(smap), _engine.dptr(d_dst),
                                         _engine.stream_ptr()))
         want = np.full((nplanes, nrows, ncols), -7.0)
@@ -325,9 +325,9 @@ def test_sharded_image_argument_checks(kg):
     opts = _lib.ImageOpts(0, 2, 0, 0, 1.0, 0.1, 230e9)
     x = _engine.to_device(np.zeros(12))
     null = ctypes.cast(None, _lib.c_double_p)
-    for smap in (_lib.ShardMap(5, 1, 0, 12, 0, 0),       # 12 pixels are not whole rows of 5
-                 _lib.ShardMap(4, 0, 0, 12, 0, 0),       # row_step 0
-                 _lib.ShardMap(4, 2, 1, 12, 0, 0)):      # destination plane (rows 1, 3, 5 -> 24 pixels) larger than plane_stride
+    for smap in (_lib.ShardMap(5, 1, 0, 12, 0),       # 12 pixels are not whole rows of 5
+                 _lib.ShardMap(4, 0, 0, 12, 0),       # row_step 0
+                 _lib.ShardMap(4, 2, 1, 12, 0)):      # destination plane (rows 1, 3, 5 -> 24 pixels) larger than plane_stride
         rc = L.kgeo_equatorial_image_sharded(ctypes.byref(obs), ctypes.byref(M), ctypes.byref(opts), 12, _engine.dptr(x),
                                              _engine.dptr(x), ctypes.byref(smap), *([null] * 12), None)
         assert rc == _lib.KGEO_E_BADARG, L.kgeo_last_error()

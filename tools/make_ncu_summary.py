@@ -92,26 +92,35 @@ if args.track:
     }
 if args.image:
     rows, U = raw(args.image), units_of(args.image)
-    imgs = [r for r in rows if "image_kernel" in r["Kernel Name"]]
-    big = [r for r in imgs if f(r, "launch__grid_size") > 10000]
+    # an image = r_equatorial_kernel (geometry) + image_emission_kernel; tools/profile_image.py runs 256^2 and 4096^2, unpolarized
+    # default models and polarized + path length, then r_equatorial alone
+    ker = [r for r in rows if "image_emission_kernel" in r["Kernel Name"] or "r_equatorial_kernel" in r["Kernel Name"]]
+    pairs = [(ker[i - 1], ker[i]) for i in range(1, len(ker)) if "image_emission_kernel" in ker[i]["Kernel Name"]
+             and "r_equatorial_kernel" in ker[i - 1]["Kernel Name"]]
+    big = [p for p in pairs if f(p[1], "launch__grid_size") > 10000]
+    dram = lambda r: to_bytes(f(r, "dram__bytes_read.sum"), U["dram__bytes_read.sum"]) + to_bytes(f(r, "dram__bytes_write.sum"), U["dram__bytes_write.sum"])
+    pipe = lambda r: f(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100
+    ms = lambda r: f(r, "gpu__time_duration.sum")
     if big:
-        r = big[0]    # 4096^2 unpolarized default models (the launch bench.py's secondary metric times)
-        fl, n = flops(r)
+        g, e = big[0]  # 4096^2 unpolarized default models (the launches bench.py's secondary metric times)
+        fl = flops(g)[0] + flops(e)[0]
         summ["image_kernel"] = {
-            "source": os.path.basename(args.image), "flop_per_pixel": fl / args.pixels,
-            "fp64_pipe_active": f(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100,
-            "issue_active": f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") / 100,
-            "ms": f(r, "gpu__time_duration.sum"), "registers": f(r, "launch__registers_per_thread"),
-            "warp_inst_per_32_pixels": f(r, "smsp__inst_executed.sum") * 32 / args.pixels,
-            "dram_bytes_per_launch": to_bytes(f(r, "dram__bytes_read.sum"), U["dram__bytes_read.sum"]) + to_bytes(f(r, "dram__bytes_write.sum"), U["dram__bytes_write.sum"]),
-            "launches": [{"grid": f(x, "launch__grid_size"), "ms": f(x, "gpu__time_duration.sum"),
-                          "fp64_pipe_active": f(x, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100} for x in imgs]}
-    req = [r for r in rows if "r_equatorial_kernel" in r["Kernel Name"]]
+            "source": os.path.basename(args.image), "kernels": "r_equatorial_kernel (geometry) + image_emission_kernel",
+            "flop_per_pixel": fl / args.pixels,
+            "fp64_pipe_active": (pipe(g) * ms(g) + pipe(e) * ms(e)) / (ms(g) + ms(e)),
+            "issue_active": (f(g, "smsp__issue_active.avg.pct_of_peak_sustained_active") * ms(g) +
+                             f(e, "smsp__issue_active.avg.pct_of_peak_sustained_active") * ms(e)) / (ms(g) + ms(e)) / 100,
+            "ms": ms(g) + ms(e), "geometry_ms": ms(g), "emission_ms": ms(e),
+            "registers": [f(g, "launch__registers_per_thread"), f(e, "launch__registers_per_thread")],
+            "warp_inst_per_32_pixels": (f(g, "smsp__inst_executed.sum") + f(e, "smsp__inst_executed.sum")) * 32 / args.pixels,
+            "dram_bytes_per_launch": dram(g) + dram(e),
+            "launches": [{"grid": f(x, "launch__grid_size"), "kernel": x["Kernel Name"].split("(")[0], "ms": ms(x), "fp64_pipe_active": pipe(x)}
+                         for pr in pairs for x in pr]}
+    req = [r for r in ker if "r_equatorial_kernel" in r["Kernel Name"] and f(r, "launch__grid_size") > 10000]
     if req:
-        r = req[0]
+        r = req[-1]    # the stand-alone r_equatorial call (n = 0..2, with Nmax planes)
         fl, n = flops(r)
-        summ["r_equatorial_kernel"] = {"flop_per_pixel": fl / args.pixels, "ms": f(r, "gpu__time_duration.sum"),
-                                       "fp64_pipe_active": f(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100,
-                                       "dram_bytes_per_launch": to_bytes(f(r, "dram__bytes_read.sum"), U["dram__bytes_read.sum"]) + to_bytes(f(r, "dram__bytes_write.sum"), U["dram__bytes_write.sum"])}
+        summ["r_equatorial_kernel"] = {"flop_per_pixel": fl / args.pixels, "ms": ms(r), "fp64_pipe_active": pipe(r),
+                                       "dram_bytes_per_launch": dram(r)}
 json.dump(summ, open(args.out, "w"), indent=1)
 print(json.dumps(summ, indent=1))
