@@ -73,6 +73,43 @@ def test_argument_errors_without_a_gpu(lib):
         lib.check(lib.KGEO_E_MODEL)
 
 
+def test_argument_errors_of_the_round_2_entry_points(lib):
+    """The integrals, curve-library, sharded-image and scatter entry points validate before any CUDA call."""
+    L = lib.lib()
+    null = ctypes.cast(None, lib.c_double_p)
+    inull = ctypes.cast(None, lib.c_int32_p)
+    x = np.zeros(12)
+    px = x.ctypes.data_as(lib.c_double_p)          # never dereferenced: every call below fails validation first
+    fl = np.zeros(12, dtype=np.int32).ctypes.data_as(lib.c_int32_p)
+    obs = lib.Observer(0.5, 1000., 0.3)
+    assert L.kgeo_ray_setup_conserved(ctypes.byref(obs), 4, null, px, null, 3, 1, px, fl, None) == lib.KGEO_E_BADARG
+    inf = lib.Observer(0.5, float("inf"), 0.3)
+    assert L.kgeo_ray_setup_conserved(ctypes.byref(inf), 4, px, px, null, 3, 1, px, fl, None) == lib.KGEO_E_RANGE
+    assert b"finite" in L.kgeo_last_error()
+    assert L.kgeo_track_integrals(ctypes.byref(obs), 4, px, fl, 3, null, 4, 1, *([null] * 7), 4, None) == lib.KGEO_E_BADARG
+    assert L.kgeo_track_integrals(ctypes.byref(obs), 4, px, fl, 3, px, 4, 1, *([null] * 7), 3, None) == lib.KGEO_E_BADARG
+    assert b"leading dimension" in L.kgeo_last_error()
+    assert L.kgeo_rho_library(2, px, px, px, 3, 1, 12, px, 2e-12, 1e-15, 100, px, inull, None) == lib.KGEO_E_BADARG
+    assert L.kgeo_rho_library(2, px, px, px, 0, 1, 12, px, 0.0, 1e-15, 100, px, inull, None) == lib.KGEO_E_BADARG
+    assert L.kgeo_rho_library(0, null, null, null, 0, 1, 12, null, 2e-12, 1e-15, 100, null, inull, None) == 0     # nothing to do
+    for smap in (lib.ShardMap(5, 1, 0, 12, 0), lib.ShardMap(4, 0, 0, 12, 0), lib.ShardMap(0, 1, 0, 12, 0)):
+        assert L.kgeo_shard_scatter(px, 2, 12, ctypes.byref(smap), px, None) == lib.KGEO_E_BADARG
+    assert L.kgeo_shard_scatter(px, 0, 12, ctypes.byref(lib.ShardMap(4, 1, 0, 12, 0)), px, None) == 0
+    M = lib.Models()
+    opts = lib.ImageOpts(0, 2, 0, 0, 1.0, 0.1, 230e9)
+    for smap in (lib.ShardMap(5, 1, 0, 12, 0), lib.ShardMap(4, 0, 0, 12, 0), lib.ShardMap(4, 2, 1, 12, 0)):
+        rc = L.kgeo_equatorial_image_sharded(ctypes.byref(inf), ctypes.byref(M), ctypes.byref(opts), 12, px, px, ctypes.byref(smap),
+                                             *([null] * 12), None)
+        assert rc == lib.KGEO_E_BADARG, L.kgeo_last_error()
+    assert L.kgeo_equatorial_image_sharded(ctypes.byref(inf), ctypes.byref(M), ctypes.byref(opts), 12, px, px, None, *([null] * 12),
+                                           None) == lib.KGEO_E_BADARG
+    h = lib.PeerHandle()
+    p = ctypes.c_void_p()
+    assert L.kgeo_peer_alloc(0, ctypes.byref(p), ctypes.byref(h)) == lib.KGEO_E_BADARG
+    assert L.kgeo_peer_open(None, ctypes.byref(p)) == lib.KGEO_E_BADARG
+    assert L.kgeo_peer_close(None) == 0 and L.kgeo_peer_free(None) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     import kgeo_b200
