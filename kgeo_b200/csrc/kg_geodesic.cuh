@@ -491,8 +491,16 @@ enum SetupMode { M_ANY_ETA_POS = 1, M_ANY_ETA_NONPOS = 2, M_CLAMP_LOWSPIN_ETA = 
 // ray_setup_conserved takes the conserved quantities themselves (lam, eta, and the sign s_o of the observer's polar momentum =
 // sign(beta)): what th_integrate / r_integrate receive from their callers (kgeo/kerr_raytracing_ana.py:195,368); ray_setup derives
 // them from the image coordinates (:76-79).
-template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
+// PART splits the work for the track setup's two launches (each half of the ~15 k instructions stays in the instruction caches;
+// the halves share nothing but lam and eta): 0 = everything, 1 = conserved quantities + polar motion, 2 = radial motion (the
+// caller passes the flags part 1 left in *flags_out; every slot and flag is written by exactly one part).
+KG_HD constexpr bool slot_is_radial(int i) {
+    return (i >= R_K && i <= R_Q10) || i == R_I2K || (i >= R_C0 && i <= R_RDC) || (i >= R_TH && i <= R_TH_END) || (i >= R_LAD && i <= R_LAD_END) ||
+           i == S_TAUTOT;
+}
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*, int PART = 0>
 KG_HD void ray_setup_conserved(const Observer& o, double lam, double eta, bool s_pos, int mode, P w, int* flags_out) {
+    static_assert(PART == 0 || LADDER, "the split setup is for the grouped track workspace");
     const int any_eta_pos = mode & M_ANY_ETA_POS, any_eta_nonpos = mode & M_ANY_ETA_NONPOS;
     // Two-kernel setup (DEFER): the AGM ladders are only read by the Carlson fallback, so they are built where the theta path
     // is turned down (theta_setup, or at the end of this function for motions that never were candidates) instead of for every
@@ -507,11 +515,13 @@ KG_HD void ray_setup_conserved(const Observer& o, double lam, double eta, bool s
     } else {
         for (int i = 0; i < NW; ++i) {
             if (DEFER && ((i >= T_LAD && i <= R_LAD_END) || (i >= T_TH && i <= R_TH_END))) continue;
+            if (PART != 0 && slot_is_radial(i) != (PART == 2)) continue;
             w[i] = 0.0;
         }
     }
-    int flags = 0;
+    int flags = (PART == 2) ? *flags_out : 0;
     if (o.lowspin && (mode & M_CLAMP_LOWSPIN_ETA) && eta < 0.0) eta = kEP;   // kgeo/kerr_raytracing_ana.py:80-82 (tracks only)
+  if constexpr (PART != 2) {
     if (o.lowspin) flags |= F_LOWSPIN;
     w[S_LAM] = lam;
     w[S_ETA] = eta;
@@ -615,6 +625,8 @@ KG_HD void ray_setup_conserved(const Observer& o, double lam, double eta, bool s
         }
     }
 
+  }
+  if constexpr (PART != 1) {
     // ---------------- radial motion (kgeo/kerr_raytracing_ana.py:368-633, utils :382-548) ----------------
     Roots R = quartic_roots(o, lam, eta, (mode & M_POLISH_ROOTS) != 0);
     flags |= (R.region << F_REGION_SHIFT);
@@ -812,17 +824,18 @@ KG_HD void ray_setup_conserved(const Observer& o, double lam, double eta, bool s
         if (DEFER) flags |= F_R_PENDING;            // k and the characteristics are in w[R_K], w[R_N0..2]
         else radial_theta_setup(th_k, th_n, w, &flags);
     }
+  }
     if (mode & M_CARLSON_ONLY) flags &= ~(F_TH_THETA | F_R_THETA | F_TH_PENDING | F_R_PENDING);
     if (LADDER && defer_ladders) {      // motions theta_setup will not visit keep the Carlson path: their ladders are built here
-        if (!(flags & F_TH_PENDING) && (flags & (F_TH_ORD | F_TH_VORT))) jacobi_make_ladder(w[T_M], w + T_LAD);
-        if (!(flags & F_R_PENDING)) jacobi_make_ladder(w[R_K], w + R_LAD);
+        if (PART != 2 && !(flags & F_TH_PENDING) && (flags & (F_TH_ORD | F_TH_VORT))) jacobi_make_ladder(w[T_M], w + T_LAD);
+        if (PART != 1 && !(flags & F_R_PENDING)) jacobi_make_ladder(w[R_K], w + R_LAD);
     }
     *flags_out = flags;
 }
 
-template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*>
+template <bool PHI_T, bool LADDER = true, bool DEFER = false, class P = double*, int PART = 0>
 KG_HD void ray_setup(const Observer& o, double alpha, double beta, int mode, P w, int* flags_out) {
-    ray_setup_conserved<PHI_T, LADDER, DEFER, P>(o, -alpha * o.sth, conserved_eta(o, alpha, beta), beta >= 0.0, mode, w, flags_out);
+    ray_setup_conserved<PHI_T, LADDER, DEFER, P, PART>(o, -alpha * o.sth, conserved_eta(o, alpha, beta), beta >= 0.0, mode, w, flags_out);
 }
 
 // Second half of the two-kernel setup: builds the theta blocks ray_setup<.., DEFER = true> left pending.  Splitting the

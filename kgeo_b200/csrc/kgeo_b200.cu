@@ -142,11 +142,16 @@ __global__ void __launch_bounds__(EW_THREADS) ew_jacobi_kernel(size_t n, const d
 #endif
 constexpr int SETUP_THREADS = KG_SETUP_THREADS;
 
+#ifndef KG_SETUP_SPLIT
+#define KG_SETUP_SPLIT 1              // the per-ray setup as two launches (polar | radial); 0: one
+#endif
 #ifndef KG_SETUP_MINBLOCKS
 #define KG_SETUP_MINBLOCKS 2          // CTAs per SM the two setup kernels are compiled for (register cap = 65536/(threads*n))
 #endif
 
-template <bool PHI_T>
+// PART 1 = conserved quantities + polar motion, PART 2 = radial motion (two launches: the ~15.6 k instructions of the whole
+// setup, walked once per warp, stalled on instruction fetch 3.4 cycles per issue; see ray_setup_conserved), 0 = both.
+template <bool PHI_T, int PART>
 __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_kernel(Observer o, size_t npix, const double* __restrict__ alpha,
                                                                   const double* __restrict__ beta, int mode,
                                                                   double* __restrict__ w_out, int32_t* __restrict__ flags_out) {
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, KG_SETUP_MINBLOCKS) ray_setup_k
     // lines, was measured: no change, 1.75 ms either way.)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    int fl;
-    ray_setup<PHI_T, true, true>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
+    int fl = (PART == 2) ? flags_out[i] : 0;
+    ray_setup<PHI_T, true, true, WsPtr, PART>(o, alpha[i], beta[i], mode, ray_ptr(w_out, i), &fl);   // constants go straight to the grouped workspace
     flags_out[i] = fl;
 }
 
@@ -1366,9 +1371,15 @@ int kgeo_special_ellipj(size_t n, const double* u, const double* m, double* sn, 
 // pending) and theta_setup_kernel (the theta-function blocks); see theta_setup in kg_geodesic.cuh
 static int launch_setup(const Observer& o, size_t npix, const double* alpha, const double* beta, int mode, double* w,
                          int32_t* flags, cudaStream_t stream) {
-    ray_setup_kernel<true><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, alpha, beta,
-                                                                                      mode, w, flags);
+#if KG_SETUP_SPLIT
+    ray_setup_kernel<true, 1><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, alpha, beta, mode, w, flags);
     LAUNCHED("ray_setup_kernel");
+    ray_setup_kernel<true, 2><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, alpha, beta, mode, w, flags);
+    LAUNCHED("ray_setup_kernel");
+#else
+    ray_setup_kernel<true, 0><<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, alpha, beta, mode, w, flags);
+    LAUNCHED("ray_setup_kernel");
+#endif
     if (!(mode & M_CARLSON_ONLY)) {
         theta_setup_kernel<<<grid_for(npix, SETUP_THREADS), SETUP_THREADS, 0, stream>>>(o, npix, w, flags);
         LAUNCHED("theta_setup_kernel");

@@ -26,6 +26,21 @@ void hostsim_math(int which, size_t n, const double* x, const double* y, double*
         }
     }
 }
+// the setup as the track kernels launch it (DEFER = true): whole (PART 0) and as its two parts (PART 1 then PART 2) into
+// workspaces pre-filled with a sentinel; [npix][NW] each.  Bit-identical by construction; checked by tests/test_abi_and_host.py.
+int hostsim_setup_parts(double a, double r_o, double th_o, size_t npix, const double* alpha, const double* beta, int mode,
+                        double* w_whole, int32_t* fl_whole, double* w_parts, int32_t* fl_parts) {
+    Observer o = make_observer(a, r_o, th_o);
+    for (size_t i = 0; i < npix; ++i) {
+        int f0 = 0, f1 = 0;
+        ray_setup<true, true, true, double*, 0>(o, alpha[i], beta[i], mode, w_whole + i * NW, &f0);
+        ray_setup<true, true, true, double*, 1>(o, alpha[i], beta[i], mode, w_parts + i * NW, &f1);
+        ray_setup<true, true, true, double*, 2>(o, alpha[i], beta[i], mode, w_parts + i * NW, &f1);
+        fl_whole[i] = f0;
+        fl_parts[i] = f1;
+    }
+    return 0;
+}
 int hostsim_slot(int which) { const int v[] = {T_TH, R_TH, R_K, T_M, S_TAUTOT, TB_SIZE, TP_SIZE, R_N0}; return v[which]; }
 
 // tracks for npix rays, ntau samples each (numpy.linspace(0, maxtaufrac*tau_tot, ntau)); outputs [ntau][npix] row-major.

@@ -74,3 +74,32 @@ def test_ff_boost_and_gammamax_on_the_host(tmp_path, golden):
         for k, got in zip(('i', 'q', 'u'), outs[:3]):
             ref = g[name + '_raw_' + k]
             assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref)), (name, k)
+
+
+def test_split_ray_setup_equals_the_whole_on_the_host(tmp_path):
+    """The track setup runs as two launches (conserved quantities + polar motion | radial motion).  Host build of the same
+    functions: both parts into one workspace == the one-pass setup, every slot and flag bit for bit, for all root classes,
+    vortical rays, zero spin and the southern observer."""
+    import ctypes
+    import numpy as np
+    so = str(tmp_path / "_hostsim.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "kgeo_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"), "-o", so], check=True, capture_output=True, timeout=600)
+    L = ctypes.CDLL(so)
+    NW = L.hostsim_slots()
+    P, I = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    seen = 0
+    for a, th_o, half, mode in ((0.94, 17 * np.pi / 180, 8., 3), (0.998, 10 * np.pi / 180, 3., 3), (0.0, 45 * np.pi / 180, 8., 7),
+                                (0.7, 135 * np.pi / 180, 8., 3), (0.94, 80 * np.pi / 180, 3., 3)):
+        x = np.linspace(-half, half, 29)
+        A, B = [v.flatten().copy() for v in np.meshgrid(x, x)]
+        n = A.size
+        w0, w1 = np.full((n, NW), -123.0), np.full((n, NW), -123.0)
+        f0, f1 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        L.hostsim_setup_parts(ctypes.c_double(a), ctypes.c_double(1000.), ctypes.c_double(th_o), ctypes.c_size_t(n),
+                              A.ctypes.data_as(P), B.ctypes.data_as(P), mode, w0.ctypes.data_as(P), f0.ctypes.data_as(I),
+                              w1.ctypes.data_as(P), f1.ctypes.data_as(I))
+        assert np.array_equal(f0, f1)
+        assert ((w0 == w1) | (np.isnan(w0) & np.isnan(w1))).all()
+        seen |= int(np.bitwise_or.reduce(f0))
+    assert seen & 4 and seen & 8 and seen & 16 and seen & 1 and seen & 2      # radial cases 2, 3, 4; ordinary and vortical polar motion

@@ -10,6 +10,6 @@ for name, extra in runs:
                          capture_output=True, text=True)
     try:
         d = json.loads(out.stdout.strip().splitlines()[-1])
-        print("%-28s step %.2f ms  track pass %.2f ms" % (name, d["ms_per_step"], d["track_kernel_ms"]), flush=True)
+        print("%-28s step %.2f ms  track pass %.2f ms  setup %.3f ms" % (name, d["ms_per_step"], d["track_kernel_ms"], d["setup_kernel_ms"]), flush=True)
     except Exception:
         print(name, "FAILED", out.stderr[-300:], flush=True)
