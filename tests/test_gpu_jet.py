@@ -1,7 +1,7 @@
 """Off-equatorial jet pipeline on the device (rest: kgeo_b200.off_eq.getstokes) vs off_eq.getstokes of the unmodified
 reference (tests/golden/jet_pipeline.npz).
 
-Written on the CPU (device functions, densities and host scalars checked there first: tests/test_offeq_hostbuild.py,
+Written on the CPU (device functions, densities and host scalars checked there first: tests/test_device_code_hostbuild.py,
 tests/test_abi_and_host.py::test_jet_host_scalars); passed on a B200 on its first run, with the last GPU seconds of round 1."""
 import json
 
@@ -48,7 +48,7 @@ def test_getstokes_ff_boost_and_gammamax_against_reference(golden):
     # Gate 1e-7 on the Stokes parameters: the crossings come out of the secant solve at the reference's own tolerance (|d tau| <
     # 1e-8, and a different but equally converged last iterate), and the energy-conserving boost amplifies a crossing's position
     # error (with the REFERENCE's crossings the same device code reproduces its Stokes parameters to 1e-15:
-    # tests/test_offeq_hostbuild.py::test_ff_boost_and_gammamax_on_the_host).  Crossings themselves: 1e-8.
+    # tests/test_device_code_hostbuild.py::test_ff_boost_and_gammamax_on_the_host).  Crossings themselves: 1e-8.
     for name, kw in zip(json.loads(str(g['names'])), json.loads(str(g['kwargs']))):
         raw = off_eq.getstokes(psit, A, B, r_o, th_o, a, int(ngeo), neqmax=int(neqmax), model='mono', sigma=2, sumsubring=False, **kw)
         for k, v in zip(['i', 'q', 'u', 'neq', 'r', 'th'], raw[:6]):
