@@ -174,7 +174,8 @@ int kgeo_track_integrals(const kgeo_observer* obs, size_t npix, const double* w_
                          double* r_dev, double* Iph_dev, double* It_dev, double* Isig_dev, size_t ld, void* stream);
 /* Unpacked per-ray summary for the host API: roots_dev[8*npix] = Re r1..r4, Im r1..r4 (plane-major), rclass_dev = the
  * reference's region label 1..4 (0 on a boundary), tau_tot_dev, u_plus/u_minus/uratio/a2u_minus, outside_dev =
- * is_outside_crit, thplus/thminus = angular_turning's turning points.  Any output may be NULL.
+ * is_outside_crit, thplus/thminus = angular_turning's turning points.  Any output may be NULL.  Unlike the geodesic entry points
+ * this one takes any inclination 0 <= th_o <= pi (the reference's uplus_uminus / angular_turning do not restrict it).
  * (kerr_raytracing_utils.py:242-328,330-380,382-548,794-826) */
 int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha_dev, const double* beta_dev, int mode,
                      double* roots_dev, int32_t* rclass_dev, double* tau_tot_dev, double* uplus_dev, double* uminus_dev,

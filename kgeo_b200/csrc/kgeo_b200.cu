@@ -57,13 +57,19 @@ static int fail_cuda(cudaError_t e, const char* where) {
         if (e_ != cudaSuccess) return fail_cuda(e_, name);    \
     } while (0)
 
-static int check_observer(const kgeo_observer* obs, bool allow_inf) {
+// any_inclination: the per-ray summary (uplus_uminus, angular_turning, radial_roots, mino_total: kerr_raytracing_utils.py:242-548)
+// takes every th_o, as the reference's functions do (their inclination checks are commented out; n_angular_turnings calls them for
+// an equatorial observer); the geodesic entry points need th_o off the equatorial plane (kerr_raytracing_ana.py:63-66)
+static int check_observer(const kgeo_observer* obs, bool allow_inf, bool any_inclination = false) {
     if (!obs) return fail_arg(KGEO_E_BADARG, "observer is NULL");
     if (!(fabs(obs->a) < 1.0)) return fail_arg(KGEO_E_RANGE, "a should be a float in range (-1,1)");
     if (!(obs->r_o >= 100.0)) return fail_arg(KGEO_E_RANGE, "r_o should be a float > 100");
     if (!allow_inf && isinf(obs->r_o)) return fail_arg(KGEO_E_RANGE, "r_o must be finite for this entry point");
-    if (!(obs->th_o > 0.0 && obs->th_o < kPi) || obs->th_o == 0.5 * kPi)
+    if (any_inclination) {
+        if (!(obs->th_o >= 0.0 && obs->th_o <= kPi)) return fail_arg(KGEO_E_RANGE, "th_o should be a float in range [0,pi]");
+    } else if (!(obs->th_o > 0.0 && obs->th_o < kPi) || obs->th_o == 0.5 * kPi) {
         return fail_arg(KGEO_E_RANGE, "th_o should be a float in range (0,pi/2) or (pi/2,pi)");
+    }
     return 0;
 }
 static int check_models(const kgeo_models* m) {
@@ -1444,7 +1450,7 @@ int kgeo_ray_slot(size_t npix, const double* w, int slot, double* out, void* str
 int kgeo_ray_summary(const kgeo_observer* obs, size_t npix, const double* alpha, const double* beta, int mode, double* roots,
                      int32_t* rclass, double* tau_tot, double* uplus, double* uminus, double* uratio, double* a2uminus,
                      double* outside, double* thplus, double* thminus, void* stream) {
-    int rc = check_observer(obs, true);
+    int rc = check_observer(obs, true, true);
     if (rc) return rc;
     if (npix && (!alpha || !beta)) return fail_arg(KGEO_E_BADARG, "kgeo_ray_summary: NULL pointer");
     if (npix == 0) return 0;

@@ -308,6 +308,50 @@ def n_poloidal_orbits(a, th_o, alpha, beta, tau):
     return _counts(a, th_o, alpha, beta, tau, "pol")
 
 
+def n_angular_turnings(a, th_o, alpha, beta, tau):
+    """the fractional number of angular turnings at Mino time tau -- kgeo/kerr_raytracing_utils.py:686-792 (same checks and
+    messages; the reference's own comments call its vortical branch unfinished: it is reproduced as it is).  Per-ray constants
+    (u+-, F0, K) from the device library, the per-sample expression is linear in tau."""
+    if not (isinstance(a, float) and (0 <= np.abs(a) < 1)):
+        raise Exception("|a| should be a float in range [0,1)")
+    if not (isinstance(th_o, float) and (0 <= th_o <= np.pi / 2.)):
+        raise Exception("th_o should be a float in range (0,pi/2]")
+    if not isinstance(alpha, np.ndarray):
+        alpha = np.array([alpha]).flatten()
+    if not isinstance(beta, np.ndarray):
+        beta = np.array([beta]).flatten()
+    if len(alpha) != len(beta):
+        raise Exception("alpha, beta are different lengths!")
+    alltau = len(tau.shape) != 1
+    tau2 = tau if alltau else tau.reshape(1, tau.shape[0])
+    if not (tau2.shape[1] == len(alpha)):
+        raise Exception("tau has incompatible shape in n_poloidal_orbits!")
+    ellipkinc = lambda phi, m: _engine.elementwise("kgeo_special_ellipkinc", (phi, m))
+    lam = -alpha * np.sin(th_o)
+    eta = (alpha ** 2 - a ** 2) * np.cos(th_o) ** 2 + beta ** 2
+    out = np.empty(tau2.shape)
+    vort = eta <= 0
+    for vortical, mask in ((False, ~vort), (True, vort)):
+        if not np.any(mask):
+            continue
+        up, um, ratio, a2um = uplus_uminus(a, th_o, lam[mask], eta[mask])
+        t, b = tau2[:, mask], beta[mask]
+        if vortical:
+            m = 1 - ratio
+            F0 = ellipkinc(np.arcsin(np.sqrt((np.cos(th_o) ** 2 - um) / (up - um))), m)
+            w = np.sqrt(a2um)
+        else:
+            m = ratio
+            F0 = ellipkinc(np.arcsin(np.cos(th_o) / np.sqrt(up)), m)
+            w = np.sqrt(-a2um)
+        K = ellipkinc(np.full(m.shape, 0.5 * np.pi), m)
+        first = (t * w - F0) / (2 * K) + 0.5
+        if vortical:
+            first = np.where(first > 0.5, first + 0.5, first)
+        out[:, mask] = np.where(b <= 0, first, (t * w + F0) / (2 * K) + 0.5)
+    return out if alltau else out[0]
+
+
 def n_equatorial_crossings(a, th_o, alpha, beta, tau):
     """Number of equatorial crossings up to Mino time tau (GL19b Eq 82) -- kgeo/kerr_raytracing_utils.py:605-684"""
     return _counts(a, th_o, alpha, beta, tau, "eq")

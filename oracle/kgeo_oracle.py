@@ -639,6 +639,32 @@ def n_equatorial(a, th_o, alpha, beta, tau):
     return out
 
 
+def n_angular_turnings(a, th_o, alpha, beta, tau):
+    """Fractional number of angular turnings at Mino time tau (kerr_raytracing_utils.py:686-792): ordinary rays
+    (tau w -+ F0)/(2K) + 1/2 with the sign by beta <= 0 / > 0; the vortical branch with its own amplitude, parameter 1 - u+/u-
+    and the reference's extra half turn once the first one is complete (beta <= 0)."""
+    lam, eta = conserved(a, th_o, alpha, beta)
+    tau = np.asarray(tau, dtype=float)
+    out = np.empty(tau.shape)
+    vort = eta <= 0
+    reg = ~vort
+    if reg.any():
+        F0, K, w = _crossing_terms(a, th_o, lam[reg], eta[reg])
+        sgn = np.where(beta[reg] <= 0, -1.0, 1.0)
+        out[..., reg] = (tau[..., reg] * w + sgn * F0) / (2 * K) + 0.5
+    if vort.any():
+        up, um, ratio, a2um = angular_consts(a, th_o, lam[vort], eta[vort])
+        nu = np.arcsin(np.sqrt((np.cos(th_o) ** 2 - um) / (up - um)))
+        F0 = sp.ellipkinc(nu, 1 - ratio)
+        K = sp.ellipkinc(0.5 * np.pi, 1 - ratio)
+        w = np.sqrt(a2um)
+        neg = beta[vort] <= 0
+        first = (tau[..., vort] * w - F0) / (2 * K) + 0.5
+        first = np.where(first > 0.5, first + 0.5, first)
+        out[..., vort] = np.where(neg, first, (tau[..., vort] * w + F0) / (2 * K) + 0.5)
+    return out
+
+
 def r_equatorial(a, r_o, th_o, mbar, alpha, beta):
     """(r_s, Ir, Imax, Nmax) of the mbar-th equatorial crossing (equatorial_lensing.py:85-196)."""
     alpha, beta = _arr(alpha), _arr(beta)

@@ -259,6 +259,20 @@ def counts():
          neq=n_equatorial_crossings(a, th_o, A, B, tau), npol=n_poloidal_orbits(a, th_o, A, B, tau))
 
 
+def turnings():
+    """n_angular_turnings (kerr_raytracing_utils.py:686-792) on (ntau, npix) and (npix,) tau arrays, ordinary and vortical rays."""
+    from kgeo.kerr_raytracing_utils import n_angular_turnings
+    out = {}
+    cases = [(0.94, 17 * DEG, 8., 18), (0.998, 10 * DEG, 3., 16), (0.5, 90 * DEG, 6., 12)]
+    for i, (a, th_o, half, n) in enumerate(cases):
+        A, B = grid(n, half)
+        tau = np.linspace(0.0, 4.0, 7)[:, None] * np.ones(len(A))[None, :]
+        out.update({'c%d_par' % i: np.array([a, th_o]), 'c%d_alpha' % i: A, 'c%d_beta' % i: B, 'c%d_tau' % i: tau,
+                    'c%d_n' % i: n_angular_turnings(a, th_o, A, B, tau), 'c%d_n1' % i: n_angular_turnings(a, th_o, A, B, tau[3])})
+    out['ncases'] = np.array(len(cases))
+    save('turnings', **out)
+
+
 TABLE_FILE = '/root/reference/tests/data/a0p6_inflow.csv'      # committed copy: tests/golden/a0p6_inflow.csv
 
 
@@ -510,7 +524,7 @@ def integrals():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('integrals', 'setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('integrals', 'turnings', 'setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -527,5 +541,6 @@ if __name__ == '__main__':
     jet_pipeline()
     jet_boost()
     integrals()
+    turnings()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

@@ -59,6 +59,22 @@ def test_counts_against_reference(golden, kg):
     assert np.array_equal(kg.n_equatorial_crossings(a, th_o, g['alpha'], g['beta'], g['tau'][2]), g['neq'][2])
 
 
+def test_angular_turnings_against_reference(golden, kg):
+    """n_angular_turnings (kerr_raytracing_utils.py:686-792), ordinary and vortical rays, 2-D and 1-D tau, an equatorial observer."""
+    g = golden('turnings')
+    for i in range(int(g['ncases'])):
+        a, th_o = [float(x) for x in g['c%d_par' % i]]
+        A, B, tau = g['c%d_alpha' % i], g['c%d_beta' % i], g['c%d_tau' % i]
+        got = kg.n_angular_turnings(a, th_o, A, B, tau)
+        assert got.shape == tau.shape
+        assert_close(got, g['c%d_n' % i], 1e-10, floor=1e-3, what='turnings %d' % i)
+        got1 = kg.n_angular_turnings(a, th_o, A, B, tau[3])
+        assert got1.shape == (len(A),)
+        assert_close(got1, g['c%d_n1' % i], 1e-10, floor=1e-3, what='turnings %d (1-D tau)' % i)
+    with pytest.raises(Exception, match=r"range \(0,pi/2\]"):
+        kg.n_angular_turnings(0.5, 2.0, np.zeros(2), np.zeros(2), np.zeros((1, 2)))
+
+
 def test_models_against_reference(golden, kg):
     g = golden('models')
     spec = json.loads(str(g['spec']))

@@ -400,3 +400,12 @@ def test_integrals_oracle_against_reference(golden):
         assert_close(got, g[k], 1e-12, floor=1e-6, what=k)
     for (rho, vp, a_, t_, m), want in zip(g['obj_pts'], g['obj_r']):
         assert ko.r_equatorial2(rho, vp, a_, t_, mbar=int(m)) == pytest.approx(want, rel=1e-12)
+
+
+def test_angular_turnings_oracle_against_reference(golden):
+    g = golden('turnings')
+    for i in range(int(g['ncases'])):
+        a, th_o = [float(x) for x in g['c%d_par' % i]]
+        A, B, tau = g['c%d_alpha' % i], g['c%d_beta' % i], g['c%d_tau' % i]
+        assert_close(ko.n_angular_turnings(a, th_o, A, B, tau), g['c%d_n' % i], 1e-12, floor=1e-3, what='case %d' % i)
+        assert_close(ko.n_angular_turnings(a, th_o, A, B, tau[3]), g['c%d_n1' % i], 1e-12, floor=1e-3, what='case %d, 1-D tau' % i)
