@@ -7,7 +7,7 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/ho
 KGEO_BENCH_PROFILE=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"track_hot_kernel|track_kernel" -s 6 -c 2 -o gpurun_out/r02_track_pass python bench.py --steps 1 --warmup 3 > gpurun_out/s23_ncu_track.log 2>&1
 PROFILE_ONCE=1 timeout 600 ncu --set full --clock-control none -k regex:"image_emission_kernel|r_equatorial_kernel" -o /tmp/r02_image python tools/profile_image.py 1 > gpurun_out/s23_ncu_image.log 2>&1
 KGEO_BENCH_PROFILE=1 timeout 600 ncu --set full --clock-control none -k regex:"ray_setup_kernel|theta_setup_kernel" -s 9 -c 3 -o /tmp/r02_setup python bench.py --steps 1 --warmup 3 > gpurun_out/s23_ncu_setup.log 2>&1
-KGEO_GIT_SHA=a30a9af python tools/make_ncu_summary.py --track gpurun_out/r02_track_pass.ncu-rep --image /tmp/r02_image.ncu-rep > gpurun_out/s23_summary.log 2>&1
+KGEO_GIT_SHA=0f98296 python tools/make_ncu_summary.py --track gpurun_out/r02_track_pass.ncu-rep --image /tmp/r02_image.ncu-rep > gpurun_out/s23_summary.log 2>&1
 cp profiles/r02_ncu_summary.json gpurun_out/r02_ncu_summary.json
 ncu -i /tmp/r02_image.ncu-rep --page raw --csv > gpurun_out/r02_image_raw.csv 2>/dev/null
 ncu -i /tmp/r02_setup.ncu-rep --page raw --csv > gpurun_out/r02_setup_raw.csv 2>/dev/null
