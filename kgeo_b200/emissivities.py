@@ -85,3 +85,16 @@ class Emissivity(object):
                                            _engine.dptr(ds), _engine.dptr(db), float(nu_obs), float(specind),
                                            _engine.dptr(out), _engine.stream_ptr()))
         return out.cpu().numpy().reshape(r.shape)
+
+
+# ---- the reference's module-level emissivity profiles (kgeo/emissivities.py:121-139), evaluated by the device library ----
+def emisBPL(a, r, p1=P1E_230, p2=P2E_230):
+    """emissivity at radius r - broken power law model fit to GRMHD"""
+    return Emissivity('bpl', p1=p1, p2=p2).jrest(a, r)
+
+
+def emisGLM(a, r, gamma_off=GAMMAOFF, sigma=SIGMA_GLM, mu_ring=False):
+    """emissivity at radius r from GLM paper (mu_ring: the ring radius instead of r_-)"""
+    if mu_ring:
+        return Emissivity('ring', r_ring=mu_ring, gamma_off=gamma_off, sigma=sigma).jrest(a, r)
+    return Emissivity('glm', gamma_off=gamma_off, sigma=sigma).jrest(a, r)

@@ -116,3 +116,51 @@ class Velocity(object):
         _lib.check(L.kgeo_velocity_u_lab(ctypes.byref(M), float(a), n, _engine.dptr(dr), *[_engine.dptr(o) for o in outs],
                                          _engine.stream_ptr()))
         return tuple(o.cpu().numpy().reshape(r.shape) for o in outs)
+
+
+# ---- the reference's module-level closed forms (kgeo/velocities.py:179-470): same signatures, evaluated by the device library ----
+def _spin_check(a):
+    if not (isinstance(a, float) and (0 <= np.abs(a) < 1)):
+        raise Exception("|a| should be a float in range [0,1)")
+
+
+def u_zamo(a, r):
+    """velocity for zero angular momentum frame (kgeo/velocities.py:179-208); components are arrays of r's shape"""
+    _spin_check(a)
+    return Velocity('zamo').u_lab(a, r)
+
+
+def u_infall(a, r):
+    """velocity for geodesic equatorial infall from infinity (:211-226)"""
+    _spin_check(a)
+    return Velocity('infall').u_lab(a, r)
+
+
+def u_kep(a, r, retrograde=False):
+    """Cunningham velocity for material on keplerian orbits and infalling inside isco (:229-281)"""
+    _spin_check(a)
+    return Velocity('kep', retrograde=retrograde).u_lab(a, r)
+
+
+def u_subkep(a, r, fac_subkep=1, retrograde=False):
+    """(equatorial) subkeplerian velocities (:284-359)"""
+    _spin_check(a)
+    return Velocity('subkep', retrograde=retrograde, fac_subkep=fac_subkep).u_lab(a, r)
+
+
+def u_gelles(a, r, beta=0.3, chi=-150 * (np.pi / 180.)):
+    """velocity prescription from Gelles+2021, Eq A4 (:362-389)"""
+    _spin_check(a)
+    return Velocity('gelles', gelles_beta=beta, gelles_chi=chi).u_lab(a, r)
+
+
+def u_grmhd_fit(a, r, ell_isco=ELLISCO, vr_isco=VRISCO, p1=P1, p2=P2, dd=DD):
+    """velocity for power laws fit to grmhd ell, conserved inside isco (:392-439)"""
+    _spin_check(a)
+    return Velocity('simfit', ell_isco=ell_isco, vr_isco=vr_isco, p1=p1, p2=p2, dd=dd).u_lab(a, r)
+
+
+def u_general(a, r, fac_subkep=1, beta_phi=1, beta_r=1, retrograde=False):
+    """general velocity model from AART paper, keplerian by default (:442-470)"""
+    _spin_check(a)
+    return Velocity('general', retrograde=retrograde, fac_subkep=fac_subkep, beta_phi=beta_phi, beta_r=beta_r).u_lab(a, r)

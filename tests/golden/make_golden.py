@@ -273,6 +273,28 @@ def turnings():
     save('turnings', **out)
 
 
+def model_functions():
+    """The module-level closed forms of velocities.py (:179-470) and emissivities.py (:121-139) called directly."""
+    from kgeo import velocities as kv, emissivities as ke
+    out = {}
+    r = np.concatenate([np.linspace(1.2, 3.0, 60), np.linspace(3.0, 60.0, 140)])
+    out['r'] = r
+    for a in (0.0, 0.5, 0.94):
+        tag = 'a%02d' % int(round(100 * a))
+        rr = r[r > 1 + np.sqrt(1 - a * a) + 1e-3]
+        out[tag + '_r'] = rr
+        calls = dict(zamo=kv.u_zamo(a, rr), infall=kv.u_infall(a, rr), kep=kv.u_kep(a, rr), kep_retro=kv.u_kep(a, rr, retrograde=True),
+                     subkep=kv.u_subkep(a, rr, fac_subkep=0.7), gelles=kv.u_gelles(a, rr, beta=0.4, chi=-2.0),
+                     simfit=kv.u_grmhd_fit(a, rr), general=kv.u_general(a, rr, fac_subkep=0.7, beta_phi=0.6, beta_r=0.8))
+        for k, u in calls.items():
+            out[tag + '_u_' + k] = np.array([np.broadcast_to(np.asarray(c, dtype=float), rr.shape) for c in u])
+        out[tag + '_bpl'] = ke.emisBPL(a, rr)
+        out[tag + '_bpl2'] = ke.emisBPL(a, rr, p1=-1.5, p2=-0.3)
+        out[tag + '_glm'] = ke.emisGLM(a, rr)
+        out[tag + '_ring'] = ke.emisGLM(a, rr, gamma_off=0.2, sigma=0.7, mu_ring=4.5)
+    save('model_functions', **out)
+
+
 TABLE_FILE = '/root/reference/tests/data/a0p6_inflow.csv'      # committed copy: tests/golden/a0p6_inflow.csv
 
 
@@ -524,7 +546,7 @@ def integrals():
 
 if __name__ == '__main__':
     np.seterr(all='ignore')
-    if len(sys.argv) > 1 and sys.argv[1] in ('integrals', 'turnings', 'setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ('integrals', 'turnings', 'model_functions', 'setup', 'inverse_lensing', 'fromfile_models', 'bz_models', 'fieldline_crossings', 'jet_pipeline', 'jet_boost'):     # add one fixture without touching the others
         globals()[sys.argv[1]]()
         sys.exit(0)
     special()
@@ -542,5 +564,6 @@ if __name__ == '__main__':
     jet_boost()
     integrals()
     turnings()
+    model_functions()
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0]), f)

@@ -227,3 +227,37 @@ def test_device_image_code_on_the_host_against_reference(golden, hostsim_image_l
         else:
             assert_close(got, ref, IMAGE_RTOL if key in ('I', 'g', 'sinthb', 'lp', 'Ie', 'np') else TRACK_RTOL, floor=1e-300,
                          what='%s %s' % (name, key))
+
+
+def test_device_model_code_on_the_host_against_reference(golden, hostsim_image_lib):
+    """The velocity and emissivity closed forms of the image kernels (kg_image.cuh) on the host against the reference's module-level
+    u_zamo ... u_general (velocities.py:179-470) and emisBPL / emisGLM (emissivities.py:121-139)."""
+    import ctypes
+    import numpy as np
+    import kgeo_b200 as kg
+    from kgeo_b200.models import pack_models
+    from helpers import assert_close
+    L = hostsim_image_lib
+    P = ctypes.POINTER(ctypes.c_double)
+    g = golden('model_functions')
+    null = ctypes.cast(None, P)
+    for a in (0.0, 0.5, 0.94):
+        tag = 'a%02d' % int(round(100 * a))
+        r = np.ascontiguousarray(g[tag + '_r'], dtype=float)
+        n = r.size
+        vels = dict(zamo=kg.Velocity('zamo'), infall=kg.Velocity('infall'), kep=kg.Velocity('kep'), kep_retro=kg.Velocity('kep', retrograde=True),
+                    subkep=kg.Velocity('subkep', fac_subkep=0.7), gelles=kg.Velocity('gelles', gelles_beta=0.4, gelles_chi=-2.0),
+                    simfit=kg.Velocity('simfit'), general=kg.Velocity('general', fac_subkep=0.7, beta_phi=0.6, beta_r=0.8))
+        for k, v in vels.items():
+            M = pack_models(velocity=v)
+            u = np.zeros((4, n))
+            L.hs_velocity(ctypes.byref(M), ctypes.c_double(a), n, r.ctypes.data_as(P), u.ctypes.data_as(P))
+            assert_close(u, g[tag + '_u_' + k], 1e-10, floor=1e-12, what='%s %s' % (tag, k))
+        emis = dict(bpl=kg.Emissivity('bpl'), bpl2=kg.Emissivity('bpl', p1=-1.5, p2=-0.3), glm=kg.Emissivity('glm'),
+                    ring=kg.Emissivity('ring', r_ring=4.5, gamma_off=0.2, sigma=0.7))
+        for k, e in emis.items():
+            M = pack_models(emissivity=e)
+            j = np.zeros(n)
+            L.hs_emis(ctypes.byref(M), ctypes.c_double(a), n, r.ctypes.data_as(P), null, null, null, ctypes.c_double(230e9),
+                      ctypes.c_double(1.0), j.ctypes.data_as(P))
+            assert_close(j, g[tag + '_' + k], 1e-10, floor=1e-300, what='%s %s' % (tag, k))

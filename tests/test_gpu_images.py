@@ -75,6 +75,25 @@ def test_angular_turnings_against_reference(golden, kg):
         kg.n_angular_turnings(0.5, 2.0, np.zeros(2), np.zeros(2), np.zeros((1, 2)))
 
 
+def test_module_level_model_functions_against_reference(golden, kg):
+    """u_zamo ... u_general (velocities.py:179-470) and emisBPL / emisGLM (emissivities.py:121-139) called as module functions."""
+    from kgeo_b200 import velocities as kv, emissivities as ke
+    g = golden('model_functions')
+    for a in (0.0, 0.5, 0.94):
+        tag = 'a%02d' % int(round(100 * a))
+        r = g[tag + '_r']
+        calls = dict(zamo=kv.u_zamo(a, r), infall=kv.u_infall(a, r), kep=kv.u_kep(a, r), kep_retro=kv.u_kep(a, r, retrograde=True),
+                     subkep=kv.u_subkep(a, r, fac_subkep=0.7), gelles=kv.u_gelles(a, r, beta=0.4, chi=-2.0), simfit=kv.u_grmhd_fit(a, r),
+                     general=kv.u_general(a, r, fac_subkep=0.7, beta_phi=0.6, beta_r=0.8))
+        for k, u in calls.items():
+            assert_close(np.array(u), g[tag + '_u_' + k], 1e-10, floor=1e-12, what='%s %s' % (tag, k))
+        for k, j in (('bpl', ke.emisBPL(a, r)), ('bpl2', ke.emisBPL(a, r, p1=-1.5, p2=-0.3)), ('glm', ke.emisGLM(a, r)),
+                     ('ring', ke.emisGLM(a, r, gamma_off=0.2, sigma=0.7, mu_ring=4.5))):
+            assert_close(j, g[tag + '_' + k], 1e-10, floor=1e-300, what='%s %s' % (tag, k))
+    with pytest.raises(Exception, match="should be a float in range"):
+        kv.u_kep(2, r)
+
+
 def test_models_against_reference(golden, kg):
     g = golden('models')
     spec = json.loads(str(g['spec']))

@@ -409,3 +409,17 @@ def test_angular_turnings_oracle_against_reference(golden):
         A, B, tau = g['c%d_alpha' % i], g['c%d_beta' % i], g['c%d_tau' % i]
         assert_close(ko.n_angular_turnings(a, th_o, A, B, tau), g['c%d_n' % i], 1e-12, floor=1e-3, what='case %d' % i)
         assert_close(ko.n_angular_turnings(a, th_o, A, B, tau[3]), g['c%d_n1' % i], 1e-12, floor=1e-3, what='case %d, 1-D tau' % i)
+
+
+def test_model_functions_oracle_against_reference(golden):
+    """The oracle's closed forms against the reference's module-level u_* functions (velocities.py:179-470)."""
+    g = golden('model_functions')
+    for a in (0.0, 0.5, 0.94):
+        tag = 'a%02d' % int(round(100 * a))
+        r = g[tag + '_r']
+        calls = dict(zamo=ko.u_zamo(a, r), infall=ko.u_infall(a, r), kep=ko.u_kep(a, r), kep_retro=ko.u_kep(a, r, retrograde=True),
+                     subkep=ko.u_subkep(a, r, fac_subkep=0.7), gelles=ko.u_gelles(a, r, beta=0.4, chi=-2.0), simfit=ko.u_simfit(a, r),
+                     general=ko.u_general(a, r, fac_subkep=0.7, beta_phi=0.6, beta_r=0.8))
+        for k, u in calls.items():
+            got = np.array([np.broadcast_to(np.asarray(c, dtype=float), r.shape) for c in u])
+            assert_close(got, g[tag + '_u_' + k], 1e-12, floor=1e-12, what='%s %s' % (tag, k))
