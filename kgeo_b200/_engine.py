@@ -67,6 +67,8 @@ def to_device(x, dev=None):
     if isinstance(x, t.Tensor):
         return x.to(device=dev or device(), dtype=t.float64).contiguous()
     arr = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    if not arr.flags.writeable:             # torch.from_numpy warns on read-only arrays (np.load, broadcast views); the copy is host-side only
+        arr = arr.copy()
     return t.from_numpy(arr).to(dev or device())
 
 
