@@ -203,3 +203,39 @@ class Bfield(object):
         """b^2 in the frame u^mu of `velocity`, ideal MHD"""
         _checks.require_equatorial(th, "Bfield.bsq")
         return self._run(a, r, velocity, True)
+
+
+# ---- the reference's module-level field configurations of the image path (kgeo/bfields.py:429-542, 712-746): same signatures,
+# evaluated by the device library in the equatorial plane (th must be pi/2, as everywhere in this package) ----
+def _spin_check(a):
+    if not (isinstance(a, float) and (0 <= np.abs(a) < 1)):
+        raise Exception("|a| should be a float in range [0,1)")
+
+
+def Bfield_simple(a, r, coeffs):
+    """magnetic field vector (Br, Bth, Bph) in the lab frame in equatorial plane, simple configurations: |Br| falls off as
+    1/r^2, |Bvert| and |Bph| as 1/r; coeffs = (arad, avert, ator)"""
+    _spin_check(a)
+    (arad, avert, ator) = coeffs
+    return Bfield('simple', Cr=arad, Cvert=avert, Cph=ator).bfield_lab(a, r)
+
+
+def Bfield_simple_rm1(a, r, coeffs):
+    """as Bfield_simple, all components fall off as 1/r"""
+    _spin_check(a)
+    (arad, avert, ator) = coeffs
+    return Bfield('simple_rm1', Cr=arad, Cvert=avert, Cph=ator).bfield_lab(a, r)
+
+
+def Bfield_BZmagic(a, r, th, C=1):
+    """guess ratio for Bphi/Br from the split monopole: (Br, Bth, Bph, OmegaBZ)"""
+    _spin_check(a)
+    bf = Bfield('bz_guess', C=C)
+    return bf.bfield_lab(a, r, th) + (bf.omega_field(a, r, th),)
+
+
+def Bfield_gen_power(a, r, th, n_I, p_val, isAbove):
+    """generalised power-law stream function: (Br, Bth, Bph, Omega_H / 2)"""
+    _spin_check(a)
+    bf = Bfield('gen_power', n_I=n_I, p_val=p_val, isAbove=isAbove)
+    return bf.bfield_lab(a, r, th) + (bf.omega_field(a, r, th),)

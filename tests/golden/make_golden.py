@@ -292,6 +292,13 @@ def model_functions():
         out[tag + '_bpl2'] = ke.emisBPL(a, rr, p1=-1.5, p2=-0.3)
         out[tag + '_glm'] = ke.emisGLM(a, rr)
         out[tag + '_ring'] = ke.emisGLM(a, rr, gamma_off=0.2, sigma=0.7, mu_ring=4.5)
+        from kgeo import bfields as kb
+        th = np.pi / 2
+        bcalls = dict(simple=kb.Bfield_simple(a, rr, (0.87, 0.3, -0.5)), simple_rm1=kb.Bfield_simple_rm1(a, rr, (0.4, -0.7, 0.2)))
+        if a > 0:
+            bcalls.update(bzmagic=kb.Bfield_BZmagic(a, rr, th, C=-1.5), gen_power=kb.Bfield_gen_power(a, rr, th, 0.5, 0.8, True))
+        for k, b in bcalls.items():
+            out[tag + '_B_' + k] = np.array([np.broadcast_to(np.asarray(c, dtype=float), rr.shape) for c in b])
     save('model_functions', **out)
 
 

@@ -68,6 +68,9 @@ void hs_velocity(const kgeo_models* M, double a, int n, const double* r, double*
 void hs_bfield(const kgeo_models* M, double a, int n, const double* r, double* B, double* bsq) {
     for (int i = 0; i < n; ++i) { bfield_lab(*M, a, r[i], B + i, B + n + i, B + 2 * n + i); bsq[i] = bfield_bsq(*M, a, r[i], velocity_u_lab(*M, a, r[i])); }
 }
+void hs_bfield_omega(const kgeo_models* M, double a, int n, const double* r, double* B, double* omega) {
+    for (int i = 0; i < n; ++i) bfield_lab_omega(*M, a, r[i], B + i, B + n + i, B + 2 * n + i, omega + i);
+}
 void hs_emis(const kgeo_models* M, double a, int n, const double* r, const double* g, const double* s, const double* Bm, double nu, double specind, double* j) {
     for (int i = 0; i < n; ++i) j[i] = emissivity_jrest(*M, a, r[i], g != nullptr, g ? g[i] : 1.0, s != nullptr, s ? s[i] : 1.0, Bm ? Bm[i] : 0.0, nu, specind);
 }

@@ -261,3 +261,31 @@ def test_device_model_code_on_the_host_against_reference(golden, hostsim_image_l
             L.hs_emis(ctypes.byref(M), ctypes.c_double(a), n, r.ctypes.data_as(P), null, null, null, ctypes.c_double(230e9),
                       ctypes.c_double(1.0), j.ctypes.data_as(P))
             assert_close(j, g[tag + '_' + k], 1e-10, floor=1e-300, what='%s %s' % (tag, k))
+
+
+def test_device_bfield_code_on_the_host_against_reference(golden, hostsim_image_lib):
+    """The B-field closed forms of the image kernels on the host against the reference's module-level Bfield_simple, Bfield_simple_rm1,
+    Bfield_BZmagic and Bfield_gen_power (bfields.py:429-542, 712-746), field-line angular speed included."""
+    import ctypes
+    import numpy as np
+    import kgeo_b200 as kg
+    from kgeo_b200.models import pack_models
+    from helpers import assert_close
+    L = hostsim_image_lib
+    P = ctypes.POINTER(ctypes.c_double)
+    g = golden('model_functions')
+    for a in (0.0, 0.5, 0.94):
+        tag = 'a%02d' % int(round(100 * a))
+        r = np.ascontiguousarray(g[tag + '_r'], dtype=float)
+        n = r.size
+        fields = dict(simple=kg.Bfield('simple', Cr=0.87, Cvert=0.3, Cph=-0.5), simple_rm1=kg.Bfield('simple_rm1', Cr=0.4, Cvert=-0.7, Cph=0.2))
+        if a > 0:
+            fields.update(bzmagic=kg.Bfield('bz_guess', C=-1.5), gen_power=kg.Bfield('gen_power', n_I=0.5, p_val=0.8, isAbove=True))
+        for k, bf in fields.items():
+            M = pack_models(bfield=bf)
+            B, om = np.zeros((3, n)), np.zeros(n)
+            L.hs_bfield_omega(ctypes.byref(M), ctypes.c_double(a), n, r.ctypes.data_as(P), B.ctypes.data_as(P), om.ctypes.data_as(P))
+            ref = g[tag + '_B_' + k]
+            assert_close(B, ref[:3], 1e-10, floor=1e-6 * np.max(np.abs(ref[:3])), what='%s B %s' % (tag, k))
+            if ref.shape[0] == 4:
+                assert_close(om, ref[3], 1e-12, what='%s omega %s' % (tag, k))

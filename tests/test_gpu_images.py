@@ -90,6 +90,15 @@ def test_module_level_model_functions_against_reference(golden, kg):
         for k, j in (('bpl', ke.emisBPL(a, r)), ('bpl2', ke.emisBPL(a, r, p1=-1.5, p2=-0.3)), ('glm', ke.emisGLM(a, r)),
                      ('ring', ke.emisGLM(a, r, gamma_off=0.2, sigma=0.7, mu_ring=4.5))):
             assert_close(j, g[tag + '_' + k], 1e-10, floor=1e-300, what='%s %s' % (tag, k))
+        from kgeo_b200 import bfields as kb
+        th = np.pi / 2
+        bcalls = dict(simple=kb.Bfield_simple(a, r, (0.87, 0.3, -0.5)), simple_rm1=kb.Bfield_simple_rm1(a, r, (0.4, -0.7, 0.2)))
+        if a > 0:
+            bcalls.update(bzmagic=kb.Bfield_BZmagic(a, r, th, C=-1.5), gen_power=kb.Bfield_gen_power(a, r, th, 0.5, 0.8, True))
+        for k, b in bcalls.items():
+            ref = g[tag + '_B_' + k]
+            assert len(b) == ref.shape[0]
+            assert_close(np.array(b), ref, 1e-10, floor=1e-6 * np.max(np.abs(ref)), what='%s B %s' % (tag, k))
     with pytest.raises(Exception, match="should be a float in range"):
         kv.u_kep(2, r)
 
