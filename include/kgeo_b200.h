@@ -250,7 +250,7 @@ int kgeo_critical_curve(double a, double r_minus, double r_plus, double sin_th0,
                         double* alpha_dev, double* beta_dev, void* stream);
 
 /* ---- equatorial image (kgeo/equatorial_images.py:23-544) -------------------------------------------------------
- * Fused n = mbar_min..mbar_max image: per pixel one setup, then per order the crossing radius, redshift, (polarization,)
+ * n = mbar_min..mbar_max image in one call (two launches: geometry, then emission): per pixel one setup, then per order the crossing radius, redshift, (polarization,)
  * emissivity and Stokes I,Q,U.  Planes are [mbar_max-mbar_min+1, npix] (order-major); the Python wrapper exposes them with the
  * reference's (npix, mbar_max+1) indexing.  nmax_dev = Nmax of the last order, npol_dev = nmax_poloidal, imax_dev = the
  * total Mino time (Iobs's Imax; -1 for vortical rays); lp/Ie only when opts->pathlength.  Any output may be NULL. */

@@ -1,5 +1,6 @@
 """Drop-in for kgeo/equatorial_images.py: make_image (:23-122) and Iobs (:124-264) with the reference's signatures and
-return tuples, computed by ONE fused kernel launch per call (all orders; no geodesic array goes through HBM).
+return tuples, computed by ONE library call per image (all orders: a geometry and an emission launch; no geodesic array goes
+through HBM).
 """
 import ctypes
 import time
@@ -36,7 +37,7 @@ def pixel_grid(alpha_min, alpha_max, beta_min, beta_max, psize):
 
 def image_device(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, velocity, bfield, polarization, pathlength,
                  specind, diskangle, nu_obs, dev=None):
-    """Launch the fused image kernel; alpha/beta may be NumPy arrays or CUDA tensors.  Returns a dict of CUDA tensors:
+    """Launch the image kernels (all orders in one call); alpha/beta may be NumPy arrays or CUDA tensors.  Returns a dict of CUDA tensors:
     planes [norder, npix] for I,Q,U,r,Ir,g,sinthb(,lp,Ie) and [npix] for nmax, npol, imax."""
     L = _lib.lib()
     _engine.require_cuda()
@@ -66,7 +67,7 @@ _DST_ORDER = _PLANES + ("nmax", "npol", "imax", "lp", "Ie")
 
 def image_into(a, r_o, th_o, mbar_min, mbar_max, alpha, beta, emissivity, velocity, bfield, polarization, pathlength,
                specind, diskangle, nu_obs, dst, cols, row_step, row_offset, plane_stride, dev=None):
-    """The fused image kernel for a shard of whole pixel rows (alpha/beta: NumPy arrays or CUDA tensors, `cols` pixels per row),
+    """The image kernels for a shard of whole pixel rows (alpha/beta: NumPy arrays or CUDA tensors, `cols` pixels per row),
     every result stored at its place in DESTINATION planes (kgeo_equatorial_image_sharded): `dst` maps an output name
     ('I','Q','U','r','Ir','g','sinthb','nmax','npol','imax','lp','Ie') to the device address (int) of its first plane --
     memory of this GPU or of another GPU of the box mapped by sharding.PeerBuffer; local row lr lands in row

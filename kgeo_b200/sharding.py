@@ -113,7 +113,8 @@ class PeerBuffer(object):
                     raise PeerUnavailable("PeerBuffer: a rank could not map the root's memory%s" % (": " + err if err else ""))
 
     def tensor(self, shape=None):
-        """The root's float64 torch view of the buffer (None on the other ranks)."""
+        """The root's float64 torch view of the buffer (None on the other ranks).  Valid until close(): the view does not own the
+        memory."""
         if not self.is_root:
             return None
         import torch
