@@ -289,3 +289,59 @@ def test_device_bfield_code_on_the_host_against_reference(golden, hostsim_image_
             assert_close(B, ref[:3], 1e-10, floor=1e-6 * np.max(np.abs(ref[:3])), what='%s B %s' % (tag, k))
             if ref.shape[0] == 4:
                 assert_close(om, ref[3], 1e-12, what='%s omega %s' % (tag, k))
+
+
+def test_device_special_functions_on_the_host_against_scipy_fixture(golden, tmp_path):
+    """The special-function layer of the kernels (kg_special.cuh: Carlson RF/RD/RJ/RC, Legendre F/E/K, the reference's Pi with its
+    special-value rules, Jacobi sn/cn/dn/am) on the host against the values the reference's SciPy calls produce
+    (tests/golden/special.npz), with the gates of tests/test_gpu_special.py."""
+    import ctypes
+    import numpy as np
+    from helpers import rel_err
+    so = str(tmp_path / "_hostsim_special.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "kgeo_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "hostsim", "hostsim_special.cpp"), "-o", so], check=True, capture_output=True, timeout=600)
+    L = ctypes.CDLL(so)
+    P = ctypes.POINTER(ctypes.c_double)
+    g = golden('special')
+
+    def call(fn, *arrs, nout=1):
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=float), np.shape(arrs[0])), dtype=float) for x in arrs]
+        outs = [np.zeros(arrs[0].shape) for _ in range(nout)]
+        getattr(L, fn)(arrs[0].size, *[x.ctypes.data_as(P) for x in arrs], *[o.ctypes.data_as(P) for o in outs])
+        return outs[0] if nout == 1 else outs
+
+    assert rel_err(call('hs_rf', g['c_x'], g['c_y'], g['c_z']), g['rf']) < 4e-15
+    assert rel_err(call('hs_rd', g['c_x'], g['c_y'], g['c_z']), g['rd']) < 4e-15
+    assert rel_err(call('hs_rj', g['c_x'], g['c_y'], g['c_z'], g['c_p']), g['rj']) < 2e-14
+    assert rel_err(call('hs_rc', g['c_x'], g['c_y']), g['rc']) < 4e-15
+    assert rel_err(call('hs_F', g['fe_phi'], g['fe_m']), g['F']) < 1e-14
+    assert rel_err(call('hs_E', g['fe_phi'], g['fe_m']), g['E'], floor=1e-2) < 1e-14
+    assert rel_err(call('hs_K', g['fe_m']), g['K']) < 4e-15
+    assert rel_err(call('hs_Pi', np.full(18, .8), g['pi_list_phi'], np.full(18, -.33)), g['pi_list']) < 2e-15
+    assert rel_err(call('hs_Pi', g['pi_n'], g['pi_phi'], g['pi_m']), g['pi'], floor=0.1) < 2e-13
+    got, ref = call('hs_Pi', g['pisp_n'], g['pisp_phi'], g['pisp_m']), g['pisp']
+    keep = np.array([0, 1, 2, 4, 5, 6, 7])           # entry 3: n == 1 at |phi| < pi/2, ill-conditioned in the reference itself
+    assert rel_err(got[keep], ref[keep]) < 1e-13
+    sn, cn, dn, am = call('hs_jacobi', g['j_u'], g['j_m'], nout=4)
+    assert np.max(np.abs(sn - g['sn'])) < 2e-14 and np.max(np.abs(cn - g['cn'])) < 2e-14
+    assert np.max(np.abs(dn - g['dn'])) < 2e-12       # SciPy's own dn loses digits as m -> 1 (DESIGN.md)
+    assert np.max(np.abs(am - g['am'])) < 3e-14
+
+
+def test_device_crossing_counts_on_the_host_against_reference(golden, hostsim_image_lib):
+    """n_equatorial_crossings / n_poloidal_orbits device code (kerr_raytracing_utils.py:551-684) on the host, full (ntau, npix) tau."""
+    import ctypes
+    import numpy as np
+    from helpers import assert_close
+    L = hostsim_image_lib
+    P = ctypes.POINTER(ctypes.c_double)
+    g = golden('counts')
+    a, th_o = [float(x) for x in g['par']]
+    A, B = np.ascontiguousarray(g['alpha'], dtype=float), np.ascontiguousarray(g['beta'], dtype=float)
+    tau = np.ascontiguousarray(g['tau'], dtype=float)
+    neq, npol = np.zeros(tau.shape), np.zeros(tau.shape)
+    L.hs_counts(ctypes.c_double(a), ctypes.c_double(th_o), A.size, tau.shape[0], A.ctypes.data_as(P), B.ctypes.data_as(P),
+                tau.ctypes.data_as(P), neq.ctypes.data_as(P), npol.ctypes.data_as(P))
+    assert np.array_equal(neq, g['neq'])
+    assert_close(npol, g['npol'], 1e-12, what='n_poloidal')
