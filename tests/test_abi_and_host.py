@@ -291,3 +291,16 @@ def test_savegeos_loadgeos_roundtrip(tmp_path):
     assert g2.a == g.a and g2.r_o == g.r_o and g2.th_o == g.th_o
     for x, y in zip(g.geo_coords + [g.mino_times, g.affine_times], g2.geo_coords + [g2.mino_times, g2.affine_times]):
         assert np.array_equal(x, y)
+
+
+def test_ncu_summary_belongs_to_the_current_kernels():
+    """bench.py takes its roofline constants (executed flops per point / pixel, pipe activity, DRAM traffic) from
+    profiles/r02_ncu_summary.json only while the CUDA sources hash to the value recorded with the capture.  A mismatch is not an
+    error (the bench then prints null) but it means the capture has to be redone: reported as a skip."""
+    import json
+    import bench
+    summ = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+    if summ.get("csrc_sha256_16") != bench.kernel_source_hash():
+        pytest.skip("kgeo_b200/csrc changed since the ncu capture (%s): re-run tools/gpu_session23.sh" % summ.get("git_sha"))
+    assert bench.ncu_summary() is not None
+    assert 400 < summ["track_pass"]["flop_per_point"] < 800 and summ["track_pass"]["registers_hot"] == 64
